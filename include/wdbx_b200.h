@@ -1,0 +1,173 @@
+/* wdbx_b200.h -- C ABI of libwdbx_b200.so, the B200 (sm_100a) exact-search engine that sits under
+ * WDBX's VectorIndex / VectorStore.search boundary.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the reference
+ * repository donaldfilimon/wdbx-py).  The reference-side binding is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary;
+ *   - every call returns WDBX_B200_OK (0) or a negative error code, never throws, never exits;
+ *     wdbx_b200_last_error() returns a thread-local message for the last failure;
+ *   - one engine owns the row partitions ("segments", one per logical WDBX shard) that live in
+ *     the HBM of ONE device; one process drives one GPU, multi-GPU runs are one engine per rank
+ *     and exchange packed keys (NCCL all-gather in the host layer) that wdbx_b200_merge() reduces;
+ *   - there is NO CPU fallback: without a usable CUDA device every compute call fails with
+ *     WDBX_B200_ERR_CUDA.
+ *
+ * Ranking key (shared by the scan kernels, the merge kernel and the cross-GPU exchange):
+ *   key = (monotone_u32(score) << 32) | ~gid        -- bigger key = better hit
+ *   so "higher score first, equal score => lower global insertion id first" is an integer max.
+ *   key 0 is "empty".  NaN scores are ranked as -inf.
+ */
+#ifndef WDBX_B200_H
+#define WDBX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WDBX_B200_ABI_VERSION 1
+
+/* error codes */
+#define WDBX_B200_OK 0
+#define WDBX_B200_ERR_ARG (-1)    /* bad argument (dimension, k, segment, NULL pointer ...) */
+#define WDBX_B200_ERR_CUDA (-2)   /* CUDA runtime failure (no device, launch error, ...) */
+#define WDBX_B200_ERR_OOM (-3)    /* device or host allocation failed */
+#define WDBX_B200_ERR_LIMIT (-4)  /* unsupported size (dim too large, k > WDBX_B200_MAX_K, ...) */
+
+/* storage element type of the stored embedding matrix */
+#define WDBX_B200_F32 0
+#define WDBX_B200_BF16 1 /* rows rounded to bf16 (RNE) at ingest; queries and accumulation stay fp32 */
+
+/* similarity; larger score is always better (VectorStore.search sorts descending,
+ * wdbx/core/vector_store.py:330) */
+#define WDBX_B200_COSINE 0 /* <x,q>/(|x||q|); 0 if either norm is 0 (FaissIndex._normalize_vector, indexing.py:851-856) */
+#define WDBX_B200_IP 1     /* <x,q>  (extension; IndexFlatIP without the normalisation) */
+#define WDBX_B200_L2 2     /* -sum (x-q)^2  (extension) */
+
+#define WDBX_B200_MAX_SEGMENTS 64
+#define WDBX_B200_MAX_K 1024
+#define WDBX_B200_ALL_SEGMENTS (-1)
+
+typedef struct wdbx_b200_engine wdbx_b200_engine;
+
+typedef struct wdbx_b200_stats {
+  int32_t abi_version;
+  int32_t device;
+  int32_t dim;          /* logical vector dimension */
+  int32_t dim_padded;   /* stored row length in elements (16-byte multiple) */
+  int32_t dtype;
+  int32_t num_segments;
+  int32_t sm_count;
+  int32_t reserved0;
+  int64_t rows_total;     /* rows appended over all segments (tombstoned rows included) */
+  int64_t rows_live;      /* rows_total minus tombstones */
+  int64_t capacity_rows;  /* rows that fit without growing */
+  int64_t bytes_resident; /* HBM bytes held by the engine */
+  int64_t kernel_launches;     /* kernels launched by this engine since creation */
+  int64_t searches;            /* search calls served */
+  double last_search_ms;       /* device time of the last wdbx_b200_search_host call */
+  int64_t seg_rows[WDBX_B200_MAX_SEGMENTS];
+  int64_t seg_live[WDBX_B200_MAX_SEGMENTS];
+} wdbx_b200_stats;
+
+/* ABI version of the loaded library (== WDBX_B200_ABI_VERSION). */
+int wdbx_b200_version(void);
+
+/* Thread-local text of the last error raised on the calling thread ("" if none). */
+const char* wdbx_b200_last_error(void);
+
+/* Number of CUDA devices visible, or a negative error code.  Used by the host layer to fail
+ * loudly when enable_gpu is requested on a box without a GPU. */
+int wdbx_b200_device_count(void);
+
+/* Create an engine on `device` holding `num_segments` independent row partitions of
+ * `dim`-dimensional vectors.
+ * Replaces: VectorStore._init_indices (wdbx/core/vector_store.py:111-134), which builds one
+ * FaissIndex/HNSWIndex per shard, and FaissIndex._create_index (wdbx/core/indexing.py:709-758)
+ * including its dead `use_gpu` branch (indexing.py:742-748). */
+int wdbx_b200_create(int device, int dim, int dtype, int num_segments, wdbx_b200_engine** out);
+
+/* Release every device and host resource of the engine.
+ * Replaces: FaissIndex.shutdown (indexing.py:845-849) minus persistence. */
+void wdbx_b200_destroy(wdbx_b200_engine* e);
+
+/* Make room for `rows` rows in `segment` without further growth (optional; append grows
+ * geometrically).  Replaces hnswlib's init_index(max_elements=...) (indexing.py:274-278). */
+int wdbx_b200_reserve(wdbx_b200_engine* e, int segment, int64_t rows);
+
+/* Append n rows (row-major [n, dim] fp32, host memory or device memory of the engine's device)
+ * to `segment`; stores them (optionally as bf16), computes 1/|x| and |x|^2 per row (kernel K4)
+ * and records gids[i] (host array, may be NULL => gid = running row count of the engine) as
+ * the global insertion id used for tie-breaking and returned by search.
+ * *first_row_out receives the segment-local index of the first appended row.
+ * Replaces: FaissIndex.add / batch_add (indexing.py:858-905, :921-968): normalise + index.add. */
+int wdbx_b200_append(wdbx_b200_engine* e, int segment, const float* rows, int64_t n,
+                     int src_is_device, const uint32_t* gids, int64_t* first_row_out);
+
+/* Overwrite one stored row in place (same gid) and clear its tombstone.
+ * Replaces: the duplicate-id branch of HNSWIndex.add (indexing.py:370-375, replace_vector). */
+int wdbx_b200_overwrite(wdbx_b200_engine* e, int segment, int64_t row, const float* v_host);
+
+/* Mark a row dead (dead=1) or alive (dead=0).  Dead rows are never returned.
+ * Replaces: FaissIndex.remove / HNSWIndex.remove (indexing.py:1050-1074, :525-560), whose rows
+ * keep competing in the top-k (SURVEY.md section 8c decision 1). */
+int wdbx_b200_tombstone(wdbx_b200_engine* e, int segment, int64_t row, int dead);
+
+/* Drop all rows of one segment (or all with WDBX_B200_ALL_SEGMENTS); capacity is kept.
+ * Replaces: FaissIndex.clear (indexing.py:1089-1112). */
+int wdbx_b200_clear(wdbx_b200_engine* e, int segment);
+
+/* Copy one stored row back to the host as fp32 (dim floats).
+ * Serves VectorStore.get (vector_store.py:579-596) without a host-side copy of every vector. */
+int wdbx_b200_read_row(wdbx_b200_engine* e, int segment, int64_t row, float* out_host);
+
+/* Exact top-k of B queries over one segment, or over all segments merged (segment ==
+ * WDBX_B200_ALL_SEGMENTS), entirely on the device and asynchronously on `cuda_stream`
+ * (a cudaStream_t; NULL = legacy default stream).  q_dev: [B, dim] fp32 on the device.
+ * Outputs (device pointers, any may be NULL): keys_out [B,k] packed ranking keys best-first
+ * (0 = empty slot), scores_out [B,k] fp32, gids_out [B,k] int64 (-1 = empty), counts_out [B].
+ * Scores never go to HBM: kernel K1 streams the rows once and keeps the running top-k in
+ * registers.  No allocation, no synchronisation => CUDA-graph capturable.
+ * Replaces: FaissIndex.search (indexing.py:983-1030) -- normalise the query (:1002),
+ * IndexFlatIP.search (:1013) -- and, for ALL_SEGMENTS, the per-shard loop + sort of
+ * VectorStore.search (vector_store.py:323-330, :345). */
+int wdbx_b200_search(wdbx_b200_engine* e, int segment, const float* q_dev, int B, int k,
+                     int metric, uint64_t* keys_out, float* scores_out, int64_t* gids_out,
+                     int32_t* counts_out, void* cuda_stream);
+
+/* Same search with HOST buffers: copies the queries in, runs the kernels, copies results out
+ * and synchronises.  per_segment != 0 returns one top-k per segment ([num_segments, B, k]
+ * outputs, counts [num_segments, B]) -- the candidate set VectorStore.search builds before its
+ * metadata post-filter (vector_store.py:323-342) -- otherwise one merged top-k ([B, k]).
+ * This is the call the reference-facing plugin makes. */
+int wdbx_b200_search_host(wdbx_b200_engine* e, int per_segment, const float* q_host, int B, int k,
+                          int metric, float* scores_host, int64_t* gids_host, uint64_t* keys_host,
+                          int32_t* counts_host);
+
+/* k-way merge of G best-first key lists per query (keys_dev [G, B, k], e.g. the output of an
+ * NCCL all-gather of every rank's wdbx_b200_search keys) into one best-first top-k per query.
+ * Replaces: the cross-shard concat + sort + [:limit] of VectorStore.search
+ * (vector_store.py:324-330, :345) when shards live on different GPUs. */
+int wdbx_b200_merge(wdbx_b200_engine* e, const uint64_t* keys_dev, int G, int B, int k,
+                    uint64_t* keys_out, float* scores_out, int64_t* gids_out, int32_t* counts_out,
+                    void* cuda_stream);
+
+/* Override the scan kernel's launch geometry (0 / -1 = automatic): consumer warps per CTA,
+ * TMA pipeline stages per warp, rows held per lane group (1, 2, 4), CTAs, L2 evict-first hint.
+ * Benchmark / profiling hook; the counterpart of the reference's HNSW_EF_SEARCH / FAISS_NPROBE
+ * knobs (indexing.py:242-245, :689-690) in the sense of "search-time tuning", results are
+ * identical for every setting. */
+int wdbx_b200_set_tuning(wdbx_b200_engine* e, int warps, int stages, int rows_unroll, int grid,
+                         int evict_first);
+
+/* Fill *out.  Replaces: FaissIndex.get_stats / size (indexing.py:1161-1183). */
+int wdbx_b200_get_stats(wdbx_b200_engine* e, wdbx_b200_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WDBX_B200_H */

@@ -1,0 +1,180 @@
+"""GPU parity: the CUDA scan/top-k path (through the C ABI) vs the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import exact_search as oracle  # noqa: E402
+
+
+def _engine(dim, nseg=1, dtype="fp32"):
+    import wdbx_b200
+
+    return wdbx_b200.Engine(device=0, dim=dim, dtype=dtype, num_segments=nseg)
+
+
+def _check(X, Q, k, metric, scores, gids, counts, dead=None):
+    for b in range(Q.shape[0]):
+        c = int(counts[b])
+        rep = oracle.check_topk(X, Q[b], metric, k, gids[b, :c], scores[b, :c], dead=dead)
+        assert rep["count_ok"], (b, rep, c)
+        assert rep["hard_mismatch"] == 0 and rep["recall"] == 1.0, (metric, b, rep)
+        assert rep["max_err_over_tol"] <= 1.0, (metric, b, rep)
+        assert rep["sorted"], (metric, b, rep)
+        assert np.all(gids[b, c:] == -1)
+
+
+@pytest.mark.parametrize("metric", ["cosine", "ip", "l2"])
+@pytest.mark.parametrize("n,dim,k", [(1, 4, 10), (10, 4, 10), (37, 5, 4), (1000, 20, 7), (5000, 96, 10),
+                                     (10000, 384, 5), (20011, 768, 10), (3000, 1536, 10), (777, 200, 33),
+                                     (4096, 384, 100), (2000, 3072, 10)])
+def test_scan_matches_oracle(built_lib, metric, n, dim, k):
+    rng = np.random.default_rng(n * 31 + dim)
+    X = rng.standard_normal((n, dim), dtype=np.float32)
+    Q = rng.standard_normal((3, dim), dtype=np.float32)
+    eng = _engine(dim)
+    eng.append(0, X)
+    scores, gids, counts = eng.search_host(Q, k, metric=metric)
+    assert np.all(counts == min(k, n))
+    _check(X, Q, k, metric, scores, gids, counts)
+    eng.close()
+
+
+def test_multi_segment_merge_and_per_segment(built_lib):
+    rng = np.random.default_rng(5)
+    n, dim, k, S = 9000, 384, 10, 3
+    X = rng.standard_normal((n, dim), dtype=np.float32)
+    Q = rng.standard_normal((2, dim), dtype=np.float32)
+    seg_of = rng.integers(0, S, size=n)
+    eng = _engine(dim, nseg=S)
+    for s in range(S):
+        rows = np.flatnonzero(seg_of == s)
+        eng.append(s, X[rows], gids=rows.astype(np.uint32))
+    scores, gids, counts = eng.search_host(Q, k)
+    _check(X, Q, k, "cosine", scores, gids, counts)
+    ps, pg, pc = eng.search_host(Q, k, per_segment=True)
+    assert ps.shape == (S, 2, k)
+    for s in range(S):
+        dead = seg_of != s
+        _check(X, Q, k, "cosine", ps[s], pg[s], pc[s], dead=dead)
+    eng.close()
+
+
+def test_edge_cases(built_lib):
+    dim = 8
+    eng = _engine(dim)
+    q = np.ones((1, dim), dtype=np.float32)
+    # empty store
+    s, g, c = eng.search_host(q, 5)
+    assert c[0] == 0 and np.all(g == -1)
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((50, dim), dtype=np.float32)
+    X[7] = 0.0                # zero row -> cosine 0
+    X[30] = X[3]              # exact duplicate -> tie broken by lower gid
+    X[40, 2] = np.nan         # NaN row ranks last
+    eng.append(0, X)
+    s, g, c = eng.search_host(X[3][None, :], 50)
+    assert c[0] == 50
+    assert list(g[0, :2]) == [3, 30] and s[0, 0] == s[0, 1]
+    assert g[0, -1] == 40 and np.isneginf(s[0, -1])
+    zr = list(g[0]).index(7)
+    assert s[0, zr] == 0.0
+    # zero query: every finite score is 0, order = gid ascending
+    s, g, c = eng.search_host(np.zeros((1, dim), np.float32), 5)
+    assert list(g[0]) == [0, 1, 2, 3, 4] and np.all(s[0] == 0.0)
+    # k > n
+    s, g, c = eng.search_host(q, 100)
+    assert c[0] == 50 and np.all(g[0, 50:] == -1)
+    # tombstones
+    eng.tombstone(0, 3)
+    s, g, c = eng.search_host(X[3][None, :], 50)
+    assert c[0] == 49 and 3 not in g[0] and g[0, 0] == 30
+    eng.tombstone(0, 3, dead=False)
+    s, g, c = eng.search_host(X[3][None, :], 2)
+    assert list(g[0]) == [3, 30]
+    # overwrite keeps the gid
+    eng.overwrite(0, 10, X[3] * 2.0)
+    s, g, c = eng.search_host(X[3][None, :], 3)
+    assert list(g[0]) == [3, 10, 30]
+    np.testing.assert_allclose(eng.read_row(0, 10), X[3] * 2.0)
+    # clear
+    eng.clear()
+    s, g, c = eng.search_host(q, 5)
+    assert c[0] == 0
+    eng.close()
+
+
+def test_ascending_scores_worst_case(built_lib):
+    """Every row beats the running k-th best: the insert path runs for each row."""
+    n, dim, k = 20000, 16, 10
+    X = np.zeros((n, dim), dtype=np.float32)
+    X[:, 0] = 1.0
+    X[:, 1] = np.linspace(-1.0, 1.0, n, dtype=np.float32)
+    q = np.zeros((1, dim), dtype=np.float32)
+    q[0, 1] = 1.0
+    eng = _engine(dim)
+    eng.append(0, X)
+    for metric in ("cosine", "ip"):
+        s, g, c = eng.search_host(q, k, metric=metric)
+        assert list(g[0]) == list(range(n - 1, n - 1 - k, -1))
+    eng.close()
+
+
+def test_bf16_storage(built_lib):
+    rng = np.random.default_rng(9)
+    n, dim, k = 30000, 384, 100
+    X = rng.standard_normal((n, dim), dtype=np.float32)
+    Q = rng.standard_normal((2, dim), dtype=np.float32)
+    eng = _engine(dim, dtype="bf16")
+    eng.append(0, X)
+    Xr = oracle.bf16_round(X)
+    np.testing.assert_array_equal(eng.read_row(0, 123), Xr[123])
+    for metric in ("ip", "cosine", "l2"):
+        s, g, c = eng.search_host(Q, k, metric=metric)
+        _check(Xr, Q, k, metric, s, g, c)
+    eng.close()
+
+
+def test_growth_and_large_k(built_lib):
+    rng = np.random.default_rng(13)
+    dim = 64
+    eng = _engine(dim)
+    parts = [rng.standard_normal((m, dim), dtype=np.float32) for m in (100, 2000, 7000, 1)]
+    for p in parts:
+        eng.append(0, p)
+    X = np.concatenate(parts)
+    Q = rng.standard_normal((2, dim), dtype=np.float32)
+    s, g, c = eng.search_host(Q, 1000)
+    _check(X, Q, 1000, "cosine", s, g, c)
+    st = eng.stats()
+    assert st["rows_total"] == X.shape[0] and st["kernel_launches"] > 0
+    eng.close()
+
+
+def test_device_search_and_merge(built_lib):
+    import torch
+
+    rng = np.random.default_rng(21)
+    n, dim, k = 8000, 128, 10
+    X = rng.standard_normal((n, dim), dtype=np.float32)
+    Q = rng.standard_normal((5, dim), dtype=np.float32)
+    # two engines on one GPU emulate two ranks
+    engs = [_engine(dim), _engine(dim)]
+    half = n // 2
+    engs[0].append(0, torch.from_numpy(X[:half]).cuda(), gids=np.arange(0, half, dtype=np.uint32))
+    engs[1].append(0, torch.from_numpy(X[half:]).cuda(), gids=np.arange(half, n, dtype=np.uint32))
+    qd = torch.from_numpy(Q).cuda()
+    outs = [e.search(qd, k) for e in engs]
+    keys = torch.stack([o["keys"] for o in outs])
+    merged = engs[0].merge(keys)
+    torch.cuda.synchronize()
+    _check(X, Q, k, "cosine", merged["scores"].cpu().numpy(), merged["gids"].cpu().numpy(),
+           merged["counts"].cpu().numpy())
+    # identical to a single engine holding everything (bit-exact scores, same ids)
+    one = _engine(dim)
+    one.append(0, X)
+    s, g, c = one.search_host(Q, k)
+    np.testing.assert_array_equal(g, merged["gids"].cpu().numpy())
+    np.testing.assert_array_equal(s, merged["scores"].cpu().numpy())
+    for e in engs + [one]:
+        e.close()

@@ -1,0 +1,161 @@
+// common.cuh -- shared device helpers for libwdbx_b200 (sm_100a only).
+//   * ranking key packing (score desc, gid asc as one u64 max)
+//   * warp-distributed sorted top-k list with threshold insert
+//   * mbarrier / cp.async.bulk (TMA bulk copy, SASS UBLKCP) wrappers
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace wdbx {
+
+constexpr unsigned FULL_MASK = 0xFFFFFFFFu;
+
+// ---------------------------------------------------------------- ranking key
+// monotone map float -> u32 (bigger float => bigger u32); NaN ranks as -inf, -0 == +0.
+__device__ __forceinline__ uint32_t mono_u32(float s) {
+  s = (s != s) ? __int_as_float(0xff800000) : (s + 0.0f);
+  uint32_t b = __float_as_uint(s);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float unmono_f32(uint32_t m) {
+  uint32_t b = (m & 0x80000000u) ? (m & 0x7FFFFFFFu) : ~m;
+  return __uint_as_float(b);
+}
+__device__ __forceinline__ uint64_t pack_key(float score, uint32_t gid) {
+  return (static_cast<uint64_t>(mono_u32(score)) << 32) | static_cast<uint64_t>(~gid);
+}
+__device__ __forceinline__ float key_score(uint64_t key) { return unmono_f32(static_cast<uint32_t>(key >> 32)); }
+__device__ __forceinline__ uint32_t key_gid(uint64_t key) { return ~static_cast<uint32_t>(key); }
+
+// ---------------------------------------------------------------- warp top-k list
+// Sorted (descending) list of 32*KS keys distributed over a warp: element e lives in lane
+// e % 32, slot e / 32.  Only the first k entries matter; thr caches entry k-1 so that the
+// streaming loop rejects almost every row with one compare.  All arguments are warp-uniform.
+template <int KS>
+struct WarpTopK {
+  uint64_t v[KS];
+  uint64_t thr;
+
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int s = 0; s < KS; ++s) v[s] = 0ull;
+    thr = 0ull;
+  }
+
+  __device__ __forceinline__ uint64_t entry(int e) const {  // broadcast entry e to the warp
+    uint64_t r = 0ull;
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      uint64_t t = __shfl_sync(FULL_MASK, v[s], e & 31);
+      if ((e >> 5) == s) r = t;
+    }
+    return r;
+  }
+
+  // precondition: nk > thr (so its position is < k)
+  __device__ __forceinline__ void insert(uint64_t nk, int k, int lane) {
+    int pos = 0;
+#pragma unroll
+    for (int s = 0; s < KS; ++s) pos += __popc(__ballot_sync(FULL_MASK, v[s] > nk));
+#pragma unroll
+    for (int s = KS - 1; s >= 0; --s) {
+      uint64_t up = __shfl_up_sync(FULL_MASK, v[s], 1);
+      if (s > 0) {
+        uint64_t carry = __shfl_sync(FULL_MASK, v[s - 1], 31);
+        if (lane == 0) up = carry;
+      }
+      const int idx = s * 32 + lane;
+      if (idx > pos) v[s] = up;
+      else if (idx == pos) v[s] = nk;
+    }
+    thr = entry(k - 1);
+  }
+
+  __device__ __forceinline__ void offer(uint64_t nk, int k, int lane) {
+    if (nk > thr) insert(nk, k, lane);
+  }
+
+  // store the first k entries to dst[0..k)
+  __device__ __forceinline__ void store(uint64_t* dst, int k, int lane) const {
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      const int idx = s * 32 + lane;
+      if (idx < k) dst[idx] = v[s];
+    }
+  }
+};
+
+// Decode the first k entries of a warp list into the user-visible outputs of one query.
+template <int KS>
+__device__ __forceinline__ void emit_outputs(const WarpTopK<KS>& L, int k, int lane, uint64_t* keys_out,
+                                             float* scores_out, long long* gids_out, int* count_out) {
+  int cnt = 0;
+#pragma unroll
+  for (int s = 0; s < KS; ++s) {
+    const int idx = s * 32 + lane;
+    const bool in = idx < k;
+    const uint64_t key = in ? L.v[s] : 0ull;
+    cnt += __popc(__ballot_sync(FULL_MASK, key != 0ull));
+    if (in) {
+      if (keys_out) keys_out[idx] = key;
+      if (scores_out) scores_out[idx] = key ? key_score(key) : __int_as_float(0xff800000);
+      if (gids_out) gids_out[idx] = key ? static_cast<long long>(key_gid(key)) : -1ll;
+    }
+  }
+  if (count_out && lane == 0) *count_out = cnt;
+}
+
+// ---------------------------------------------------------------- mbarrier + bulk async copy
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (complete_tx::bytes).
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                              uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+
+__device__ __forceinline__ float4 lds128(const void* p) { return *reinterpret_cast<const float4*>(p); }
+
+}  // namespace wdbx

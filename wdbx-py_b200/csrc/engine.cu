@@ -1,0 +1,668 @@
+// engine.cu -- C ABI of libwdbx_b200.so (see include/wdbx_b200.h for the contract and the
+// reference interfaces each entry point replaces).  Host-side runtime: device-resident segment
+// store (rows + norms + gids + tombstones in HBM), growth, per-stream workspaces, the pinned
+// host path, and the launch plumbing for kernels K1/K3/K4.
+#include "../../include/wdbx_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace wdbx;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess) {                                                                           \
+      cudaGetLastError();                                                                              \
+      return fail(_e == cudaErrorMemoryAllocation ? WDBX_B200_ERR_OOM : WDBX_B200_ERR_CUDA, "%s: %s", \
+                  #expr, cudaGetErrorString(_e));                                                      \
+    }                                                                                                  \
+  } while (0)
+
+struct Segment {
+  unsigned char* rows = nullptr;
+  float* inv_norm = nullptr;
+  float* sqnorm = nullptr;
+  uint32_t* gids = nullptr;
+  uint32_t* tomb = nullptr;  // device bitmap, allocated on first tombstone
+  std::vector<uint32_t> tomb_host;
+  int64_t n_rows = 0, cap_rows = 0, n_dead = 0;
+};
+
+struct Workspace {
+  cudaStream_t stream = nullptr;
+  uint64_t* cand = nullptr;
+  size_t cand_keys = 0;
+  unsigned int* counters = nullptr;
+  int n_counters = 0;
+};
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+struct wdbx_b200_engine {
+  int device = 0, dim = 0, dpad = 0, dtype = 0, elem_bytes = 4, nseg = 1, sm_count = 148;
+  Segment seg[kMaxSeg];
+  std::mutex mu;  // segments, workspaces, launches
+  uint32_t next_gid = 0;
+  std::vector<Workspace> ws;
+  ScanTuning tune{0, 0, 0, 0, -1};
+  cudaStream_t mstream = nullptr;  // mutations
+  // staging for host-sourced appends
+  float* stage_rows = nullptr;
+  size_t stage_rows_bytes = 0;
+  uint32_t* stage_gids = nullptr;
+  size_t stage_gids_n = 0;
+  // host search path
+  std::mutex host_mu;
+  cudaStream_t hstream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float* hq_pinned = nullptr;
+  float* dq = nullptr;
+  size_t q_floats = 0;
+  unsigned char* hres_pinned = nullptr;
+  unsigned char* dres = nullptr;
+  size_t res_bytes = 0;
+  // stats
+  std::atomic<long long> launches{0}, searches{0};
+  double last_search_ms = 0.0;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+    ok = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+size_t row_bytes(const wdbx_b200_engine* e) { return static_cast<size_t>(e->dpad) * e->elem_bytes; }
+
+int64_t round_cap(int64_t rows) { return (rows + 127) / 128 * 128; }
+
+void free_segment(Segment& s) {
+  cudaFree(s.rows);
+  cudaFree(s.inv_norm);
+  cudaFree(s.sqnorm);
+  cudaFree(s.gids);
+  cudaFree(s.tomb);
+  s = Segment();
+}
+
+// grow segment to hold at least `rows` rows.  Caller holds e->mu.
+int ensure_capacity(wdbx_b200_engine* e, Segment& s, int64_t rows) {
+  if (rows <= s.cap_rows) return WDBX_B200_OK;
+  int64_t cap = std::max<int64_t>(round_cap(rows), 1024);
+  if (s.cap_rows > 0) cap = std::max<int64_t>(cap, round_cap(s.cap_rows + s.cap_rows / 2));
+  const size_t rb = row_bytes(e);
+  unsigned char* nrows = nullptr;
+  float *ninv = nullptr, *nsq = nullptr;
+  uint32_t *ngid = nullptr, *ntomb = nullptr;
+  auto cleanup = [&] {
+    cudaFree(nrows); cudaFree(ninv); cudaFree(nsq); cudaFree(ngid); cudaFree(ntomb);
+  };
+  cudaError_t err;
+  if ((err = cudaMalloc(&nrows, static_cast<size_t>(cap) * rb)) != cudaSuccess ||
+      (err = cudaMalloc(&ninv, static_cast<size_t>(cap) * 4)) != cudaSuccess ||
+      (err = cudaMalloc(&nsq, static_cast<size_t>(cap) * 4)) != cudaSuccess ||
+      (err = cudaMalloc(&ngid, static_cast<size_t>(cap) * 4)) != cudaSuccess) {
+    cleanup();
+    cudaGetLastError();
+    return fail(WDBX_B200_ERR_OOM, "cudaMalloc for %lld rows of %zu bytes failed: %s", (long long)cap, rb,
+                cudaGetErrorString(err));
+  }
+  if (s.tomb) {
+    if ((err = cudaMalloc(&ntomb, static_cast<size_t>(cap / 32) * 4)) != cudaSuccess) {
+      cleanup();
+      cudaGetLastError();
+      return fail(WDBX_B200_ERR_OOM, "cudaMalloc tombstones failed: %s", cudaGetErrorString(err));
+    }
+    s.tomb_host.resize(static_cast<size_t>(cap / 32), 0u);
+  }
+  if (s.n_rows > 0) {
+    CU_TRY(cudaMemcpyAsync(nrows, s.rows, static_cast<size_t>(s.n_rows) * rb, cudaMemcpyDeviceToDevice, e->mstream));
+    CU_TRY(cudaMemcpyAsync(ninv, s.inv_norm, static_cast<size_t>(s.n_rows) * 4, cudaMemcpyDeviceToDevice, e->mstream));
+    CU_TRY(cudaMemcpyAsync(nsq, s.sqnorm, static_cast<size_t>(s.n_rows) * 4, cudaMemcpyDeviceToDevice, e->mstream));
+    CU_TRY(cudaMemcpyAsync(ngid, s.gids, static_cast<size_t>(s.n_rows) * 4, cudaMemcpyDeviceToDevice, e->mstream));
+  }
+  if (ntomb) {
+    CU_TRY(cudaMemcpyAsync(ntomb, s.tomb_host.data(), s.tomb_host.size() * 4, cudaMemcpyHostToDevice, e->mstream));
+  }
+  // in-flight searches (any stream) may still read the old buffers
+  CU_TRY(cudaDeviceSynchronize());
+  cudaFree(s.rows); cudaFree(s.inv_norm); cudaFree(s.sqnorm); cudaFree(s.gids); cudaFree(s.tomb);
+  s.rows = nrows; s.inv_norm = ninv; s.sqnorm = nsq; s.gids = ngid; s.tomb = ntomb;
+  s.cap_rows = cap;
+  return WDBX_B200_OK;
+}
+
+int get_workspace(wdbx_b200_engine* e, cudaStream_t stream, size_t cand_keys, int n_counters, Workspace** out) {
+  Workspace* w = nullptr;
+  for (auto& x : e->ws)
+    if (x.stream == stream) { w = &x; break; }
+  if (!w) {
+    if (e->ws.size() >= 64) return fail(WDBX_B200_ERR_LIMIT, "too many distinct streams (64) used with one engine");
+    e->ws.emplace_back();
+    w = &e->ws.back();
+    w->stream = stream;
+  }
+  if (w->cand_keys < cand_keys || w->n_counters < n_counters) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cs);
+    if (cs != cudaStreamCaptureStatusNone)
+      return fail(WDBX_B200_ERR_ARG, "workspace must grow during stream capture: run one warm-up search of this shape first");
+    CU_TRY(cudaStreamSynchronize(stream));
+    if (w->cand_keys < cand_keys) {
+      cudaFree(w->cand);
+      w->cand = nullptr;
+      w->cand_keys = 0;
+      CU_TRY(cudaMalloc(&w->cand, cand_keys * 8));
+      w->cand_keys = cand_keys;
+    }
+    if (w->n_counters < n_counters) {
+      cudaFree(w->counters);
+      w->counters = nullptr;
+      w->n_counters = 0;
+      const int n = std::max(n_counters, 64);
+      CU_TRY(cudaMalloc(&w->counters, static_cast<size_t>(n) * 4));
+      CU_TRY(cudaMemsetAsync(w->counters, 0, static_cast<size_t>(n) * 4, stream));
+      w->n_counters = n;
+    }
+  }
+  *out = w;
+  return WDBX_B200_OK;
+}
+
+// Launch one K1 scan over segments [s0, s1).  Caller holds e->mu and has set the device.
+int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B, int k, int metric,
+                  uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream) {
+  ScanPlan plan;
+  const int rc = scan_plan(e->dim, e->dpad, e->elem_bytes, k, e->sm_count, e->tune, &plan);
+  if (rc == -4) return fail(WDBX_B200_ERR_LIMIT, "dimension %d too large for the scan kernel's shared-memory stage", e->dim);
+  if (rc != 0) return fail(WDBX_B200_ERR_ARG, "invalid scan shape (dim=%d k=%d)", e->dim, k);
+  ScanParams p;
+  memset(&p, 0, sizeof(p));
+  long long tiles = 0, bytes = 0;
+  int n = 0;
+  for (int s = s0; s < s1; ++s) {
+    const Segment& sg = e->seg[s];
+    p.seg[n].rows = sg.rows;
+    p.seg[n].inv_norm = sg.inv_norm;
+    p.seg[n].gids = sg.gids;
+    p.seg[n].tomb = sg.n_dead > 0 ? sg.tomb : nullptr;
+    p.seg[n].n_rows = sg.n_rows;
+    tiles += (sg.n_rows + plan.tile_rows - 1) / plan.tile_rows;
+    bytes += sg.n_rows * static_cast<long long>(row_bytes(e));
+    p.tile_end[n] = tiles;
+    ++n;
+  }
+  p.n_seg = n;
+  p.total_tiles = tiles;
+  // small stores: fewer CTAs than SMs would idle warps; keep one CTA per SM but never more CTAs than tiles
+  long long want = (tiles + plan.warps - 1) / plan.warps;
+  if (want < 1) want = 1;
+  if (want < plan.grid) plan.grid = static_cast<int>(want);
+  p.q = q_dev;
+  p.B = B;
+  p.dim = e->dim;
+  p.dpad = e->dpad;
+  p.row_bytes = static_cast<int>(row_bytes(e));
+  p.cpr = p.row_bytes / 16;
+  p.lpr_log2 = plan.lpr_log2;
+  p.nch = plan.nch;
+  p.tile_rows = plan.tile_rows;
+  p.stages = plan.stages;
+  p.stage_bytes = plan.stage_bytes;
+  p.k = k;
+  p.metric = metric;
+  // streamed-once data should not evict the rest of L2; small stores want to stay resident
+  p.evict_first = e->tune.evict_first >= 0 ? e->tune.evict_first : (bytes > (96ll << 20) ? 1 : 0);
+  Workspace* w = nullptr;
+  const int wrc = get_workspace(e, stream, static_cast<size_t>(B) * plan.grid * k, B, &w);
+  if (wrc != WDBX_B200_OK) return wrc;
+  p.cand = w->cand;
+  p.counters = w->counters;
+  p.keys_out = keys_out;
+  p.scores_out = scores_out;
+  p.gids_out = gids_out;
+  p.counts_out = counts_out;
+  CU_TRY(launch_scan_topk(p, plan, e->dtype == WDBX_B200_BF16, stream));
+  e->launches.fetch_add(1, std::memory_order_relaxed);
+  return WDBX_B200_OK;
+}
+
+int check_search_args(wdbx_b200_engine* e, int B, int k, int metric) {
+  if (!e) return fail(WDBX_B200_ERR_ARG, "engine is NULL");
+  if (B <= 0) return fail(WDBX_B200_ERR_ARG, "B must be positive (got %d)", B);
+  if (k <= 0) return fail(WDBX_B200_ERR_ARG, "k must be positive (got %d)", k);
+  if (k > WDBX_B200_MAX_K) return fail(WDBX_B200_ERR_LIMIT, "k=%d exceeds WDBX_B200_MAX_K=%d", k, WDBX_B200_MAX_K);
+  if (B > 65535) return fail(WDBX_B200_ERR_LIMIT, "B=%d exceeds 65535 queries per call", B);
+  if (metric < 0 || metric > 2) return fail(WDBX_B200_ERR_ARG, "unknown metric %d", metric);
+  return WDBX_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wdbx_b200_version(void) { return WDBX_B200_ABI_VERSION; }
+
+const char* wdbx_b200_last_error(void) { return g_err; }
+
+int wdbx_b200_device_count(void) {
+  int n = 0;
+  cudaError_t err = cudaGetDeviceCount(&n);
+  if (err != cudaSuccess) {
+    cudaGetLastError();
+    return fail(WDBX_B200_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(err));
+  }
+  return n;
+}
+
+int wdbx_b200_create(int device, int dim, int dtype, int num_segments, wdbx_b200_engine** out) {
+  if (!out) return fail(WDBX_B200_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (dim <= 0) return fail(WDBX_B200_ERR_ARG, "dim must be positive (got %d)", dim);
+  if (dtype != WDBX_B200_F32 && dtype != WDBX_B200_BF16) return fail(WDBX_B200_ERR_ARG, "unknown dtype %d", dtype);
+  if (num_segments < 1 || num_segments > WDBX_B200_MAX_SEGMENTS)
+    return fail(WDBX_B200_ERR_LIMIT, "num_segments=%d outside [1, %d]", num_segments, WDBX_B200_MAX_SEGMENTS);
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(WDBX_B200_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback",
+                err != cudaSuccess ? cudaGetErrorString(err) : "0 devices");
+  }
+  if (device < 0 || device >= ndev) return fail(WDBX_B200_ERR_ARG, "device %d outside [0, %d)", device, ndev);
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(WDBX_B200_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(WDBX_B200_ERR_CUDA, "device %d is sm_%d%d; libwdbx_b200 is built for sm_100a only", device, prop.major,
+                prop.minor);
+  wdbx_b200_engine* e = new (std::nothrow) wdbx_b200_engine();
+  if (!e) return fail(WDBX_B200_ERR_OOM, "host allocation failed");
+  e->device = device;
+  e->dim = dim;
+  e->dtype = dtype;
+  e->elem_bytes = dtype == WDBX_B200_BF16 ? 2 : 4;
+  const int epc = 16 / e->elem_bytes;
+  e->dpad = (dim + epc - 1) / epc * epc;
+  e->nseg = num_segments;
+  e->sm_count = prop.multiProcessorCount;
+  e->tune.warps = env_int("WDBX_B200_WARPS", 0);
+  e->tune.stages = env_int("WDBX_B200_STAGES", 0);
+  e->tune.rows_unroll = env_int("WDBX_B200_UNROLL", 0);
+  e->tune.grid = env_int("WDBX_B200_GRID", 0);
+  e->tune.evict_first = env_int("WDBX_B200_EVICT_FIRST", -1);
+  ScanPlan plan;
+  if (scan_plan(dim, e->dpad, e->elem_bytes, 10, e->sm_count, e->tune, &plan) != 0) {
+    delete e;
+    return fail(WDBX_B200_ERR_LIMIT, "dim=%d is too large for the scan kernel (row must fit a shared-memory stage)", dim);
+  }
+  cudaError_t e1 = cudaStreamCreateWithFlags(&e->mstream, cudaStreamNonBlocking);
+  cudaError_t e2 = cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking);
+  cudaError_t e3 = cudaEventCreate(&e->ev0);
+  cudaError_t e4 = cudaEventCreate(&e->ev1);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+    wdbx_b200_destroy(e);
+    return fail(WDBX_B200_ERR_CUDA, "stream/event creation failed");
+  }
+  *out = e;
+  return WDBX_B200_OK;
+}
+
+void wdbx_b200_destroy(wdbx_b200_engine* e) {
+  if (!e) return;
+  DeviceGuard guard(e->device);
+  cudaDeviceSynchronize();
+  for (int s = 0; s < kMaxSeg; ++s) free_segment(e->seg[s]);
+  for (auto& w : e->ws) {
+    cudaFree(w.cand);
+    cudaFree(w.counters);
+  }
+  cudaFree(e->stage_rows);
+  cudaFree(e->stage_gids);
+  cudaFree(e->dq);
+  cudaFree(e->dres);
+  cudaFreeHost(e->hq_pinned);
+  cudaFreeHost(e->hres_pinned);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->mstream) cudaStreamDestroy(e->mstream);
+  if (e->hstream) cudaStreamDestroy(e->hstream);
+  cudaGetLastError();
+  delete e;
+}
+
+int wdbx_b200_set_tuning(wdbx_b200_engine* e, int warps, int stages, int rows_unroll, int grid, int evict_first) {
+  if (!e) return fail(WDBX_B200_ERR_ARG, "engine is NULL");
+  std::lock_guard<std::mutex> lk(e->mu);
+  ScanTuning t{warps, stages, rows_unroll, grid, evict_first};
+  ScanPlan plan;
+  if (scan_plan(e->dim, e->dpad, e->elem_bytes, 10, e->sm_count, t, &plan) != 0)
+    return fail(WDBX_B200_ERR_ARG, "tuning does not fit shared memory");
+  e->tune = t;
+  return WDBX_B200_OK;
+}
+
+int wdbx_b200_reserve(wdbx_b200_engine* e, int segment, int64_t rows) {
+  if (!e) return fail(WDBX_B200_ERR_ARG, "engine is NULL");
+  if (segment < 0 || segment >= e->nseg) return fail(WDBX_B200_ERR_ARG, "segment %d outside [0, %d)", segment, e->nseg);
+  if (rows < 0 || rows > 0xFFFFFFF0ll) return fail(WDBX_B200_ERR_LIMIT, "rows=%lld outside [0, 2^32)", (long long)rows);
+  DeviceGuard guard(e->device);
+  std::lock_guard<std::mutex> lk(e->mu);
+  return ensure_capacity(e, e->seg[segment], rows);
+}
+
+int wdbx_b200_append(wdbx_b200_engine* e, int segment, const float* rows, int64_t n, int src_is_device,
+                     const uint32_t* gids, int64_t* first_row_out) {
+  if (!e) return fail(WDBX_B200_ERR_ARG, "engine is NULL");
+  if (segment < 0 || segment >= e->nseg) return fail(WDBX_B200_ERR_ARG, "segment %d outside [0, %d)", segment, e->nseg);
+  if (n < 0) return fail(WDBX_B200_ERR_ARG, "n must be >= 0");
+  if (n > 0 && !rows) return fail(WDBX_B200_ERR_ARG, "rows is NULL");
+  DeviceGuard guard(e->device);
+  std::lock_guard<std::mutex> lk(e->mu);
+  Segment& s = e->seg[segment];
+  if (first_row_out) *first_row_out = s.n_rows;
+  if (n == 0) return WDBX_B200_OK;
+  if (s.n_rows + n > 0xFFFFFFF0ll) return fail(WDBX_B200_ERR_LIMIT, "segment would exceed 2^32 rows");
+  int rc = ensure_capacity(e, s, s.n_rows + n);
+  if (rc != WDBX_B200_OK) return rc;
+  const size_t rb = row_bytes(e);
+  const bool bf16 = e->dtype == WDBX_B200_BF16;
+  const int64_t chunk_rows = std::max<int64_t>(1, (64ll << 20) / (static_cast<int64_t>(e->dim) * 4));
+  for (int64_t done = 0; done < n; done += chunk_rows) {
+    const int64_t m = std::min(chunk_rows, n - done);
+    const float* src = rows + done * e->dim;
+    if (!src_is_device) {
+      const size_t need = static_cast<size_t>(m) * e->dim * 4;
+      if (e->stage_rows_bytes < need) {
+        cudaFree(e->stage_rows);
+        e->stage_rows = nullptr;
+        e->stage_rows_bytes = 0;
+        CU_TRY(cudaMalloc(&e->stage_rows, need));
+        e->stage_rows_bytes = need;
+      }
+      CU_TRY(cudaMemcpyAsync(e->stage_rows, src, need, cudaMemcpyHostToDevice, e->mstream));
+      src = e->stage_rows;
+    }
+    const uint32_t* gsrc = nullptr;
+    if (gids) {
+      if (e->stage_gids_n < static_cast<size_t>(m)) {
+        cudaFree(e->stage_gids);
+        e->stage_gids = nullptr;
+        e->stage_gids_n = 0;
+        CU_TRY(cudaMalloc(&e->stage_gids, static_cast<size_t>(m) * 4));
+        e->stage_gids_n = static_cast<size_t>(m);
+      }
+      CU_TRY(cudaMemcpyAsync(e->stage_gids, gids + done, static_cast<size_t>(m) * 4, cudaMemcpyHostToDevice, e->mstream));
+      gsrc = e->stage_gids;
+    }
+    const int64_t r0 = s.n_rows + done;
+    CU_TRY(launch_append_rows(src, m, e->dim, e->dpad, bf16, s.rows + static_cast<size_t>(r0) * rb, s.inv_norm + r0,
+                              s.sqnorm + r0, s.gids + r0, gsrc, e->next_gid + static_cast<uint32_t>(done), e->mstream));
+    e->launches.fetch_add(1, std::memory_order_relaxed);
+    // the staging buffers are reused by the next chunk
+    CU_TRY(cudaStreamSynchronize(e->mstream));
+  }
+  s.n_rows += n;
+  e->next_gid += static_cast<uint32_t>(n);
+  return WDBX_B200_OK;
+}
+
+int wdbx_b200_overwrite(wdbx_b200_engine* e, int segment, int64_t row, const float* v_host) {
+  if (!e || !v_host) return fail(WDBX_B200_ERR_ARG, "NULL argument");
+  if (segment < 0 || segment >= e->nseg) return fail(WDBX_B200_ERR_ARG, "segment %d outside [0, %d)", segment, e->nseg);
+  DeviceGuard guard(e->device);
+  std::lock_guard<std::mutex> lk(e->mu);
+  Segment& s = e->seg[segment];
+  if (row < 0 || row >= s.n_rows) return fail(WDBX_B200_ERR_ARG, "row %lld outside [0, %lld)", (long long)row, (long long)s.n_rows);
+  const size_t need = static_cast<size_t>(e->dim) * 4 + 4;
+  if (e->stage_rows_bytes < need) {
+    cudaFree(e->stage_rows);
+    e->stage_rows = nullptr;
+    e->stage_rows_bytes = 0;
+    CU_TRY(cudaMalloc(&e->stage_rows, need));
+    e->stage_rows_bytes = need;
+  }
+  if (e->stage_gids_n < 1) {
+    CU_TRY(cudaMalloc(&e->stage_gids, 4 * 32));
+    e->stage_gids_n = 32;
+  }
+  CU_TRY(cudaMemcpyAsync(e->stage_rows, v_host, static_cast<size_t>(e->dim) * 4, cudaMemcpyHostToDevice, e->mstream));
+  // keep the row's gid
+  CU_TRY(cudaMemcpyAsync(e->stage_gids, s.gids + row, 4, cudaMemcpyDeviceToDevice, e->mstream));
+  CU_TRY(launch_append_rows(e->stage_rows, 1, e->dim, e->dpad, e->dtype == WDBX_B200_BF16,
+                            s.rows + static_cast<size_t>(row) * row_bytes(e), s.inv_norm + row, s.sqnorm + row,
+                            s.gids + row, e->stage_gids, 0, e->mstream));
+  e->launches.fetch_add(1, std::memory_order_relaxed);
+  if (s.tomb && ((s.tomb_host[row >> 5] >> (row & 31)) & 1u)) {
+    s.tomb_host[row >> 5] &= ~(1u << (row & 31));
+    s.n_dead -= 1;
+    CU_TRY(cudaMemcpyAsync(s.tomb + (row >> 5), &s.tomb_host[row >> 5], 4, cudaMemcpyHostToDevice, e->mstream));
+  }
+  CU_TRY(cudaStreamSynchronize(e->mstream));
+  return WDBX_B200_OK;
+}
+
+int wdbx_b200_tombstone(wdbx_b200_engine* e, int segment, int64_t row, int dead) {
+  if (!e) return fail(WDBX_B200_ERR_ARG, "engine is NULL");
+  if (segment < 0 || segment >= e->nseg) return fail(WDBX_B200_ERR_ARG, "segment %d outside [0, %d)", segment, e->nseg);
+  DeviceGuard guard(e->device);
+  std::lock_guard<std::mutex> lk(e->mu);
+  Segment& s = e->seg[segment];
+  if (row < 0 || row >= s.n_rows) return fail(WDBX_B200_ERR_ARG, "row %lld outside [0, %lld)", (long long)row, (long long)s.n_rows);
+  if (!s.tomb) {
+    if (!dead) return WDBX_B200_OK;
+    const size_t words = static_cast<size_t>(s.cap_rows / 32);
+    CU_TRY(cudaMalloc(&s.tomb, words * 4));
+    CU_TRY(cudaMemsetAsync(s.tomb, 0, words * 4, e->mstream));
+    s.tomb_host.assign(words, 0u);
+  }
+  uint32_t& w = s.tomb_host[row >> 5];
+  const uint32_t bit = 1u << (row & 31);
+  const bool was = (w & bit) != 0;
+  if (dead && !was) { w |= bit; s.n_dead += 1; }
+  else if (!dead && was) { w &= ~bit; s.n_dead -= 1; }
+  else return WDBX_B200_OK;
+  CU_TRY(cudaMemcpyAsync(s.tomb + (row >> 5), &w, 4, cudaMemcpyHostToDevice, e->mstream));
+  CU_TRY(cudaStreamSynchronize(e->mstream));
+  return WDBX_B200_OK;
+}
+
+int wdbx_b200_clear(wdbx_b200_engine* e, int segment) {
+  if (!e) return fail(WDBX_B200_ERR_ARG, "engine is NULL");
+  if (segment != WDBX_B200_ALL_SEGMENTS && (segment < 0 || segment >= e->nseg))
+    return fail(WDBX_B200_ERR_ARG, "segment %d outside [0, %d)", segment, e->nseg);
+  DeviceGuard guard(e->device);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU_TRY(cudaDeviceSynchronize());
+  const int s0 = segment == WDBX_B200_ALL_SEGMENTS ? 0 : segment;
+  const int s1 = segment == WDBX_B200_ALL_SEGMENTS ? e->nseg : segment + 1;
+  for (int i = s0; i < s1; ++i) {
+    Segment& s = e->seg[i];
+    s.n_rows = 0;
+    s.n_dead = 0;
+    if (s.tomb) {
+      std::fill(s.tomb_host.begin(), s.tomb_host.end(), 0u);
+      CU_TRY(cudaMemset(s.tomb, 0, s.tomb_host.size() * 4));
+    }
+  }
+  return WDBX_B200_OK;
+}
+
+int wdbx_b200_read_row(wdbx_b200_engine* e, int segment, int64_t row, float* out_host) {
+  if (!e || !out_host) return fail(WDBX_B200_ERR_ARG, "NULL argument");
+  if (segment < 0 || segment >= e->nseg) return fail(WDBX_B200_ERR_ARG, "segment %d outside [0, %d)", segment, e->nseg);
+  DeviceGuard guard(e->device);
+  std::lock_guard<std::mutex> lk(e->mu);
+  Segment& s = e->seg[segment];
+  if (row < 0 || row >= s.n_rows) return fail(WDBX_B200_ERR_ARG, "row %lld outside [0, %lld)", (long long)row, (long long)s.n_rows);
+  const size_t need = static_cast<size_t>(e->dim) * 4;
+  if (e->stage_rows_bytes < need) {
+    cudaFree(e->stage_rows);
+    e->stage_rows = nullptr;
+    e->stage_rows_bytes = 0;
+    CU_TRY(cudaMalloc(&e->stage_rows, need));
+    e->stage_rows_bytes = need;
+  }
+  CU_TRY(launch_export_row(s.rows + static_cast<size_t>(row) * row_bytes(e), e->dim, e->dtype == WDBX_B200_BF16,
+                           e->stage_rows, e->mstream));
+  e->launches.fetch_add(1, std::memory_order_relaxed);
+  CU_TRY(cudaMemcpyAsync(out_host, e->stage_rows, need, cudaMemcpyDeviceToHost, e->mstream));
+  CU_TRY(cudaStreamSynchronize(e->mstream));
+  return WDBX_B200_OK;
+}
+
+int wdbx_b200_search(wdbx_b200_engine* e, int segment, const float* q_dev, int B, int k, int metric,
+                     uint64_t* keys_out, float* scores_out, int64_t* gids_out, int32_t* counts_out,
+                     void* cuda_stream) {
+  int rc = check_search_args(e, B, k, metric);
+  if (rc != WDBX_B200_OK) return rc;
+  if (!q_dev) return fail(WDBX_B200_ERR_ARG, "q_dev is NULL");
+  if (segment != WDBX_B200_ALL_SEGMENTS && (segment < 0 || segment >= e->nseg))
+    return fail(WDBX_B200_ERR_ARG, "segment %d outside [0, %d)", segment, e->nseg);
+  DeviceGuard guard(e->device);
+  std::lock_guard<std::mutex> lk(e->mu);
+  const int s0 = segment == WDBX_B200_ALL_SEGMENTS ? 0 : segment;
+  const int s1 = segment == WDBX_B200_ALL_SEGMENTS ? e->nseg : segment + 1;
+  rc = scan_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, reinterpret_cast<long long*>(gids_out),
+                     counts_out, static_cast<cudaStream_t>(cuda_stream));
+  if (rc == WDBX_B200_OK) e->searches.fetch_add(1, std::memory_order_relaxed);
+  return rc;
+}
+
+int wdbx_b200_search_host(wdbx_b200_engine* e, int per_segment, const float* q_host, int B, int k, int metric,
+                          float* scores_host, int64_t* gids_host, uint64_t* keys_host, int32_t* counts_host) {
+  int rc = check_search_args(e, B, k, metric);
+  if (rc != WDBX_B200_OK) return rc;
+  if (!q_host) return fail(WDBX_B200_ERR_ARG, "q_host is NULL");
+  DeviceGuard guard(e->device);
+  std::lock_guard<std::mutex> hlk(e->host_mu);
+  const int lists = per_segment ? e->nseg : 1;
+  const size_t nq = static_cast<size_t>(B) * e->dim;
+  const size_t nres = static_cast<size_t>(lists) * B * k;
+  // result block layout: keys[nres] u64 | gids[nres] i64 | scores[nres] f32 | counts[lists*B] i32
+  const size_t off_keys = 0, off_gids = nres * 8, off_scores = nres * 16, off_counts = nres * 20;
+  const size_t bytes = off_counts + static_cast<size_t>(lists) * B * 4;
+  if (e->q_floats < nq) {
+    cudaFreeHost(e->hq_pinned); e->hq_pinned = nullptr;
+    cudaFree(e->dq); e->dq = nullptr;
+    e->q_floats = 0;
+    CU_TRY(cudaMallocHost(&e->hq_pinned, nq * 4));
+    CU_TRY(cudaMalloc(&e->dq, nq * 4));
+    e->q_floats = nq;
+  }
+  if (e->res_bytes < bytes) {
+    cudaFreeHost(e->hres_pinned); e->hres_pinned = nullptr;
+    cudaFree(e->dres); e->dres = nullptr;
+    e->res_bytes = 0;
+    CU_TRY(cudaMallocHost(&e->hres_pinned, bytes));
+    CU_TRY(cudaMalloc(&e->dres, bytes));
+    e->res_bytes = bytes;
+  }
+  memcpy(e->hq_pinned, q_host, nq * 4);
+  cudaStream_t st = e->hstream;
+  CU_TRY(cudaMemcpyAsync(e->dq, e->hq_pinned, nq * 4, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaEventRecord(e->ev0, st));
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    for (int l = 0; l < lists; ++l) {
+      const size_t o = static_cast<size_t>(l) * B * k;
+      rc = scan_segments(e, per_segment ? l : 0, per_segment ? l + 1 : e->nseg, e->dq, B, k, metric,
+                         reinterpret_cast<uint64_t*>(e->dres + off_keys) + o,
+                         reinterpret_cast<float*>(e->dres + off_scores) + o,
+                         reinterpret_cast<long long*>(e->dres + off_gids) + o,
+                         reinterpret_cast<int*>(e->dres + off_counts) + static_cast<size_t>(l) * B, st);
+      if (rc != WDBX_B200_OK) return rc;
+    }
+  }
+  CU_TRY(cudaEventRecord(e->ev1, st));
+  CU_TRY(cudaMemcpyAsync(e->hres_pinned, e->dres, bytes, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  float ms = 0.0f;
+  if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_search_ms = ms;
+  if (keys_host) memcpy(keys_host, e->hres_pinned + off_keys, nres * 8);
+  if (gids_host) memcpy(gids_host, e->hres_pinned + off_gids, nres * 8);
+  if (scores_host) memcpy(scores_host, e->hres_pinned + off_scores, nres * 4);
+  if (counts_host) memcpy(counts_host, e->hres_pinned + off_counts, static_cast<size_t>(lists) * B * 4);
+  e->searches.fetch_add(1, std::memory_order_relaxed);
+  return WDBX_B200_OK;
+}
+
+int wdbx_b200_merge(wdbx_b200_engine* e, const uint64_t* keys_dev, int G, int B, int k, uint64_t* keys_out,
+                    float* scores_out, int64_t* gids_out, int32_t* counts_out, void* cuda_stream) {
+  int rc = check_search_args(e, B, k, 0);
+  if (rc != WDBX_B200_OK) return rc;
+  if (!keys_dev) return fail(WDBX_B200_ERR_ARG, "keys_dev is NULL");
+  if (G <= 0) return fail(WDBX_B200_ERR_ARG, "G must be positive");
+  DeviceGuard guard(e->device);
+  CU_TRY(launch_merge_topk(keys_dev, G, B, k, keys_out, scores_out, reinterpret_cast<long long*>(gids_out), counts_out,
+                           static_cast<cudaStream_t>(cuda_stream)));
+  e->launches.fetch_add(1, std::memory_order_relaxed);
+  return WDBX_B200_OK;
+}
+
+int wdbx_b200_get_stats(wdbx_b200_engine* e, wdbx_b200_stats* out) {
+  if (!e || !out) return fail(WDBX_B200_ERR_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  memset(out, 0, sizeof(*out));
+  out->abi_version = WDBX_B200_ABI_VERSION;
+  out->device = e->device;
+  out->dim = e->dim;
+  out->dim_padded = e->dpad;
+  out->dtype = e->dtype;
+  out->num_segments = e->nseg;
+  out->sm_count = e->sm_count;
+  const int64_t per_row = static_cast<int64_t>(row_bytes(e)) + 12;
+  for (int s = 0; s < e->nseg; ++s) {
+    const Segment& sg = e->seg[s];
+    out->rows_total += sg.n_rows;
+    out->rows_live += sg.n_rows - sg.n_dead;
+    out->capacity_rows += sg.cap_rows;
+    out->bytes_resident += sg.cap_rows * per_row + (sg.tomb ? sg.cap_rows / 8 : 0);
+    out->seg_rows[s] = sg.n_rows;
+    out->seg_live[s] = sg.n_rows - sg.n_dead;
+  }
+  out->kernel_launches = e->launches.load();
+  out->searches = e->searches.load();
+  out->last_search_ms = e->last_search_ms;
+  return WDBX_B200_OK;
+}
+
+}  // extern "C"

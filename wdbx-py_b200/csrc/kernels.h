@@ -1,0 +1,81 @@
+// kernels.h -- host-visible launch interface between engine.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wdbx {
+
+constexpr int kMaxSeg = 64;
+constexpr int kMaxK = 1024;
+
+enum Metric : int { kCosine = 0, kIP = 1, kL2 = 2 };
+
+struct SegDesc {
+  const unsigned char* rows;  // [n_rows][row_bytes]
+  const float* inv_norm;      // [n_rows] 1/|x| (0 for zero rows)
+  const uint32_t* gids;       // [n_rows] global insertion ids
+  const uint32_t* tomb;       // bitmap, 1 = dead; may be NULL when the segment has no tombstones
+  long long n_rows;
+};
+
+// Tuning knobs of the streaming scan (K1); 0 = pick automatically.
+struct ScanTuning {
+  int warps;      // consumer warps per CTA (each owns a private TMA pipeline)
+  int stages;     // pipeline depth per warp
+  int rows_unroll;  // U: rows held per lane group per tile (1, 2 or 4)
+  int grid;       // CTAs (default: one per SM)
+  int evict_first;  // -1 auto, 0 off, 1 on
+};
+
+struct ScanParams {
+  SegDesc seg[kMaxSeg];
+  long long tile_end[kMaxSeg];  // exclusive prefix sum of tiles per segment
+  int n_seg;
+  long long total_tiles;
+  const float* q;  // [B][dim] fp32
+  int B;
+  int dim;        // logical dimension
+  int dpad;       // stored elements per row
+  int row_bytes;  // dpad * sizeof(elem)
+  int cpr;        // 16-byte chunks per row
+  int lpr_log2;   // log2(lanes per row)
+  int nch;        // chunks per lane = ceil(cpr / lanes_per_row)
+  int tile_rows;  // rows per warp tile = U * (32 >> lpr_log2)
+  int stages;
+  int stage_bytes;
+  int k;
+  int metric;
+  int evict_first;
+  uint64_t* cand;          // [B][grid][k] per-CTA partial lists
+  unsigned int* counters;  // [gridDim.y] last-block-done tickets (zero between launches)
+  uint64_t* keys_out;      // [B][k] or NULL
+  float* scores_out;       // [B][k] or NULL
+  long long* gids_out;     // [B][k] or NULL
+  int* counts_out;         // [B] or NULL
+};
+
+struct ScanPlan {
+  int lpr_log2, nch, U, KS, tile_rows, stage_bytes, stages, warps, grid;
+  size_t smem_bytes;
+  int queries_per_block;
+};
+
+// Fill the derived fields (plan) for the given shape.  Returns 0 or a negative wdbx error code.
+int scan_plan(int dim, int dpad, int elem_bytes, int k, int sm_count, const ScanTuning& tune, ScanPlan* plan);
+
+// Launch K1 (+ fused last-block merge).  p.seg / tile_end / totals must be consistent with plan.
+cudaError_t launch_scan_topk(const ScanParams& p, const ScanPlan& plan, bool bf16, cudaStream_t stream);
+
+// K3: merge G best-first lists per query.
+cudaError_t launch_merge_topk(const uint64_t* keys, int G, int B, int k, uint64_t* keys_out, float* scores_out,
+                              long long* gids_out, int* counts_out, cudaStream_t stream);
+
+// K4: ingest rows (fp32 source) into the stored layout + norms.
+cudaError_t launch_append_rows(const float* src, long long n, int dim, int dpad, bool bf16, unsigned char* dst_rows,
+                               float* inv_norm, float* sqnorm, uint32_t* gids_dst, const uint32_t* gids_src,
+                               uint32_t gid_base, cudaStream_t stream);
+
+// stored row -> fp32 (read_row)
+cudaError_t launch_export_row(const unsigned char* row, int dim, bool bf16, float* dst, cudaStream_t stream);
+
+}  // namespace wdbx

@@ -1,0 +1,201 @@
+"""Thin Python handle over the C ABI (one engine = the row partitions of one GPU)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import ALL_SEGMENTS, B200Error, DTYPES, METRICS, check
+
+
+def _metric_code(metric) -> int:
+    if isinstance(metric, int):
+        return metric
+    try:
+        return METRICS[str(metric).lower()]
+    except KeyError:
+        raise ValueError(f"unknown metric {metric!r}; expected one of {sorted(METRICS)}") from None
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """Device-resident exact-search engine for ONE GPU.
+
+    Segments are the logical WDBX shards (``VectorStore.indices[i]``, wdbx/core/vector_store.py:111-134);
+    rows carry a global insertion id (gid) that the caller maps back to string ids.
+    """
+
+    def __init__(self, device: int = 0, dim: int = 384, dtype: str = "fp32", num_segments: int = 1):
+        self._lib = _lib.load_library()
+        self.device, self.dim, self.num_segments = int(device), int(dim), int(num_segments)
+        self.dtype = str(dtype).lower()
+        if self.dtype not in DTYPES:
+            raise ValueError(f"unknown dtype {dtype!r}")
+        h = C.c_void_p()
+        check(self._lib.wdbx_b200_create(self.device, self.dim, DTYPES[self.dtype], self.num_segments, C.byref(h)))
+        self._h = h
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.wdbx_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _handle(self):
+        if not self._h:
+            raise B200Error(_lib.ERR_ARG, "engine is closed")
+        return self._h
+
+    # ------------------------------------------------------------------ mutation
+    def reserve(self, segment: int, rows: int):
+        check(self._lib.wdbx_b200_reserve(self._handle(), segment, rows))
+
+    def append(self, segment: int, rows, gids: Optional[np.ndarray] = None) -> int:
+        """Append [n, dim] fp32 rows (numpy array, or a CUDA torch tensor on this device).
+        Returns the segment-local index of the first appended row."""
+        first = C.c_int64(-1)
+        g = None
+        if gids is not None:
+            g = np.ascontiguousarray(gids, dtype=np.uint32)
+        if isinstance(rows, np.ndarray) or not hasattr(rows, "data_ptr"):
+            a = np.ascontiguousarray(rows, dtype=np.float32)
+            if a.ndim == 1:
+                a = a[None, :]
+            if a.ndim != 2 or a.shape[1] != self.dim:
+                raise ValueError(f"Vector dimension mismatch: expected {self.dim}, got {a.shape[-1]}")
+            if g is not None and g.shape[0] != a.shape[0]:
+                raise ValueError("gids length mismatch")
+            check(self._lib.wdbx_b200_append(self._handle(), segment, _np_ptr(a), a.shape[0], 0, _np_ptr(g), C.byref(first)))
+        else:
+            import torch
+
+            t = rows
+            if t.dim() == 1:
+                t = t[None, :]
+            if not t.is_cuda or t.device.index != self.device:
+                raise ValueError("tensor rows must live on the engine's CUDA device")
+            if t.dtype != torch.float32 or t.dim() != 2 or t.shape[1] != self.dim:
+                raise ValueError(f"Vector dimension mismatch: expected fp32 [n, {self.dim}]")
+            t = t.contiguous()
+            if g is not None and g.shape[0] != t.shape[0]:
+                raise ValueError("gids length mismatch")
+            torch.cuda.current_stream(t.device).synchronize()  # the ingest kernel runs on the engine's own stream
+            check(self._lib.wdbx_b200_append(self._handle(), segment, C.c_void_p(t.data_ptr()), t.shape[0], 1,
+                                             _np_ptr(g), C.byref(first)))
+        return int(first.value)
+
+    def overwrite(self, segment: int, row: int, vector):
+        v = np.ascontiguousarray(vector, dtype=np.float32).reshape(-1)
+        if v.shape[0] != self.dim:
+            raise ValueError(f"Vector dimension mismatch: expected {self.dim}, got {v.shape[0]}")
+        check(self._lib.wdbx_b200_overwrite(self._handle(), segment, row, _np_ptr(v)))
+
+    def tombstone(self, segment: int, row: int, dead: bool = True):
+        check(self._lib.wdbx_b200_tombstone(self._handle(), segment, row, 1 if dead else 0))
+
+    def clear(self, segment: int = ALL_SEGMENTS):
+        check(self._lib.wdbx_b200_clear(self._handle(), segment))
+
+    def read_row(self, segment: int, row: int) -> np.ndarray:
+        out = np.empty(self.dim, dtype=np.float32)
+        check(self._lib.wdbx_b200_read_row(self._handle(), segment, row, _np_ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ search
+    def search_host(self, queries, k: int, metric="cosine", per_segment: bool = False,
+                    want_keys: bool = False):
+        """Host-buffer search (H2D + kernels + D2H inside the call).
+
+        Returns (scores, gids, counts[, keys]); shapes [B, k] / [B], or with ``per_segment``
+        [num_segments, B, k] / [num_segments, B]."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"Vector dimension mismatch: expected {self.dim}, got {q.shape[-1]}")
+        B = q.shape[0]
+        lead = (self.num_segments, B) if per_segment else (B,)
+        scores = np.empty(lead + (k,), dtype=np.float32)
+        gids = np.empty(lead + (k,), dtype=np.int64)
+        counts = np.empty(lead, dtype=np.int32)
+        keys = np.empty(lead + (k,), dtype=np.uint64) if want_keys else None
+        check(self._lib.wdbx_b200_search_host(self._handle(), 1 if per_segment else 0, _np_ptr(q), B, k,
+                                              _metric_code(metric), _np_ptr(scores), _np_ptr(gids), _np_ptr(keys),
+                                              _np_ptr(counts)))
+        return (scores, gids, counts, keys) if want_keys else (scores, gids, counts)
+
+    def search(self, q_dev, k: int, metric="cosine", segment: int = ALL_SEGMENTS, out: Optional[Dict] = None,
+               stream=None) -> Dict:
+        """Device-resident search: q_dev is a CUDA fp32 tensor [B, dim]; outputs are CUDA tensors
+        (allocated here unless ``out`` carries preallocated ones -- required under graph capture).
+        Asynchronous on the current (or given) torch stream."""
+        import torch
+
+        if q_dev.dim() == 1:
+            q_dev = q_dev[None, :]
+        if not q_dev.is_cuda or q_dev.dtype != torch.float32 or q_dev.shape[1] != self.dim or not q_dev.is_contiguous():
+            raise ValueError(f"q_dev must be a contiguous CUDA fp32 tensor [B, {self.dim}]")
+        B = q_dev.shape[0]
+        dev = q_dev.device
+        if out is None:
+            out = {
+                "keys": torch.empty((B, k), dtype=torch.int64, device=dev),
+                "scores": torch.empty((B, k), dtype=torch.float32, device=dev),
+                "gids": torch.empty((B, k), dtype=torch.int64, device=dev),
+                "counts": torch.empty((B,), dtype=torch.int32, device=dev),
+            }
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        p = lambda name: C.c_void_p(out[name].data_ptr()) if out.get(name) is not None else None  # noqa: E731
+        check(self._lib.wdbx_b200_search(self._handle(), segment, C.c_void_p(q_dev.data_ptr()), B, k,
+                                         _metric_code(metric), p("keys"), p("scores"), p("gids"), p("counts"),
+                                         C.c_void_p(st.cuda_stream)))
+        return out
+
+    def merge(self, keys, out: Optional[Dict] = None, stream=None) -> Dict:
+        """k-way merge of keys [G, B, k] (int64 view of the packed u64 keys) on the device."""
+        import torch
+
+        if keys.dim() != 3 or keys.dtype != torch.int64 or not keys.is_cuda or not keys.is_contiguous():
+            raise ValueError("keys must be a contiguous CUDA int64 tensor [G, B, k]")
+        G, B, k = keys.shape
+        dev = keys.device
+        if out is None:
+            out = {
+                "keys": torch.empty((B, k), dtype=torch.int64, device=dev),
+                "scores": torch.empty((B, k), dtype=torch.float32, device=dev),
+                "gids": torch.empty((B, k), dtype=torch.int64, device=dev),
+                "counts": torch.empty((B,), dtype=torch.int32, device=dev),
+            }
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        p = lambda name: C.c_void_p(out[name].data_ptr()) if out.get(name) is not None else None  # noqa: E731
+        check(self._lib.wdbx_b200_merge(self._handle(), C.c_void_p(keys.data_ptr()), G, B, k, p("keys"), p("scores"),
+                                        p("gids"), p("counts"), C.c_void_p(st.cuda_stream)))
+        return out
+
+    # ------------------------------------------------------------------ misc
+    def set_tuning(self, warps: int = 0, stages: int = 0, rows_unroll: int = 0, grid: int = 0, evict_first: int = -1):
+        check(self._lib.wdbx_b200_set_tuning(self._handle(), warps, stages, rows_unroll, grid, evict_first))
+
+    def stats(self) -> Dict:
+        st = _lib.Stats()
+        check(self._lib.wdbx_b200_get_stats(self._handle(), C.byref(st)))
+        d = {name: getattr(st, name) for name, _ in _lib.Stats._fields_ if not name.startswith(("seg_", "reserved"))}
+        d["seg_rows"] = list(st.seg_rows)[: self.num_segments]
+        d["seg_live"] = list(st.seg_live)[: self.num_segments]
+        return d
+
+
+def device_count() -> int:
+    """Number of visible CUDA devices; raises B200Error when CUDA is unusable."""
+    return check(_lib.load_library().wdbx_b200_device_count())
