@@ -50,7 +50,8 @@ extern "C" {
 
 #define WDBX_B200_MAX_SEGMENTS 64
 #define WDBX_B200_MAX_K 1024
-#define WDBX_B200_ALL_SEGMENTS (-1)
+#define WDBX_B200_ALL_SEGMENTS (-1)  /* one top-k over all segments merged */
+#define WDBX_B200_EACH_SEGMENT (-2)  /* one top-k per segment (search_host only) */
 
 typedef struct wdbx_b200_engine wdbx_b200_engine;
 
@@ -140,11 +141,13 @@ int wdbx_b200_search(wdbx_b200_engine* e, int segment, const float* q_dev, int B
                      int32_t* counts_out, void* cuda_stream);
 
 /* Same search with HOST buffers: copies the queries in, runs the kernels, copies results out
- * and synchronises.  per_segment != 0 returns one top-k per segment ([num_segments, B, k]
- * outputs, counts [num_segments, B]) -- the candidate set VectorStore.search builds before its
- * metadata post-filter (vector_store.py:323-342) -- otherwise one merged top-k ([B, k]).
+ * and synchronises.  segment >= 0: that segment only (VectorIndex.search on one shard,
+ * indexing.py:983-1030); WDBX_B200_ALL_SEGMENTS: one merged top-k ([B, k] outputs);
+ * WDBX_B200_EACH_SEGMENT: one top-k per segment ([num_segments, B, k] outputs, counts
+ * [num_segments, B]) -- the candidate set VectorStore.search builds before its metadata
+ * post-filter (vector_store.py:323-342).  Any output pointer may be NULL.
  * This is the call the reference-facing plugin makes. */
-int wdbx_b200_search_host(wdbx_b200_engine* e, int per_segment, const float* q_host, int B, int k,
+int wdbx_b200_search_host(wdbx_b200_engine* e, int segment, const float* q_host, int B, int k,
                           int metric, float* scores_host, int64_t* gids_host, uint64_t* keys_host,
                           int32_t* counts_host);
 

@@ -1,0 +1,85 @@
+"""CPU, world_size 2 over gloo: the SPMD path of VectorStore (row striping, all-gather of packed
+keys, k-way merge) returns exactly what a single rank returns."""
+import json
+import os
+import socket
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _dataset():
+    rng = np.random.default_rng(42)
+    X = rng.standard_normal((301, 16), dtype=np.float32)
+    X[40] = X[7]  # tie across ranks
+    Q = rng.standard_normal((3, 16), dtype=np.float32)
+    return X, Q
+
+
+def _run_store(store):
+    X, Q = _dataset()
+    ids = [f"id{i}" for i in range(X.shape[0])]
+    meta = {ids[i]: {"i": i, "even": i % 2 == 0} for i in range(len(ids))}
+    store.batch_store({ids[i]: X[i] for i in range(200)}, meta)
+    for i in range(200, X.shape[0]):
+        store.store(ids[i], X[i].tolist(), meta[ids[i]])
+    store.delete("id5")
+    store.store("id9", X[11].tolist(), {"i": 9, "even": False})  # overwrite
+    out = {"plain": [], "filtered": [], "batch": None, "get": None}
+    for b in range(Q.shape[0]):
+        out["plain"].append([(i, s) for i, s, _ in store.search(Q[b].tolist(), limit=10)])
+        out["filtered"].append([(i, s) for i, s, _ in store.search(Q[b].tolist(), limit=6, filter_metadata={"even": True})])
+    out["tie"] = [(i, s) for i, s, _ in store.search(X[7].tolist(), limit=3)]
+    out["batch"] = store.search_batch(Q, limit=10).as_lists()
+    out["get"] = store.get("id40")[0]
+    out["shard0"] = store.indices[0].search(Q[0], limit=5)
+    out["count"] = store.count()
+    return out
+
+
+def _worker(rank, world, port, outdir):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "wdbx-py_b200"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    import wdbx_b200
+    from tests.fake_engine import FakeEngine
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = wdbx_b200.DistContext(rank, world, rank)
+    store = wdbx_b200.VectorStore(16, tempfile.mkdtemp(), num_shards=3, dist=ctx, _engine_factory=FakeEngine)
+    out = _run_store(store)
+    out["local_rows"] = store.engine.stats()["rows_total"]
+    Path(outdir, f"rank{rank}.json").write_text(json.dumps(out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_world2_matches_single_rank():
+    import wdbx_b200
+    from tests.fake_engine import FakeEngine
+
+    single = wdbx_b200.VectorStore(16, tempfile.mkdtemp(), num_shards=3, dist=wdbx_b200.DistContext(0, 1, 0),
+                                   _engine_factory=FakeEngine)
+    want = json.loads(json.dumps(_run_store(single)))
+    with tempfile.TemporaryDirectory() as outdir:
+        mp.spawn(_worker, args=(2, _free_port(), outdir), nprocs=2, join=True)
+        got = [json.loads(Path(outdir, f"rank{r}.json").read_text()) for r in range(2)]
+    rows = [g.pop("local_rows") for g in got]
+    assert sum(rows) == 301 and abs(rows[0] - rows[1]) <= 3  # striped: balanced within one row per shard
+    assert got[0] == got[1] == want
+    assert [i for i, _ in want["tie"][:2]] == ["id7", "id40"]

@@ -1,0 +1,110 @@
+"""GPU: the public API (WDBX / VectorStore / VectorIndex facades) over the real engine reproduces
+the reference's golden outputs and the reference's own test assertions (tests/test_core.py)."""
+import asyncio
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import wdbx_b200  # noqa: E402
+from oracle import exact_search as oracle  # noqa: E402
+from tests import golden_checks as gc  # noqa: E402
+
+
+def make_store(dim, shards, **cfg):
+    cfg.setdefault("GPU_STRICT", True)
+    return wdbx_b200.VectorStore(dim, tempfile.mkdtemp(), num_shards=shards, config=wdbx_b200.WDBXConfig(cfg))
+
+
+def test_ramp_golden(built_lib, golden):
+    for case in golden["ramp"]:
+        gc.check_ramp(make_store, case)
+
+
+def test_self_query_golden(built_lib, golden):
+    for case in golden["self_query"]:
+        gc.check_self_query(make_store, case)
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+def test_random_golden(built_lib, golden, idx):
+    gc.check_random(make_store, golden["random"][idx])
+
+
+def test_quickstart_c1_through_public_api(built_lib):
+    """BASELINE.json configs[0]: WDBX(vector_dimension=384, num_shards=2), 10k vectors, limit=5, cosine."""
+    rng = np.random.default_rng(1234)
+    X = rng.standard_normal((10000, 384), dtype=np.float32)
+    Q = rng.standard_normal((6, 384), dtype=np.float32)
+    with tempfile.TemporaryDirectory() as tmp:
+        db = wdbx_b200.WDBX(vector_dimension=384, num_shards=2, data_dir=tmp, enable_gpu=True, log_level="WARNING")
+
+        async def go():
+            await db.initialize()
+            ids = [f"doc{i}" for i in range(X.shape[0])]
+            n = db.vector_store.batch_store({ids[i]: X[i] for i in range(5000)}, {i_: {"n": j} for j, i_ in enumerate(ids)})
+            assert n == 5000
+            for i in range(5000, 5050):
+                await db.vector_store_async(X[i].tolist(), {"n": i}, id=ids[i])
+            db.vector_store.batch_store({ids[i]: X[i] for i in range(5050, 10000)})
+            assert db.count_vectors() == 10000
+            ost = oracle.OracleStore(384, 1)
+            for i in range(X.shape[0]):
+                ost.add(0, ids[i], X[i])
+            for b in range(Q.shape[0]):
+                got = db.vector_search(Q[b].tolist(), limit=5)
+                want = ost.search(Q[b], 5)
+                gc.assert_same_results([(g[0], g[1], None) for g in got], [(w[0], w[1], None) for w in want])
+                got_a = await db.vector_search_async(Q[b].tolist(), limit=5)
+                assert got_a == got
+            br = db.vector_search_batch(Q, limit=5)
+            assert br.ids() == [[r[0] for r in db.vector_search(Q[b].tolist(), limit=5)] for b in range(Q.shape[0])]
+            # self query / dimension error / stats (tests/test_core.py:135-142, :245-247, :341)
+            r = db.vector_search(X[77].tolist(), limit=1)
+            assert r[0][0] == "doc77" and r[0][1] > 0.99
+            with pytest.raises(ValueError, match="dimension mismatch"):
+                db.vector_search([0.0] * 3)
+            st = db.get_stats()
+            assert len(st["indices"]) == 2 and st["gpu"]["engine"]["kernel_launches"] > 0
+            vec, meta = db.get_vector("doc5001")
+            np.testing.assert_array_equal(np.asarray(vec, np.float32), X[5001])
+            await db.shutdown()
+
+        asyncio.run(go())
+
+
+def test_crud_on_device(built_lib):
+    st = make_store(4, 2)
+    assert st.store("a", [1, 0, 0, 0], {"t": 1}) and st.store("b", [0, 1, 0, 0]) and st.store("c", [1, 1, 0, 0])
+    assert st.store("a", [0, 0, 1, 0], {"t": 2}) and st.count() == 3
+    assert st.get("a") == ([0.0, 0.0, 1.0, 0.0], {"t": 2})
+    assert [r[0] for r in st.search([0, 0, 1, 0], limit=1)] == ["a"]
+    assert st.delete("c") and len(st.search([1, 1, 0, 0], limit=10)) == 2
+    assert st.clear() == 2 and st.search([0, 1, 0, 0]) == []
+    assert st.store("a", [1, 0, 0, 0]) and st.search([1, 0, 0, 0], limit=5)[0][:2] == ("a", 1.0)
+    st.close()
+
+
+def test_metrics_and_bf16_through_store(built_lib):
+    rng = np.random.default_rng(2)
+    X = rng.standard_normal((3000, 96), dtype=np.float32)
+    Q = rng.standard_normal((3, 96), dtype=np.float32)
+    for metric, dtype in (("ip", "fp32"), ("l2", "fp32"), ("ip", "bf16")):
+        st = make_store(96, 2, GPU_METRIC=metric, GPU_DTYPE=dtype)
+        st.bulk_load(X)
+        Xs = oracle.bf16_round(X) if dtype == "bf16" else X
+        res = st.search_batch(Q, limit=10)
+        for b in range(3):
+            rep = oracle.check_topk(Xs, Q[b], metric, 10, res.gids[b], res.scores[b])
+            assert rep["hard_mismatch"] == 0 and rep["recall"] == 1.0 and rep["max_err_over_tol"] <= 1.0, rep
+        st.close()
+
+
+def test_engine_errors_follow_reference_convention(built_lib):
+    st = make_store(4, 1, GPU_STRICT=False)
+    st.store("a", [1, 0, 0, 0])
+    st.engine.close()  # break the engine: reference convention = log + [] (indexing.py:1028-1030)
+    assert st.search([1, 0, 0, 0]) == []
+    assert st.store("b", [0, 1, 0, 0]) is False

@@ -1,0 +1,126 @@
+"""CPU: host-side logic of wdbx_b200.VectorStore / WDBX against the reference's golden outputs,
+with the device engine replaced by the numpy double (tests/fake_engine.py)."""
+import asyncio
+import tempfile
+
+import numpy as np
+import pytest
+
+import wdbx_b200
+from tests import golden_checks as gc
+from tests.fake_engine import FakeEngine, pack_keys, unpack_keys
+
+
+def make_store(dim, shards, **cfg):
+    return wdbx_b200.VectorStore(dim, tempfile.mkdtemp(), num_shards=shards, config=wdbx_b200.WDBXConfig(cfg),
+                                 dist=wdbx_b200.DistContext(0, 1, 0), _engine_factory=FakeEngine)
+
+
+def test_ramp_golden(golden):
+    for case in golden["ramp"]:
+        gc.check_ramp(make_store, case)
+
+
+def test_self_query_golden(golden):
+    for case in golden["self_query"]:
+        gc.check_self_query(make_store, case)
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_random_golden(golden, idx):
+    gc.check_random(make_store, golden["random"][idx])
+
+
+def test_crud_semantics():
+    st = make_store(4, 2)
+    assert st.store("a", [1, 0, 0, 0], {"t": 1}) and st.store("b", [0, 1, 0, 0]) and st.store("c", [1, 1, 0, 0])
+    assert st.count() == 3
+    assert st.get("a") == ([1.0, 0.0, 0.0, 0.0], {"t": 1}) and st.get("zz") is None
+    # duplicate id overwrites in place (HNSW intent, indexing.py:370-375), no ghost row
+    assert st.store("a", [0, 0, 1, 0], {"t": 2})
+    assert st.count() == 3 and st.get("a")[0] == [0.0, 0.0, 1.0, 0.0] and st.get("a")[1] == {"t": 2}
+    assert [r[0] for r in st.search([0, 0, 1, 0], limit=1)] == ["a"]
+    # deleted ids are never returned (SURVEY.md 8c decision 1)
+    assert st.delete("c") and not st.delete("c") and st.count() == 2
+    assert "c" not in [r[0] for r in st.search([1, 1, 0, 0], limit=10)]
+    assert len(st.search([1, 1, 0, 0], limit=10)) == 2
+    assert st.update_metadata("b", {"x": 1}) and not st.update_metadata("nope", {})
+    assert st.search([0, 1, 0, 0], limit=1)[0] == ("b", 1.0, {"x": 1})
+    # limit <= 0 and empty store
+    assert st.search([0, 1, 0, 0], limit=0) == []
+    assert st.clear() == 2 and st.count() == 0 and st.search([0, 1, 0, 0]) == []
+    # ids keep working after clear
+    assert st.store("a", [1, 0, 0, 0]) and st.search([1, 0, 0, 0], limit=5)[0][0] == "a"
+    stats = st.get_stats()
+    assert stats["use_gpu"] is True and stats["num_shards"] == 2 and len(stats["indices"]) == 2
+    assert sum(i["size"] for i in stats["indices"]) == 1
+
+
+def test_batch_and_bulk_apis():
+    st = make_store(8, 3)
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((100, 8), dtype=np.float32)
+    assert st.bulk_load(X, id_prefix="v") == 100
+    more = {f"m{i}": rng.standard_normal(8).astype(np.float32) for i in range(10)}
+    assert st.batch_store(more) == 10 and st.count() == 110
+    allX = np.concatenate([X, np.stack(list(more.values()))])
+    ids = [f"v{i}" for i in range(100)] + list(more)
+    Q = rng.standard_normal((4, 8), dtype=np.float32)
+    res = st.search_batch(Q, limit=7)
+    from oracle import exact_search as oracle
+    for b in range(4):
+        rows, sc = oracle.topk_desc(oracle.scores_fp32(allX, Q[b], "cosine"), 7)
+        assert res.ids()[b] == [ids[r] for r in rows]
+    assert st.get("v17")[0] == pytest.approx(X[17].tolist())
+    assert st.delete("v17") and st.get("v17") is None and "v17" not in sum(st.search_batch(Q, 110).ids(), [])
+    with pytest.raises(ValueError):
+        st.bulk_load(X, id_prefix="v")
+
+
+def test_facade_contract():
+    with tempfile.TemporaryDirectory() as tmp:
+        import wdbx_b200.wdbx as facade
+
+        class _W(facade.WDBX):
+            def _init_vector_store(self):
+                self._store = wdbx_b200.VectorStore(self.vector_dim, self.data_dir, self.num_shards, config=self.config,
+                                                    dist=wdbx_b200.DistContext(0, 1, 0), _engine_factory=FakeEngine)
+
+        db = _W(vector_dimension=4, num_shards=2, data_dir=tmp, config={"WDBX_TEST_OPTION": "x"}, enable_plugins=False)
+        assert db.config.get("WDBX_TEST_OPTION") == "x"
+
+        async def go():
+            await db.initialize()
+            vid = await db.vector_store_async([0.1, 0.2, 0.3, 0.4], {"source": "test"})
+            res = await db.vector_search_async([0.1, 0.2, 0.3, 0.4], limit=1)
+            assert res[0][0] == vid and res[0][1] > 0.99 and res[0][2] == {"source": "test"}   # test_core.py:167-174
+            assert db.vector_search([0.1, 0.2, 0.3, 0.4], limit=1)[0][0] == vid             # test_core.py:135-142
+            with pytest.raises(ValueError, match="dimension mismatch"):                      # test_core.py:245-247
+                db.vector_search([0.1, 0.2, 0.3])
+            with pytest.raises(ValueError, match="dimension mismatch"):
+                await db.vector_store_async([0.1], {})
+            assert db.get_vector("nonexistent_id") is None
+            assert db.count_vectors() == 1 and db.delete_vector(vid) and db.count_vectors() == 0
+            st = db.get_stats()
+            assert st["gpu_enabled"] is True and len(st["indices"]) == 2 and st["total_vectors"] == 0
+            await db.shutdown()
+
+        asyncio.run(go())
+
+
+def test_no_cpu_fallback():
+    with tempfile.TemporaryDirectory() as tmp:
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            wdbx_b200.VectorStore(4, tmp, use_gpu=False)
+
+
+def test_key_packing_roundtrip():
+    s = np.array([1.5, -2.0, 0.0, -0.0, np.inf, -np.inf, np.nan, 1e-30], np.float32)
+    g = np.arange(8)
+    k = pack_keys(s, g)
+    sc, gi = unpack_keys(k)
+    assert list(gi) == list(g)
+    np.testing.assert_array_equal(sc[:6], np.array([1.5, -2.0, 0.0, 0.0, np.inf, -np.inf], np.float32))
+    assert np.isneginf(sc[6])
+    order = np.argsort(-k.astype(np.float64), kind="stable")
+    assert list(order[:3]) == [4, 0, 7] and k[2] > k[3]  # +0 == -0 -> lower gid first

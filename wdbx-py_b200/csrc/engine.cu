@@ -567,13 +567,16 @@ int wdbx_b200_search(wdbx_b200_engine* e, int segment, const float* q_dev, int B
   return rc;
 }
 
-int wdbx_b200_search_host(wdbx_b200_engine* e, int per_segment, const float* q_host, int B, int k, int metric,
+int wdbx_b200_search_host(wdbx_b200_engine* e, int segment, const float* q_host, int B, int k, int metric,
                           float* scores_host, int64_t* gids_host, uint64_t* keys_host, int32_t* counts_host) {
   int rc = check_search_args(e, B, k, metric);
   if (rc != WDBX_B200_OK) return rc;
   if (!q_host) return fail(WDBX_B200_ERR_ARG, "q_host is NULL");
+  if (segment < WDBX_B200_EACH_SEGMENT || segment >= e->nseg)
+    return fail(WDBX_B200_ERR_ARG, "segment %d outside [-2, %d)", segment, e->nseg);
   DeviceGuard guard(e->device);
   std::lock_guard<std::mutex> hlk(e->host_mu);
+  const bool per_segment = segment == WDBX_B200_EACH_SEGMENT;
   const int lists = per_segment ? e->nseg : 1;
   const size_t nq = static_cast<size_t>(B) * e->dim;
   const size_t nres = static_cast<size_t>(lists) * B * k;
@@ -604,7 +607,9 @@ int wdbx_b200_search_host(wdbx_b200_engine* e, int per_segment, const float* q_h
     std::lock_guard<std::mutex> lk(e->mu);
     for (int l = 0; l < lists; ++l) {
       const size_t o = static_cast<size_t>(l) * B * k;
-      rc = scan_segments(e, per_segment ? l : 0, per_segment ? l + 1 : e->nseg, e->dq, B, k, metric,
+      const int s0 = per_segment ? l : (segment >= 0 ? segment : 0);
+      const int s1 = per_segment ? l + 1 : (segment >= 0 ? segment + 1 : e->nseg);
+      rc = scan_segments(e, s0, s1, e->dq, B, k, metric,
                          reinterpret_cast<uint64_t*>(e->dres + off_keys) + o,
                          reinterpret_cast<float*>(e->dres + off_scores) + o,
                          reinterpret_cast<long long*>(e->dres + off_gids) + o,

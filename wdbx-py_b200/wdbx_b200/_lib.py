@@ -14,6 +14,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libwdbx_b200.so"
 MAX_SEGMENTS = 64
 MAX_K = 1024
 ALL_SEGMENTS = -1
+EACH_SEGMENT = -2
 OK, ERR_ARG, ERR_CUDA, ERR_OOM, ERR_LIMIT = 0, -1, -2, -3, -4
 F32, BF16 = 0, 1
 COSINE, IP, L2 = 0, 1, 2

@@ -7,7 +7,7 @@ from typing import Dict, Optional, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import ALL_SEGMENTS, B200Error, DTYPES, METRICS, check
+from ._lib import ALL_SEGMENTS, EACH_SEGMENT, B200Error, DTYPES, METRICS, check
 
 
 def _metric_code(metric) -> int:
@@ -113,8 +113,17 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ search
+    def upload(self, queries):
+        """Host fp32 array -> CUDA tensor on this engine's device (queries of the SPMD path)."""
+        import torch
+
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        return torch.from_numpy(q).to(torch.device("cuda", self.device), non_blocking=False)
+
     def search_host(self, queries, k: int, metric="cosine", per_segment: bool = False,
-                    want_keys: bool = False):
+                    want_keys: bool = False, segment: int = ALL_SEGMENTS):
         """Host-buffer search (H2D + kernels + D2H inside the call).
 
         Returns (scores, gids, counts[, keys]); shapes [B, k] / [B], or with ``per_segment``
@@ -130,7 +139,8 @@ class Engine:
         gids = np.empty(lead + (k,), dtype=np.int64)
         counts = np.empty(lead, dtype=np.int32)
         keys = np.empty(lead + (k,), dtype=np.uint64) if want_keys else None
-        check(self._lib.wdbx_b200_search_host(self._handle(), 1 if per_segment else 0, _np_ptr(q), B, k,
+        sel = EACH_SEGMENT if per_segment else int(segment)
+        check(self._lib.wdbx_b200_search_host(self._handle(), sel, _np_ptr(q), B, k,
                                               _metric_code(metric), _np_ptr(scores), _np_ptr(gids), _np_ptr(keys),
                                               _np_ptr(counts)))
         return (scores, gids, counts, keys) if want_keys else (scores, gids, counts)

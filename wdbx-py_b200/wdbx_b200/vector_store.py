@@ -1,0 +1,588 @@
+"""Device-resident VectorStore: the host-side mirror of wdbx/core/vector_store.py for the search path.
+
+Same public surface as the reference class (``store / store_async / batch_store(_async) / search /
+search_async / delete / get / count / clear / get_stats / update_metadata``; vector_store.py:22-815)
+with the same argument meaning, result shape ``[(vector_id, score, metadata)]`` and error
+behaviour, but:
+
+* the per-shard index objects share ONE device engine (libwdbx_b200.so): an unfiltered
+  ``search`` is a single kernel launch that returns the already merged global top-k instead of
+  the reference's sequential per-shard loop + host sort (vector_store.py:323-330);
+* with ``filter_metadata`` the engine returns one top-``limit`` list per shard, which is exactly
+  the candidate set the reference builds before its post-filter (vector_store.py:323-342), so
+  filtered results are identical to the reference's (including its truncation quirk);
+* vectors live only in HBM (no host dict of ndarrays, vector_store.py:66): ``get`` reads the row
+  back from the device;
+* under ``torchrun`` (WORLD_SIZE > 1) the store is SPMD: every rank makes the same calls, rows of
+  each shard are striped over the ranks (shard_map.py) and ``search`` is a collective
+  (local top-k -> NCCL all-gather of packed keys -> merge kernel).
+
+Additive API for the batch configs: ``search_batch`` and ``bulk_load``.
+There is no CPU fallback: construction fails if the CUDA library or a device is missing.
+"""
+from __future__ import annotations
+
+import asyncio
+import bisect
+import json
+import logging
+import os
+import threading
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .config import WDBXConfig
+from .dist import DistContext
+from .indexing import B200FlatIndex
+from .shard_map import ShardMap, shard_for_id
+
+logger = logging.getLogger(__name__)
+
+ALL, EACH = _lib.ALL_SEGMENTS, _lib.EACH_SEGMENT
+
+
+class BatchResult:
+    """Result of ``search_batch``: device-merged [B, k] arrays + lazy id mapping."""
+
+    def __init__(self, gids: np.ndarray, scores: np.ndarray, counts: np.ndarray, store: "VectorStore"):
+        self.gids, self.scores, self.counts, self._store = gids, scores, counts, store
+
+    def ids(self) -> List[List[str]]:
+        s = self._store
+        return [[s._id_of(int(g)) for g in self.gids[b, : self.counts[b]]] for b in range(self.gids.shape[0])]
+
+    def as_lists(self) -> List[List[Tuple[str, float]]]:
+        s = self._store
+        return [[(s._id_of(int(g)), float(v)) for g, v in zip(self.gids[b, :c], self.scores[b, :c])]
+                for b, c in enumerate(self.counts)]
+
+
+class VectorStore:
+    def __init__(
+        self,
+        vector_dim: int,
+        data_dir: Path,
+        num_shards: int = 1,
+        use_gpu: bool = True,
+        index_type: str = "b200",
+        config: Optional[WDBXConfig] = None,
+        *,
+        dist: Optional[DistContext] = None,
+        _engine_factory=None,  # test seam (tests/ inject a numpy double); the product never sets it
+    ):
+        if not use_gpu:
+            raise RuntimeError(
+                "wdbx_b200.VectorStore implements only the enable_gpu=True path of WDBX; "
+                "there is no CPU fallback (use the reference package for CPU search)")
+        if index_type not in ("b200", "flat", "faiss", "hnsw"):
+            raise ValueError(f"Unsupported index type: {index_type}")
+        if num_shards < 1 or num_shards > _lib.MAX_SEGMENTS:
+            raise ValueError(f"num_shards must be in [1, {_lib.MAX_SEGMENTS}]")
+        self.vector_dim = int(vector_dim)
+        self.data_dir = Path(data_dir)
+        self.num_shards = int(num_shards)
+        self.use_gpu = True
+        self.index_type = "b200"
+        self.config = config if config is not None else WDBXConfig({})
+        self.metric = str(self.config.get("GPU_METRIC", "cosine")).lower()
+        if self.metric not in _lib.METRICS:
+            raise ValueError(f"unknown GPU_METRIC {self.metric!r}")
+        self.dtype = str(self.config.get("GPU_DTYPE", "fp32")).lower()
+        self.strict = bool(self.config.get("GPU_STRICT", False))
+
+        self.dist = dist if dist is not None else DistContext.from_env(self.config.get("GPU_DEVICE", None))
+        self.shard_map = ShardMap(self.num_shards, self.dist.world)
+
+        # host-side bookkeeping (ids and metadata only; vectors live in HBM)
+        self.metadata: Dict[str, Dict[str, Any]] = {}
+        self._loc: Dict[str, Tuple[int, int, int]] = {}      # id -> (shard, n-th row of the shard, gid)
+        self._gid_to_id: List[Optional[str]] = []
+        self._bulk: List[Tuple[int, int, str]] = []          # (gid0, gid1, prefix) ranges from bulk_load
+        self._bulk_starts: List[int] = []
+        self._bulk_rows: Dict[int, Tuple[int, int]] = {}     # gid0 -> (first n per shard base, n rows) for lookups
+        self._bulk_dead: set = set()
+        self._shard_count = [0] * self.num_shards            # rows ever appended per shard (all ranks)
+        self._shard_live = [0] * self.num_shards
+        self._lock = threading.RLock()
+        self.thread_pool = ThreadPoolExecutor(
+            max_workers=int(self.config.get("VECTOR_STORE_THREADS", min(8, os.cpu_count() or 4))))
+
+        self._create_dirs()
+        if _engine_factory is not None:
+            self.engine = _engine_factory(self.dist.device, self.vector_dim, self.dtype, self.num_shards)
+        else:
+            from .engine import Engine  # raises ImportError / B200Error loudly when the GPU path is unusable
+
+            self.engine = Engine(self.dist.device, self.vector_dim, self.dtype, self.num_shards)
+        cap = int(self.config.get("GPU_CAPACITY_ROWS", 0) or 0)
+        if cap > 0:
+            for s in range(self.num_shards):
+                self.engine.reserve(s, self.shard_map.local_count(cap, self.dist.rank))
+        self._init_indices()
+        logger.info("VectorStore initialized: %d shards on %d GPU(s), dim=%d, metric=%s, dtype=%s",
+                    self.num_shards, self.dist.world, self.vector_dim, self.metric, self.dtype)
+
+    # ------------------------------------------------------------------ setup
+    def _create_dirs(self):
+        """Same on-disk layout as the reference (vector_store.py:88-109)."""
+        for sub in ("vectors", "metadata", "indices"):
+            (self.data_dir / sub).mkdir(parents=True, exist_ok=True)
+        for shard in range(self.num_shards):
+            (self.data_dir / f"shard_{shard}").mkdir(parents=True, exist_ok=True)
+
+    def _init_indices(self):
+        self.indices = [
+            B200FlatIndex(self.vector_dim, self.data_dir / f"shard_{s}" / "index", self.config, store=self, shard=s)
+            for s in range(self.num_shards)
+        ]
+
+    def _get_shard_for_id(self, vector_id: str) -> int:
+        return shard_for_id(vector_id, self.num_shards)
+
+    async def initialize(self):
+        await asyncio.gather(*[ix.initialize() for ix in self.indices])
+
+    async def shutdown(self):
+        """Reference: save metadata + vectors, then every index (vector_store.py:202-217)."""
+        loop = asyncio.get_event_loop()
+        await loop.run_in_executor(self.thread_pool, self._save_metadata)
+        self.thread_pool.shutdown(wait=True)
+        self.close()
+
+    def close(self):
+        eng = getattr(self, "engine", None)
+        if eng is not None:
+            eng.close()
+            self.engine = None
+
+    def _save_metadata(self):
+        if self.dist.rank != 0:
+            return
+        try:
+            with open(self.data_dir / "metadata" / "metadata.json", "w") as f:
+                json.dump(self.metadata, f)
+        except Exception as e:  # reference logs and continues (vector_store.py:165-166)
+            logger.error(f"Error saving metadata: {e}")
+
+    # ------------------------------------------------------------------ error convention
+    def _guard(self, default, fn, *args):
+        """Reference convention: index errors are logged and swallowed (indexing.py:1028-1030);
+        GPU_STRICT re-raises."""
+        try:
+            return fn(*args)
+        except ValueError:
+            raise
+        except Exception as e:
+            if self.strict:
+                raise
+            logger.error(f"Error in B200 index operation {getattr(fn, '__name__', fn)}: {e}")
+            return default
+
+    async def _run(self, fn, *args):
+        loop = asyncio.get_event_loop()
+        return await loop.run_in_executor(self.thread_pool, fn, *args)
+
+    # ------------------------------------------------------------------ id bookkeeping
+    def _id_of(self, gid: int) -> str:
+        if gid < len(self._gid_to_id):
+            v = self._gid_to_id[gid]
+            if v is not None:
+                return v
+        i = bisect.bisect_right(self._bulk_starts, gid) - 1
+        if i >= 0:
+            g0, g1, prefix = self._bulk[i]
+            if g0 <= gid < g1:
+                return f"{prefix}{gid - g0}"
+        return str(gid)  # same fallback as the reference's index_to_id.get(idx, str(idx)) (indexing.py:1021)
+
+    def _locate(self, vector_id: str) -> Optional[Tuple[int, int, int]]:
+        loc = self._loc.get(vector_id)
+        if loc is not None:
+            return loc
+        for g0, g1, prefix in self._bulk:
+            if vector_id.startswith(prefix):
+                tail = vector_id[len(prefix):]
+                if tail.isdigit():
+                    gid = g0 + int(tail)
+                    if gid < g1 and gid not in self._bulk_dead:
+                        i = gid - g0
+                        base = self._bulk_rows[g0]
+                        shard = i % self.num_shards
+                        return shard, base[shard] + i // self.num_shards, gid
+        return None
+
+    # ------------------------------------------------------------------ mutation
+    def _add_rows(self, shard: int, ids: Sequence[str], mat: np.ndarray) -> bool:
+        """Append (or overwrite, for ids already present) rows of one shard."""
+        if mat.ndim != 2 or mat.shape[1] != self.vector_dim:
+            raise ValueError(f"Vector dimension mismatch: expected {self.vector_dim}, got {mat.shape[-1]}")
+        rank, world = self.dist.rank, self.dist.world
+        with self._lock:
+            fresh: List[int] = []
+            for i, vid in enumerate(ids):
+                loc = self._locate(vid)
+                if loc is None:
+                    fresh.append(i)
+                    continue
+                s0, n0, _gid = loc
+                owner, local = self.shard_map.owner(n0)
+                if owner == rank:
+                    self.engine.overwrite(s0, local, mat[i])
+            if not fresh:
+                return True
+            n0 = self._shard_count[shard]
+            g0 = len(self._gid_to_id)
+            m = len(fresh)
+            ns = np.arange(n0, n0 + m)
+            gids = np.arange(g0, g0 + m, dtype=np.uint32)
+            mine = (ns % world) == rank
+            if mine.any():
+                sel = np.asarray(fresh)[mine]
+                rows = mat if len(sel) == mat.shape[0] else mat[sel]
+                first = self.engine.append(shard, rows, gids=gids[mine])
+                expect = self.shard_map.owner(int(ns[mine][0]))[1]
+                if first != expect:
+                    raise RuntimeError(f"shard {shard}: device row {first} != expected {expect} (store out of sync)")
+            for j, i in enumerate(fresh):
+                self._loc[ids[i]] = (shard, n0 + j, g0 + j)
+                self._gid_to_id.append(ids[i])
+            self._shard_count[shard] += m
+            self._shard_live[shard] += m
+        return True
+
+    def _remove_row(self, vector_id: str, shard: Optional[int] = None) -> bool:
+        with self._lock:
+            loc = self._locate(vector_id)
+            if loc is None or (shard is not None and loc[0] != shard):
+                return False
+            s, n, gid = loc
+            owner, local = self.shard_map.owner(n)
+            if owner == self.dist.rank:
+                self.engine.tombstone(s, local, True)
+            if vector_id in self._loc:
+                del self._loc[vector_id]
+                self._gid_to_id[gid] = None
+            else:
+                self._bulk_dead.add(gid)
+            self._shard_live[s] -= 1
+            return True
+
+    def _clear_shard(self, shard: int) -> bool:
+        with self._lock:
+            self.engine.clear(shard)
+            for vid in [v for v, loc in self._loc.items() if loc[0] == shard]:
+                gid = self._loc.pop(vid)[2]
+                self._gid_to_id[gid] = None
+                self.metadata.pop(vid, None)
+            self._shard_count[shard] = 0
+            self._shard_live[shard] = 0
+        return True
+
+    def store(self, vector_id: str, vector: List[float], metadata: Optional[Dict[str, Any]] = None) -> bool:
+        """Reference: vector_store.py:219-256 (returns False on error, never raises)."""
+        try:
+            vec = np.array(vector, dtype=np.float32)
+            shard = self._get_shard_for_id(vector_id)
+            with self._lock:
+                loc = self._locate(vector_id)
+                ok = self.indices[loc[0] if loc else shard].add(vector_id, vec)
+                if ok:
+                    self.metadata[vector_id] = metadata or {}
+            if ok and self.config.get("VECTOR_STORE_SAVE_IMMEDIATELY", False):
+                self._save_metadata()
+            return bool(ok)
+        except Exception as e:
+            logger.error(f"Error storing vector: {e}")
+            return False
+
+    async def store_async(self, vector_id: str, vector: List[float],
+                          metadata: Optional[Dict[str, Any]] = None) -> bool:
+        """Reference: vector_store.py:258-299."""
+        return await self._run(self.store, vector_id, vector, metadata)
+
+    def batch_store(self, vectors: Dict[str, List[float]],
+                    metadata: Optional[Dict[str, Dict[str, Any]]] = None) -> int:
+        """Reference: vector_store.py:720-766 -- group by shard, one batch_add per shard."""
+        metadata = metadata or {}
+        shard_vectors: Dict[int, Dict[str, np.ndarray]] = {}
+        with self._lock:
+            for vector_id, vector in vectors.items():
+                vec = np.array(vector, dtype=np.float32)
+                loc = self._locate(vector_id)
+                shard = loc[0] if loc else self._get_shard_for_id(vector_id)
+                shard_vectors.setdefault(shard, {})[vector_id] = vec
+            stored = 0
+            for shard, vecs in shard_vectors.items():
+                if self.indices[shard].batch_add(vecs):
+                    stored += len(vecs)
+                    for vid in vecs:
+                        self.metadata[vid] = metadata.get(vid, {})
+        if self.config.get("VECTOR_STORE_SAVE_IMMEDIATELY", False):
+            self._save_metadata()
+        return stored
+
+    async def batch_store_async(self, vectors: Dict[str, List[float]],
+                                metadata: Optional[Dict[str, Dict[str, Any]]] = None) -> int:
+        return await self._run(self.batch_store, vectors, metadata)
+
+    def bulk_load(self, rows, id_prefix: str = "v") -> int:
+        """Additive bulk ingest: append an [n, dim] fp32 matrix (numpy, or
+        a CUDA tensor holding THIS rank's rows when ``rows`` is a dict {"local": tensor, "total": n})
+        with synthetic ids ``f"{id_prefix}{i}"``.  Row i goes to shard ``i % num_shards``; inside a shard
+        rows are striped over ranks as usual.  No per-row Python work."""
+        S, world, rank = self.num_shards, self.dist.world, self.dist.rank
+        with self._lock:
+            if isinstance(rows, dict):
+                if S != 1:
+                    raise ValueError("pre-partitioned bulk_load needs num_shards == 1")
+                n = int(rows["total"])
+                local = rows["local"]
+            else:
+                n = int(rows.shape[0])
+                local = None
+            for g0_, g1_, p_ in self._bulk:
+                if p_ == id_prefix:
+                    raise ValueError(f"id_prefix {id_prefix!r} already used by a bulk_load")
+            g0 = len(self._gid_to_id)
+            base = list(self._shard_count)
+            for s in range(S):
+                cnt = (n - s + S - 1) // S if n > s else 0
+                if cnt == 0:
+                    continue
+                n0 = base[s]
+                ns = np.arange(n0, n0 + cnt)
+                mine = (ns % world) == rank
+                src_idx = s + S * np.arange(cnt)
+                gids = (g0 + src_idx).astype(np.uint32)
+                if local is not None:
+                    if int(mine.sum()) != int(local.shape[0]):
+                        raise ValueError("local tensor does not match this rank's stripe")
+                    self.engine.append(s, local, gids=gids[mine])
+                elif mine.any():
+                    sel = src_idx[mine]
+                    part = rows[sel] if not (S == 1 and world == 1) else rows
+                    self.engine.append(s, part, gids=gids[mine])
+                self._shard_count[s] += cnt
+                self._shard_live[s] += cnt
+            self._gid_to_id.extend([None] * n)
+            self._bulk.append((g0, g0 + n, id_prefix))
+            self._bulk_starts.append(g0)
+            self._bulk_rows[g0] = tuple(base)
+        return n
+
+    def delete(self, vector_id: str) -> bool:
+        """Reference: vector_store.py:465-492."""
+        with self._lock:
+            if self._locate(vector_id) is None:
+                return False
+            ok = self._guard(False, self._remove_row, vector_id)
+            self.metadata.pop(vector_id, None)
+        if self.config.get("VECTOR_STORE_SAVE_IMMEDIATELY", False):
+            self._save_metadata()
+        return bool(ok)
+
+    async def delete_async(self, vector_id: str) -> bool:
+        return await self._run(self.delete, vector_id)
+
+    def update_metadata(self, vector_id: str, metadata: Dict[str, Any]) -> bool:
+        """Reference: vector_store.py:526-548."""
+        with self._lock:
+            if self._locate(vector_id) is None:
+                return False
+            self.metadata[vector_id] = metadata
+        if self.config.get("VECTOR_STORE_SAVE_IMMEDIATELY", False):
+            self._save_metadata()
+        return True
+
+    async def update_metadata_async(self, vector_id: str, metadata: Dict[str, Any]) -> bool:
+        return self.update_metadata(vector_id, metadata)
+
+    def get(self, vector_id: str) -> Optional[Tuple[List[float], Dict[str, Any]]]:
+        """Reference: vector_store.py:579-596; the vector is read back from HBM."""
+        with self._lock:
+            loc = self._locate(vector_id)
+            if loc is None:
+                return None
+            s, n, _gid = loc
+            owner, local = self.shard_map.owner(n)
+            if self.dist.world == 1:
+                vec = self.engine.read_row(s, local)
+            else:
+                vec = self.engine.read_row(s, local) if owner == self.dist.rank else np.zeros(self.vector_dim, np.float32)
+                vec = self.dist.broadcast_array(vec, owner)
+            return vec.tolist(), self.metadata.get(vector_id, {})
+
+    async def get_async(self, vector_id: str):
+        return self.get(vector_id)
+
+    def count(self) -> int:
+        return sum(self._shard_live)
+
+    def clear(self) -> int:
+        """Reference: vector_store.py:620-641."""
+        with self._lock:
+            count = self.count()
+            self.engine.clear(ALL)
+            self.metadata = {}
+            self._loc = {}
+            self._gid_to_id = [None] * len(self._gid_to_id)  # gids keep growing: keys stay unique
+            self._bulk, self._bulk_starts, self._bulk_rows, self._bulk_dead = [], [], {}, set()
+            self._shard_count = [0] * self.num_shards
+            self._shard_live = [0] * self.num_shards
+        self._save_metadata()
+        return count
+
+    async def clear_async(self) -> int:
+        return await self._run(self.clear)
+
+    def optimize(self) -> bool:
+        return True
+
+    async def optimize_async(self) -> bool:
+        return True
+
+    # ------------------------------------------------------------------ search
+    def _search_arrays(self, Q: np.ndarray, k: int, sel: int, metric: Optional[str] = None):
+        """(scores, gids, counts) numpy arrays; leading dim = num_shards when sel == EACH."""
+        metric = metric or self.metric
+        if self.dist.world == 1:
+            return self.engine.search_host(Q, k, metric=metric, per_segment=(sel == EACH),
+                                           segment=(sel if sel >= 0 else ALL))
+        # SPMD: local top-k on every rank -> all-gather packed keys -> merge kernel
+        qd = self.engine.upload(Q)
+        if sel == EACH:
+            import torch
+
+            keys = torch.cat([self.engine.search(qd, k, metric, segment=s)["keys"] for s in range(self.num_shards)])
+        else:
+            keys = self.engine.search(qd, k, metric, segment=sel)["keys"]
+        merged = self.engine.merge(self.dist.all_gather_keys(keys))
+        scores = merged["scores"].cpu().numpy()
+        gids = merged["gids"].cpu().numpy()
+        counts = merged["counts"].cpu().numpy()
+        if sel == EACH:
+            B = Q.shape[0]
+            return (scores.reshape(self.num_shards, B, k), gids.reshape(self.num_shards, B, k),
+                    counts.reshape(self.num_shards, B))
+        return scores, gids, counts
+
+    def _search_lists(self, q: np.ndarray, limit: int, sel: int) -> List[List[Tuple[str, float]]]:
+        """Best-first [(id, score)] lists for ONE query: one list (merged / single shard) or one per shard."""
+        q = np.asarray(q, dtype=np.float32).reshape(-1)
+        if q.shape[0] != self.vector_dim:
+            raise ValueError(f"Vector dimension mismatch: expected {self.vector_dim}, got {q.shape[0]}")
+        nlists = self.num_shards if sel == EACH else 1
+        if sel >= 0:
+            scope = self._shard_live[sel]
+        elif sel == EACH:
+            scope = max(self._shard_live)
+        else:
+            scope = sum(self._shard_live)
+        k = min(int(limit), scope, _lib.MAX_K)   # limit clipped to the live size (indexing.py:1005)
+        if k <= 0:
+            return [[] for _ in range(nlists)]
+        if limit > _lib.MAX_K and scope > _lib.MAX_K:
+            logger.warning("limit=%d clipped to the engine maximum of %d", limit, _lib.MAX_K)
+        scores, gids, counts = self._search_arrays(q[None, :], k, sel)
+        if sel == EACH:
+            return [[(self._id_of(int(g)), float(s)) for g, s in zip(gids[i, 0, : counts[i, 0]], scores[i, 0, : counts[i, 0]])]
+                    for i in range(nlists)]
+        c = int(counts[0])
+        return [[(self._id_of(int(g)), float(s)) for g, s in zip(gids[0, :c], scores[0, :c])]]
+
+    def search(self, query_vector: List[float], limit: int = 10, threshold: float = 0.0,
+               filter_metadata: Optional[Dict[str, Any]] = None) -> List[Tuple[str, float, Dict[str, Any]]]:
+        """Reference: vector_store.py:301-353 (same result list, same filter / threshold order)."""
+        query_np = np.array(query_vector, dtype=np.float32)
+        sel = EACH if filter_metadata else ALL
+        lists = self._guard([], self._search_lists, query_np, limit, sel)
+        all_results: List[Tuple[str, float]] = []
+        for results in lists:
+            all_results.extend(results)
+        if len(lists) > 1:
+            all_results.sort(key=lambda x: x[1], reverse=True)
+        if threshold > 0:
+            all_results = [r for r in all_results if r[1] >= threshold]
+        if filter_metadata:
+            all_results = [r for r in all_results if self._matches_filter(r[0], filter_metadata)]
+        all_results = all_results[:limit]
+        return [(vid, score, self.metadata.get(vid, {})) for vid, score in all_results]
+
+    async def search_async(self, query_vector: List[float], limit: int = 10, threshold: float = 0.0,
+                           filter_metadata: Optional[Dict[str, Any]] = None):
+        """Reference: vector_store.py:355-412.  One thread-pool hop (the ctypes call releases the GIL)
+        instead of one per shard."""
+        return await self._run(self.search, query_vector, limit, threshold, filter_metadata)
+
+    def search_batch(self, queries, limit: int = 10, metric: Optional[str] = None) -> BatchResult:
+        """Additive batch entry point: [B, dim] queries -> device-merged top-``limit`` per query."""
+        Q = np.ascontiguousarray(queries, dtype=np.float32)
+        if Q.ndim != 2 or Q.shape[1] != self.vector_dim:
+            raise ValueError(f"Vector dimension mismatch: expected {self.vector_dim}, got {Q.shape[-1]}")
+        k = min(int(limit), max(self.count(), 1), _lib.MAX_K)
+        scores, gids, counts = self._search_arrays(Q, k, ALL, metric)
+        return BatchResult(gids, scores, counts, self)
+
+    def _matches_filter(self, vector_id: str, filter_metadata: Dict[str, Any]) -> bool:
+        """Mongo-style post filter, same operator set and semantics as vector_store.py:414-463."""
+        metadata = self.metadata.get(vector_id, {})
+        for key, value in filter_metadata.items():
+            if isinstance(value, dict) and list(value.keys())[0].startswith("$"):
+                op = list(value.keys())[0]
+                op_value = value[op]
+                present = key in metadata
+                if op == "$gt":
+                    if not present or metadata[key] <= op_value:
+                        return False
+                elif op == "$lt":
+                    if not present or metadata[key] >= op_value:
+                        return False
+                elif op == "$gte":
+                    if not present or metadata[key] < op_value:
+                        return False
+                elif op == "$lte":
+                    if not present or metadata[key] > op_value:
+                        return False
+                elif op == "$in":
+                    if not present or metadata[key] not in op_value:
+                        return False
+                elif op == "$nin":
+                    if present and metadata[key] in op_value:
+                        return False
+                elif op == "$exists":
+                    if bool(op_value) != present:
+                        return False
+            elif key not in metadata or metadata[key] != value:
+                return False
+        return True
+
+    # ------------------------------------------------------------------ stats
+    def get_stats(self) -> Dict[str, Any]:
+        """Same keys as vector_store.py:670-696 plus the engine's device counters."""
+        index_stats = [
+            {"shard": i, "type": self.index_type, "size": ix.size(), "stats": ix.get_stats()}
+            for i, ix in enumerate(self.indices)
+        ]
+        est = self.engine.stats() if self.engine is not None else {}
+        return {
+            "vector_count": self.count(),
+            "metadata_count": len(self.metadata),
+            "index_type": self.index_type,
+            "num_shards": self.num_shards,
+            "vector_dim": self.vector_dim,
+            "use_gpu": self.use_gpu,
+            "indices": index_stats,
+            "gpu": {
+                "world_size": self.dist.world,
+                "rank": self.dist.rank,
+                "device": self.dist.device,
+                "metric": self.metric,
+                "dtype": self.dtype,
+                "engine": est,
+                "shard_allocation": self.shard_map.allocation(self._shard_count),
+            },
+        }
