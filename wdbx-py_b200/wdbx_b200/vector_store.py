@@ -470,6 +470,16 @@ class VectorStore:
                     counts.reshape(self.num_shards, B))
         return scores, gids, counts
 
+    def search_device(self, q_dev, limit: int = 10, metric: Optional[str] = None):
+        """Additive, fully device-resident search: ``q_dev`` is a CUDA fp32 tensor [B, dim] on this
+        rank's GPU (the same queries on every rank); returns CUDA tensors ``keys / scores / gids /
+        counts`` of the global top-``limit``.  No host copy, no synchronisation."""
+        metric = metric or self.metric
+        out = self.engine.search(q_dev, limit, metric)
+        if self.dist.world == 1:
+            return out
+        return self.engine.merge(self.dist.all_gather_keys(out["keys"]))
+
     def _search_lists(self, q: np.ndarray, limit: int, sel: int) -> List[List[Tuple[str, float]]]:
         """Best-first [(id, score)] lists for ONE query: one list (merged / single shard) or one per shard."""
         q = np.asarray(q, dtype=np.float32).reshape(-1)
