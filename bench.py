@@ -51,7 +51,7 @@ def _traffic_from_profile():
     """DRAM bytes per launch of the scan kernel from the committed ncu capture, if any."""
     p = ROOT / "profiles" / "scan_topk_c3_ncu_summary.json"
     try:
-        return json.loads(p.read_text()).get("dram_bytes_per_launch")
+        return float(json.loads(p.read_text()).get("dram_bytes_per_launch"))
     except Exception:
         return None
 
@@ -133,6 +133,7 @@ def _cpu_scan_qps(steps: int, warmup: int, rows: int = CPU_SAMPLE_ROWS, X=None, 
     if Q is None:
         Q = np.random.default_rng(4321).standard_normal((N_QUERIES, DIM), dtype=np.float32)
     X = np.ascontiguousarray(X, dtype=np.float32)
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     lib.oracle_normalize_rows(X.ctypes.data, X.shape[0], DIM)       # FaissIndex.add normalises at ingest
     out_r = np.empty(K, np.int64)
     out_s = np.empty(K, np.float32)
@@ -143,7 +144,7 @@ def _cpu_scan_qps(steps: int, warmup: int, rows: int = CPU_SAMPLE_ROWS, X=None, 
         nrm = np.linalg.norm(q)
         qn = (q / nrm if nrm > 0 else q).astype(np.float32)        # FaissIndex.search normalises the query
         n = lib.oracle_flat_search(X.ctypes.data, X.shape[0], DIM, qn.ctypes.data, 0, K, None, out_r.ctypes.data,
-                                   out_s.ctypes.data, 0)
+                                   out_s.ctypes.data, cores)   # explicit: torchrun exports OMP_NUM_THREADS=1
         assert n == min(K, X.shape[0])
         return out_r.copy(), out_s.copy()
 
@@ -153,7 +154,7 @@ def _cpu_scan_qps(steps: int, warmup: int, rows: int = CPU_SAMPLE_ROWS, X=None, 
     for i in range(steps):
         results.append(one(i))
     dt = time.perf_counter() - t0
-    return steps / dt, min(cores, lib.oracle_num_threads()), dt, results
+    return steps / dt, cores, dt, results
 
 
 def run_reference(args):
@@ -282,6 +283,13 @@ def run_gpu(args):
     algo_bytes = local_rows * DIM * 4 + local_rows * 4          # rows + 1/|x| per row
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
     peak, peak_src = _peaks()
+    traffic = _traffic_from_profile()   # ncu --set full capture of this kernel on the 10M-row matrix (N=1)
+    traffic_src = None
+    if traffic is not None:
+        traffic_src = "profiles/scan_topk_c3_ncu_summary.json (dram read+write per launch, 10M rows on one GPU)"
+        if local_rows != N_ROWS:
+            traffic = traffic * local_rows / N_ROWS
+            traffic_src += f", scaled by rows_per_gpu/{N_ROWS}"
 
     # ---- e2e: public host API (list of floats in, tuples out), H2D + D2H + id mapping inside
     n_e2e = max(10, min(steps, 100))
@@ -323,7 +331,7 @@ def run_gpu(args):
                        "l2_policy": "inputs larger than L2 (>=3.8 GB per GPU streamed per step vs 126 MB L2); "
                                     "64 distinct queries cycled"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": _traffic_from_profile(), "kernel": "scan_topk_kernel (K1)",
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "scan_topk_kernel (K1)",
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": DIM * 4,

@@ -178,3 +178,30 @@ def test_device_search_and_merge(built_lib):
     np.testing.assert_array_equal(s, merged["scores"].cpu().numpy())
     for e in engs + [one]:
         e.close()
+
+
+@pytest.mark.parametrize("B,k,dim,metric,dtype", [(2, 10, 384, "cosine", "fp32"), (3, 10, 768, "cosine", "fp32"),
+                                                   (5, 7, 96, "l2", "fp32"), (8, 10, 768, "ip", "fp32"),
+                                                   (9, 100, 384, "ip", "bf16"), (17, 10, 1536, "l2", "fp32"),
+                                                   (4, 200, 64, "cosine", "fp32"), (33, 5, 20, "cosine", "fp32")])
+def test_query_batches(built_lib, B, k, dim, metric, dtype):
+    """Several queries per pass (QB x U register block) must give exactly the single-query results."""
+    rng = np.random.default_rng(B * 1000 + dim)
+    n = 6000
+    X = rng.standard_normal((n, dim), dtype=np.float32)
+    Q = rng.standard_normal((B, dim), dtype=np.float32)
+    eng = _engine(dim, nseg=2, dtype=dtype)
+    eng.append(0, X[:2500])
+    eng.append(1, X[2500:])
+    eng.tombstone(1, 17)
+    dead = np.zeros(n, bool)
+    dead[2500 + 17] = True
+    Xs = oracle.bf16_round(X) if dtype == "bf16" else X
+    s, g, c = eng.search_host(Q, k, metric=metric)
+    _check(Xs, Q, k, metric, s, g, c, dead=dead)
+    # bit-identical to one query at a time
+    for b in range(B):
+        s1, g1, c1 = eng.search_host(Q[b], k, metric=metric)
+        np.testing.assert_array_equal(g1[0], g[b])
+        np.testing.assert_array_equal(s1[0], s[b])
+    eng.close()

@@ -73,7 +73,7 @@ struct wdbx_b200_engine {
   std::mutex mu;  // segments, workspaces, launches
   uint32_t next_gid = 0;
   std::vector<Workspace> ws;
-  ScanTuning tune{0, 0, 0, 0, -1};
+  ScanTuning tune{0, 0, 0, 0, -1, 0};
   cudaStream_t mstream = nullptr;  // mutations
   // staging for host-sourced appends
   float* stage_rows = nullptr;
@@ -210,7 +210,7 @@ int get_workspace(wdbx_b200_engine* e, cudaStream_t stream, size_t cand_keys, in
 int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B, int k, int metric,
                   uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream) {
   ScanPlan plan;
-  const int rc = scan_plan(e->dim, e->dpad, e->elem_bytes, k, e->sm_count, e->tune, &plan);
+  const int rc = scan_plan(e->dim, e->dpad, e->elem_bytes, k, B, e->sm_count, e->tune, &plan);
   if (rc == -4) return fail(WDBX_B200_ERR_LIMIT, "dimension %d too large for the scan kernel's shared-memory stage", e->dim);
   if (rc != 0) return fail(WDBX_B200_ERR_ARG, "invalid scan shape (dim=%d k=%d)", e->dim, k);
   ScanParams p;
@@ -329,8 +329,9 @@ int wdbx_b200_create(int device, int dim, int dtype, int num_segments, wdbx_b200
   e->tune.rows_unroll = env_int("WDBX_B200_UNROLL", 0);
   e->tune.grid = env_int("WDBX_B200_GRID", 0);
   e->tune.evict_first = env_int("WDBX_B200_EVICT_FIRST", -1);
+  e->tune.queries_per_pass = env_int("WDBX_B200_QUERIES_PER_PASS", 0);
   ScanPlan plan;
-  if (scan_plan(dim, e->dpad, e->elem_bytes, 10, e->sm_count, e->tune, &plan) != 0) {
+  if (scan_plan(dim, e->dpad, e->elem_bytes, 10, 1, e->sm_count, e->tune, &plan) != 0) {
     delete e;
     return fail(WDBX_B200_ERR_LIMIT, "dim=%d is too large for the scan kernel (row must fit a shared-memory stage)", dim);
   }
@@ -372,9 +373,9 @@ void wdbx_b200_destroy(wdbx_b200_engine* e) {
 int wdbx_b200_set_tuning(wdbx_b200_engine* e, int warps, int stages, int rows_unroll, int grid, int evict_first) {
   if (!e) return fail(WDBX_B200_ERR_ARG, "engine is NULL");
   std::lock_guard<std::mutex> lk(e->mu);
-  ScanTuning t{warps, stages, rows_unroll, grid, evict_first};
+  ScanTuning t{warps, stages, rows_unroll, grid, evict_first, e->tune.queries_per_pass};
   ScanPlan plan;
-  if (scan_plan(e->dim, e->dpad, e->elem_bytes, 10, e->sm_count, t, &plan) != 0)
+  if (scan_plan(e->dim, e->dpad, e->elem_bytes, 10, 1, e->sm_count, t, &plan) != 0)
     return fail(WDBX_B200_ERR_ARG, "tuning does not fit shared memory");
   e->tune = t;
   return WDBX_B200_OK;

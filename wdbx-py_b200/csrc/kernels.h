@@ -25,6 +25,7 @@ struct ScanTuning {
   int rows_unroll;  // U: rows held per lane group per tile (1, 2 or 4)
   int grid;       // CTAs (default: one per SM)
   int evict_first;  // -1 auto, 0 off, 1 on
+  int queries_per_pass;  // QB: queries scored per streamed row (1, 2, 4, 8); 0 = auto (up to 8)
 };
 
 struct ScanParams {
@@ -61,7 +62,7 @@ struct ScanPlan {
 };
 
 // Fill the derived fields (plan) for the given shape.  Returns 0 or a negative wdbx error code.
-int scan_plan(int dim, int dpad, int elem_bytes, int k, int sm_count, const ScanTuning& tune, ScanPlan* plan);
+int scan_plan(int dim, int dpad, int elem_bytes, int k, int B, int sm_count, const ScanTuning& tune, ScanPlan* plan);
 
 // Launch K1 (+ fused last-block merge).  p.seg / tile_end / totals must be consistent with plan.
 cudaError_t launch_scan_topk(const ScanParams& p, const ScanPlan& plan, bool bf16, cudaStream_t stream);
