@@ -58,6 +58,8 @@ struct Workspace {
   size_t cand_keys = 0;
   unsigned int* counters = nullptr;
   int n_counters = 0;
+  float* qsplit = nullptr;  // K2: q_hi | q_lo | 1/|q| | |q|^2
+  size_t qsplit_floats = 0;
 };
 
 int env_int(const char* name, int dflt) {
@@ -74,6 +76,7 @@ struct wdbx_b200_engine {
   uint32_t next_gid = 0;
   std::vector<Workspace> ws;
   ScanTuning tune{0, 0, 0, 0, -1, 0};
+  int gemm_min_batch = 48;  // B >= this => tcgen05 GEMM path (0 = never)
   cudaStream_t mstream = nullptr;  // mutations
   // staging for host-sourced appends
   float* stage_rows = nullptr;
@@ -169,7 +172,8 @@ int ensure_capacity(wdbx_b200_engine* e, Segment& s, int64_t rows) {
   return WDBX_B200_OK;
 }
 
-int get_workspace(wdbx_b200_engine* e, cudaStream_t stream, size_t cand_keys, int n_counters, Workspace** out) {
+int get_workspace(wdbx_b200_engine* e, cudaStream_t stream, size_t cand_keys, int n_counters, Workspace** out,
+                  size_t qsplit_floats = 0) {
   Workspace* w = nullptr;
   for (auto& x : e->ws)
     if (x.stream == stream) { w = &x; break; }
@@ -179,7 +183,7 @@ int get_workspace(wdbx_b200_engine* e, cudaStream_t stream, size_t cand_keys, in
     w = &e->ws.back();
     w->stream = stream;
   }
-  if (w->cand_keys < cand_keys || w->n_counters < n_counters) {
+  if (w->cand_keys < cand_keys || w->n_counters < n_counters || w->qsplit_floats < qsplit_floats) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(stream, &cs);
     if (cs != cudaStreamCaptureStatusNone)
@@ -191,6 +195,13 @@ int get_workspace(wdbx_b200_engine* e, cudaStream_t stream, size_t cand_keys, in
       w->cand_keys = 0;
       CU_TRY(cudaMalloc(&w->cand, cand_keys * 8));
       w->cand_keys = cand_keys;
+    }
+    if (w->qsplit_floats < qsplit_floats) {
+      cudaFree(w->qsplit);
+      w->qsplit = nullptr;
+      w->qsplit_floats = 0;
+      CU_TRY(cudaMalloc(&w->qsplit, qsplit_floats * 4));
+      w->qsplit_floats = qsplit_floats;
     }
     if (w->n_counters < n_counters) {
       cudaFree(w->counters);
@@ -221,6 +232,7 @@ int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B
     const Segment& sg = e->seg[s];
     p.seg[n].rows = sg.rows;
     p.seg[n].inv_norm = sg.inv_norm;
+    p.seg[n].sqnorm = sg.sqnorm;
     p.seg[n].gids = sg.gids;
     p.seg[n].tomb = sg.n_dead > 0 ? sg.tomb : nullptr;
     p.seg[n].n_rows = sg.n_rows;
@@ -262,6 +274,56 @@ int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B
   CU_TRY(launch_scan_topk(p, plan, e->dtype == WDBX_B200_BF16, stream));
   e->launches.fetch_add(1, std::memory_order_relaxed);
   return WDBX_B200_OK;
+}
+
+// K2 path: split the queries once, one tcgen05 GEMM + top-k launch per segment, one K3 merge.
+// Caller holds e->mu and has set the device.
+int gemm_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B, int k, int metric,
+                  uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream) {
+  int slices[kMaxSeg];
+  int total_slices = 0;
+  for (int s = s0; s < s1; ++s) {
+    slices[s] = e->seg[s].n_rows > 0 ? gemm_slices_for(e->seg[s].n_rows, B, e->sm_count) : 0;
+    total_slices += slices[s];
+  }
+  if (total_slices == 0) total_slices = 1;  // empty store: merge one all-zero list
+  Workspace* w = nullptr;
+  const int wrc = get_workspace(e, stream, static_cast<size_t>(total_slices) * B * k, 64, &w,
+                                gemm_query_workspace_floats(B, e->dim));
+  if (wrc != WDBX_B200_OK) return wrc;
+  CU_TRY(cudaMemsetAsync(w->cand, 0, static_cast<size_t>(total_slices) * B * k * 8, stream));
+  CU_TRY(launch_split_queries(q_dev, B, e->dim, w->qsplit, stream));
+  e->launches.fetch_add(1, std::memory_order_relaxed);
+  int base = 0;
+  for (int s = s0; s < s1; ++s) {
+    const Segment& sg = e->seg[s];
+    if (slices[s] == 0) continue;
+    SegDesc d;
+    d.rows = sg.rows;
+    d.inv_norm = sg.inv_norm;
+    d.sqnorm = sg.sqnorm;
+    d.gids = sg.gids;
+    d.tomb = sg.n_dead > 0 ? sg.tomb : nullptr;
+    d.n_rows = sg.n_rows;
+    CU_TRY(launch_gemm_topk(d, e->dim, e->dpad, w->qsplit, B, k, metric, slices[s], base, w->cand, stream));
+    e->launches.fetch_add(1, std::memory_order_relaxed);
+    base += slices[s];
+  }
+  CU_TRY(launch_merge_topk(w->cand, total_slices, B, k, keys_out, scores_out, gids_out, counts_out, stream));
+  e->launches.fetch_add(1, std::memory_order_relaxed);
+  return WDBX_B200_OK;
+}
+
+// Regime choice (north star): small batches stream X once per QB queries on CUDA cores (K1, HBM
+// bound); from gemm_min_batch queries on, the scan is a dense contraction and runs on tcgen05 (K2).
+bool use_gemm(const wdbx_b200_engine* e, int B, int k) {
+  return e->dtype == WDBX_B200_F32 && e->gemm_min_batch > 0 && B >= e->gemm_min_batch && k <= gemm_max_k();
+}
+
+int search_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B, int k, int metric,
+                    uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream) {
+  if (use_gemm(e, B, k)) return gemm_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream);
+  return scan_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream);
 }
 
 int check_search_args(wdbx_b200_engine* e, int B, int k, int metric) {
@@ -330,6 +392,7 @@ int wdbx_b200_create(int device, int dim, int dtype, int num_segments, wdbx_b200
   e->tune.grid = env_int("WDBX_B200_GRID", 0);
   e->tune.evict_first = env_int("WDBX_B200_EVICT_FIRST", -1);
   e->tune.queries_per_pass = env_int("WDBX_B200_QUERIES_PER_PASS", 0);
+  e->gemm_min_batch = env_int("WDBX_B200_GEMM_MIN_BATCH", e->gemm_min_batch);
   ScanPlan plan;
   if (scan_plan(dim, e->dpad, e->elem_bytes, 10, 1, e->sm_count, e->tune, &plan) != 0) {
     delete e;
@@ -355,6 +418,7 @@ void wdbx_b200_destroy(wdbx_b200_engine* e) {
   for (auto& w : e->ws) {
     cudaFree(w.cand);
     cudaFree(w.counters);
+    cudaFree(w.qsplit);
   }
   cudaFree(e->stage_rows);
   cudaFree(e->stage_gids);
@@ -562,7 +626,7 @@ int wdbx_b200_search(wdbx_b200_engine* e, int segment, const float* q_dev, int B
   std::lock_guard<std::mutex> lk(e->mu);
   const int s0 = segment == WDBX_B200_ALL_SEGMENTS ? 0 : segment;
   const int s1 = segment == WDBX_B200_ALL_SEGMENTS ? e->nseg : segment + 1;
-  rc = scan_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, reinterpret_cast<long long*>(gids_out),
+  rc = search_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, reinterpret_cast<long long*>(gids_out),
                      counts_out, static_cast<cudaStream_t>(cuda_stream));
   if (rc == WDBX_B200_OK) e->searches.fetch_add(1, std::memory_order_relaxed);
   return rc;
@@ -610,7 +674,7 @@ int wdbx_b200_search_host(wdbx_b200_engine* e, int segment, const float* q_host,
       const size_t o = static_cast<size_t>(l) * B * k;
       const int s0 = per_segment ? l : (segment >= 0 ? segment : 0);
       const int s1 = per_segment ? l + 1 : (segment >= 0 ? segment + 1 : e->nseg);
-      rc = scan_segments(e, s0, s1, e->dq, B, k, metric,
+      rc = search_segments(e, s0, s1, e->dq, B, k, metric,
                          reinterpret_cast<uint64_t*>(e->dres + off_keys) + o,
                          reinterpret_cast<float*>(e->dres + off_scores) + o,
                          reinterpret_cast<long long*>(e->dres + off_gids) + o,

@@ -13,6 +13,7 @@ enum Metric : int { kCosine = 0, kIP = 1, kL2 = 2 };
 struct SegDesc {
   const unsigned char* rows;  // [n_rows][row_bytes]
   const float* inv_norm;      // [n_rows] 1/|x| (0 for zero rows)
+  const float* sqnorm;        // [n_rows] |x|^2 (GEMM path, l2)
   const uint32_t* gids;       // [n_rows] global insertion ids
   const uint32_t* tomb;       // bitmap, 1 = dead; may be NULL when the segment has no tombstones
   long long n_rows;
@@ -66,6 +67,14 @@ int scan_plan(int dim, int dpad, int elem_bytes, int k, int B, int sm_count, con
 
 // Launch K1 (+ fused last-block merge).  p.seg / tile_end / totals must be consistent with plan.
 cudaError_t launch_scan_topk(const ScanParams& p, const ScanPlan& plan, bool bf16, cudaStream_t stream);
+
+// K2: tcgen05 GEMM + fused top-k (large batches, fp32 storage).  See gemm_topk.cu.
+size_t gemm_query_workspace_floats(int B, int dim);
+int gemm_max_k();
+int gemm_slices_for(long long n_rows, int B, int sm_count);
+cudaError_t launch_split_queries(const float* q, int B, int dim, float* workspace, cudaStream_t stream);
+cudaError_t launch_gemm_topk(const SegDesc& seg, int dim, int dpad, const float* workspace, int B, int k, int metric,
+                             int n_slices, int slice_base, uint64_t* out_lists, cudaStream_t stream);
 
 // K3: merge G best-first lists per query.
 cudaError_t launch_merge_topk(const uint64_t* keys, int G, int B, int k, uint64_t* keys_out, float* scores_out,
