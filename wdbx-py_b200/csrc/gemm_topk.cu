@@ -17,7 +17,8 @@
 //
 // CTA = 12 warps: 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 idle | 4-7 epilogue (one
 // query = one TMEM lane = one thread, running top-k list in shared memory) | 8-11 converters.
-// Tile: 128 queries (M) x 256 rows (N) x 32 dims (K block, one 128-byte swizzle atom), 2 stages.
+// Tile: 128 queries (M) x 256 rows (N) x 16 dims (K block, one 64-byte swizzle atom), 4 stages;
+// two accumulator tiles in TMEM (512 columns) so the epilogue of tile t overlaps the MMAs of t+1.
 // Grid: (query blocks) x (row slices); every CTA sweeps the row tiles of its slice for its query
 // block and writes k keys per query; K3 (merge_topk) folds the slices.
 #include <cuda.h>
@@ -34,14 +35,15 @@ namespace {
 
 constexpr int BM = 128;       // queries per CTA (TMEM lanes)
 constexpr int BN = 256;       // database rows per accumulator tile (TMEM columns)
-constexpr int BK = 32;        // fp32 elements per K block = 128 bytes = one swizzle atom row
-constexpr int STAGES = 2;
+constexpr int BK = 16;        // fp32 elements per K block = 64 bytes = one SWIZZLE_64B atom row
+constexpr int STAGES = 4;     // small stages, deep ring: TMA latency + split + MMA of a stage overlap 3 others
 constexpr int kThreads = 384;
 constexpr int kMaxKGemm = 16;  // per-thread list length limit (shared memory)
 
-constexpr uint32_t X_TILE_BYTES = BN * BK * 4;  // 32 KB
-constexpr uint32_t Q_TILE_BYTES = BM * BK * 4;  // 16 KB
-constexpr uint32_t STAGE_BYTES = 2 * X_TILE_BYTES + 2 * Q_TILE_BYTES;  // x, x_lo, q_hi, q_lo = 96 KB
+constexpr uint32_t X_TILE_BYTES = BN * BK * 4;  // 16 KB
+constexpr uint32_t Q_TILE_BYTES = BM * BK * 4;  // 8 KB
+constexpr uint32_t STAGE_BYTES = 2 * X_TILE_BYTES + 2 * Q_TILE_BYTES;  // x, x_lo, q_hi, q_lo = 48 KB
+constexpr uint32_t TMEM_COLS = 2 * BN;          // two accumulator tiles: epilogue of tile t overlaps MMAs of t+1
 
 struct GemmParams {
   const float* inv_norm;   // [n_rows]
@@ -109,16 +111,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start address >> 4 | LBO (unused for one swizzle atom along K) | SBO = 1024 B between 8-row groups |
-// version 1 (Blackwell) | layout SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+// K-major, 64-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start address >> 4 | LBO (unused for one swizzle atom along K) | SBO = 8 rows x 64 B between
+// 8-row groups | version 1 (Blackwell) | layout SWIZZLE_64B (= 4).
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
   d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>((8 * BK * 4) >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(4) << 61;
   return d;
 }
 // cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, A and B K-major.
@@ -161,22 +163,37 @@ __global__ void split_queries_kernel(const float* __restrict__ q, int B, int dim
 }
 
 // ---------------------------------------------------------------- the GEMM + top-k kernel
+// Insert `key` into thread `et`'s sorted list (column-major [k][BM] so lanes never bank-conflict).
+__device__ __forceinline__ float list_push(uint64_t* lists, int k, int et, uint64_t key) {
+  int i = k - 1;
+  while (i > 0) {
+    const uint64_t prev = lists[static_cast<size_t>(i - 1) * BM + et];
+    if (prev >= key) break;
+    lists[static_cast<size_t>(i) * BM + et] = prev;
+    --i;
+  }
+  lists[static_cast<size_t>(i) * BM + et] = key;
+  const uint64_t last = lists[static_cast<size_t>(k - 1) * BM + et];
+  return last ? key_score(last) : __int_as_float(0xff800000);
+}
+
+template <int METRIC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_qhi,
                  const __grid_constant__ CUtensorMap tm_qlo, const GemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // carve-up: stages (1024-aligned) | per-thread lists [k][128] u64 | column scale tile [BN] | barriers | tmem ptr
+  // carve-up: stages (1024-aligned) | per-thread lists [k][128] u64 | column scales [2][BN] | barriers | tmem ptr
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* stage_base = smem;
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // [k][BM]
-  float* colscale = reinterpret_cast<float*>(lists + static_cast<size_t>(kMaxKGemm) * BM);  // [BN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(colscale + BN);
-  uint64_t* full_bar = bars;               // [STAGES] TMA landed
-  uint64_t* conv_bar = bars + STAGES;      // [STAGES] x_hi / x_lo written
-  uint64_t* empty_bar = bars + 2 * STAGES; // [STAGES] MMAs of the stage retired
-  uint64_t* tmem_full = bars + 3 * STAGES; // accumulator tile complete
-  uint64_t* tmem_empty = tmem_full + 1;    // epilogue drained the accumulator
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  float* colscale = reinterpret_cast<float*>(lists + static_cast<size_t>(kMaxKGemm) * BM);  // [2][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(colscale + 2 * BN);
+  uint64_t* full_bar = bars;                // [STAGES] TMA landed
+  uint64_t* conv_bar = bars + STAGES;       // [STAGES] x_hi / x_lo written
+  uint64_t* empty_bar = bars + 2 * STAGES;  // [STAGES] MMAs of the stage retired
+  uint64_t* tmem_full = bars + 3 * STAGES;  // [2] accumulator tile complete
+  uint64_t* tmem_empty = tmem_full + 2;     // [2] epilogue drained the accumulator
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x;      // query block
@@ -192,11 +209,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       mbar_init(smem_u32(conv_bar + s), 4);
       mbar_init(smem_u32(empty_bar + s), 1);
     }
-    mbar_init(smem_u32(tmem_full), 1);
-    mbar_init(smem_u32(tmem_empty), 4);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(tmem_full + a), 1);
+      mbar_init(smem_u32(tmem_empty + a), 4);
+    }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_ptr), BN);
+  if (warp == 2) tmem_alloc(smem_u32(tmem_ptr), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -224,34 +243,37 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread)
+    // ===== MMA issuer (one thread); accumulator tile t lives in TMEM columns [(t&1)*BN, +BN)
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < my_tiles; ++t) {
-        mbar_wait(smem_u32(tmem_empty), (static_cast<uint32_t>(t) & 1u) ^ 1u);  // epilogue drained tile t-1
+        const int a = t & 1;
+        const uint32_t aphase = (static_cast<uint32_t>(t) >> 1) & 1u;
+        mbar_wait(smem_u32(tmem_empty + a), aphase ^ 1u);  // epilogue drained tile t-2
         tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(a * BN);
         for (int kb = 0; kb < p.n_kblocks; ++kb) {
           mbar_wait(smem_u32(conv_bar + stage), phase);
           tc_fence_after();
           const uint32_t sb = smem_u32(stage_base + static_cast<size_t>(stage) * STAGE_BYTES);
-          const uint64_t d_xhi = make_desc_sw128(sb);
-          const uint64_t d_xlo = make_desc_sw128(sb + X_TILE_BYTES);
-          const uint64_t d_qhi = make_desc_sw128(sb + 2 * X_TILE_BYTES);
-          const uint64_t d_qlo = make_desc_sw128(sb + 2 * X_TILE_BYTES + Q_TILE_BYTES);
+          const uint64_t d_xhi = make_desc_sw64(sb);
+          const uint64_t d_xlo = make_desc_sw64(sb + X_TILE_BYTES);
+          const uint64_t d_qhi = make_desc_sw64(sb + 2 * X_TILE_BYTES);
+          const uint64_t d_qlo = make_desc_sw64(sb + 2 * X_TILE_BYTES + Q_TILE_BYTES);
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {
             const uint64_t adv = static_cast<uint64_t>((kk * 8 * 4) >> 4);  // 32 bytes per K=8 step
             // small terms first, then the dominant hi.hi product
-            umma_tf32(tmem_base, d_qlo + adv, d_xhi + adv, idesc, (kb | kk) ? 1u : 0u);
-            umma_tf32(tmem_base, d_qhi + adv, d_xlo + adv, idesc, 1u);
-            umma_tf32(tmem_base, d_qhi + adv, d_xhi + adv, idesc, 1u);
+            umma_tf32(d_tmem, d_qlo + adv, d_xhi + adv, idesc, (kb | kk) ? 1u : 0u);
+            umma_tf32(d_tmem, d_qhi + adv, d_xlo + adv, idesc, 1u);
+            umma_tf32(d_tmem, d_qhi + adv, d_xhi + adv, idesc, 1u);
           }
           umma_commit(smem_u32(empty_bar + stage));  // frees the stage when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(smem_u32(tmem_full));  // accumulator tile t complete
+        umma_commit(smem_u32(tmem_full + a));  // accumulator tile t complete
       }
     }
   } else if (warp >= 8) {
@@ -264,8 +286,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       mbar_wait(smem_u32(full_bar + stage), phase);
       uint4* xs = reinterpret_cast<uint4*>(stage_base + static_cast<size_t>(stage) * STAGE_BYTES);
       uint4* xl = reinterpret_cast<uint4*>(stage_base + static_cast<size_t>(stage) * STAGE_BYTES + X_TILE_BYTES);
-#pragma unroll 4
-      for (int c = ct; c < static_cast<int>(X_TILE_BYTES / 16); c += 128) {
+#pragma unroll
+      for (int i = 0; i < static_cast<int>(X_TILE_BYTES / 16 / 128); ++i) {
+        const int c = ct + i * 128;
         uint4 v = xs[c];
         uint4 h, l;
         h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
@@ -282,7 +305,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: thread = query row (TMEM lane), running top-k in shared memory
+    // ===== epilogue: thread = query row (TMEM lane), running top-k in shared memory.
+    // Overlaps the MMAs of the next tile (two accumulator tiles in TMEM).
     const int et = threadIdx.x - 128;           // 0..127 == TMEM lane == query inside the block
     const int q = qb * BM + et;
     const bool q_valid = q < p.B;
@@ -292,51 +316,51 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     float thr = __int_as_float(0xff800000);     // -inf until the list is full
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     for (int t = 0; t < my_tiles; ++t) {
+      const int a = t & 1;
       const long long row0 = static_cast<long long>(slice + t * p.n_slices) * BN;
       const long long rem = p.n_rows - row0;
       const int valid = rem < BN ? static_cast<int>(rem) : BN;
-      // per-column scale of this tile (cosine: 1/|x|, l2: |x|^2)
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
-      for (int c = et; c < BN; c += 128) {
-        float v = 0.0f;
-        if (c < valid) v = (p.metric == kCosine) ? __ldg(p.inv_norm + row0 + c) : (p.metric == kL2 ? __ldg(p.sqnorm + row0 + c) : 0.0f);
-        colscale[c] = v;
+      float* cs = colscale + a * BN;
+      // per-column scale of this tile (cosine: 1/|x|, l2: |x|^2); cs[a] was last read for tile t-2
+      if (METRIC != kIP) {
+        for (int c = et; c < BN; c += 128) {
+          float v = 0.0f;
+          if (c < valid) v = (METRIC == kCosine) ? __ldg(p.inv_norm + row0 + c) : __ldg(p.sqnorm + row0 + c);
+          cs[c] = v;
+        }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_wait(smem_u32(tmem_full), static_cast<uint32_t>(t) & 1u);
+      mbar_wait(smem_u32(tmem_full + a), (static_cast<uint32_t>(t) >> 1) & 1u);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         __syncwarp();
-        tmem_ld32(lane_base + static_cast<uint32_t>(c0), r);
+        tmem_ld32(lane_base + static_cast<uint32_t>(a * BN + c0), r);
         tmem_ld_wait();
         if (c0 < valid && q_valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = __uint_as_float(r[j]);
-            float s;
-            if (p.metric == kCosine) s = d * colscale[c0 + j] * qinv;
-            else if (p.metric == kL2) s = -((colscale[c0 + j] - 2.0f * d) + qsq);
-            else s = d;
-            s = (s != s) ? __int_as_float(0xff800000) : s;
-            if (s >= thr && (c0 + j) < valid) {
-              const long long row = row0 + c0 + j;
-              bool dead = false;
-              if (p.tomb != nullptr) dead = (__ldg(p.tomb + (row >> 5)) >> (row & 31)) & 1u;
-              if (!dead) {
-                const uint64_t key = pack_key(s, __ldg(p.gids + row));
-                if (key > lists[static_cast<size_t>(k - 1) * BM + et]) {
-                  int i = k - 1;
-                  while (i > 0) {
-                    const uint64_t prev = lists[static_cast<size_t>(i - 1) * BM + et];
-                    if (prev >= key) break;
-                    lists[static_cast<size_t>(i) * BM + et] = prev;
-                    --i;
-                  }
-                  lists[static_cast<size_t>(i) * BM + et] = key;
-                  const uint64_t last = lists[static_cast<size_t>(k - 1) * BM + et];
-                  thr = last ? key_score(last) : __int_as_float(0xff800000);
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (METRIC != kIP) c4 = *reinterpret_cast<const float4*>(cs + c0 + j4);  // warp-wide broadcast
+            const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = j4 + jj;
+              const float d = __uint_as_float(r[j]);
+              float s;
+              if (METRIC == kCosine) s = d * cc[jj] * qinv;
+              else if (METRIC == kL2) s = -((cc[jj] - 2.0f * d) + qsq);
+              else s = d;
+              // !(s < thr) also lets NaN through; the slow path ranks it as -inf like K1 does
+              if (!(s < thr) && (c0 + j) < valid) {
+                s = (s != s) ? __int_as_float(0xff800000) : s;
+                const long long row = row0 + c0 + j;
+                bool dead = false;
+                if (p.tomb != nullptr) dead = (__ldg(p.tomb + (row >> 5)) >> (row & 31)) & 1u;
+                if (!dead) {
+                  const uint64_t key = pack_key(s, __ldg(p.gids + row));
+                  if (key > lists[static_cast<size_t>(k - 1) * BM + et]) thr = list_push(lists, k, et, key);
                 }
               }
             }
@@ -345,7 +369,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(tmem_empty));
+      if (lane == 0) mbar_arrive(smem_u32(tmem_empty + a));
     }
     if (q_valid) {
       uint64_t* out = p.out_lists + (static_cast<size_t>(p.slice_base + slice) * p.B + q) * k;
@@ -357,12 +381,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
 constexpr size_t kGemmSmem = 1024 + static_cast<size_t>(STAGES) * STAGE_BYTES + static_cast<size_t>(kMaxKGemm) * BM * 8 +
-                             BN * 4 + (3 * STAGES + 2) * 8 + 16;
+                             2 * BN * 4 + (3 * STAGES + 4) * 8 + 16;
 
 // ---------------------------------------------------------------- tensor maps (driver entry point, no libcuda link)
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
@@ -378,7 +402,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-// [rows, ld] fp32 row-major, logical width `cols`; box = 32 floats x box_rows, 128B swizzle, OOB -> 0.
+// [rows, ld] fp32 row-major, logical width `cols`; box = BK floats x box_rows, 64B swizzle, OOB -> 0.
 bool encode_map(CUtensorMap* map, const void* base, long long rows, int cols, int ld, int box_rows) {
   auto fn = get_encode();
   if (!fn) return false;
@@ -387,7 +411,7 @@ bool encode_map(CUtensorMap* map, const void* base, long long rows, int cols, in
   cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -429,7 +453,11 @@ cudaError_t launch_gemm_topk(const SegDesc& seg, int dim, int dpad, const float*
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
+    attr_err = cudaFuncSetAttribute(gemm_topk_kernel<kCosine>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gemm_topk_kernel<kIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gemm_topk_kernel<kL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
   });
   if (attr_err != cudaSuccess) return attr_err;
   const int ld = (dim + 3) / 4 * 4;
@@ -458,7 +486,9 @@ cudaError_t launch_gemm_topk(const SegDesc& seg, int dim, int dpad, const float*
   p.out_lists = out_lists;
   p.slice_base = slice_base;
   dim3 grid((B + BM - 1) / BM, n_slices, 1), block(kThreads, 1, 1);
-  gemm_topk_kernel<<<grid, block, kGemmSmem, stream>>>(tm_x, tm_qhi, tm_qlo, p);
+  if (metric == kCosine) gemm_topk_kernel<kCosine><<<grid, block, kGemmSmem, stream>>>(tm_x, tm_qhi, tm_qlo, p);
+  else if (metric == kL2) gemm_topk_kernel<kL2><<<grid, block, kGemmSmem, stream>>>(tm_x, tm_qhi, tm_qlo, p);
+  else gemm_topk_kernel<kIP><<<grid, block, kGemmSmem, stream>>>(tm_x, tm_qhi, tm_qlo, p);
   return cudaGetLastError();
 }
 
