@@ -1,0 +1,108 @@
+"""GPU parity at BASELINE.json's full sizes (C2..C5 as they land on ONE GPU).  The oracle for these
+sizes is a chunked fp64 torch scan on the device (checker only), cross-validated against the numpy
+oracle on a prefix; data is regenerated chunk by chunk from seeds instead of being held twice."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import exact_search as oracle  # noqa: E402
+
+CHUNK = 1 << 20
+
+
+def _chunks(n, dim, seed, dev):
+    import torch
+
+    for c in range((n + CHUNK - 1) // CHUNK):
+        m = min(CHUNK, n - c * CHUNK)
+        g = torch.Generator(device=dev).manual_seed(seed + c)
+        yield c * CHUNK, torch.randn((m, dim), generator=g, device=dev, dtype=torch.float32)
+
+
+def _fill(eng, n, dim, seed, dev):
+    eng.reserve(0, n)
+    for _, x in _chunks(n, dim, seed, dev):
+        eng.append(0, x)
+
+
+def _checker_topk(n, dim, seed, dev, Q, k, metric, bf16):
+    """fp64 top-k of every query in Q [b, dim] (checker; Q small)."""
+    import torch
+
+    best_s, best_i = None, None
+    Qd = Q.double()
+    for r0, x in _chunks(n, dim, seed, dev):
+        if bf16:
+            x = x.to(torch.bfloat16).to(torch.float32)
+        xd = x.double()
+        if metric == "cosine":
+            s = (Qd @ xd.T) / (Qd.norm(dim=1, keepdim=True) * xd.norm(dim=1)[None, :])
+        elif metric == "ip":
+            s = Qd @ xd.T
+        else:
+            s = -((Qd * Qd).sum(1, keepdim=True) - 2.0 * (Qd @ xd.T) + (xd * xd).sum(1)[None, :])
+        v, i = torch.topk(s, min(k, s.shape[1]), dim=1)
+        i = i + r0
+        if best_s is None:
+            best_s, best_i = v, i
+        else:
+            cs, ci = torch.cat([best_s, v], 1), torch.cat([best_i, i], 1)
+            v2, sel = torch.topk(cs, k, dim=1)
+            best_s, best_i = v2, torch.gather(ci, 1, sel)
+        del x, xd, s
+    return best_s.cpu().numpy(), best_i.cpu().numpy()
+
+
+def _assert_match(got_s, got_g, want_s, want_i, metric, dim, scale=1.0):
+    # ids equal except inside the documented fp32 tie window; scores within the oracle tolerance
+    tie = 8.0 * np.sqrt(dim) * 2.0 ** -24 * scale
+    for b in range(want_i.shape[0]):
+        if not np.array_equal(got_g[b], want_i[b]):
+            bad = got_g[b] != want_i[b]
+            assert set(got_g[b]) == set(want_i[b]) or np.all(np.abs(np.diff(want_s[b]))[bad[:-1] | bad[1:]] <= tie), (b, got_g[b], want_i[b])
+        tol = 1e-5 * np.abs(want_s[b]) + 1e-6 * scale
+        assert np.all(np.abs(got_s[b].astype(np.float64) - want_s[b]) <= tol), (b, np.abs(got_s[b] - want_s[b]).max())
+        assert np.all(np.diff(got_s[b]) <= 0)
+
+
+@pytest.mark.parametrize("name,n,dim,dtype,metric,k,B,gemm", [
+    ("C2", 1_000_000, 384, "fp32", "cosine", 10, 1, 0),
+    ("C3-B1", 10_000_000, 768, "fp32", "cosine", 10, 1, 0),
+    ("C3-B1024", 10_000_000, 768, "fp32", "cosine", 10, 1024, 48),
+    ("C4-shard", 12_500_000, 384, "bf16", "ip", 100, 1, 0),
+    ("C5", 5_000_000, 1536, "fp32", "l2", 10, 4096, 48),
+])
+def test_full_size_config(built_lib, name, n, dim, dtype, metric, k, B, gemm):
+    import torch
+    import wdbx_b200
+
+    dev = torch.device("cuda", 0)
+    seed = 9000 + dim
+    os.environ["WDBX_B200_GEMM_MIN_BATCH"] = str(gemm)
+    try:
+        eng = wdbx_b200.Engine(0, dim, dtype, 1)
+    finally:
+        os.environ.pop("WDBX_B200_GEMM_MIN_BATCH", None)
+    _fill(eng, n, dim, seed, dev)
+    Q = torch.randn((B, dim), generator=torch.Generator(device=dev).manual_seed(77), device=dev)
+    out = eng.search(Q, k, metric)
+    torch.cuda.synchronize()
+    got_s, got_g, cnt = out["scores"].cpu().numpy(), out["gids"].cpu().numpy(), out["counts"].cpu().numpy()
+    assert np.all(cnt == k)
+    assert np.all(np.diff(got_s, axis=1) <= 0)           # sorted, all B queries
+    assert np.all((got_g >= 0) & (got_g < n))
+    sel = np.unique(np.linspace(0, B - 1, min(B, 12)).astype(int))   # fp64 check on a spread of queries
+    want_s, want_i = _checker_topk(n, dim, seed, dev, Q[sel], k, metric, dtype == "bf16")
+    scale = 1.0 if metric == "cosine" else float(dim) * (2.0 if metric == "l2" else 1.0)
+    _assert_match(got_s[sel], got_g[sel], want_s, want_i, metric, dim, scale)
+    # the device checker itself is pinned to the numpy oracle on a prefix
+    if name == "C2":
+        x0 = next(_chunks(n, dim, seed, dev))[1][:50000]
+        rows, sc = oracle.topk_desc(oracle.scores_fp64(x0.cpu().numpy(), Q[0].cpu().numpy(), metric), k)
+        ws, wi = _checker_topk(50000, dim, seed, dev, Q[:1], k, metric, False)
+        assert list(rows) == list(wi[0])
+        np.testing.assert_allclose(sc, ws[0], rtol=1e-12)
+    eng.close()

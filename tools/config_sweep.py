@@ -1,0 +1,75 @@
+"""Measure every BASELINE.json config on ONE GPU (device-resident queries, CUDA events) and write
+gpurun_out/config_sweep.json.  C4 is its per-GPU shard (12.5M of the 100M rows)."""
+import json, os, sys, time, tempfile
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "wdbx-py_b200"))
+import numpy as np, torch
+import wdbx_b200
+
+PEAK = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
+
+def fill(eng, n, dim, seed):
+    eng.reserve(0, n)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    done = 0
+    while done < n:
+        m = min(1 << 20, n - done); eng.append(0, torch.randn((m, dim), generator=g, device="cuda")); done += m
+
+def timed(fn, iters, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+res = []
+def run(name, n, dim, dtype, metric, k, B, iters, gemm=48):
+    os.environ["WDBX_B200_GEMM_MIN_BATCH"] = str(gemm)
+    eng = wdbx_b200.Engine(0, dim, dtype, 1)
+    fill(eng, n, dim, 1)
+    qs = torch.randn((8, B, dim), device="cuda")
+    out = eng.search(qs[0], k, metric)
+    i = [0]
+    def step():
+        eng.search(qs[i[0] % 8], k, metric, out=out); i[0] += 1
+    ms = timed(step, iters)
+    eb = 2 if dtype == "bf16" else 4
+    byts = n * dim * eb + (4 * n if metric == "cosine" else 0)
+    r = {"config": name, "rows": n, "dim": dim, "dtype": dtype, "metric": metric, "k": k, "batch": B,
+         "ms_per_call": ms, "qps": B / ms * 1e3}
+    if B < 48 or gemm == 0:
+        passes = (B + 7) // 8
+        r.update(kernel="K1 scan_topk", hbm_gbs=byts * passes / ms / 1e6, frac_of_measured_peak=byts * passes / ms / 1e6 / PEAK)
+    else:
+        fl = 2.0 * n * dim * B
+        r.update(kernel="K2 gemm_topk (3xTF32)", useful_tflops=fl / ms / 1e9, issued_tf32_tflops=3 * fl / ms / 1e9, hbm_floor_ms=byts / PEAK / 1e6)
+    print(json.dumps(r), flush=True)
+    res.append(r)
+    eng.close()
+
+# C1 through the public API (host lists in, tuples out)
+tmp = tempfile.mkdtemp()
+db = wdbx_b200.WDBX(vector_dimension=384, num_shards=2, data_dir=tmp, log_level="WARNING")
+X = np.random.default_rng(0).standard_normal((10000, 384)).astype(np.float32)
+db.vector_store.batch_store({f"d{i}": X[i] for i in range(10000)})
+ql = [np.random.default_rng(i).standard_normal(384).astype(np.float32).tolist() for i in range(32)]
+for q in ql[:5]: db.vector_search(q, limit=5)
+t0 = time.perf_counter()
+for j in range(200): db.vector_search(ql[j % 32], limit=5)
+us = (time.perf_counter() - t0) / 200 * 1e6
+r = {"config": "C1 quick-start 10k x 384, 2 shards, k=5, public API end to end", "us_per_query": us, "qps": 1e6 / us,
+     "engine_device_ms": db.get_stats()["gpu"]["engine"]["last_search_ms"]}
+print(json.dumps(r), flush=True); res.append(r)
+db.close()
+
+run("C2 1M x 384 fp32 cosine B=1", 1_000_000, 384, "fp32", "cosine", 10, 1, 50)
+run("C3 10M x 768 fp32 cosine B=1", 10_000_000, 768, "fp32", "cosine", 10, 1, 20)
+run("C3 10M x 768 fp32 cosine B=8 (K1, 8 queries per pass)", 10_000_000, 768, "fp32", "cosine", 10, 8, 10)
+run("C3 10M x 768 fp32 cosine B=1024", 10_000_000, 768, "fp32", "cosine", 10, 1024, 3)
+run("C4 shard 12.5M x 384 bf16 ip k=100 B=1", 12_500_000, 384, "bf16", "ip", 100, 1, 20)
+run("C5 5M x 1536 fp32 l2 B=4096", 5_000_000, 1536, "fp32", "l2", 10, 4096, 2)
+Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
+(ROOT / "gpurun_out" / "config_sweep.json").write_text(json.dumps(res, indent=1))
