@@ -470,7 +470,9 @@ int wdbx_b200_append(wdbx_b200_engine* e, int segment, const float* rows, int64_
   if (rc != WDBX_B200_OK) return rc;
   const size_t rb = row_bytes(e);
   const bool bf16 = e->dtype == WDBX_B200_BF16;
-  const int64_t chunk_rows = std::max<int64_t>(1, (64ll << 20) / (static_cast<int64_t>(e->dim) * 4));
+  // host sources go through a 64 MB device staging buffer; device sources are ingested in one launch
+  const int64_t chunk_rows =
+      src_is_device ? n : std::max<int64_t>(1, (64ll << 20) / (static_cast<int64_t>(e->dim) * 4));
   for (int64_t done = 0; done < n; done += chunk_rows) {
     const int64_t m = std::min(chunk_rows, n - done);
     const float* src = rows + done * e->dim;
