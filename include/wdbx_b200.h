@@ -159,6 +159,26 @@ int wdbx_b200_merge(wdbx_b200_engine* e, const uint64_t* keys_dev, int G, int B,
                     uint64_t* keys_out, float* scores_out, int64_t* gids_out, int32_t* counts_out,
                     void* cuda_stream);
 
+/* Fused cross-GPU merge (one process per GPU, all GPUs of one box).  Instead of "local top-k ->
+ * NCCL all-gather -> merge kernel", the scan kernel's last CTA pushes its k keys per query into
+ * every peer's exchange buffer with NVLink peer-to-peer stores, waits (bounded) for the peers'
+ * pushes and merges the G lists itself: one launch per query batch on every rank, no collective
+ * call.  Replaces: the cross-shard concat + sort + [:limit] of VectorStore.search
+ * (vector_store.py:324-330, :345) for shards that live on different GPUs.
+ *   1. every rank: wdbx_b200_exchange_init -> 64-byte CUDA IPC handle of its exchange buffer;
+ *   2. the host layer all-gathers the handles (torch.distributed) and every rank calls
+ *      wdbx_b200_exchange_attach with the world x 64 byte array (rank order);
+ *   3. wdbx_b200_search_exchange is then a COLLECTIVE: every rank must call it with the same
+ *      (B, k, metric) in the same order; every rank receives the merged global top-k.
+ * Limits: B <= 8 queries (one pass), k <= 128, world <= 8.  counts_out = -1 signals that a peer
+ * did not show up within ~3 s. */
+#define WDBX_B200_IPC_HANDLE_BYTES 64
+int wdbx_b200_exchange_init(wdbx_b200_engine* e, int rank, int world, void* ipc_handle_out);
+int wdbx_b200_exchange_attach(wdbx_b200_engine* e, int world, const void* ipc_handles);
+int wdbx_b200_search_exchange(wdbx_b200_engine* e, const float* q_dev, int B, int k, int metric,
+                              uint64_t* keys_out, float* scores_out, int64_t* gids_out,
+                              int32_t* counts_out, void* cuda_stream);
+
 /* Override the scan kernel's launch geometry (0 / -1 = automatic): consumer warps per CTA,
  * TMA pipeline stages per warp, rows held per lane group (1, 2, 4), CTAs, L2 evict-first hint.
  * Benchmark / profiling hook; the counterpart of the reference's HNSW_EF_SEARCH / FAISS_NPROBE

@@ -93,6 +93,12 @@ struct wdbx_b200_engine {
   unsigned char* hres_pinned = nullptr;
   unsigned char* dres = nullptr;
   size_t res_bytes = 0;
+  // fused cross-GPU exchange (peer-mapped buffers, see kernels.h)
+  uint64_t* xbuf = nullptr;
+  uint64_t* xpeer[kMaxPeers] = {nullptr};
+  bool xopened[kMaxPeers] = {false};
+  int xworld = 0, xrank = 0;
+  unsigned int xseq = 0;
   // stats
   std::atomic<long long> launches{0}, searches{0};
   double last_search_ms = 0.0;
@@ -219,7 +225,8 @@ int get_workspace(wdbx_b200_engine* e, cudaStream_t stream, size_t cand_keys, in
 
 // Launch one K1 scan over segments [s0, s1).  Caller holds e->mu and has set the device.
 int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B, int k, int metric,
-                  uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream) {
+                  uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream,
+                  bool exchange = false) {
   ScanPlan plan;
   const int rc = scan_plan(e->dim, e->dpad, e->elem_bytes, k, B, e->sm_count, e->tune, &plan);
   if (rc == -4) return fail(WDBX_B200_ERR_LIMIT, "dimension %d too large for the scan kernel's shared-memory stage", e->dim);
@@ -271,6 +278,17 @@ int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B
   p.scores_out = scores_out;
   p.gids_out = gids_out;
   p.counts_out = counts_out;
+  if (exchange) {
+    if (e->xworld < 2) return fail(WDBX_B200_ERR_ARG, "exchange not attached (call wdbx_b200_exchange_init/attach first)");
+    if (B > plan.queries_per_block || B > kXchgMaxB || k > kXchgMaxK)
+      return fail(WDBX_B200_ERR_LIMIT, "fused exchange supports B <= %d queries in one pass and k <= %d", kXchgMaxB, kXchgMaxK);
+    e->xseq += 1;
+    for (int r = 0; r < e->xworld; ++r) p.xchg_peer[r] = e->xpeer[r];
+    p.xchg_world = e->xworld;
+    p.xchg_rank = e->xrank;
+    p.xchg_seq = e->xseq;
+    p.xchg_slot = static_cast<int>(e->xseq & 1u);
+  }
   CU_TRY(launch_scan_topk(p, plan, e->dtype == WDBX_B200_BF16, stream));
   e->launches.fetch_add(1, std::memory_order_relaxed);
   return WDBX_B200_OK;
@@ -420,6 +438,9 @@ void wdbx_b200_destroy(wdbx_b200_engine* e) {
     cudaFree(w.counters);
     cudaFree(w.qsplit);
   }
+  for (int r = 0; r < kMaxPeers; ++r)
+    if (e->xopened[r]) cudaIpcCloseMemHandle(e->xpeer[r]);
+  cudaFree(e->xbuf);
   cudaFree(e->stage_rows);
   cudaFree(e->stage_gids);
   cudaFree(e->dq);
@@ -708,6 +729,63 @@ int wdbx_b200_merge(wdbx_b200_engine* e, const uint64_t* keys_dev, int G, int B,
                            static_cast<cudaStream_t>(cuda_stream)));
   e->launches.fetch_add(1, std::memory_order_relaxed);
   return WDBX_B200_OK;
+}
+
+int wdbx_b200_exchange_init(wdbx_b200_engine* e, int rank, int world, void* ipc_handle_out) {
+  if (!e || !ipc_handle_out) return fail(WDBX_B200_ERR_ARG, "NULL argument");
+  if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(WDBX_B200_ERR_ARG, "exchange needs 2 <= world <= %d and 0 <= rank < world", kMaxPeers);
+  static_assert(sizeof(cudaIpcMemHandle_t) == WDBX_B200_IPC_HANDLE_BYTES, "ipc handle size");
+  DeviceGuard guard(e->device);
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->xbuf) {
+    CU_TRY(cudaMalloc(&e->xbuf, kXchgBytes));
+    CU_TRY(cudaMemset(e->xbuf, 0, kXchgBytes));
+  }
+  cudaIpcMemHandle_t h;
+  CU_TRY(cudaIpcGetMemHandle(&h, e->xbuf));
+  memcpy(ipc_handle_out, &h, sizeof(h));
+  e->xrank = rank;
+  e->xworld = 0;  // armed by attach
+  e->xseq = 0;
+  (void)world;
+  return WDBX_B200_OK;
+}
+
+int wdbx_b200_exchange_attach(wdbx_b200_engine* e, int world, const void* ipc_handles) {
+  if (!e || !ipc_handles) return fail(WDBX_B200_ERR_ARG, "NULL argument");
+  if (!e->xbuf) return fail(WDBX_B200_ERR_ARG, "call wdbx_b200_exchange_init first");
+  if (world < 2 || world > kMaxPeers) return fail(WDBX_B200_ERR_ARG, "world outside [2, %d]", kMaxPeers);
+  DeviceGuard guard(e->device);
+  std::lock_guard<std::mutex> lk(e->mu);
+  const unsigned char* hs = static_cast<const unsigned char*>(ipc_handles);
+  for (int r = 0; r < world; ++r) {
+    if (r == e->xrank) {
+      e->xpeer[r] = e->xbuf;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, hs + static_cast<size_t>(r) * sizeof(h), sizeof(h));
+    void* ptr = nullptr;
+    CU_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    e->xpeer[r] = static_cast<uint64_t*>(ptr);
+    e->xopened[r] = true;
+  }
+  e->xworld = world;
+  return WDBX_B200_OK;
+}
+
+int wdbx_b200_search_exchange(wdbx_b200_engine* e, const float* q_dev, int B, int k, int metric, uint64_t* keys_out,
+                              float* scores_out, int64_t* gids_out, int32_t* counts_out, void* cuda_stream) {
+  int rc = check_search_args(e, B, k, metric);
+  if (rc != WDBX_B200_OK) return rc;
+  if (!q_dev) return fail(WDBX_B200_ERR_ARG, "q_dev is NULL");
+  DeviceGuard guard(e->device);
+  std::lock_guard<std::mutex> lk(e->mu);
+  rc = scan_segments(e, 0, e->nseg, q_dev, B, k, metric, keys_out, scores_out, reinterpret_cast<long long*>(gids_out),
+                     counts_out, static_cast<cudaStream_t>(cuda_stream), true);
+  if (rc == WDBX_B200_OK) e->searches.fetch_add(1, std::memory_order_relaxed);
+  return rc;
 }
 
 int wdbx_b200_get_stats(wdbx_b200_engine* e, wdbx_b200_stats* out) {

@@ -10,6 +10,14 @@ constexpr int kMaxK = 1024;
 
 enum Metric : int { kCosine = 0, kIP = 1, kL2 = 2 };
 
+// Exchange buffer layout (per rank, peer-mapped): keys [2 slots][kMaxPeers][kXchgMaxB][kXchgMaxK] u64,
+// then flags [2 slots][kMaxPeers] u32 (sequence number of the last completed push of that peer).
+constexpr int kMaxPeers = 8;
+constexpr int kXchgMaxB = 8;
+constexpr int kXchgMaxK = 128;
+constexpr size_t kXchgKeyCount = 2ull * kMaxPeers * kXchgMaxB * kXchgMaxK;
+constexpr size_t kXchgBytes = kXchgKeyCount * 8 + 2 * kMaxPeers * 4 + 64;
+
 struct SegDesc {
   const unsigned char* rows;  // [n_rows][row_bytes]
   const float* inv_norm;      // [n_rows] 1/|x| (0 for zero rows)
@@ -50,6 +58,14 @@ struct ScanParams {
   int evict_first;
   uint64_t* cand;          // [B][grid][k] per-CTA partial lists
   unsigned int* counters;  // [gridDim.y] last-block-done tickets (zero between launches)
+  // fused cross-GPU exchange (world > 1, gridDim.y == 1): the last CTA pushes its k keys per query
+  // into every peer's exchange buffer over NVLink (P2P stores), waits for the peers' pushes and
+  // merges the G lists itself -- no NCCL call, no second kernel.
+  uint64_t* xchg_peer[kMaxPeers];  // base of every rank's exchange buffer (own rank included)
+  int xchg_world;                  // 0/1 = exchange disabled
+  int xchg_rank;
+  int xchg_slot;                   // seq & 1
+  unsigned int xchg_seq;           // collective sequence number (same on all ranks)
   uint64_t* keys_out;      // [B][k] or NULL
   float* scores_out;       // [B][k] or NULL
   long long* gids_out;     // [B][k] or NULL

@@ -391,12 +391,64 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
       list_clear(final_list, k, lane);
       uint64_t thr = 0ull;
       absorb_keys<false>(final_list, k, thr, scratch, nwarps * k, 0, 1, lane);
+      if (p.xchg_world > 1) {
+        // push this rank's list for query b into every rank's exchange buffer (NVLink P2P stores)
+        for (int r = 0; r < p.xchg_world; ++r) {
+          uint64_t* dst = p.xchg_peer[r] +
+                          ((static_cast<size_t>(p.xchg_slot) * kMaxPeers + p.xchg_rank) * kXchgMaxB + b) * kXchgMaxK;
+          for (int i = lane; i < k; i += 32) dst[i] = final_list[i];
+        }
+      } else {
+        emit_list(final_list, k, lane, p.keys_out ? p.keys_out + static_cast<size_t>(qi) * k : nullptr,
+                  p.scores_out ? p.scores_out + static_cast<size_t>(qi) * k : nullptr,
+                  p.gids_out ? p.gids_out + static_cast<size_t>(qi) * k : nullptr,
+                  p.counts_out ? p.counts_out + qi : nullptr);
+      }
+    }
+    __syncthreads();
+  }
+  if (p.xchg_world > 1 && warp == 0) {
+    // publish: release-store the sequence number into every peer's flag slot for this rank
+    __threadfence_system();
+    __syncwarp();
+    if (lane < p.xchg_world) {
+      unsigned int* flag = reinterpret_cast<unsigned int*>(p.xchg_peer[lane] + kXchgKeyCount) +
+                           p.xchg_slot * kMaxPeers + p.xchg_rank;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(p.xchg_seq) : "memory");
+    }
+    // wait for every peer's push into OUR buffer (bounded spin: a missing peer must not hang the GPU)
+    const unsigned int* my_flags = reinterpret_cast<const unsigned int*>(p.xchg_peer[p.xchg_rank] + kXchgKeyCount) +
+                                   p.xchg_slot * kMaxPeers;
+    bool ok = true;
+    if (lane < p.xchg_world) {
+      const long long t0 = clock64();
+      unsigned int v;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(my_flags + lane) : "memory");
+        if (v == p.xchg_seq) break;
+        if (clock64() - t0 > 6000000000ll) { ok = false; break; }  // ~3 s
+        __nanosleep(100);
+      } while (true);
+    }
+    ok = __all_sync(FULL_MASK, ok);
+    __threadfence_system();
+    for (int b = 0; b < nq; ++b) {
+      const int qi = qbase + b;
+      list_clear(final_list, k, lane);
+      uint64_t thr = 0ull;
+      if (ok) {
+        for (int r = 0; r < p.xchg_world; ++r) {
+          const uint64_t* src = p.xchg_peer[p.xchg_rank] +
+                                ((static_cast<size_t>(p.xchg_slot) * kMaxPeers + r) * kXchgMaxB + b) * kXchgMaxK;
+          absorb_keys<true>(final_list, k, thr, src, k, 0, 1, lane);
+        }
+      }
       emit_list(final_list, k, lane, p.keys_out ? p.keys_out + static_cast<size_t>(qi) * k : nullptr,
                 p.scores_out ? p.scores_out + static_cast<size_t>(qi) * k : nullptr,
                 p.gids_out ? p.gids_out + static_cast<size_t>(qi) * k : nullptr,
                 p.counts_out ? p.counts_out + qi : nullptr);
+      if (!ok && p.counts_out && lane == 0) p.counts_out[qi] = -1;  // exchange timed out
     }
-    __syncthreads();
   }
   if (tid == 0) p.counters[blockIdx.y] = 0u;  // re-arm for the next launch
 }

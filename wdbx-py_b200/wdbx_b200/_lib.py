@@ -50,6 +50,9 @@ SIGNATURES = {
     "wdbx_b200_search": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "wdbx_b200_search_host": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "wdbx_b200_merge": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "wdbx_b200_exchange_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "wdbx_b200_exchange_attach": (C.c_int, [_P, C.c_int, _P]),
+    "wdbx_b200_search_exchange": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "wdbx_b200_set_tuning": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "wdbx_b200_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
 }

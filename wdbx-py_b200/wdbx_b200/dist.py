@@ -53,6 +53,16 @@ class DistContext:
             dist.all_gather(parts, keys.contiguous(), group=self.group)
         return out
 
+    def all_gather_bytes(self, payload: bytes):
+        """Gather one small bytes object per rank (rank order) -- IPC handles of the exchange buffers."""
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return [payload]
+        out = [None] * self.world
+        dist.all_gather_object(out, payload, group=self.group)
+        return out
+
     def broadcast_array(self, arr, src: int):
         """Broadcast a numpy fp32 array from rank `src` (used by VectorStore.get)."""
         import numpy as np

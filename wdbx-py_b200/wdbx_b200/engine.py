@@ -172,6 +172,47 @@ class Engine:
                                          C.c_void_p(st.cuda_stream)))
         return out
 
+    # ------------------------------------------------------------------ fused cross-GPU exchange
+    exchange_ready = False
+    XCHG_MAX_B, XCHG_MAX_K = 8, 128
+
+    def exchange_setup(self, rank: int, world: int, all_gather_bytes) -> None:
+        """Create this rank's peer-mapped exchange buffer and attach every peer's.
+        ``all_gather_bytes(b: bytes) -> List[bytes]`` gathers one 64-byte IPC handle per rank
+        (rank order); the host layer implements it with torch.distributed."""
+        h = (C.c_ubyte * 64)()
+        check(self._lib.wdbx_b200_exchange_init(self._handle(), rank, world, C.cast(h, C.c_void_p)))
+        handles = all_gather_bytes(bytes(h))
+        if len(handles) != world or any(len(x) != 64 for x in handles):
+            raise ValueError("exchange_setup: expected one 64-byte handle per rank")
+        blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+        check(self._lib.wdbx_b200_exchange_attach(self._handle(), world, C.cast(blob, C.c_void_p)))
+        self.exchange_ready = True
+
+    def search_exchange(self, q_dev, k: int, metric="cosine", out: Optional[Dict] = None, stream=None) -> Dict:
+        """COLLECTIVE fused search: scan + NVLink key push + global merge in ONE kernel per rank."""
+        import torch
+
+        if q_dev.dim() == 1:
+            q_dev = q_dev[None, :]
+        if not q_dev.is_cuda or q_dev.dtype != torch.float32 or q_dev.shape[1] != self.dim or not q_dev.is_contiguous():
+            raise ValueError(f"q_dev must be a contiguous CUDA fp32 tensor [B, {self.dim}]")
+        B = q_dev.shape[0]
+        dev = q_dev.device
+        if out is None:
+            out = {
+                "keys": torch.empty((B, k), dtype=torch.int64, device=dev),
+                "scores": torch.empty((B, k), dtype=torch.float32, device=dev),
+                "gids": torch.empty((B, k), dtype=torch.int64, device=dev),
+                "counts": torch.empty((B,), dtype=torch.int32, device=dev),
+            }
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        p = lambda name: C.c_void_p(out[name].data_ptr()) if out.get(name) is not None else None  # noqa: E731
+        check(self._lib.wdbx_b200_search_exchange(self._handle(), C.c_void_p(q_dev.data_ptr()), B, k,
+                                                  _metric_code(metric), p("keys"), p("scores"), p("gids"), p("counts"),
+                                                  C.c_void_p(st.cuda_stream)))
+        return out
+
     def merge(self, keys, out: Optional[Dict] = None, stream=None) -> Dict:
         """k-way merge of keys [G, B, k] (int64 view of the packed u64 keys) on the device."""
         import torch

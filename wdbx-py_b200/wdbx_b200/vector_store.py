@@ -122,6 +122,15 @@ class VectorStore:
         if cap > 0:
             for s in range(self.num_shards):
                 self.engine.reserve(s, self.shard_map.local_count(cap, self.dist.rank))
+        # one box, several GPUs: fuse the cross-GPU merge into the scan kernel (NVLink P2P key push)
+        self._fused = False
+        if (self.dist.world > 1 and _engine_factory is None and hasattr(self.engine, "exchange_setup")
+                and bool(self.config.get("GPU_FUSED_EXCHANGE", True))):
+            try:
+                self.engine.exchange_setup(self.dist.rank, self.dist.world, self.dist.all_gather_bytes)
+                self._fused = True
+            except Exception as e:  # e.g. > 8 ranks or no peer access: NCCL all-gather + merge kernel instead
+                logger.warning(f"fused exchange unavailable, using NCCL all-gather: {e}")
         self._init_indices()
         logger.info("VectorStore initialized: %d shards on %d GPU(s), dim=%d, metric=%s, dtype=%s",
                     self.num_shards, self.dist.world, self.vector_dim, self.metric, self.dtype)
@@ -454,6 +463,10 @@ class VectorStore:
                                            segment=(sel if sel >= 0 else ALL))
         # SPMD: local top-k on every rank -> all-gather packed keys -> merge kernel
         qd = self.engine.upload(Q)
+        if sel == ALL and self._fused and Q.shape[0] <= self.engine.XCHG_MAX_B and k <= self.engine.XCHG_MAX_K:
+            merged = self.engine.search_exchange(qd, k, metric)
+            packed = merged  # single D2H below
+            return (packed["scores"].cpu().numpy(), packed["gids"].cpu().numpy(), packed["counts"].cpu().numpy())
         if sel == EACH:
             import torch
 
@@ -475,9 +488,11 @@ class VectorStore:
         rank's GPU (the same queries on every rank); returns CUDA tensors ``keys / scores / gids /
         counts`` of the global top-``limit``.  No host copy, no synchronisation."""
         metric = metric or self.metric
-        out = self.engine.search(q_dev, limit, metric)
         if self.dist.world == 1:
-            return out
+            return self.engine.search(q_dev, limit, metric)
+        if self._fused and q_dev.shape[0] <= self.engine.XCHG_MAX_B and limit <= self.engine.XCHG_MAX_K:
+            return self.engine.search_exchange(q_dev, limit, metric)
+        out = self.engine.search(q_dev, limit, metric)
         return self.engine.merge(self.dist.all_gather_keys(out["keys"]))
 
     def _search_lists(self, q: np.ndarray, limit: int, sel: int) -> List[List[Tuple[str, float]]]:
