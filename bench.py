@@ -303,6 +303,14 @@ def run_gpu(args):
     e2e_s = reduce_max(time.perf_counter() - t0)
     e2e_qps = n_e2e / e2e_s
     assert len(res) == K
+    # where the end-to-end time goes (informational): C-ABI host call alone vs the Python facade
+    e2e_detail = {"device_ms_last_call": store.engine.stats().get("last_search_ms")}
+    if world == 1:
+        t0 = time.perf_counter()
+        for i in range(20):
+            store.engine.search_host(Qh[i % N_QUERIES], K, metric=METRIC)
+        e2e_detail["c_abi_search_host_ms"] = (time.perf_counter() - t0) / 20 * 1e3
+        e2e_detail["device_ms_last_call"] = store.engine.stats().get("last_search_ms")
     sampler.stop()
 
     # ---- parity gate on the timed data: exact fp64 re-score of the returned rows' neighbourhood
@@ -336,7 +344,7 @@ def run_gpu(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": DIM * 4,
                     "d2h_bytes_per_step": K * 20 + 4, "api": "VectorStore.search (host list in, tuples out)",
-                    "steps": n_e2e},
+                    "steps": n_e2e, "ms_per_step": e2e_s / n_e2e * 1e3, "detail": e2e_detail},
             "gpu_launches": int(gpu_launches),
             "clocks": sampler.summary(),
             "parity": parity,

@@ -126,6 +126,11 @@ int wdbx_b200_clear(wdbx_b200_engine* e, int segment);
  * Serves VectorStore.get (vector_store.py:579-596) without a host-side copy of every vector. */
 int wdbx_b200_read_row(wdbx_b200_engine* e, int segment, int64_t row, float* out_host);
 
+/* Copy n consecutive stored rows back to the host as dense fp32 [n, dim].
+ * Serves persistence: VectorStore._save_vectors (vector_store.py:168-176, a pickle of the host
+ * dict) becomes "dump the device partition". */
+int wdbx_b200_read_rows(wdbx_b200_engine* e, int segment, int64_t row0, int64_t n, float* out_host);
+
 /* Exact top-k of B queries over one segment, or over all segments merged (segment ==
  * WDBX_B200_ALL_SEGMENTS), entirely on the device and asynchronously on `cuda_stream`
  * (a cudaStream_t; NULL = legacy default stream).  q_dev: [B, dim] fp32 on the device.

@@ -86,6 +86,9 @@ class FakeEngine:
     def read_row(self, segment, row):
         return self.rows[segment][row].copy()
 
+    def read_rows(self, segment, row0, n):
+        return self.rows[segment][row0:row0 + n].copy()
+
     # search
     def _keys(self, Q, k, metric, segs):
         Q = np.asarray(Q, np.float32).reshape(-1, self.dim)

@@ -108,3 +108,42 @@ def test_engine_errors_follow_reference_convention(built_lib):
     st.engine.close()  # break the engine: reference convention = log + [] (indexing.py:1028-1030)
     assert st.search([1, 0, 0, 0]) == []
     assert st.store("b", [0, 1, 0, 0]) is False
+
+
+def test_async_micro_batching_on_device(built_lib):
+    st = make_store(96, 2, GPU_BATCH_MAX=8, GPU_BATCH_WINDOW_US=5000)
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((20000, 96), dtype=np.float32)
+    st.bulk_load(X)
+    Q = rng.standard_normal((40, 96), dtype=np.float32)
+    want = [st.search(Q[b].tolist(), limit=10) for b in range(40)]
+    n0 = st.engine.stats()["searches"]
+
+    async def go():
+        return await asyncio.gather(*[st.search_async(Q[b].tolist(), limit=10) for b in range(40)])
+
+    got = asyncio.run(go())
+    assert got == want                                   # multi-query passes are bit-identical to single
+    used = st.engine.stats()["searches"] - n0
+    assert used == st._batcher.batches and used <= 12    # 40 requests -> a handful of launches
+    st.close()
+
+
+def test_persistence_roundtrip_on_device(built_lib):
+    d = tempfile.mkdtemp()
+    rng = np.random.default_rng(6)
+    X = rng.standard_normal((5000, 64), dtype=np.float32)
+    for dtype in ("fp32", "bf16"):
+        dd = d + dtype
+        cfg = wdbx_b200.WDBXConfig({"GPU_STRICT": True, "GPU_DTYPE": dtype})
+        st = wdbx_b200.VectorStore(64, dd, num_shards=3, config=cfg)
+        st.bulk_load(X[:3000], id_prefix="b")
+        st.batch_store({f"e{i}": X[3000 + i] for i in range(2000)}, {f"e{i}": {"i": i} for i in range(2000)})
+        st.delete("e7"); st.delete("b3")
+        Q = rng.standard_normal((4, 64), dtype=np.float32)
+        want = [st.search(Q[b].tolist(), limit=20) for b in range(4)]
+        asyncio.run(st.shutdown())
+        st2 = wdbx_b200.VectorStore(64, dd, num_shards=3, config=cfg)
+        assert st2.count() == 4998
+        assert [st2.search(Q[b].tolist(), limit=20) for b in range(4)] == want   # bit-identical after reload
+        st2.close()

@@ -124,3 +124,62 @@ def test_key_packing_roundtrip():
     assert np.isneginf(sc[6])
     order = np.argsort(-k.astype(np.float64), kind="stable")
     assert list(order[:3]) == [4, 0, 7] and k[2] > k[3]  # +0 == -0 -> lower gid first
+
+
+def test_async_micro_batching_matches_sync():
+    st = make_store(8, 2, GPU_BATCH_MAX=8, GPU_BATCH_WINDOW_US=20000)
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((300, 8), dtype=np.float32)
+    st.batch_store({f"r{i}": X[i] for i in range(300)}, {f"r{i}": {"i": i} for i in range(300)})
+    Q = rng.standard_normal((20, 8), dtype=np.float32)
+    want = [st.search(Q[b].tolist(), limit=3 + b % 4, threshold=0.2 if b % 5 == 0 else 0.0) for b in range(20)]
+    launches0 = st.engine.launches
+
+    async def go():
+        return await asyncio.gather(*[st.search_async(Q[b].tolist(), limit=3 + b % 4,
+                                                      threshold=0.2 if b % 5 == 0 else 0.0) for b in range(20)])
+
+    got = asyncio.run(go())
+    assert got == want
+    assert st._batcher.requests == 20 and st._batcher.batches <= 6      # 20 requests coalesced into few launches
+    assert st.engine.launches - launches0 == st._batcher.batches
+    # filtered requests bypass the batcher and keep the reference semantics
+    f = asyncio.run(st.search_async(Q[0].tolist(), limit=5, filter_metadata={"i": {"$lt": 100}}))
+    assert f == st.search(Q[0].tolist(), limit=5, filter_metadata={"i": {"$lt": 100}})
+    with pytest.raises(ValueError, match="dimension mismatch"):
+        asyncio.run(st.search_async([0.0] * 3))
+    st.close()
+
+
+def test_persistence_roundtrip():
+    import tempfile as tf
+
+    d = tf.mkdtemp()
+    rng = np.random.default_rng(8)
+    X = rng.standard_normal((120, 8), dtype=np.float32)
+
+    def mk():
+        return wdbx_b200.VectorStore(8, d, num_shards=3, config=wdbx_b200.WDBXConfig({"GPU_STRICT": True}),
+                                     dist=wdbx_b200.DistContext(0, 1, 0), _engine_factory=FakeEngine)
+
+    st = mk()
+    st.bulk_load(X[:60], id_prefix="b")
+    st.batch_store({f"e{i}": X[60 + i] for i in range(60)}, {f"e{i}": {"i": i} for i in range(60)})
+    st.delete("e7"); st.delete("b3")
+    st.store("e9", X[0].tolist(), {"i": 900})     # overwrite
+    Q = rng.standard_normal((5, 8), dtype=np.float32)
+    want = [st.search(Q[b].tolist(), limit=12) for b in range(5)]
+    want_f = st.search(Q[0].tolist(), limit=4, filter_metadata={"i": {"$gte": 30}})
+    asyncio.run(st.shutdown())                     # reference: shutdown persists (vector_store.py:202-217)
+    st2 = mk()
+    assert st2.count() == 118 and st2.get("e7") is None and st2.get("b3") is None
+    assert [st2.search(Q[b].tolist(), limit=12) for b in range(5)] == want
+    assert st2.search(Q[0].tolist(), limit=4, filter_metadata={"i": {"$gte": 30}}) == want_f
+    assert st2.get("e9")[1] == {"i": 900} and st2.get("b10")[0] == pytest.approx(X[10].tolist())
+    # the store keeps working after a reload: new ids, deletes, another save/load cycle
+    st2.store("new", X[5].tolist(), {"i": -1})
+    assert st2.search(X[5].tolist(), limit=2)[0][0] in ("b5", "new")
+    assert st2.save()
+    st3 = mk()
+    assert st3.count() == 119 and st3.search(X[5].tolist(), limit=3) == st2.search(X[5].tolist(), limit=3)
+    st2.close(); st3.close()

@@ -614,27 +614,36 @@ int wdbx_b200_clear(wdbx_b200_engine* e, int segment) {
   return WDBX_B200_OK;
 }
 
-int wdbx_b200_read_row(wdbx_b200_engine* e, int segment, int64_t row, float* out_host) {
+int wdbx_b200_read_rows(wdbx_b200_engine* e, int segment, int64_t row0, int64_t n, float* out_host) {
   if (!e || !out_host) return fail(WDBX_B200_ERR_ARG, "NULL argument");
   if (segment < 0 || segment >= e->nseg) return fail(WDBX_B200_ERR_ARG, "segment %d outside [0, %d)", segment, e->nseg);
   DeviceGuard guard(e->device);
   std::lock_guard<std::mutex> lk(e->mu);
   Segment& s = e->seg[segment];
-  if (row < 0 || row >= s.n_rows) return fail(WDBX_B200_ERR_ARG, "row %lld outside [0, %lld)", (long long)row, (long long)s.n_rows);
-  const size_t need = static_cast<size_t>(e->dim) * 4;
-  if (e->stage_rows_bytes < need) {
-    cudaFree(e->stage_rows);
-    e->stage_rows = nullptr;
-    e->stage_rows_bytes = 0;
-    CU_TRY(cudaMalloc(&e->stage_rows, need));
-    e->stage_rows_bytes = need;
+  if (row0 < 0 || n < 0 || row0 + n > s.n_rows)
+    return fail(WDBX_B200_ERR_ARG, "rows [%lld, %lld) outside [0, %lld)", (long long)row0, (long long)(row0 + n), (long long)s.n_rows);
+  const int64_t chunk_rows = std::max<int64_t>(1, (64ll << 20) / (static_cast<int64_t>(e->dim) * 4));
+  for (int64_t done = 0; done < n; done += chunk_rows) {
+    const int64_t m = std::min(chunk_rows, n - done);
+    const size_t need = static_cast<size_t>(m) * e->dim * 4;
+    if (e->stage_rows_bytes < need) {
+      cudaFree(e->stage_rows);
+      e->stage_rows = nullptr;
+      e->stage_rows_bytes = 0;
+      CU_TRY(cudaMalloc(&e->stage_rows, need));
+      e->stage_rows_bytes = need;
+    }
+    CU_TRY(launch_export_rows(s.rows + static_cast<size_t>(row0 + done) * row_bytes(e), m, e->dim,
+                              static_cast<int>(row_bytes(e)), e->dtype == WDBX_B200_BF16, e->stage_rows, e->mstream));
+    e->launches.fetch_add(1, std::memory_order_relaxed);
+    CU_TRY(cudaMemcpyAsync(out_host + done * e->dim, e->stage_rows, need, cudaMemcpyDeviceToHost, e->mstream));
+    CU_TRY(cudaStreamSynchronize(e->mstream));
   }
-  CU_TRY(launch_export_row(s.rows + static_cast<size_t>(row) * row_bytes(e), e->dim, e->dtype == WDBX_B200_BF16,
-                           e->stage_rows, e->mstream));
-  e->launches.fetch_add(1, std::memory_order_relaxed);
-  CU_TRY(cudaMemcpyAsync(out_host, e->stage_rows, need, cudaMemcpyDeviceToHost, e->mstream));
-  CU_TRY(cudaStreamSynchronize(e->mstream));
   return WDBX_B200_OK;
+}
+
+int wdbx_b200_read_row(wdbx_b200_engine* e, int segment, int64_t row, float* out_host) {
+  return wdbx_b200_read_rows(e, segment, row, 1, out_host);
 }
 
 int wdbx_b200_search(wdbx_b200_engine* e, int segment, const float* q_dev, int B, int k, int metric,

@@ -102,6 +102,7 @@ cudaError_t launch_append_rows(const float* src, long long n, int dim, int dpad,
                                uint32_t gid_base, cudaStream_t stream);
 
 // stored row -> fp32 (read_row)
-cudaError_t launch_export_row(const unsigned char* row, int dim, bool bf16, float* dst, cudaStream_t stream);
+cudaError_t launch_export_rows(const unsigned char* rows, long long n, int dim, int row_bytes, bool bf16, float* dst,
+                               cudaStream_t stream);
 
 }  // namespace wdbx

@@ -77,10 +77,14 @@ __global__ void append_rows_kernel(const float* __restrict__ src, long long n, i
   }
 }
 
+// stored rows -> dense fp32 [n, dim] (VectorStore.get / persistence); one CTA per row
 template <bool BF16>
-__global__ void export_row_kernel(const unsigned char* __restrict__ row, int dim, float* __restrict__ dst) {
+__global__ void export_rows_kernel(const unsigned char* __restrict__ rows, int dim, int row_bytes,
+                                   float* __restrict__ dst) {
+  const unsigned char* row = rows + static_cast<size_t>(blockIdx.x) * row_bytes;
+  float* out = dst + static_cast<size_t>(blockIdx.x) * dim;
   for (int c = threadIdx.x; c < dim; c += blockDim.x) {
-    dst[c] = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(row)[c])
+    out[c] = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(row)[c])
                   : reinterpret_cast<const float*>(row)[c];
   }
 }
@@ -107,9 +111,12 @@ cudaError_t launch_append_rows(const float* src, long long n, int dim, int dpad,
   return cudaGetLastError();
 }
 
-cudaError_t launch_export_row(const unsigned char* row, int dim, bool bf16, float* dst, cudaStream_t stream) {
-  if (bf16) export_row_kernel<true><<<1, 128, 0, stream>>>(row, dim, dst);
-  else export_row_kernel<false><<<1, 128, 0, stream>>>(row, dim, dst);
+cudaError_t launch_export_rows(const unsigned char* rows, long long n, int dim, int row_bytes, bool bf16, float* dst,
+                               cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const dim3 grid(static_cast<unsigned>(n)), block(128);
+  if (bf16) export_rows_kernel<true><<<grid, block, 0, stream>>>(rows, dim, row_bytes, dst);
+  else export_rows_kernel<false><<<grid, block, 0, stream>>>(rows, dim, row_bytes, dst);
   return cudaGetLastError();
 }
 

@@ -47,6 +47,7 @@ SIGNATURES = {
     "wdbx_b200_tombstone": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int]),
     "wdbx_b200_clear": (C.c_int, [_P, C.c_int]),
     "wdbx_b200_read_row": (C.c_int, [_P, C.c_int, C.c_int64, _P]),
+    "wdbx_b200_read_rows": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P]),
     "wdbx_b200_search": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "wdbx_b200_search_host": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "wdbx_b200_merge": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),

@@ -1,0 +1,88 @@
+"""Micro-batching front-end for ``vector_search_async``.
+
+The reference serves concurrent async searches with a 4-thread pool per index
+(wdbx/core/indexing.py:692, :1045-1048): every request is its own full scan.  On the GPU a scan of
+up to 8 queries costs the same HBM pass as one (kernel K1 scores QB queries per streamed row), so
+concurrent single-query requests (REST ``POST /api/v1/vectors/search`` wdbx/api/server.py:141-152,
+CLI wdbx/cli.py:541) are coalesced for a short window into ONE launch.  Callers are untouched: they
+still await one result list per request.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+import time
+from concurrent.futures import Future
+from typing import List, Tuple
+
+import numpy as np
+
+
+class MicroBatcher:
+    def __init__(self, store, max_batch: int = 8, window_us: float = 200.0):
+        self._store = store
+        self.max_batch = max(1, int(max_batch))
+        self.window_s = max(0.0, float(window_us)) * 1e-6
+        self._q: "queue.Queue" = queue.Queue()
+        self.batches = 0          # launches issued
+        self.requests = 0         # requests served
+        self._thread = threading.Thread(target=self._run, name="wdbx-b200-batcher", daemon=True)
+        self._thread.start()
+
+    def submit(self, query: np.ndarray, limit: int, threshold: float) -> Future:
+        fut: Future = Future()
+        self._q.put((query, int(limit), float(threshold), fut))
+        return fut
+
+    def close(self):
+        self._q.put(None)
+        self._thread.join(timeout=5)
+
+    # ------------------------------------------------------------------ worker
+    def _run(self):
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            batch = [item]
+            deadline = time.monotonic() + self.window_s
+            while len(batch) < self.max_batch:
+                left = deadline - time.monotonic()
+                try:
+                    nxt = self._q.get(timeout=left) if left > 0 else self._q.get_nowait()
+                except queue.Empty:
+                    break
+                if nxt is None:
+                    self._q.put(None)
+                    break
+                batch.append(nxt)
+            self._serve(batch)
+
+    def _serve(self, batch: List[Tuple[np.ndarray, int, float, Future]]):
+        store = self._store
+        try:
+            Q = np.stack([b[0] for b in batch])
+            live = store.count()
+            k = min(max(b[1] for b in batch), live, store.max_k)
+            if k <= 0:
+                for _, _, _, fut in batch:
+                    fut.set_result([])
+                return
+            scores, gids, counts = store._search_arrays(Q, k, store.ALL)
+            self.batches += 1
+            self.requests += len(batch)
+            for i, (_, limit, threshold, fut) in enumerate(batch):
+                c = min(int(counts[i]), limit)
+                res = [(store._id_of(int(g)), float(s)) for g, s in zip(gids[i, :c], scores[i, :c])]
+                if threshold > 0:
+                    res = [r for r in res if r[1] >= threshold]
+                fut.set_result([(vid, sc, store.metadata.get(vid, {})) for vid, sc in res])
+        except Exception as e:  # reference convention: log + [] unless strict (indexing.py:1028-1030)
+            for _, _, _, fut in batch:
+                if fut.done():
+                    continue
+                if store.strict:
+                    fut.set_exception(e)
+                else:
+                    store._log_error(e)
+                    fut.set_result([])

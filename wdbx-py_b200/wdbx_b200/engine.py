@@ -23,6 +23,33 @@ def _np_ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def new_out(B: int, k: int, dev):
+    """Result tensors of one search as views of ONE packed device buffer
+    (keys i64 [B,k] | gids i64 [B,k] | scores f32 [B,k] | counts i32 [B]) so that the host path
+    needs a single device-to-host copy (``unpack_out``)."""
+    import torch
+
+    n = B * k
+    packed = torch.empty(n * 20 + B * 4, dtype=torch.uint8, device=dev)
+    return {
+        "packed": packed,
+        "keys": packed[: n * 8].view(torch.int64).view(B, k),
+        "gids": packed[n * 8: n * 16].view(torch.int64).view(B, k),
+        "scores": packed[n * 16: n * 20].view(torch.float32).view(B, k),
+        "counts": packed[n * 20:].view(torch.int32),
+    }
+
+
+def unpack_out(out: Dict, B: int, k: int):
+    """One D2H copy of a ``new_out`` result -> (scores, gids, counts) numpy arrays."""
+    host = out["packed"].cpu().numpy()
+    n = B * k
+    gids = host[n * 8: n * 16].view(np.int64).reshape(B, k)
+    scores = host[n * 16: n * 20].view(np.float32).reshape(B, k)
+    counts = host[n * 20:].view(np.int32)
+    return scores, gids, counts
+
+
 class Engine:
     """Device-resident exact-search engine for ONE GPU.
 
@@ -112,6 +139,12 @@ class Engine:
         check(self._lib.wdbx_b200_read_row(self._handle(), segment, row, _np_ptr(out)))
         return out
 
+    def read_rows(self, segment: int, row0: int, n: int) -> np.ndarray:
+        out = np.empty((n, self.dim), dtype=np.float32)
+        if n > 0:
+            check(self._lib.wdbx_b200_read_rows(self._handle(), segment, row0, n, _np_ptr(out)))
+        return out
+
     # ------------------------------------------------------------------ search
     def upload(self, queries):
         """Host fp32 array -> CUDA tensor on this engine's device (queries of the SPMD path)."""
@@ -159,12 +192,7 @@ class Engine:
         B = q_dev.shape[0]
         dev = q_dev.device
         if out is None:
-            out = {
-                "keys": torch.empty((B, k), dtype=torch.int64, device=dev),
-                "scores": torch.empty((B, k), dtype=torch.float32, device=dev),
-                "gids": torch.empty((B, k), dtype=torch.int64, device=dev),
-                "counts": torch.empty((B,), dtype=torch.int32, device=dev),
-            }
+            out = new_out(B, k, dev)
         st = stream if stream is not None else torch.cuda.current_stream(dev)
         p = lambda name: C.c_void_p(out[name].data_ptr()) if out.get(name) is not None else None  # noqa: E731
         check(self._lib.wdbx_b200_search(self._handle(), segment, C.c_void_p(q_dev.data_ptr()), B, k,
@@ -200,12 +228,7 @@ class Engine:
         B = q_dev.shape[0]
         dev = q_dev.device
         if out is None:
-            out = {
-                "keys": torch.empty((B, k), dtype=torch.int64, device=dev),
-                "scores": torch.empty((B, k), dtype=torch.float32, device=dev),
-                "gids": torch.empty((B, k), dtype=torch.int64, device=dev),
-                "counts": torch.empty((B,), dtype=torch.int32, device=dev),
-            }
+            out = new_out(B, k, dev)
         st = stream if stream is not None else torch.cuda.current_stream(dev)
         p = lambda name: C.c_void_p(out[name].data_ptr()) if out.get(name) is not None else None  # noqa: E731
         check(self._lib.wdbx_b200_search_exchange(self._handle(), C.c_void_p(q_dev.data_ptr()), B, k,
@@ -222,12 +245,7 @@ class Engine:
         G, B, k = keys.shape
         dev = keys.device
         if out is None:
-            out = {
-                "keys": torch.empty((B, k), dtype=torch.int64, device=dev),
-                "scores": torch.empty((B, k), dtype=torch.float32, device=dev),
-                "gids": torch.empty((B, k), dtype=torch.int64, device=dev),
-                "counts": torch.empty((B,), dtype=torch.int32, device=dev),
-            }
+            out = new_out(B, k, dev)
         st = stream if stream is not None else torch.cuda.current_stream(dev)
         p = lambda name: C.c_void_p(out[name].data_ptr()) if out.get(name) is not None else None  # noqa: E731
         check(self._lib.wdbx_b200_merge(self._handle(), C.c_void_p(keys.data_ptr()), G, B, k, p("keys"), p("scores"),

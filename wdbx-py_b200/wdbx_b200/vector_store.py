@@ -105,6 +105,7 @@ class VectorStore:
         self._bulk_starts: List[int] = []
         self._bulk_rows: Dict[int, Tuple[int, int]] = {}     # gid0 -> (first n per shard base, n rows) for lookups
         self._bulk_dead: set = set()
+        self._row_gids: List[List[np.ndarray]] = [[] for _ in range(self.num_shards)]  # gid of every row, per shard
         self._shard_count = [0] * self.num_shards            # rows ever appended per shard (all ranks)
         self._shard_live = [0] * self.num_shards
         self._lock = threading.RLock()
@@ -131,7 +132,16 @@ class VectorStore:
                 self._fused = True
             except Exception as e:  # e.g. > 8 ranks or no peer access: NCCL all-gather + merge kernel instead
                 logger.warning(f"fused exchange unavailable, using NCCL all-gather: {e}")
+        # async front-end: coalesce concurrent single-query requests (single process only: under SPMD
+        # every rank would have to form identical batches)
+        self._batcher = None
+        bmax = int(self.config.get("GPU_BATCH_MAX", 8) or 0)
+        if self.dist.world == 1 and bmax > 1:
+            from .batcher import MicroBatcher
+
+            self._batcher = MicroBatcher(self, bmax, float(self.config.get("GPU_BATCH_WINDOW_US", 200)))
         self._init_indices()
+        self._load_data()
         logger.info("VectorStore initialized: %d shards on %d GPU(s), dim=%d, metric=%s, dtype=%s",
                     self.num_shards, self.dist.world, self.vector_dim, self.metric, self.dtype)
 
@@ -158,11 +168,14 @@ class VectorStore:
     async def shutdown(self):
         """Reference: save metadata + vectors, then every index (vector_store.py:202-217)."""
         loop = asyncio.get_event_loop()
-        await loop.run_in_executor(self.thread_pool, self._save_metadata)
+        await loop.run_in_executor(self.thread_pool, self.save)
         self.thread_pool.shutdown(wait=True)
         self.close()
 
     def close(self):
+        if getattr(self, "_batcher", None) is not None:
+            self._batcher.close()
+            self._batcher = None
         eng = getattr(self, "engine", None)
         if eng is not None:
             eng.close()
@@ -176,6 +189,111 @@ class VectorStore:
                 json.dump(self.metadata, f)
         except Exception as e:  # reference logs and continues (vector_store.py:165-166)
             logger.error(f"Error saving metadata: {e}")
+
+    # ------------------------------------------------------------------ persistence
+    # Reference: metadata.json + a pickle of the id -> ndarray dict (vector_store.py:158-176) and one
+    # index file + mapping pickle per shard (indexing.py:805-838).  Here: metadata.json unchanged,
+    # ids / placement in vectors/state.json, and every rank dumps its device partition of every
+    # shard as a raw .npy that is appended straight back to HBM at start-up.
+    STATE_VERSION = 1
+
+    def save(self) -> bool:
+        try:
+            with self._lock:
+                self._save_metadata()
+                rank, world = self.dist.rank, self.dist.world
+                for s in range(self.num_shards):
+                    n_local = self.shard_map.local_count(self._shard_count[s], rank)
+                    rows = self.engine.read_rows(s, 0, n_local)
+                    np.save(self.data_dir / f"shard_{s}" / f"rows.rank{rank}of{world}.npy", rows)
+                if rank == 0:
+                    for s in range(self.num_shards):
+                        order = (np.concatenate(self._row_gids[s]) if self._row_gids[s]
+                                 else np.empty(0, np.uint32))
+                        np.save(self.data_dir / f"shard_{s}" / "row_gids.npy", order.astype(np.uint32))
+                    state = {
+                        "version": self.STATE_VERSION, "dim": self.vector_dim, "dtype": self.dtype,
+                        "num_shards": self.num_shards, "world": world, "shard_count": self._shard_count,
+                        "next_gid": len(self._gid_to_id),
+                        "ids": [[g, v] for g, v in enumerate(self._gid_to_id) if v is not None],
+                        "bulk": [[g0, g1, p, list(self._bulk_rows[g0])] for g0, g1, p in self._bulk],
+                        "bulk_dead": sorted(self._bulk_dead),
+                    }
+                    tmp = self.data_dir / "vectors" / "state.json.tmp"
+                    tmp.write_text(json.dumps(state))
+                    tmp.replace(self.data_dir / "vectors" / "state.json")
+            self.dist.barrier()
+            return True
+        except Exception as e:
+            logger.error(f"Error saving vectors: {e}")
+            if self.strict:
+                raise
+            return False
+
+    def _load_data(self) -> int:
+        """Start-up load (reference: vector_store.py:136-156): rebuild the device partitions from disk."""
+        path = self.data_dir / "vectors" / "state.json"
+        if not path.exists():
+            return 0
+        try:
+            state = json.loads(path.read_text())
+            rank, world = self.dist.rank, self.dist.world
+            for key, have in (("version", self.STATE_VERSION), ("dim", self.vector_dim), ("dtype", self.dtype),
+                              ("num_shards", self.num_shards), ("world", world)):
+                if state.get(key) != have:
+                    raise ValueError(f"saved store has {key}={state.get(key)!r}, this instance {have!r}")
+            n_gid = int(state["next_gid"])
+            gid_to_id: List[Optional[str]] = [None] * n_gid
+            for g, v in state["ids"]:
+                gid_to_id[g] = v
+            bulk = [(g0, g1, p) for g0, g1, p, _ in state["bulk"]]
+            in_bulk = np.zeros(n_gid, bool)
+            for g0, g1, _ in bulk:
+                in_bulk[g0:g1] = True
+            dead = np.array([v is None for v in gid_to_id], bool) & ~in_bulk
+            dead[np.asarray(state["bulk_dead"], np.int64)] = True
+            loc: Dict[str, Tuple[int, int, int]] = {}
+            live = [0] * self.num_shards
+            row_gids: List[List[np.ndarray]] = [[] for _ in range(self.num_shards)]
+            for s in range(self.num_shards):
+                order = np.load(self.data_dir / f"shard_{s}" / "row_gids.npy")
+                if order.shape[0] != state["shard_count"][s]:
+                    raise ValueError(f"shard {s}: row_gids.npy does not match state.json")
+                rows = np.load(self.data_dir / f"shard_{s}" / f"rows.rank{rank}of{world}.npy")
+                mine = order[rank::world]
+                if rows.shape != (mine.shape[0], self.vector_dim):
+                    raise ValueError(f"shard {s}: partition file has shape {rows.shape}")
+                if mine.shape[0]:
+                    self.engine.append(s, rows, gids=mine)
+                    for local in np.flatnonzero(dead[mine]):
+                        self.engine.tombstone(s, int(local), True)
+                for n, g in enumerate(order.tolist()):
+                    v = gid_to_id[g]
+                    if v is not None:
+                        loc[v] = (s, n, g)
+                live[s] = int((~dead[order]).sum())
+                row_gids[s] = [order]
+            self._gid_to_id, self._loc, self._row_gids = gid_to_id, loc, row_gids
+            self._bulk = bulk
+            self._bulk_starts = [g0 for g0, _, _ in bulk]
+            self._bulk_rows = {g0: tuple(base) for g0, _, _, base in state["bulk"]}
+            self._bulk_dead = set(state["bulk_dead"])
+            self._shard_count = list(state["shard_count"])
+            self._shard_live = live
+            meta = self.data_dir / "metadata" / "metadata.json"
+            if meta.exists():
+                self.metadata = json.loads(meta.read_text())
+            logger.info(f"Loaded {self.count()} vectors from {self.data_dir}")
+            return self.count()
+        except Exception as e:
+            logger.error(f"Error loading vectors: {e}")
+            try:
+                self.engine.clear(ALL)
+            except Exception:
+                pass
+            if self.strict:
+                raise
+            return 0
 
     # ------------------------------------------------------------------ error convention
     def _guard(self, default, fn, *args):
@@ -259,6 +377,7 @@ class VectorStore:
             for j, i in enumerate(fresh):
                 self._loc[ids[i]] = (shard, n0 + j, g0 + j)
                 self._gid_to_id.append(ids[i])
+            self._row_gids[shard].append(gids)
             self._shard_count[shard] += m
             self._shard_live[shard] += m
         return True
@@ -287,6 +406,7 @@ class VectorStore:
                 gid = self._loc.pop(vid)[2]
                 self._gid_to_id[gid] = None
                 self.metadata.pop(vid, None)
+            self._row_gids[shard] = []
             self._shard_count[shard] = 0
             self._shard_live[shard] = 0
         return True
@@ -375,6 +495,7 @@ class VectorStore:
                     sel = src_idx[mine]
                     part = rows[sel] if not (S == 1 and world == 1) else rows
                     self.engine.append(s, part, gids=gids[mine])
+                self._row_gids[s].append(gids)
                 self._shard_count[s] += cnt
                 self._shard_live[s] += cnt
             self._gid_to_id.extend([None] * n)
@@ -442,6 +563,7 @@ class VectorStore:
             self._bulk, self._bulk_starts, self._bulk_rows, self._bulk_dead = [], [], {}, set()
             self._shard_count = [0] * self.num_shards
             self._shard_live = [0] * self.num_shards
+            self._row_gids = [[] for _ in range(self.num_shards)]
         self._save_metadata()
         return count
 
@@ -465,8 +587,10 @@ class VectorStore:
         qd = self.engine.upload(Q)
         if sel == ALL and self._fused and Q.shape[0] <= self.engine.XCHG_MAX_B and k <= self.engine.XCHG_MAX_K:
             merged = self.engine.search_exchange(qd, k, metric)
-            packed = merged  # single D2H below
-            return (packed["scores"].cpu().numpy(), packed["gids"].cpu().numpy(), packed["counts"].cpu().numpy())
+            scores, gids, counts = self._unpack(merged, Q.shape[0], k)
+            if (counts < 0).any():
+                raise RuntimeError("fused exchange timed out: a peer rank did not join the collective search")
+            return scores, gids, counts
         if sel == EACH:
             import torch
 
@@ -474,14 +598,21 @@ class VectorStore:
         else:
             keys = self.engine.search(qd, k, metric, segment=sel)["keys"]
         merged = self.engine.merge(self.dist.all_gather_keys(keys))
-        scores = merged["scores"].cpu().numpy()
-        gids = merged["gids"].cpu().numpy()
-        counts = merged["counts"].cpu().numpy()
+        scores, gids, counts = self._unpack(merged, keys.shape[0], k)
         if sel == EACH:
             B = Q.shape[0]
             return (scores.reshape(self.num_shards, B, k), gids.reshape(self.num_shards, B, k),
                     counts.reshape(self.num_shards, B))
         return scores, gids, counts
+
+    @staticmethod
+    def _unpack(out, B: int, k: int):
+        """Device result dict -> (scores, gids, counts) numpy; one D2H when the engine packed it."""
+        if "packed" in out:
+            from .engine import unpack_out
+
+            return unpack_out(out, B, k)
+        return out["scores"].cpu().numpy(), out["gids"].cpu().numpy(), out["counts"].cpu().numpy()
 
     def search_device(self, q_dev, limit: int = 10, metric: Optional[str] = None):
         """Additive, fully device-resident search: ``q_dev`` is a CUDA fp32 tensor [B, dim] on this
@@ -541,7 +672,19 @@ class VectorStore:
                            filter_metadata: Optional[Dict[str, Any]] = None):
         """Reference: vector_store.py:355-412.  One thread-pool hop (the ctypes call releases the GIL)
         instead of one per shard."""
+        if self._batcher is not None and not filter_metadata:
+            # micro-batching front-end: concurrent requests share one device pass (batcher.py)
+            query_np = np.array(query_vector, dtype=np.float32)
+            if query_np.shape != (self.vector_dim,):
+                raise ValueError(f"Vector dimension mismatch: expected {self.vector_dim}, got {query_np.shape[-1]}")
+            return await asyncio.wrap_future(self._batcher.submit(query_np, limit, threshold))
         return await self._run(self.search, query_vector, limit, threshold, filter_metadata)
+
+    ALL = ALL
+    max_k = _lib.MAX_K
+
+    def _log_error(self, e):
+        logger.error(f"Error in B200 batched search: {e}")
 
     def search_batch(self, queries, limit: int = 10, metric: Optional[str] = None) -> BatchResult:
         """Additive batch entry point: [B, dim] queries -> device-merged top-``limit`` per query."""
