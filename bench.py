@@ -296,15 +296,20 @@ def run_gpu(args):
     for i in range(3):
         store.search(Qlists[i], limit=K)
     barrier()
+    step_ms = []
     t0 = time.perf_counter()
     for i in range(n_e2e):
+        t1 = time.perf_counter()
         res = store.search(Qlists[i % N_QUERIES], limit=K)
+        step_ms.append((time.perf_counter() - t1) * 1e3)
     torch.cuda.synchronize()
     e2e_s = reduce_max(time.perf_counter() - t0)
     e2e_qps = n_e2e / e2e_s
     assert len(res) == K
     # where the end-to-end time goes (informational): C-ABI host call alone vs the Python facade
-    e2e_detail = {"device_ms_last_call": store.engine.stats().get("last_search_ms")}
+    e2e_detail = {"device_ms_last_call": store.engine.stats().get("last_search_ms"),
+                  "step_ms_median": statistics.median(step_ms), "step_ms_max": max(step_ms),
+                  "step_ms_first5": [round(x, 3) for x in step_ms[:5]]}
     if world == 1:
         t0 = time.perf_counter()
         for i in range(20):
