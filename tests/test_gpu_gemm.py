@@ -13,10 +13,12 @@ def _engine(dim, nseg=1, gemm_min_batch=1):
     import wdbx_b200
 
     os.environ["WDBX_B200_GEMM_MIN_BATCH"] = str(gemm_min_batch)
+    os.environ["WDBX_B200_GEMM_MODE"] = "1"   # this file tests the 3xTF32 kernel (K2); K2b: test_gpu_filter.py
     try:
         return wdbx_b200.Engine(device=0, dim=dim, dtype="fp32", num_segments=nseg)
     finally:
         os.environ.pop("WDBX_B200_GEMM_MIN_BATCH", None)
+        os.environ.pop("WDBX_B200_GEMM_MODE", None)
 
 
 def _check(X, Q, k, metric, scores, gids, counts, dead=None):

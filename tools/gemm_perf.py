@@ -8,6 +8,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 dim = int(sys.argv[2]) if len(sys.argv) > 2 else 768
 Bs = [int(a) for a in sys.argv[3:]] or [128, 1024]
 os.environ["WDBX_B200_GEMM_MIN_BATCH"] = "1"
+os.environ.setdefault("WDBX_B200_GEMM_MODE", "0")
 eng = wdbx_b200.Engine(0, dim, "fp32", 1)
 eng.reserve(0, n)
 g = torch.Generator(device="cuda").manual_seed(1)

@@ -48,6 +48,8 @@ struct Segment {
   float* sqnorm = nullptr;
   uint32_t* gids = nullptr;
   uint32_t* tomb = nullptr;  // device bitmap, allocated on first tombstone
+  void* shadow = nullptr;    // bf16 copy of the fp32 rows for the tensor-core filter (K2b), built lazily
+  int64_t shadow_rows = 0, shadow_cap = 0;
   std::vector<uint32_t> tomb_host;
   int64_t n_rows = 0, cap_rows = 0, n_dead = 0;
 };
@@ -60,6 +62,15 @@ struct Workspace {
   int n_counters = 0;
   float* qsplit = nullptr;  // K2: q_hi | q_lo | 1/|q| | |q|^2
   size_t qsplit_floats = 0;
+  // K2b: bf16 queries + norms | candidate rows [B][cap] | per-query count, shared lower bound, overflow flag
+  void* fws = nullptr;
+  size_t fws_bytes = 0;
+  unsigned long long* fcand = nullptr;
+  size_t fcand_n = 0;
+  unsigned int* fcount = nullptr;
+  unsigned int* flower = nullptr;
+  int* foverflow = nullptr;
+  int fper_query = 0;
 };
 
 int env_int(const char* name, int dflt) {
@@ -77,6 +88,7 @@ struct wdbx_b200_engine {
   std::vector<Workspace> ws;
   ScanTuning tune{0, 0, 0, 0, -1, 0};
   int gemm_min_batch = 48;  // B >= this => tcgen05 GEMM path (0 = never)
+  int gemm_mode = 0;        // 0 = bf16 filter + exact refine (K2b), 1 = 3xTF32 with fused top-k (K2)
   cudaStream_t mstream = nullptr;  // mutations
   // staging for host-sourced appends
   float* stage_rows = nullptr;
@@ -123,6 +135,7 @@ size_t row_bytes(const wdbx_b200_engine* e) { return static_cast<size_t>(e->dpad
 int64_t round_cap(int64_t rows) { return (rows + 127) / 128 * 128; }
 
 void free_segment(Segment& s) {
+  cudaFree(s.shadow);
   cudaFree(s.rows);
   cudaFree(s.inv_norm);
   cudaFree(s.sqnorm);
@@ -173,6 +186,9 @@ int ensure_capacity(wdbx_b200_engine* e, Segment& s, int64_t rows) {
   // in-flight searches (any stream) may still read the old buffers
   CU_TRY(cudaDeviceSynchronize());
   cudaFree(s.rows); cudaFree(s.inv_norm); cudaFree(s.sqnorm); cudaFree(s.gids); cudaFree(s.tomb);
+  cudaFree(s.shadow);  // rebuilt lazily by the next batched search
+  s.shadow = nullptr;
+  s.shadow_rows = s.shadow_cap = 0;
   s.rows = nrows; s.inv_norm = ninv; s.sqnorm = nsq; s.gids = ngid; s.tomb = ntomb;
   s.cap_rows = cap;
   return WDBX_B200_OK;
@@ -226,7 +242,7 @@ int get_workspace(wdbx_b200_engine* e, cudaStream_t stream, size_t cand_keys, in
 // Launch one K1 scan over segments [s0, s1).  Caller holds e->mu and has set the device.
 int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B, int k, int metric,
                   uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream,
-                  bool exchange = false) {
+                  bool exchange = false, const int* only_flag = nullptr) {
   ScanPlan plan;
   const int rc = scan_plan(e->dim, e->dpad, e->elem_bytes, k, B, e->sm_count, e->tune, &plan);
   if (rc == -4) return fail(WDBX_B200_ERR_LIMIT, "dimension %d too large for the scan kernel's shared-memory stage", e->dim);
@@ -278,6 +294,7 @@ int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B
   p.scores_out = scores_out;
   p.gids_out = gids_out;
   p.counts_out = counts_out;
+  p.only_flag = only_flag;
   if (exchange) {
     if (e->xworld < 2) return fail(WDBX_B200_ERR_ARG, "exchange not attached (call wdbx_b200_exchange_init/attach first)");
     if (B > plan.queries_per_block || B > kXchgMaxB || k > kXchgMaxK)
@@ -334,13 +351,115 @@ int gemm_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B
 
 // Regime choice (north star): small batches stream X once per QB queries on CUDA cores (K1, HBM
 // bound); from gemm_min_batch queries on, the scan is a dense contraction and runs on tcgen05 (K2).
+// K2b path: bf16 tensor-core filter over the shadow matrix + exact refine with K1's arithmetic; queries
+// whose candidate list overflowed are re-run by K1 (only_flag).  Caller holds e->mu, device is set.
+int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B, int k, int metric,
+                    uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream) {
+  const int ld16 = filter_ld16(e->dim);
+  const bool f32 = e->dtype == WDBX_B200_F32;
+  bool built = false;
+  for (int s = s0; s < s1; ++s) {
+    Segment& sg = e->seg[s];
+    if (!f32 || sg.n_rows == 0) continue;
+    if (!sg.shadow || sg.shadow_cap < sg.n_rows) {
+      CU_TRY(cudaStreamSynchronize(stream));
+      cudaFree(sg.shadow);
+      sg.shadow = nullptr;
+      sg.shadow_rows = sg.shadow_cap = 0;
+      CU_TRY(cudaMalloc(&sg.shadow, static_cast<size_t>(sg.cap_rows) * ld16 * 2));
+      sg.shadow_cap = sg.cap_rows;
+    }
+    if (sg.shadow_rows < sg.n_rows) {
+      CU_TRY(launch_shadow_rows(reinterpret_cast<const float*>(sg.rows + static_cast<size_t>(sg.shadow_rows) * row_bytes(e)),
+                                sg.n_rows - sg.shadow_rows, e->dpad, ld16,
+                                static_cast<unsigned char*>(sg.shadow) + static_cast<size_t>(sg.shadow_rows) * ld16 * 2, stream));
+      e->launches.fetch_add(1, std::memory_order_relaxed);
+      sg.shadow_rows = sg.n_rows;
+      built = true;
+    }
+  }
+  if (built) CU_TRY(cudaStreamSynchronize(stream));  // later searches on other streams must see the shadow
+  Workspace* w = nullptr;
+  int wrc = get_workspace(e, stream, 0, 0, &w);
+  if (wrc != WDBX_B200_OK) return wrc;
+  const int cap = B <= 4096 ? 4096 : std::max(512, static_cast<int>((16ll << 20) / B));
+  const size_t need_ws = filter_query_workspace_bytes(B, e->dim);
+  if (w->fws_bytes < need_ws || w->fcand_n < static_cast<size_t>(B) * cap || w->fper_query < B) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cs);
+    if (cs != cudaStreamCaptureStatusNone)
+      return fail(WDBX_B200_ERR_ARG, "workspace must grow during stream capture: run one warm-up search of this shape first");
+    CU_TRY(cudaStreamSynchronize(stream));
+    if (w->fws_bytes < need_ws) {
+      cudaFree(w->fws); w->fws = nullptr; w->fws_bytes = 0;
+      CU_TRY(cudaMalloc(&w->fws, need_ws));
+      w->fws_bytes = need_ws;
+    }
+    if (w->fcand_n < static_cast<size_t>(B) * cap) {
+      cudaFree(w->fcand); w->fcand = nullptr; w->fcand_n = 0;
+      CU_TRY(cudaMalloc(&w->fcand, static_cast<size_t>(B) * cap * 8));
+      w->fcand_n = static_cast<size_t>(B) * cap;
+    }
+    if (w->fper_query < B) {
+      cudaFree(w->fcount); cudaFree(w->flower); cudaFree(w->foverflow);
+      w->fcount = nullptr; w->flower = nullptr; w->foverflow = nullptr; w->fper_query = 0;
+      CU_TRY(cudaMalloc(&w->fcount, static_cast<size_t>(B) * 4));
+      CU_TRY(cudaMalloc(&w->flower, static_cast<size_t>(B) * 4));
+      CU_TRY(cudaMalloc(&w->foverflow, static_cast<size_t>(B) * 4));
+      w->fper_query = B;
+    }
+  }
+  CU_TRY(cudaMemsetAsync(w->fcount, 0, static_cast<size_t>(B) * 4, stream));
+  CU_TRY(cudaMemsetAsync(w->foverflow, 0, static_cast<size_t>(B) * 4, stream));
+  CU_TRY(cudaMemsetAsync(w->flower, 0, static_cast<size_t>(B) * 4, stream));  // 0 < mono(-inf): "no bound yet"
+  CU_TRY(launch_prep_queries(q_dev, B, e->dim, w->fws, stream));
+  e->launches.fetch_add(1, std::memory_order_relaxed);
+  // rigorous rounding bound relative to |x||q|: bf16 RNE is 2^-9 relative per rounded operand; the
+  // fp32 accumulation of the tensor core is bounded (very conservatively) by dim * 2^-23
+  const float eps_rel = (f32 ? 0.00390625f : 0.001953125f) * 1.002f + static_cast<float>(e->dim) * 1.2e-7f + 1e-6f;
+  SegDesc descs[kMaxSeg];
+  memset(descs, 0, sizeof(descs));
+  for (int s = s0; s < s1; ++s) {
+    const Segment& sg = e->seg[s];
+    SegDesc& d = descs[s];
+    d.rows = sg.rows;
+    d.inv_norm = sg.inv_norm;
+    d.sqnorm = sg.sqnorm;
+    d.gids = sg.gids;
+    d.tomb = sg.n_dead > 0 ? sg.tomb : nullptr;
+    d.n_rows = sg.n_rows;
+    if (sg.n_rows == 0) continue;
+    const int slices = filter_slices_for(sg.n_rows, B, e->sm_count);
+    CU_TRY(launch_gemm_filter(f32 ? sg.shadow : static_cast<const void*>(sg.rows), f32 ? ld16 : e->dpad, d, s, e->dim, w->fws,
+                              B, k, metric, eps_rel, slices, w->fcand, w->fcount, w->flower, cap, stream));
+    e->launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  ScanTuning t1 = e->tune;
+  t1.queries_per_pass = 1;
+  ScanPlan plan;
+  if (scan_plan(e->dim, e->dpad, e->elem_bytes, k, 1, e->sm_count, t1, &plan) != 0)
+    return fail(WDBX_B200_ERR_ARG, "invalid scan shape (dim=%d k=%d)", e->dim, k);
+  CU_TRY(launch_refine_topk(descs, kMaxSeg, q_dev, B, e->dim, e->dpad, e->elem_bytes, plan.lpr_log2, plan.nch, k, metric,
+                            w->fcand, w->fcount, cap, w->foverflow, keys_out, scores_out, gids_out, counts_out, stream));
+  e->launches.fetch_add(1, std::memory_order_relaxed);
+  // exact re-run (K1) of the queries whose candidate list overflowed; exits immediately otherwise
+  return scan_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream, false,
+                       w->foverflow);
+}
+
 bool use_gemm(const wdbx_b200_engine* e, int B, int k) {
-  return e->dtype == WDBX_B200_F32 && e->gemm_min_batch > 0 && B >= e->gemm_min_batch && k <= gemm_max_k();
+  if (e->gemm_min_batch <= 0 || B < e->gemm_min_batch) return false;
+  if (e->gemm_mode == 1) return e->dtype == WDBX_B200_F32 && k <= gemm_max_k();
+  return k <= filter_max_k();
 }
 
 int search_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B, int k, int metric,
                     uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream) {
-  if (use_gemm(e, B, k)) return gemm_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream);
+  if (use_gemm(e, B, k)) {
+    if (e->gemm_mode == 1)
+      return gemm_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream);
+    return filter_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream);
+  }
   return scan_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream);
 }
 
@@ -411,6 +530,7 @@ int wdbx_b200_create(int device, int dim, int dtype, int num_segments, wdbx_b200
   e->tune.evict_first = env_int("WDBX_B200_EVICT_FIRST", -1);
   e->tune.queries_per_pass = env_int("WDBX_B200_QUERIES_PER_PASS", 0);
   e->gemm_min_batch = env_int("WDBX_B200_GEMM_MIN_BATCH", e->gemm_min_batch);
+  e->gemm_mode = env_int("WDBX_B200_GEMM_MODE", 0);
   ScanPlan plan;
   if (scan_plan(dim, e->dpad, e->elem_bytes, 10, 1, e->sm_count, e->tune, &plan) != 0) {
     delete e;
@@ -437,6 +557,11 @@ void wdbx_b200_destroy(wdbx_b200_engine* e) {
     cudaFree(w.cand);
     cudaFree(w.counters);
     cudaFree(w.qsplit);
+    cudaFree(w.fws);
+    cudaFree(w.fcand);
+    cudaFree(w.fcount);
+    cudaFree(w.flower);
+    cudaFree(w.foverflow);
   }
   for (int r = 0; r < kMaxPeers; ++r)
     if (e->xopened[r]) cudaIpcCloseMemHandle(e->xpeer[r]);
@@ -559,6 +684,12 @@ int wdbx_b200_overwrite(wdbx_b200_engine* e, int segment, int64_t row, const flo
                             s.rows + static_cast<size_t>(row) * row_bytes(e), s.inv_norm + row, s.sqnorm + row,
                             s.gids + row, e->stage_gids, 0, e->mstream));
   e->launches.fetch_add(1, std::memory_order_relaxed);
+  if (s.shadow && row < s.shadow_rows) {
+    const int ld16 = filter_ld16(e->dim);
+    CU_TRY(launch_shadow_rows(reinterpret_cast<const float*>(s.rows + static_cast<size_t>(row) * row_bytes(e)), 1, e->dpad,
+                              ld16, static_cast<unsigned char*>(s.shadow) + static_cast<size_t>(row) * ld16 * 2, e->mstream));
+    e->launches.fetch_add(1, std::memory_order_relaxed);
+  }
   if (s.tomb && ((s.tomb_host[row >> 5] >> (row & 31)) & 1u)) {
     s.tomb_host[row >> 5] &= ~(1u << (row & 31));
     s.n_dead -= 1;
@@ -606,6 +737,7 @@ int wdbx_b200_clear(wdbx_b200_engine* e, int segment) {
     Segment& s = e->seg[i];
     s.n_rows = 0;
     s.n_dead = 0;
+    s.shadow_rows = 0;
     if (s.tomb) {
       std::fill(s.tomb_host.begin(), s.tomb_host.end(), 0u);
       CU_TRY(cudaMemset(s.tomb, 0, s.tomb_host.size() * 4));

@@ -1,0 +1,566 @@
+// gemm_filter.cu -- K2b: single-pass bf16 tensor-core FILTER + exact fp32 REFINE (sm_100a only).
+//
+// The batched regime of the exact search (option c).  Replaces, for a
+// batch of queries, FaissIndex.search (wdbx/core/indexing.py:1002-1024) + the shard merge of
+// VectorStore.search (wdbx/core/vector_store.py:323-330); results are BIT-IDENTICAL to the
+// streaming kernel K1 because the final scores are recomputed with K1's own fp32 arithmetic.
+//
+//   1. prep:    q -> bf16 (RNE), 1/|q|, |q|, |q|^2                                  (prep_queries_kernel)
+//   2. filter:  S~ = Qb . Xb^T on tcgen05 (kind::f16, bf16 operands, fp32 TMEM accumulators) over a
+//               bf16 SHADOW of the stored matrix (built lazily, half the HBM bytes of the fp32 rows).
+//               |s~ - s| <= eps is a rigorous rounding bound (2^-9 relative per bf16 operand), so with
+//               L = k-th best (s~ - eps) seen so far -- a lower bound on the exact k-th best score, shared
+//               between CTAs through a global atomicMax -- every row with s~ + eps >= L is appended to the
+//               query's candidate list; everything else provably cannot be in the exact top-k.
+//   3. refine:  one CTA per query re-scores its candidates (a few hundred) from the fp32 rows with K1's
+//               lane mapping, summation order and score formula, keeps the top-k with K1's list code.
+//   4. queries whose candidate list overflowed (adversarial data) are flagged and re-run by K1 itself.
+//
+// Filter CTA = 8 warps: 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 idle | 4-7 epilogue.
+// Tile 128 queries x 256 rows x 64 dims (one 128-byte swizzle atom per row), 4-stage mbarrier ring
+// (48 KB / stage), two accumulator tiles in TMEM (512 columns).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+
+#include "scan_topk_kernel.cuh"
+#include "tc05.cuh"
+
+namespace wdbx {
+
+namespace {
+
+using namespace tc05;
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;        // bf16 elements per K block = 128 bytes
+constexpr int STAGES = 4;
+constexpr int kThreads = 256;
+constexpr int kMaxKFilter = 32;
+constexpr uint32_t X_TILE_BYTES = BN * BK * 2;  // 32 KB
+constexpr uint32_t Q_TILE_BYTES = BM * BK * 2;  // 16 KB
+constexpr uint32_t STAGE_BYTES = X_TILE_BYTES + Q_TILE_BYTES;
+constexpr uint32_t TMEM_COLS = 2 * BN;
+
+struct FilterParams {
+  const float* inv_norm;   // [n_rows] 1/|x|  (exact, of the stored rows)
+  const float* sqnorm;     // [n_rows] |x|^2
+  const uint32_t* tomb;    // bitmap or NULL
+  const float* q_inv;      // [B]
+  const float* q_nrm;      // [B]
+  const float* q_sq;       // [B]
+  long long n_rows;
+  int B, k;
+  int n_kblocks, n_tiles, n_slices;
+  int seg;                 // segment index stored with each candidate
+  float eps_rel;           // rounding bound relative to |x||q|
+  unsigned long long* cand;   // [B][cap]  (seg << 32 | row)
+  unsigned int* cand_count;   // [B]
+  unsigned int* lower_glob;   // [B] monotone-mapped float: best known lower bound of the exact k-th score
+  int cap;
+};
+
+// ---------------------------------------------------------------- prep: queries -> bf16 + norms
+__global__ void prep_queries_kernel(const float* __restrict__ q, int B, int dim, int ld, __nv_bfloat16* __restrict__ qb,
+                                    float* __restrict__ q_inv, float* __restrict__ q_nrm, float* __restrict__ q_sq) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float ss = 0.0f;
+  for (int c = lane; c < ld; c += 32) {
+    const float v = c < dim ? q[static_cast<size_t>(b) * dim + c] : 0.0f;
+    qb[static_cast<size_t>(b) * ld + c] = __float2bfloat16_rn(v);
+    ss = fmaf(v, v, ss);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, o);
+  if (lane == 0) {
+    q_sq[b] = ss;
+    q_nrm[b] = sqrtf(ss);
+    q_inv[b] = ss > 0.0f ? 1.0f / sqrtf(ss) : 0.0f;
+  }
+}
+
+// fp32 stored rows -> bf16 shadow rows (RNE), one warp per row
+__global__ void shadow_rows_kernel(const float* __restrict__ rows, long long n, int dpad, int ld16,
+                                   __nv_bfloat16* __restrict__ dst) {
+  const int lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n) return;
+  const float* s = rows + r * dpad;
+  __nv_bfloat16* d = dst + r * ld16;
+  for (int c = lane; c < ld16; c += 32) d[c] = __float2bfloat16_rn(c < dpad ? s[c] : 0.0f);
+}
+
+// ---------------------------------------------------------------- filter kernel
+// thread-private sorted list (descending) of the k best LOWER bounds, column-major [k][BM]
+__device__ __forceinline__ float lower_push(float* lows, int k, int et, float v) {
+  int i = k - 1;
+  while (i > 0) {
+    const float prev = lows[static_cast<size_t>(i - 1) * BM + et];
+    if (prev >= v) break;
+    lows[static_cast<size_t>(i) * BM + et] = prev;
+    --i;
+  }
+  lows[static_cast<size_t>(i) * BM + et] = v;
+  return lows[static_cast<size_t>(k - 1) * BM + et];
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_q,
+                   const FilterParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* stage_base = smem;
+  float* lows = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);        // [k][BM]
+  float* colscale = lows + static_cast<size_t>(kMaxKFilter) * BM;             // [2][BN] score scale per column
+  float* coleps = colscale + 2 * BN;                                          // [2][BN] eps scale per column
+  uint64_t* bars = reinterpret_cast<uint64_t*>(coleps + 2 * BN);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, slice = blockIdx.y;
+  const int k = p.k;
+  const float NEG_INF = __int_as_float(0xff800000);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_x);
+    prefetch_tmap(&tm_q);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(full_bar + s), 1);
+      mbar_init(smem_u32(empty_bar + s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(tmem_full + a), 1);
+      mbar_init(smem_u32(tmem_empty + a), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_ptr), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int my_tiles = (p.n_tiles - slice + p.n_slices - 1) / p.n_slices;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int row0 = (slice + t * p.n_slices) * BN;
+        for (int kb = 0; kb < p.n_kblocks; ++kb) {
+          mbar_wait(smem_u32(empty_bar + stage), phase ^ 1u);
+          unsigned char* sb = stage_base + static_cast<size_t>(stage) * STAGE_BYTES;
+          const uint32_t bar = smem_u32(full_bar + stage);
+          mbar_expect_tx(bar, STAGE_BYTES);
+          tma_load_2d(smem_u32(sb), &tm_x, kb * BK, row0, bar);
+          tma_load_2d(smem_u32(sb + X_TILE_BYTES), &tm_q, kb * BK, qb * BM, bar);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BM, BN, 1u);  // BF16 x BF16 -> F32
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int a = t & 1;
+        mbar_wait(smem_u32(tmem_empty + a), ((static_cast<uint32_t>(t) >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(a * BN);
+        for (int kb = 0; kb < p.n_kblocks; ++kb) {
+          mbar_wait(smem_u32(full_bar + stage), phase);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(stage_base + static_cast<size_t>(stage) * STAGE_BYTES);
+          const uint64_t d_x = make_desc_kmajor(sb, 128, 2);
+          const uint64_t d_q = make_desc_kmajor(sb + X_TILE_BYTES, 128, 2);
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t adv = static_cast<uint64_t>((kk * 16 * 2) >> 4);  // 32 bytes per K=16 step
+            umma_f16(d_tmem, d_q + adv, d_x + adv, idesc, (kb | kk) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(empty_bar + stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(smem_u32(tmem_full + a));
+      }
+    }
+  } else if (warp >= 4) {
+    const int et = threadIdx.x - 128;
+    const int q = qb * BM + et;
+    const bool q_valid = q < p.B;
+    const float qinv = q_valid ? p.q_inv[q] : 0.0f;
+    const float qnrm = q_valid ? p.q_nrm[q] : 0.0f;
+    const float qsq = q_valid ? p.q_sq[q] : 0.0f;
+    // eps of this query: cosine eps_rel (norms cancel); ip eps_rel*|x||q|; l2 2*eps_rel*|x||q|
+    const float qeps = (METRIC == kCosine) ? p.eps_rel : (METRIC == kL2 ? 2.0f * p.eps_rel * qnrm : p.eps_rel * qnrm);
+    for (int i = 0; i < k; ++i) lows[static_cast<size_t>(i) * BM + et] = NEG_INF;
+    float L = NEG_INF;  // k-th best lower bound seen by this thread / published by any CTA
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    unsigned long long* my_cand = p.cand + static_cast<size_t>(q_valid ? q : 0) * p.cap;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int a = t & 1;
+      const long long row0 = static_cast<long long>(slice + t * p.n_slices) * BN;
+      const long long rem = p.n_rows - row0;
+      const int valid = rem < BN ? static_cast<int>(rem) : BN;
+      float* cs = colscale + a * BN;
+      float* ce = coleps + a * BN;
+      for (int c = et; c < BN; c += 128) {
+        float sc = 0.0f, ep = 0.0f;
+        if (c < valid) {
+          const float inx = __ldg(p.inv_norm + row0 + c);
+          const float sq = __ldg(p.sqnorm + row0 + c);
+          sc = (METRIC == kCosine) ? inx : (METRIC == kL2 ? sq : 0.0f);
+          ep = (METRIC == kCosine) ? 1.0f : sqrtf(sq);  // |x|
+        }
+        cs[c] = sc;
+        ce[c] = ep;
+      }
+      // share the bound: any CTA's k-th best lower bound is a valid global lower bound
+      if (q_valid) {
+        const unsigned int mine = mono_u32(L);
+        const unsigned int old = atomicMax(p.lower_glob + q, mine);
+        const float g = unmono_f32(old > mine ? old : mine);
+        L = g > L ? g : L;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(smem_u32(tmem_full + a), (static_cast<uint32_t>(t) >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(lane_base + static_cast<uint32_t>(a * BN + c0), r);
+        tmem_ld_wait();
+        if (c0 < valid && q_valid) {
+#pragma unroll
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            const float4 c4 = *reinterpret_cast<const float4*>(cs + c0 + j4);
+            const float4 e4 = *reinterpret_cast<const float4*>(ce + c0 + j4);
+            const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+            const float ee[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = j4 + jj;
+              const float d = __uint_as_float(r[j]);
+              float s;
+              if (METRIC == kCosine) s = d * cc[jj] * qinv;
+              else if (METRIC == kL2) s = -((cc[jj] - 2.0f * d) + qsq);
+              else s = d;
+              const float eps = ee[jj] * qeps;
+              // !(upper < L) also lets NaN through: the refine step ranks it exactly like K1
+              if (!(s + eps < L) && (c0 + j) < valid) {
+                const long long row = row0 + c0 + j;
+                bool dead = false;
+                if (p.tomb != nullptr) dead = (__ldg(p.tomb + (row >> 5)) >> (row & 31)) & 1u;
+                if (!dead) {
+                  const unsigned int idx = atomicAdd(p.cand_count + q, 1u);
+                  if (idx < static_cast<unsigned int>(p.cap))
+                    my_cand[idx] = (static_cast<unsigned long long>(p.seg) << 32) | static_cast<unsigned long long>(row);
+                  const float lo = s - eps;  // NaN never enters the list of lower bounds
+                  if (lo > lows[static_cast<size_t>(k - 1) * BM + et]) {
+                    const float kth = lower_push(lows, k, et, lo);
+                    L = kth > L ? kth : L;
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tmem_empty + a));
+    }
+    if (q_valid) atomicMax(p.lower_glob + q, mono_u32(L));
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+constexpr size_t kFilterSmem = 1024 + static_cast<size_t>(STAGES) * STAGE_BYTES + static_cast<size_t>(kMaxKFilter) * BM * 4 +
+                               4 * BN * 4 + (2 * STAGES + 4) * 8 + 16;
+
+// ---------------------------------------------------------------- refine kernel
+// One CTA per query.  Candidates are re-scored from the stored rows with K1's arithmetic: lanes-per-row
+// lpr, chunk c = lig + j*lpr accumulated in j order with the x,y,z,w fmaf chain, xor-butterfly over
+// lpr lanes, then the same score formula -- so keys are bit-identical to scan_topk_kernel's.
+struct RefineParams {
+  SegDesc seg[kMaxSeg];
+  const float* q;                   // [B][dim]
+  const unsigned long long* cand;   // [B][cap]
+  const unsigned int* cand_count;   // [B]
+  int* overflow;                    // [B] set to 1 when the candidate list overflowed
+  int B, dim, dpad, row_bytes, cpr, lpr_log2, nch, k, metric, cap;
+  uint64_t* keys_out;
+  float* scores_out;
+  long long* gids_out;
+  int* counts_out;
+};
+
+template <bool BF16, bool L2>
+__global__ void __launch_bounds__(256, 2) refine_topk_kernel(const __grid_constant__ RefineParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const int q = blockIdx.x;
+  const int k = p.k, dpad = p.dpad;
+  float* q_s = reinterpret_cast<float*>(smem);                                   // [dpad]
+  float* misc = reinterpret_cast<float*>(smem + scan::align128(static_cast<size_t>(dpad) * 4));
+  uint64_t* lists = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(misc) + 128);  // [nwarps][k]
+  uint64_t* final_list = lists + static_cast<size_t>(nwarps) * k;                // [k]
+
+  const unsigned int cnt_raw = p.cand_count[q];
+  if (cnt_raw > static_cast<unsigned int>(p.cap)) {   // adversarial data: let K1 redo this query exactly
+    if (tid == 0) {
+      p.overflow[q] = 1;
+      if (p.counts_out) p.counts_out[q] = 0;
+    }
+    return;
+  }
+  const int cnt = static_cast<int>(cnt_raw);
+  for (int i = tid; i < dpad; i += blockDim.x) q_s[i] = (i < p.dim) ? __ldg(p.q + static_cast<size_t>(q) * p.dim + i) : 0.0f;
+  for (int i = tid; i < nwarps * k + k; i += blockDim.x) lists[i] = 0ull;
+  __syncthreads();
+  if (warp == 0) {  // 1/|q| exactly as K1 computes it
+    float ss = 0.0f;
+    for (int i = lane; i < dpad; i += 32) ss = fmaf(q_s[i], q_s[i], ss);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, o);
+    if (lane == 0) misc[0] = ss > 0.0f ? 1.0f / sqrtf(ss) : 0.0f;
+  }
+  __syncthreads();
+  const float qinv = misc[0];
+  const bool cosine = p.metric == kCosine;
+  const int lpr_log2 = p.lpr_log2, lpr = 1 << lpr_log2, G = 32 >> lpr_log2;
+  const int g = lane >> lpr_log2, lig = lane & (lpr - 1);
+  uint64_t* my_list = lists + static_cast<size_t>(warp) * k;
+  uint64_t thr = 0ull;
+  const unsigned long long* cand = p.cand + static_cast<size_t>(q) * p.cap;
+
+  for (int base = warp * G; base < cnt; base += nwarps * G) {
+    const int ci = base + g;
+    const bool have = ci < cnt;
+    const unsigned long long ent = have ? cand[ci] : cand[0];
+    const int sg = static_cast<int>(ent >> 32);
+    const long long row = static_cast<long long>(ent & 0xFFFFFFFFull);
+    const unsigned char* rp = p.seg[sg].rows + static_cast<size_t>(row) * p.row_bytes;
+    float acc = 0.0f;
+    for (int j = 0; j < p.nch; ++j) {
+      const int c = lig + (j << lpr_log2);
+      if (c < p.cpr) {
+        if (!BF16) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(rp + c * 16));
+          const float4 qv = lds128(q_s + c * 4);
+          if (L2) {
+            const float d0 = x.x - qv.x, d1 = x.y - qv.y, d2 = x.z - qv.z, d3 = x.w - qv.w;
+            acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc); acc = fmaf(d2, d2, acc); acc = fmaf(d3, d3, acc);
+          } else {
+            acc = fmaf(x.x, qv.x, acc); acc = fmaf(x.y, qv.y, acc); acc = fmaf(x.z, qv.z, acc); acc = fmaf(x.w, qv.w, acc);
+          }
+        } else {
+          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(rp + c * 16));
+          const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+          const float4 qa = lds128(q_s + c * 8);
+          const float4 qb = lds128(q_s + c * 8 + 4);
+          const float qq[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xFFFF0000u);
+            if (L2) {
+              const float d0 = lo - qq[2 * i], d1 = hi - qq[2 * i + 1];
+              acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc);
+            } else {
+              acc = fmaf(lo, qq[2 * i], acc); acc = fmaf(hi, qq[2 * i + 1], acc);
+            }
+          }
+        }
+      }
+    }
+    for (int o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, o);
+    float s = acc;
+    if (L2) s = -s;
+    else if (cosine) s = s * __ldg(p.seg[sg].inv_norm + row) * qinv;
+    s = (s != s) ? __int_as_float(0xff800000) : s;
+    const uint64_t key = have ? pack_key(s, __ldg(p.seg[sg].gids + row)) : 0ull;
+    unsigned m = __ballot_sync(FULL_MASK, lig == 0 && have && key > thr);
+    while (m) {
+      const int src_lane = __ffs(m) - 1;
+      m &= m - 1;
+      const uint64_t kk = __shfl_sync(FULL_MASK, key, src_lane);
+      if (kk > thr) thr = scan::list_insert(my_list, k, kk, lane);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t t2 = 0ull;
+    scan::absorb_keys<false>(final_list, k, t2, lists, nwarps * k, 0, 1, lane);
+    scan::emit_list(final_list, k, lane, p.keys_out ? p.keys_out + static_cast<size_t>(q) * k : nullptr,
+                    p.scores_out ? p.scores_out + static_cast<size_t>(q) * k : nullptr,
+                    p.gids_out ? p.gids_out + static_cast<size_t>(q) * k : nullptr, p.counts_out ? p.counts_out + q : nullptr);
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_bf16() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+
+// [rows, ld] bf16 row-major, logical width `cols`; box = 64 x box_rows, 128B swizzle, OOB -> 0
+bool encode_map_bf16(CUtensorMap* map, const void* base, long long rows, int cols, int ld, int box_rows) {
+  auto fn = get_encode_bf16();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows > 0 ? rows : 1)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+int filter_max_k() { return kMaxKFilter; }
+int filter_ld16(int dim) { return (dim + 7) / 8 * 8; }
+
+// workspace layout (bytes): qb16 [B][ld16] bf16 | q_inv, q_nrm, q_sq [B] f32 each
+size_t filter_query_workspace_bytes(int B, int dim) {
+  return (static_cast<size_t>(B) * filter_ld16(dim) * 2 + 15) / 16 * 16 + 3 * static_cast<size_t>(B) * 4;
+}
+
+int filter_slices_for(long long n_rows, int B, int sm_count) {
+  const int n_qblocks = (B + BM - 1) / BM;
+  const long long n_tiles = (n_rows + BN - 1) / BN;
+  long long s = sm_count / n_qblocks;
+  if (s < 1) s = 1;
+  if (s > n_tiles) s = n_tiles;
+  if (s < 1) s = 1;
+  return static_cast<int>(s);
+}
+
+cudaError_t launch_shadow_rows(const float* rows, long long n, int dpad, int ld16, void* dst, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const int wpb = 8;
+  shadow_rows_kernel<<<static_cast<unsigned>((n + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+      rows, n, dpad, ld16, static_cast<__nv_bfloat16*>(dst));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace, cudaStream_t stream) {
+  const int ld = filter_ld16(dim);
+  __nv_bfloat16* qb = static_cast<__nv_bfloat16*>(workspace);
+  float* f = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + (static_cast<size_t>(B) * ld * 2 + 15) / 16 * 16);
+  const int wpb = 8;
+  prep_queries_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, stream>>>(q, B, dim, ld, qb, f, f + B, f + 2 * B);
+  return cudaGetLastError();
+}
+
+// One launch per segment.  xb = bf16 matrix [n_rows][ld_x] (shadow, or the stored rows of a bf16 engine).
+cudaError_t launch_gemm_filter(const void* xb, int ld_x, const SegDesc& seg, int seg_index, int dim, const void* workspace,
+                               int B, int k, int metric, float eps_rel, int n_slices, unsigned long long* cand,
+                               unsigned int* cand_count, unsigned int* lower_glob, int cap, cudaStream_t stream) {
+  if (seg.n_rows <= 0 || n_slices <= 0) return cudaSuccess;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(gemm_filter_kernel<kCosine>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFilterSmem));
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gemm_filter_kernel<kIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFilterSmem));
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gemm_filter_kernel<kL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFilterSmem));
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  const int ld = filter_ld16(dim);
+  const unsigned char* ws = static_cast<const unsigned char*>(workspace);
+  const float* f = reinterpret_cast<const float*>(ws + (static_cast<size_t>(B) * ld * 2 + 15) / 16 * 16);
+  CUtensorMap tm_x, tm_q;
+  if (!encode_map_bf16(&tm_x, xb, seg.n_rows, dim, ld_x, BN) || !encode_map_bf16(&tm_q, ws, B, dim, ld, BM))
+    return cudaErrorInvalidValue;
+  FilterParams p;
+  p.inv_norm = seg.inv_norm;
+  p.sqnorm = seg.sqnorm;
+  p.tomb = seg.tomb;
+  p.q_inv = f;
+  p.q_nrm = f + B;
+  p.q_sq = f + 2 * B;
+  p.n_rows = seg.n_rows;
+  p.B = B;
+  p.k = k;
+  p.n_kblocks = (dim + BK - 1) / BK;
+  p.n_tiles = static_cast<int>((seg.n_rows + BN - 1) / BN);
+  p.n_slices = n_slices;
+  p.seg = seg_index;
+  p.eps_rel = eps_rel;
+  p.cand = cand;
+  p.cand_count = cand_count;
+  p.lower_glob = lower_glob;
+  p.cap = cap;
+  dim3 grid((B + BM - 1) / BM, n_slices, 1), block(kThreads, 1, 1);
+  if (metric == kCosine) gemm_filter_kernel<kCosine><<<grid, block, kFilterSmem, stream>>>(tm_x, tm_q, p);
+  else if (metric == kL2) gemm_filter_kernel<kL2><<<grid, block, kFilterSmem, stream>>>(tm_x, tm_q, p);
+  else gemm_filter_kernel<kIP><<<grid, block, kFilterSmem, stream>>>(tm_x, tm_q, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_refine_topk(const SegDesc* segs, int n_seg, const float* q, int B, int dim, int dpad, int elem_bytes,
+                               int lpr_log2, int nch, int k, int metric, const unsigned long long* cand,
+                               const unsigned int* cand_count, int cap, int* overflow, uint64_t* keys_out,
+                               float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream) {
+  RefineParams p;
+  memset(&p, 0, sizeof(p));
+  for (int s = 0; s < n_seg; ++s) p.seg[s] = segs[s];
+  p.q = q;
+  p.cand = cand;
+  p.cand_count = cand_count;
+  p.overflow = overflow;
+  p.B = B;
+  p.dim = dim;
+  p.dpad = dpad;
+  p.row_bytes = dpad * elem_bytes;
+  p.cpr = p.row_bytes / 16;
+  p.lpr_log2 = lpr_log2;
+  p.nch = nch;
+  p.k = k;
+  p.metric = metric;
+  p.cap = cap;
+  p.keys_out = keys_out;
+  p.scores_out = scores_out;
+  p.gids_out = gids_out;
+  p.counts_out = counts_out;
+  const int warps = 8;
+  const size_t smem = ((static_cast<size_t>(dpad) * 4 + 127) & ~static_cast<size_t>(127)) + 128 +
+                      (static_cast<size_t>(warps) * k + k) * 8;
+  const bool bf16 = elem_bytes == 2, l2 = metric == kL2;
+  auto go = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    kern<<<B, warps * 32, smem, stream>>>(p);
+  };
+  if (bf16) { if (l2) go(refine_topk_kernel<true, true>); else go(refine_topk_kernel<true, false>); }
+  else { if (l2) go(refine_topk_kernel<false, true>); else go(refine_topk_kernel<false, false>); }
+  return cudaGetLastError();
+}
+
+}  // namespace wdbx

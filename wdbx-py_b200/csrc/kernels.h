@@ -66,6 +66,8 @@ struct ScanParams {
   int xchg_rank;
   int xchg_slot;                   // seq & 1
   unsigned int xchg_seq;           // collective sequence number (same on all ranks)
+  const int* only_flag;    // optional [B]: a query block runs only if one of its queries is flagged
+                           // (K2b re-runs queries whose candidate list overflowed); NULL = run all
   uint64_t* keys_out;      // [B][k] or NULL
   float* scores_out;       // [B][k] or NULL
   long long* gids_out;     // [B][k] or NULL
@@ -91,6 +93,21 @@ int gemm_slices_for(long long n_rows, int B, int sm_count);
 cudaError_t launch_split_queries(const float* q, int B, int dim, float* workspace, cudaStream_t stream);
 cudaError_t launch_gemm_topk(const SegDesc& seg, int dim, int dpad, const float* workspace, int B, int k, int metric,
                              int n_slices, int slice_base, uint64_t* out_lists, cudaStream_t stream);
+
+// K2b: bf16 tensor-core filter + exact fp32 refine (results bit-identical to K1).  See gemm_filter.cu.
+int filter_max_k();
+int filter_ld16(int dim);
+size_t filter_query_workspace_bytes(int B, int dim);
+int filter_slices_for(long long n_rows, int B, int sm_count);
+cudaError_t launch_shadow_rows(const float* rows, long long n, int dpad, int ld16, void* dst, cudaStream_t stream);
+cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace, cudaStream_t stream);
+cudaError_t launch_gemm_filter(const void* xb, int ld_x, const SegDesc& seg, int seg_index, int dim, const void* workspace,
+                               int B, int k, int metric, float eps_rel, int n_slices, unsigned long long* cand,
+                               unsigned int* cand_count, unsigned int* lower_glob, int cap, cudaStream_t stream);
+cudaError_t launch_refine_topk(const SegDesc* segs, int n_seg, const float* q, int B, int dim, int dpad, int elem_bytes,
+                               int lpr_log2, int nch, int k, int metric, const unsigned long long* cand,
+                               const unsigned int* cand_count, int cap, int* overflow, uint64_t* keys_out,
+                               float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream);
 
 // K3: merge G best-first lists per query.
 cudaError_t launch_merge_topk(const uint64_t* keys, int G, int B, int k, uint64_t* keys_out, float* scores_out,

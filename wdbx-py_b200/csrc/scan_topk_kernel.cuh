@@ -136,6 +136,11 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
   const int nq = (p.B - qbase) < QB ? (p.B - qbase) : QB;
   const int k = p.k;
   const int dpad = p.dpad;
+  if (p.only_flag != nullptr) {  // uniform over the whole query block (all CTAs of this blockIdx.y)
+    bool any = false;
+    for (int b = 0; b < nq; ++b) any = any || (p.only_flag[qbase + b] != 0);
+    if (!any) return;
+  }
 
   // ---- shared memory carve-up (mirrors scan_plan)
   float* q_s = reinterpret_cast<float*>(smem);  // [QB][dpad], zero padded
