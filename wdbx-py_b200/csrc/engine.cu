@@ -71,6 +71,7 @@ struct Workspace {
   unsigned int* flower = nullptr;
   int* foverflow = nullptr;
   int fper_query = 0;
+  size_t fregions = 0;
 };
 
 int env_int(const char* name, int dflt) {
@@ -87,7 +88,7 @@ struct wdbx_b200_engine {
   uint32_t next_gid = 0;
   std::vector<Workspace> ws;
   ScanTuning tune{0, 0, 0, 0, -1, 0};
-  int gemm_min_batch = 48;  // B >= this => tcgen05 GEMM path (0 = never)
+  int gemm_min_batch = 16;  // B >= this => tcgen05 path (0 = never); measured crossover vs K1 (8 queries/pass) ~ 12-16
   int gemm_mode = 0;        // 0 = bf16 filter + exact refine (K2b), 1 = 3xTF32 with fused top-k (K2)
   cudaStream_t mstream = nullptr;  // mutations
   // staging for host-sourced appends
@@ -382,9 +383,18 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   Workspace* w = nullptr;
   int wrc = get_workspace(e, stream, 0, 0, &w);
   if (wrc != WDBX_B200_OK) return wrc;
-  const int cap = B <= 4096 ? 4096 : std::max(512, static_cast<int>((16ll << 20) / B));
+  // one private candidate region per (query, row slice); B * slices is ~ (#SMs x 128) whatever B is
+  int slices[kMaxSeg];
+  int s_total = 0;
+  for (int s = s0; s < s1; ++s) {
+    slices[s] = e->seg[s].n_rows > 0 ? filter_slices_for(e->seg[s].n_rows, B, e->sm_count) : 0;
+    s_total += 2 * slices[s];  // two candidate regions per (query, slice): one per epilogue column half
+  }
+  if (s_total == 0) s_total = 2;
+  const int cap = 512;
+  const size_t n_regions = static_cast<size_t>(B) * s_total;
   const size_t need_ws = filter_query_workspace_bytes(B, e->dim);
-  if (w->fws_bytes < need_ws || w->fcand_n < static_cast<size_t>(B) * cap || w->fper_query < B) {
+  if (w->fws_bytes < need_ws || w->fcand_n < n_regions * cap || w->fper_query < B || w->fregions < n_regions) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(stream, &cs);
     if (cs != cudaStreamCaptureStatusNone)
@@ -395,21 +405,25 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
       CU_TRY(cudaMalloc(&w->fws, need_ws));
       w->fws_bytes = need_ws;
     }
-    if (w->fcand_n < static_cast<size_t>(B) * cap) {
+    if (w->fcand_n < n_regions * cap) {
       cudaFree(w->fcand); w->fcand = nullptr; w->fcand_n = 0;
-      CU_TRY(cudaMalloc(&w->fcand, static_cast<size_t>(B) * cap * 8));
-      w->fcand_n = static_cast<size_t>(B) * cap;
+      CU_TRY(cudaMalloc(&w->fcand, n_regions * cap * 8));
+      w->fcand_n = n_regions * cap;
+    }
+    if (w->fregions < n_regions) {
+      cudaFree(w->fcount); w->fcount = nullptr; w->fregions = 0;
+      CU_TRY(cudaMalloc(&w->fcount, n_regions * 4));
+      w->fregions = n_regions;
     }
     if (w->fper_query < B) {
-      cudaFree(w->fcount); cudaFree(w->flower); cudaFree(w->foverflow);
-      w->fcount = nullptr; w->flower = nullptr; w->foverflow = nullptr; w->fper_query = 0;
-      CU_TRY(cudaMalloc(&w->fcount, static_cast<size_t>(B) * 4));
+      cudaFree(w->flower); cudaFree(w->foverflow);
+      w->flower = nullptr; w->foverflow = nullptr; w->fper_query = 0;
       CU_TRY(cudaMalloc(&w->flower, static_cast<size_t>(B) * 4));
       CU_TRY(cudaMalloc(&w->foverflow, static_cast<size_t>(B) * 4));
       w->fper_query = B;
     }
   }
-  CU_TRY(cudaMemsetAsync(w->fcount, 0, static_cast<size_t>(B) * 4, stream));
+  CU_TRY(cudaMemsetAsync(w->fcount, 0, n_regions * 4, stream));
   CU_TRY(cudaMemsetAsync(w->foverflow, 0, static_cast<size_t>(B) * 4, stream));
   CU_TRY(cudaMemsetAsync(w->flower, 0, static_cast<size_t>(B) * 4, stream));  // 0 < mono(-inf): "no bound yet"
   CU_TRY(launch_prep_queries(q_dev, B, e->dim, w->fws, stream));
@@ -419,6 +433,7 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   const float eps_rel = (f32 ? 0.00390625f : 0.001953125f) * 1.002f + static_cast<float>(e->dim) * 1.2e-7f + 1e-6f;
   SegDesc descs[kMaxSeg];
   memset(descs, 0, sizeof(descs));
+  int slice_base = 0;
   for (int s = s0; s < s1; ++s) {
     const Segment& sg = e->seg[s];
     SegDesc& d = descs[s];
@@ -429,10 +444,11 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
     d.tomb = sg.n_dead > 0 ? sg.tomb : nullptr;
     d.n_rows = sg.n_rows;
     if (sg.n_rows == 0) continue;
-    const int slices = filter_slices_for(sg.n_rows, B, e->sm_count);
     CU_TRY(launch_gemm_filter(f32 ? sg.shadow : static_cast<const void*>(sg.rows), f32 ? ld16 : e->dpad, d, s, e->dim, w->fws,
-                              B, k, metric, eps_rel, slices, w->fcand, w->fcount, w->flower, cap, stream));
+                              B, k, metric, eps_rel, slices[s], w->fcand, w->fcount, w->flower, cap, slice_base, s_total,
+                              stream));
     e->launches.fetch_add(1, std::memory_order_relaxed);
+    slice_base += slices[s];
   }
   ScanTuning t1 = e->tune;
   t1.queries_per_pass = 1;
@@ -440,7 +456,8 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   if (scan_plan(e->dim, e->dpad, e->elem_bytes, k, 1, e->sm_count, t1, &plan) != 0)
     return fail(WDBX_B200_ERR_ARG, "invalid scan shape (dim=%d k=%d)", e->dim, k);
   CU_TRY(launch_refine_topk(descs, kMaxSeg, q_dev, B, e->dim, e->dpad, e->elem_bytes, plan.lpr_log2, plan.nch, k, metric,
-                            w->fcand, w->fcount, cap, w->foverflow, keys_out, scores_out, gids_out, counts_out, stream));
+                            w->fcand, w->fcount, cap, s_total, w->foverflow, keys_out, scores_out, gids_out, counts_out,
+                            stream));
   e->launches.fetch_add(1, std::memory_order_relaxed);
   // exact re-run (K1) of the queries whose candidate list overflowed; exits immediately otherwise
   return scan_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream, false,

@@ -16,7 +16,9 @@
 //               lane mapping, summation order and score formula, keeps the top-k with K1's list code.
 //   4. queries whose candidate list overflowed (adversarial data) are flagged and re-run by K1 itself.
 //
-// Filter CTA = 8 warps: 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 idle | 4-7 epilogue.
+// Filter CTA = 12 warps: 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 idle | 4-11 epilogue
+// (two threads per query, one per half of the tile's columns: a single warp per scheduler could not
+// drain a 128x256 accumulator as fast as the bf16 MMAs produce it).
 // Tile 128 queries x 256 rows x 64 dims (one 128-byte swizzle atom per row), 4-stage mbarrier ring
 // (48 KB / stage), two accumulator tiles in TMEM (512 columns).
 #include <cuda.h>
@@ -38,8 +40,9 @@ constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;        // bf16 elements per K block = 128 bytes
 constexpr int STAGES = 4;
-constexpr int kThreads = 256;
-constexpr int kMaxKFilter = 32;
+constexpr int kThreads = 384;   // 4 control warps + 8 epilogue warps
+constexpr int kMaxKFilter = 16;
+constexpr int LT = 2 * BM;       // lower-bound list slots: two epilogue threads per query
 constexpr uint32_t X_TILE_BYTES = BN * BK * 2;  // 32 KB
 constexpr uint32_t Q_TILE_BYTES = BM * BK * 2;  // 16 KB
 constexpr uint32_t STAGE_BYTES = X_TILE_BYTES + Q_TILE_BYTES;
@@ -57,10 +60,11 @@ struct FilterParams {
   int n_kblocks, n_tiles, n_slices;
   int seg;                 // segment index stored with each candidate
   float eps_rel;           // rounding bound relative to |x||q|
-  unsigned long long* cand;   // [B][cap]  (seg << 32 | row)
-  unsigned int* cand_count;   // [B]
+  unsigned long long* cand;   // [B][s_total][cap]  (seg << 32 | row): one private region per (query, row slice)
+  unsigned int* cand_count;   // [B][s_total]
   unsigned int* lower_glob;   // [B] monotone-mapped float: best known lower bound of the exact k-th score
-  int cap;
+  int cap;                    // entries per (query, slice) region
+  int slice_base, s_total;    // this launch fills slices [slice_base, slice_base + n_slices) of s_total
 };
 
 // ---------------------------------------------------------------- prep: queries -> bf16 + norms
@@ -97,16 +101,16 @@ __global__ void shadow_rows_kernel(const float* __restrict__ rows, long long n, 
 
 // ---------------------------------------------------------------- filter kernel
 // thread-private sorted list (descending) of the k best LOWER bounds, column-major [k][BM]
-__device__ __forceinline__ float lower_push(float* lows, int k, int et, float v) {
+__device__ __forceinline__ float lower_push(float* lows, int k, int lt, float v) {
   int i = k - 1;
   while (i > 0) {
-    const float prev = lows[static_cast<size_t>(i - 1) * BM + et];
+    const float prev = lows[(i - 1) * LT + lt];
     if (prev >= v) break;
-    lows[static_cast<size_t>(i) * BM + et] = prev;
+    lows[i * LT + lt] = prev;
     --i;
   }
-  lows[static_cast<size_t>(i) * BM + et] = v;
-  return lows[static_cast<size_t>(k - 1) * BM + et];
+  lows[i * LT + lt] = v;
+  return lows[(k - 1) * LT + lt];
 }
 
 template <int METRIC>
@@ -114,10 +118,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_q,
                    const FilterParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // keep the shared-memory address space visible to the compiler (LDS/STS instead of generic accesses)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* stage_base = smem;
-  float* lows = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);        // [k][BM]
-  float* colscale = lows + static_cast<size_t>(kMaxKFilter) * BM;             // [2][BN] score scale per column
+  float* lows = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);        // [k][LT]
+  float* colscale = lows + static_cast<size_t>(kMaxKFilter) * LT;             // [2][BN] score scale per column
   float* coleps = colscale + 2 * BN;                                          // [2][BN] eps scale per column
   uint64_t* bars = reinterpret_cast<uint64_t*>(coleps + 2 * BN);
   uint64_t* full_bar = bars;
@@ -140,7 +145,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(tmem_full + a), 1);
-      mbar_init(smem_u32(tmem_empty + a), 4);
+      mbar_init(smem_u32(tmem_empty + a), 8);
     }
     fence_mbar_init();
   }
@@ -196,7 +201,12 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    const int et = threadIdx.x - 128;
+    // ===== epilogue: 8 warps.  TMEM lane (= query) quarter = warp & 3; warps 4-7 take columns [0,128)
+    // of every tile, warps 8-11 columns [128,256): two threads per query, each with its own list of
+    // lower bounds (both are valid bounds) and its own candidate region.
+    const int et = (warp & 3) * 32 + lane;      // TMEM lane == query inside the block
+    const int half = (warp - 4) >> 2;           // column half of the tile
+    const int lt = half * BM + et;              // slot of this thread in the lower-bound lists
     const int q = qb * BM + et;
     const bool q_valid = q < p.B;
     const float qinv = q_valid ? p.q_inv[q] : 0.0f;
@@ -204,10 +214,13 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const float qsq = q_valid ? p.q_sq[q] : 0.0f;
     // eps of this query: cosine eps_rel (norms cancel); ip eps_rel*|x||q|; l2 2*eps_rel*|x||q|
     const float qeps = (METRIC == kCosine) ? p.eps_rel : (METRIC == kL2 ? 2.0f * p.eps_rel * qnrm : p.eps_rel * qnrm);
-    for (int i = 0; i < k; ++i) lows[static_cast<size_t>(i) * BM + et] = NEG_INF;
-    float L = NEG_INF;  // k-th best lower bound seen by this thread / published by any CTA
+    for (int i = 0; i < k; ++i) lows[i * LT + lt] = NEG_INF;
+    float L = NEG_INF;  // k-th best lower bound seen by this thread / published by any CTA of this query
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    unsigned long long* my_cand = p.cand + static_cast<size_t>(q_valid ? q : 0) * p.cap;
+    // private candidate region of this (query, slice, half): plain stores, no atomics on the hot path
+    const size_t region = static_cast<size_t>(q_valid ? q : 0) * p.s_total + 2 * (p.slice_base + slice) + half;
+    unsigned long long* my_cand = p.cand + region * p.cap;
+    unsigned int n_cand = 0;
     for (int t = 0; t < my_tiles; ++t) {
       const int a = t & 1;
       const long long row0 = static_cast<long long>(slice + t * p.n_slices) * BN;
@@ -215,8 +228,11 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       const int valid = rem < BN ? static_cast<int>(rem) : BN;
       float* cs = colscale + a * BN;
       float* ce = coleps + a * BN;
-      for (int c = et; c < BN; c += 128) {
-        float sc = 0.0f, ep = 0.0f;
+      {
+        // per-column score scale and eps scale; columns past the end get eps = -inf so that their
+        // upper bound is -inf (they only reach the slow path while L is still -inf, where they are dropped)
+        const int c = half * 128 + et;
+        float sc = 0.0f, ep = NEG_INF;
         if (c < valid) {
           const float inx = __ldg(p.inv_norm + row0 + c);
           const float sq = __ldg(p.sqnorm + row0 + c);
@@ -226,18 +242,16 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         cs[c] = sc;
         ce[c] = ep;
       }
-      // share the bound: any CTA's k-th best lower bound is a valid global lower bound
+      // share the bound: any thread's k-th best lower bound is a valid global lower bound
       if (q_valid) {
-        const unsigned int mine = mono_u32(L);
-        const unsigned int old = atomicMax(p.lower_glob + q, mine);
-        const float g = unmono_f32(old > mine ? old : mine);
+        const float g = unmono_f32(max(__ldcg(p.lower_glob + q), 0x007FFFFFu));
         L = g > L ? g : L;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(smem_u32(tmem_full + a), (static_cast<uint32_t>(t) >> 1) & 1u);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
         uint32_t r[32];
         __syncwarp();
         tmem_ld32(lane_base + static_cast<uint32_t>(a * BN + c0), r);
@@ -249,28 +263,36 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             const float4 e4 = *reinterpret_cast<const float4*>(ce + c0 + j4);
             const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
             const float ee[4] = {e4.x, e4.y, e4.z, e4.w};
+            float sv[4], up[4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-              const int j = j4 + jj;
-              const float d = __uint_as_float(r[j]);
-              float s;
-              if (METRIC == kCosine) s = d * cc[jj] * qinv;
-              else if (METRIC == kL2) s = -((cc[jj] - 2.0f * d) + qsq);
-              else s = d;
-              const float eps = ee[jj] * qeps;
-              // !(upper < L) also lets NaN through: the refine step ranks it exactly like K1
-              if (!(s + eps < L) && (c0 + j) < valid) {
-                const long long row = row0 + c0 + j;
-                bool dead = false;
-                if (p.tomb != nullptr) dead = (__ldg(p.tomb + (row >> 5)) >> (row & 31)) & 1u;
-                if (!dead) {
-                  const unsigned int idx = atomicAdd(p.cand_count + q, 1u);
-                  if (idx < static_cast<unsigned int>(p.cap))
-                    my_cand[idx] = (static_cast<unsigned long long>(p.seg) << 32) | static_cast<unsigned long long>(row);
-                  const float lo = s - eps;  // NaN never enters the list of lower bounds
-                  if (lo > lows[static_cast<size_t>(k - 1) * BM + et]) {
-                    const float kth = lower_push(lows, k, et, lo);
-                    L = kth > L ? kth : L;
+              const float d = __uint_as_float(r[j4 + jj]);
+              if (METRIC == kCosine) sv[jj] = d * cc[jj] * qinv;
+              else if (METRIC == kL2) sv[jj] = -((cc[jj] - 2.0f * d) + qsq);
+              else sv[jj] = d;
+              up[jj] = fmaf(ee[jj], qeps, sv[jj]);  // upper bound of the exact score
+            }
+            // one branch per 4 columns; !(x < L) also lets NaN through (the refine ranks it like K1)
+            if (!(up[0] < L) || !(up[1] < L) || !(up[2] < L) || !(up[3] < L)) {
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = j4 + jj;
+                if (!(up[jj] < L) && (c0 + j) < valid) {
+                  const long long row = row0 + c0 + j;
+                  bool dead = false;
+                  if (p.tomb != nullptr) dead = (__ldg(p.tomb + (row >> 5)) >> (row & 31)) & 1u;
+                  if (!dead) {
+                    if (n_cand < static_cast<unsigned int>(p.cap))
+                      my_cand[n_cand] = (static_cast<unsigned long long>(p.seg) << 32) | static_cast<unsigned long long>(row);
+                    ++n_cand;
+                    const float lo = sv[jj] - ee[jj] * qeps;  // NaN never enters the list of lower bounds
+                    if (lo > lows[(k - 1) * LT + lt]) {
+                      const float kth = lower_push(lows, k, lt, lo);
+                      if (kth > L) {
+                        L = kth;
+                        atomicMax(p.lower_glob + q, mono_u32(L));  // publish: valid for every CTA of this query
+                      }
+                    }
                   }
                 }
               }
@@ -282,7 +304,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(tmem_empty + a));
     }
-    if (q_valid) atomicMax(p.lower_glob + q, mono_u32(L));
+    if (q_valid) p.cand_count[region] = n_cand;
   }
 
   tc_fence_before();
@@ -293,7 +315,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   }
 }
 
-constexpr size_t kFilterSmem = 1024 + static_cast<size_t>(STAGES) * STAGE_BYTES + static_cast<size_t>(kMaxKFilter) * BM * 4 +
+constexpr size_t kFilterSmem = 1024 + static_cast<size_t>(STAGES) * STAGE_BYTES + static_cast<size_t>(kMaxKFilter) * LT * 4 +
                                4 * BN * 4 + (2 * STAGES + 4) * 8 + 16;
 
 // ---------------------------------------------------------------- refine kernel
@@ -303,8 +325,9 @@ constexpr size_t kFilterSmem = 1024 + static_cast<size_t>(STAGES) * STAGE_BYTES 
 struct RefineParams {
   SegDesc seg[kMaxSeg];
   const float* q;                   // [B][dim]
-  const unsigned long long* cand;   // [B][cap]
-  const unsigned int* cand_count;   // [B]
+  const unsigned long long* cand;   // [B][s_total][cap]
+  const unsigned int* cand_count;   // [B][s_total]
+  int s_total;
   int* overflow;                    // [B] set to 1 when the candidate list overflowed
   int B, dim, dpad, row_bytes, cpr, lpr_log2, nch, k, metric, cap;
   uint64_t* keys_out;
@@ -324,15 +347,19 @@ __global__ void __launch_bounds__(256, 2) refine_topk_kernel(const __grid_consta
   uint64_t* lists = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(misc) + 128);  // [nwarps][k]
   uint64_t* final_list = lists + static_cast<size_t>(nwarps) * k;                // [k]
 
-  const unsigned int cnt_raw = p.cand_count[q];
-  if (cnt_raw > static_cast<unsigned int>(p.cap)) {   // adversarial data: let K1 redo this query exactly
-    if (tid == 0) {
-      p.overflow[q] = 1;
-      if (p.counts_out) p.counts_out[q] = 0;
+  // any (query, slice) region that overflowed => adversarial data: let K1 redo this query exactly
+  {
+    int over = 0;
+    for (int sl = tid; sl < p.s_total; sl += blockDim.x)
+      over |= p.cand_count[static_cast<size_t>(q) * p.s_total + sl] > static_cast<unsigned int>(p.cap);
+    if (__syncthreads_or(over)) {
+      if (tid == 0) {
+        p.overflow[q] = 1;
+        if (p.counts_out) p.counts_out[q] = 0;
+      }
+      return;
     }
-    return;
   }
-  const int cnt = static_cast<int>(cnt_raw);
   for (int i = tid; i < dpad; i += blockDim.x) q_s[i] = (i < p.dim) ? __ldg(p.q + static_cast<size_t>(q) * p.dim + i) : 0.0f;
   for (int i = tid; i < nwarps * k + k; i += blockDim.x) lists[i] = 0ull;
   __syncthreads();
@@ -350,9 +377,10 @@ __global__ void __launch_bounds__(256, 2) refine_topk_kernel(const __grid_consta
   const int g = lane >> lpr_log2, lig = lane & (lpr - 1);
   uint64_t* my_list = lists + static_cast<size_t>(warp) * k;
   uint64_t thr = 0ull;
-  const unsigned long long* cand = p.cand + static_cast<size_t>(q) * p.cap;
-
-  for (int base = warp * G; base < cnt; base += nwarps * G) {
+  for (int sl = warp; sl < p.s_total; sl += nwarps) {
+   const int cnt = static_cast<int>(p.cand_count[static_cast<size_t>(q) * p.s_total + sl]);
+   const unsigned long long* cand = p.cand + (static_cast<size_t>(q) * p.s_total + sl) * p.cap;
+   for (int base = 0; base < cnt; base += G) {
     const int ci = base + g;
     const bool have = ci < cnt;
     const unsigned long long ent = have ? cand[ci] : cand[0];
@@ -404,6 +432,7 @@ __global__ void __launch_bounds__(256, 2) refine_topk_kernel(const __grid_consta
       const uint64_t kk = __shfl_sync(FULL_MASK, key, src_lane);
       if (kk > thr) thr = scan::list_insert(my_list, k, kk, lane);
     }
+   }
   }
   __syncthreads();
   if (warp == 0) {
@@ -481,7 +510,8 @@ cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace,
 // One launch per segment.  xb = bf16 matrix [n_rows][ld_x] (shadow, or the stored rows of a bf16 engine).
 cudaError_t launch_gemm_filter(const void* xb, int ld_x, const SegDesc& seg, int seg_index, int dim, const void* workspace,
                                int B, int k, int metric, float eps_rel, int n_slices, unsigned long long* cand,
-                               unsigned int* cand_count, unsigned int* lower_glob, int cap, cudaStream_t stream) {
+                               unsigned int* cand_count, unsigned int* lower_glob, int cap, int slice_base, int s_total,
+                               cudaStream_t stream) {
   if (seg.n_rows <= 0 || n_slices <= 0) return cudaSuccess;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -518,6 +548,8 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const SegDesc& seg, int
   p.cand_count = cand_count;
   p.lower_glob = lower_glob;
   p.cap = cap;
+  p.slice_base = slice_base;
+  p.s_total = s_total;
   dim3 grid((B + BM - 1) / BM, n_slices, 1), block(kThreads, 1, 1);
   if (metric == kCosine) gemm_filter_kernel<kCosine><<<grid, block, kFilterSmem, stream>>>(tm_x, tm_q, p);
   else if (metric == kL2) gemm_filter_kernel<kL2><<<grid, block, kFilterSmem, stream>>>(tm_x, tm_q, p);
@@ -527,7 +559,7 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const SegDesc& seg, int
 
 cudaError_t launch_refine_topk(const SegDesc* segs, int n_seg, const float* q, int B, int dim, int dpad, int elem_bytes,
                                int lpr_log2, int nch, int k, int metric, const unsigned long long* cand,
-                               const unsigned int* cand_count, int cap, int* overflow, uint64_t* keys_out,
+                               const unsigned int* cand_count, int cap, int s_total, int* overflow, uint64_t* keys_out,
                                float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream) {
   RefineParams p;
   memset(&p, 0, sizeof(p));
@@ -546,6 +578,7 @@ cudaError_t launch_refine_topk(const SegDesc* segs, int n_seg, const float* q, i
   p.k = k;
   p.metric = metric;
   p.cap = cap;
+  p.s_total = s_total;
   p.keys_out = keys_out;
   p.scores_out = scores_out;
   p.gids_out = gids_out;

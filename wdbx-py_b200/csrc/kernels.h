@@ -103,10 +103,11 @@ cudaError_t launch_shadow_rows(const float* rows, long long n, int dpad, int ld1
 cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace, cudaStream_t stream);
 cudaError_t launch_gemm_filter(const void* xb, int ld_x, const SegDesc& seg, int seg_index, int dim, const void* workspace,
                                int B, int k, int metric, float eps_rel, int n_slices, unsigned long long* cand,
-                               unsigned int* cand_count, unsigned int* lower_glob, int cap, cudaStream_t stream);
+                               unsigned int* cand_count, unsigned int* lower_glob, int cap, int slice_base, int s_total,
+                               cudaStream_t stream);
 cudaError_t launch_refine_topk(const SegDesc* segs, int n_seg, const float* q, int B, int dim, int dpad, int elem_bytes,
                                int lpr_log2, int nch, int k, int metric, const unsigned long long* cand,
-                               const unsigned int* cand_count, int cap, int* overflow, uint64_t* keys_out,
+                               const unsigned int* cand_count, int cap, int s_total, int* overflow, uint64_t* keys_out,
                                float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream);
 
 // K3: merge G best-first lists per query.
