@@ -26,7 +26,7 @@ def timed(fn, iters, warm=3):
     return e0.elapsed_time(e1) / iters
 
 res = []
-def run(name, n, dim, dtype, metric, k, B, iters, gemm=48):
+def run(name, n, dim, dtype, metric, k, B, iters, gemm=16):
     os.environ["WDBX_B200_GEMM_MIN_BATCH"] = str(gemm)
     eng = wdbx_b200.Engine(0, dim, dtype, 1)
     fill(eng, n, dim, 1)
@@ -40,12 +40,14 @@ def run(name, n, dim, dtype, metric, k, B, iters, gemm=48):
     byts = n * dim * eb + (4 * n if metric == "cosine" else 0)
     r = {"config": name, "rows": n, "dim": dim, "dtype": dtype, "metric": metric, "k": k, "batch": B,
          "ms_per_call": ms, "qps": B / ms * 1e3}
-    if B < 48 or gemm == 0:
+    if B < gemm or gemm == 0 or k > 16:
         passes = (B + 7) // 8
         r.update(kernel="K1 scan_topk", hbm_gbs=byts * passes / ms / 1e6, frac_of_measured_peak=byts * passes / ms / 1e6 / PEAK)
     else:
         fl = 2.0 * n * dim * B
-        r.update(kernel="K2 gemm_topk (3xTF32)", useful_tflops=fl / ms / 1e9, issued_tf32_tflops=3 * fl / ms / 1e9, hbm_floor_ms=byts / PEAK / 1e6)
+        bf16_peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("bf16_tflops", 1661.0) if (ROOT / "MEASURED_PEAKS.json").exists() else 1590.0
+        r.update(kernel="K2b gemm_filter (bf16 tcgen05) + exact refine", useful_tflops=fl / ms / 1e9,
+                 frac_of_measured_bf16_peak=fl / ms / 1e9 / bf16_peak, hbm_floor_ms=byts / PEAK / 1e6)
     print(json.dumps(r), flush=True)
     res.append(r)
     eng.close()
@@ -68,6 +70,7 @@ db.close()
 run("C2 1M x 384 fp32 cosine B=1", 1_000_000, 384, "fp32", "cosine", 10, 1, 50)
 run("C3 10M x 768 fp32 cosine B=1", 10_000_000, 768, "fp32", "cosine", 10, 1, 20)
 run("C3 10M x 768 fp32 cosine B=8 (K1, 8 queries per pass)", 10_000_000, 768, "fp32", "cosine", 10, 8, 10)
+run("C3 10M x 768 fp32 cosine B=64", 10_000_000, 768, "fp32", "cosine", 10, 64, 5)
 run("C3 10M x 768 fp32 cosine B=1024", 10_000_000, 768, "fp32", "cosine", 10, 1024, 3)
 run("C4 shard 12.5M x 384 bf16 ip k=100 B=1", 12_500_000, 384, "bf16", "ip", 100, 1, 20)
 run("C5 5M x 1536 fp32 l2 B=4096", 5_000_000, 1536, "fp32", "l2", 10, 4096, 2)
