@@ -156,6 +156,16 @@ int wdbx_b200_search_host(wdbx_b200_engine* e, int segment, const float* q_host,
                           int metric, float* scores_host, int64_t* gids_host, uint64_t* keys_host,
                           int32_t* counts_host);
 
+/* Opt-in "strictly better than the reference" search: metadata PRE-filter and
+ * threshold push-down.  allow_bitmaps: [num_segments] host pointers (NULL entry = all rows of that
+ * segment allowed; NULL array = no filter) to bitmaps over the segment's rows, bit = 1 means the row's
+ * metadata matches; min_score: rows scoring below it are never kept (-INFINITY = none).  Returns the
+ * exact top-k AMONG THE ALLOWED ROWS, i.e. a full k where the reference's post-filter
+ * (vector_store.py:333-342, :414-463) returns a truncated list.  Merged over all segments, host buffers. */
+int wdbx_b200_search_filtered_host(wdbx_b200_engine* e, const float* q_host, int B, int k, int metric,
+                                   float min_score, const uint32_t* const* allow_bitmaps,
+                                   float* scores_host, int64_t* gids_host, int32_t* counts_host);
+
 /* k-way merge of G best-first key lists per query (keys_dev [G, B, k], e.g. the output of an
  * NCCL all-gather of every rank's wdbx_b200_search keys) into one best-first top-k per query.
  * Replaces: the cross-shard concat + sort + [:limit] of VectorStore.search

@@ -115,6 +115,33 @@ class FakeEngine:
         counts = (keys != 0).sum(-1).astype(np.int32)
         return (scores, gids, counts, keys) if want_keys else (scores, gids, counts)
 
+    def search_filtered_host(self, queries, k, metric="cosine", min_score=float("-inf"), allow=None):
+        Q = np.asarray(queries, np.float32).reshape(-1, self.dim)
+        keys = np.zeros((Q.shape[0], k), np.uint64)
+        X = np.concatenate(self.rows)
+        g = np.concatenate(self.gids)
+        dead = np.concatenate(self.dead).copy()
+        if allow is not None:
+            ok = []
+            for s in range(self.num_segments):
+                n = self.rows[s].shape[0]
+                if allow[s] is None:
+                    ok.append(np.ones(n, bool))
+                else:
+                    bits = np.unpackbits(np.asarray(allow[s], np.uint32).view(np.uint8), bitorder="little")[:n]
+                    ok.append(bits.astype(bool))
+            dead |= ~np.concatenate(ok)
+        for b in range(Q.shape[0]):
+            if X.shape[0] == 0:
+                continue
+            s_ = oracle.scores_fp32(X, Q[b], metric)
+            live = ~dead & ~(s_ < min_score)
+            kk = np.sort(pack_keys(s_, g)[live])[::-1][:k]
+            keys[b, : len(kk)] = kk
+        self.launches += 1
+        scores, gids = unpack_keys(keys)
+        return scores, gids, (keys != 0).sum(-1).astype(np.int32)
+
     def upload(self, queries):
         q = np.ascontiguousarray(queries, np.float32)
         return torch.from_numpy(q[None, :] if q.ndim == 1 else q)

@@ -147,3 +147,25 @@ def test_persistence_roundtrip_on_device(built_lib):
         assert st2.count() == 4998
         assert [st2.search(Q[b].tolist(), limit=20) for b in range(4)] == want   # bit-identical after reload
         st2.close()
+
+
+def test_opt_in_prefilter_on_device(built_lib):
+    rng = np.random.default_rng(12)
+    n, dim = 30000, 96
+    X = rng.standard_normal((n, dim), dtype=np.float32)
+    pre = make_store(dim, 3, GPU_PREFILTER=True)
+    ref = make_store(dim, 3)
+    meta = {f"r{i}": {"i": i, "tag": "a" if i % 97 == 0 else "b"} for i in range(n)}
+    for st in (pre, ref):
+        st.batch_store({f"r{i}": X[i] for i in range(n)}, meta)
+    match = np.array([i % 97 == 0 for i in range(n)])
+    for b in range(3):
+        q = rng.standard_normal(dim).astype(np.float32)
+        got = pre.search(q.tolist(), limit=10, filter_metadata={"tag": "a"})
+        rows, sc = oracle.topk_desc(oracle.scores_fp64(X, q, "cosine"), 10, dead=~match)
+        assert [g[0] for g in got] == [f"r{r}" for r in rows]          # full k among the matching rows
+        np.testing.assert_allclose([g[1] for g in got], sc, rtol=1e-5, atol=1e-6)
+        assert len(ref.search(q.tolist(), limit=10, filter_metadata={"tag": "a"})) < 10   # reference semantics truncate
+        hi = pre.search(q.tolist(), limit=10, threshold=float(sc[4]), filter_metadata={"tag": "a"})
+        assert [g[0] for g in hi] == [f"r{r}" for r in rows[:5]]       # threshold pushed into the kernel
+    pre.close(); ref.close()

@@ -183,3 +183,29 @@ def test_persistence_roundtrip():
     st3 = mk()
     assert st3.count() == 119 and st3.search(X[5].tolist(), limit=3) == st2.search(X[5].tolist(), limit=3)
     st2.close(); st3.close()
+
+
+def test_opt_in_prefilter_returns_full_k_among_matches():
+    rng = np.random.default_rng(12)
+    X = rng.standard_normal((400, 8), dtype=np.float32)
+    meta = {f"r{i}": {"i": i, "tag": "a" if i % 7 == 0 else "b"} for i in range(400)}
+    ref = make_store(8, 3)                       # reference post-filter semantics
+    pre = make_store(8, 3, GPU_PREFILTER=True)   # opt-in device-side pre-filter
+    for st in (ref, pre):
+        st.batch_store({f"r{i}": X[i] for i in range(400)}, meta)
+    q = rng.standard_normal(8).astype(np.float32).tolist()
+    flt = {"tag": "a", "i": {"$gte": 100}}
+    got = pre.search(q, limit=5, filter_metadata=flt)
+    from oracle import exact_search as oracle
+    match = np.array([i % 7 == 0 and i >= 100 for i in range(400)])
+    rows, sc = oracle.topk_desc(oracle.scores_fp32(X, np.asarray(q, np.float32), "cosine"), 5, dead=~match)
+    assert [g[0] for g in got] == [f"r{r}" for r in rows] and len(got) == 5
+    assert all(m["tag"] == "a" and m["i"] >= 100 for _, _, m in got)
+    assert len(ref.search(q, limit=5, filter_metadata=flt)) <= len(got)   # the post-filter truncates
+    # threshold push-down and cache invalidation on mutation
+    hi = pre.search(q, limit=50, threshold=0.3, filter_metadata=flt)
+    assert all(s >= 0.3 for _, s, _ in hi)
+    pre.delete(got[0][0])
+    assert got[0][0] not in [g[0] for g in pre.search(q, limit=5, filter_metadata=flt)]
+    pre.update_metadata(got[1][0], {"i": 0, "tag": "b"})
+    assert got[1][0] not in [g[0] for g in pre.search(q, limit=5, filter_metadata=flt)]

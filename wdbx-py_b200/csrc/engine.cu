@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -48,6 +49,8 @@ struct Segment {
   float* sqnorm = nullptr;
   uint32_t* gids = nullptr;
   uint32_t* tomb = nullptr;  // device bitmap, allocated on first tombstone
+  uint32_t* allow = nullptr; // device copy of a per-search "allowed rows" bitmap (metadata pre-filter)
+  size_t allow_words = 0;
   void* shadow = nullptr;    // bf16 copy of the fp32 rows for the tensor-core filter (K2b), built lazily
   int64_t shadow_rows = 0, shadow_cap = 0;
   std::vector<uint32_t> tomb_host;
@@ -136,6 +139,7 @@ size_t row_bytes(const wdbx_b200_engine* e) { return static_cast<size_t>(e->dpad
 int64_t round_cap(int64_t rows) { return (rows + 127) / 128 * 128; }
 
 void free_segment(Segment& s) {
+  cudaFree(s.allow);
   cudaFree(s.shadow);
   cudaFree(s.rows);
   cudaFree(s.inv_norm);
@@ -243,7 +247,8 @@ int get_workspace(wdbx_b200_engine* e, cudaStream_t stream, size_t cand_keys, in
 // Launch one K1 scan over segments [s0, s1).  Caller holds e->mu and has set the device.
 int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B, int k, int metric,
                   uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream,
-                  bool exchange = false, const int* only_flag = nullptr) {
+                  bool exchange = false, const int* only_flag = nullptr, float min_score = -INFINITY,
+                  bool use_allow = false) {
   ScanPlan plan;
   const int rc = scan_plan(e->dim, e->dpad, e->elem_bytes, k, B, e->sm_count, e->tune, &plan);
   if (rc == -4) return fail(WDBX_B200_ERR_LIMIT, "dimension %d too large for the scan kernel's shared-memory stage", e->dim);
@@ -259,6 +264,7 @@ int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B
     p.seg[n].sqnorm = sg.sqnorm;
     p.seg[n].gids = sg.gids;
     p.seg[n].tomb = sg.n_dead > 0 ? sg.tomb : nullptr;
+    p.seg[n].allow = use_allow ? sg.allow : nullptr;
     p.seg[n].n_rows = sg.n_rows;
     tiles += (sg.n_rows + plan.tile_rows - 1) / plan.tile_rows;
     bytes += sg.n_rows * static_cast<long long>(row_bytes(e));
@@ -296,6 +302,7 @@ int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B
   p.gids_out = gids_out;
   p.counts_out = counts_out;
   p.only_flag = only_flag;
+  p.min_score = min_score;
   if (exchange) {
     if (e->xworld < 2) return fail(WDBX_B200_ERR_ARG, "exchange not attached (call wdbx_b200_exchange_init/attach first)");
     if (B > plan.queries_per_block || B > kXchgMaxB || k > kXchgMaxK)
@@ -340,6 +347,7 @@ int gemm_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B
     d.sqnorm = sg.sqnorm;
     d.gids = sg.gids;
     d.tomb = sg.n_dead > 0 ? sg.tomb : nullptr;
+    d.allow = nullptr;
     d.n_rows = sg.n_rows;
     CU_TRY(launch_gemm_topk(d, e->dim, e->dpad, w->qsplit, B, k, metric, slices[s], base, w->cand, stream));
     e->launches.fetch_add(1, std::memory_order_relaxed);
@@ -872,6 +880,74 @@ int wdbx_b200_search_host(wdbx_b200_engine* e, int segment, const float* q_host,
   if (gids_host) memcpy(gids_host, e->hres_pinned + off_gids, nres * 8);
   if (scores_host) memcpy(scores_host, e->hres_pinned + off_scores, nres * 4);
   if (counts_host) memcpy(counts_host, e->hres_pinned + off_counts, static_cast<size_t>(lists) * B * 4);
+  e->searches.fetch_add(1, std::memory_order_relaxed);
+  return WDBX_B200_OK;
+}
+
+int wdbx_b200_search_filtered_host(wdbx_b200_engine* e, const float* q_host, int B, int k, int metric, float min_score,
+                                   const uint32_t* const* allow_bitmaps, float* scores_host, int64_t* gids_host,
+                                   int32_t* counts_host) {
+  int rc = check_search_args(e, B, k, metric);
+  if (rc != WDBX_B200_OK) return rc;
+  if (!q_host) return fail(WDBX_B200_ERR_ARG, "q_host is NULL");
+  DeviceGuard guard(e->device);
+  std::lock_guard<std::mutex> hlk(e->host_mu);
+  const size_t nq = static_cast<size_t>(B) * e->dim;
+  const size_t nres = static_cast<size_t>(B) * k;
+  const size_t off_gids = nres * 8, off_scores = nres * 16, off_counts = nres * 20;
+  const size_t bytes = off_counts + static_cast<size_t>(B) * 4;
+  if (e->q_floats < nq) {
+    cudaFreeHost(e->hq_pinned); e->hq_pinned = nullptr;
+    cudaFree(e->dq); e->dq = nullptr;
+    e->q_floats = 0;
+    CU_TRY(cudaMallocHost(&e->hq_pinned, nq * 4));
+    CU_TRY(cudaMalloc(&e->dq, nq * 4));
+    e->q_floats = nq;
+  }
+  if (e->res_bytes < bytes) {
+    cudaFreeHost(e->hres_pinned); e->hres_pinned = nullptr;
+    cudaFree(e->dres); e->dres = nullptr;
+    e->res_bytes = 0;
+    CU_TRY(cudaMallocHost(&e->hres_pinned, bytes));
+    CU_TRY(cudaMalloc(&e->dres, bytes));
+    e->res_bytes = bytes;
+  }
+  memcpy(e->hq_pinned, q_host, nq * 4);
+  cudaStream_t st = e->hstream;
+  CU_TRY(cudaMemcpyAsync(e->dq, e->hq_pinned, nq * 4, cudaMemcpyHostToDevice, st));
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    bool use_allow = false;
+    if (allow_bitmaps) {
+      use_allow = true;
+      for (int s = 0; s < e->nseg; ++s) {
+        Segment& sg = e->seg[s];
+        const size_t words = static_cast<size_t>((sg.n_rows + 31) / 32);
+        if (words == 0) continue;
+        if (sg.allow_words < words) {
+          CU_TRY(cudaStreamSynchronize(st));
+          cudaFree(sg.allow);
+          sg.allow = nullptr;
+          sg.allow_words = 0;
+          const size_t cap_words = static_cast<size_t>(sg.cap_rows / 32 + 1);
+          CU_TRY(cudaMalloc(&sg.allow, cap_words * 4));
+          sg.allow_words = cap_words;
+        }
+        if (allow_bitmaps[s]) CU_TRY(cudaMemcpyAsync(sg.allow, allow_bitmaps[s], words * 4, cudaMemcpyHostToDevice, st));
+        else CU_TRY(cudaMemsetAsync(sg.allow, 0xFF, words * 4, st));  // NULL entry = every row allowed
+      }
+    }
+    // filtered searches always take the streaming kernel (the bitmap is only consulted for candidates)
+    rc = scan_segments(e, 0, e->nseg, e->dq, B, k, metric, nullptr, reinterpret_cast<float*>(e->dres + off_scores),
+                       reinterpret_cast<long long*>(e->dres + off_gids), reinterpret_cast<int*>(e->dres + off_counts), st,
+                       false, nullptr, min_score, use_allow);
+    if (rc != WDBX_B200_OK) return rc;
+  }
+  CU_TRY(cudaMemcpyAsync(e->hres_pinned, e->dres, bytes, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  if (gids_host) memcpy(gids_host, e->hres_pinned + off_gids, nres * 8);
+  if (scores_host) memcpy(scores_host, e->hres_pinned + off_scores, nres * 4);
+  if (counts_host) memcpy(counts_host, e->hres_pinned + off_counts, static_cast<size_t>(B) * 4);
   e->searches.fetch_add(1, std::memory_order_relaxed);
   return WDBX_B200_OK;
 }

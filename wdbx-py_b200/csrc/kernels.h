@@ -24,6 +24,7 @@ struct SegDesc {
   const float* sqnorm;        // [n_rows] |x|^2 (GEMM path, l2)
   const uint32_t* gids;       // [n_rows] global insertion ids
   const uint32_t* tomb;       // bitmap, 1 = dead; may be NULL when the segment has no tombstones
+  const uint32_t* allow;      // optional per-search bitmap, 1 = row may be returned (metadata pre-filter)
   long long n_rows;
 };
 
@@ -66,6 +67,7 @@ struct ScanParams {
   int xchg_rank;
   int xchg_slot;                   // seq & 1
   unsigned int xchg_seq;           // collective sequence number (same on all ranks)
+  float min_score;         // score floor (threshold push-down); -inf = none
   const int* only_flag;    // optional [B]: a query block runs only if one of its queries is flagged
                            // (K2b re-runs queries whose candidate list overflowed); NULL = run all
   uint64_t* keys_out;      // [B][k] or NULL

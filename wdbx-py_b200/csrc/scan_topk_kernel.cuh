@@ -187,7 +187,9 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
   const bool leader = (lig & ((lpr >> VLOG) - 1)) == 0;
   const int my_r = my_u * G + g;  // row (inside the tile) of the value this lane ends up with
   const float my_qinv = qinv_s[my_b];
-  float my_thr_f = __int_as_float(0xff800000);  // k-th score of list my_b; -inf while the list is not full
+  // k-th score of list my_b; while the list is not full: the caller's score floor (threshold
+  // push-down, -inf by default)
+  float my_thr_f = p.min_score;
   uint64_t* my_lists = lists + static_cast<size_t>(warp) * QB * k;
 
   const long long gw = static_cast<long long>(blockIdx.x) * nwarps + warp;
@@ -341,12 +343,14 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
       const long long row = T.row0 + __shfl_sync(FULL_MASK, my_r, src_lane);
       const uint32_t* tomb = p.seg[T.seg].tomb;
       if (tomb != nullptr && ((__ldg(tomb + (row >> 5)) >> (row & 31)) & 1u)) continue;
+      const uint32_t* allow = p.seg[T.seg].allow;  // opt-in metadata pre-filter: 1 = row may be returned
+      if (allow != nullptr && !((__ldg(allow + (row >> 5)) >> (row & 31)) & 1u)) continue;
       const uint32_t gid = __ldg(p.seg[T.seg].gids + row);
       const uint64_t key = pack_key(sv, gid);
       uint64_t* list = my_lists + sb_ * k;
       if (key > list[k - 1]) {
         const uint64_t nthr = list_insert(list, k, key, lane);
-        if (my_b == sb_) my_thr_f = nthr ? key_score(nthr) : __int_as_float(0xff800000);
+        if (my_b == sb_) my_thr_f = nthr ? fmaxf(key_score(nthr), p.min_score) : p.min_score;
       }
     }
 

@@ -50,6 +50,7 @@ SIGNATURES = {
     "wdbx_b200_read_rows": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P]),
     "wdbx_b200_search": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "wdbx_b200_search_host": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "wdbx_b200_search_filtered_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P]),
     "wdbx_b200_merge": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "wdbx_b200_exchange_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "wdbx_b200_exchange_attach": (C.c_int, [_P, C.c_int, _P]),

@@ -18,6 +18,7 @@ DEFAULTS: Dict[str, Any] = {
     "GPU_METRIC": "cosine",     # cosine | ip | l2
     "GPU_CAPACITY_ROWS": 0,     # rows to reserve per shard up front
     "GPU_STRICT": False,        # raise instead of "log + []" on engine errors
+    "GPU_PREFILTER": False,     # opt-in: filter_metadata becomes a device-side PRE-filter (full k among matches)
     "GPU_FUSED_EXCHANGE": True,  # multi-GPU: fuse the cross-GPU merge into the scan kernel (NVLink P2P)
     "GPU_BATCH_WINDOW_US": 200,  # micro-batching window of vector_search_async
     "GPU_BATCH_MAX": 8,          # queries coalesced into one launch by the async front-end

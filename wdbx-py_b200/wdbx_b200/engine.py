@@ -178,6 +178,38 @@ class Engine:
                                               _np_ptr(counts)))
         return (scores, gids, counts, keys) if want_keys else (scores, gids, counts)
 
+    def search_filtered_host(self, queries, k: int, metric="cosine", min_score: float = float("-inf"), allow=None):
+        """Opt-in pre-filtered search: ``allow`` is a list (one entry per segment) of uint32 bitmaps over the
+        segment's rows (bit 1 = row may be returned; None = all rows), ``min_score`` a score floor.
+        Returns (scores, gids, counts) of the exact top-k among the allowed rows, merged over segments."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"Vector dimension mismatch: expected {self.dim}, got {q.shape[-1]}")
+        B = q.shape[0]
+        scores = np.empty((B, k), dtype=np.float32)
+        gids = np.empty((B, k), dtype=np.int64)
+        counts = np.empty((B,), dtype=np.int32)
+        ptrs = None
+        keep = []
+        if allow is not None:
+            if len(allow) != self.num_segments:
+                raise ValueError("allow must have one entry per segment")
+            arr = (C.c_void_p * self.num_segments)()
+            for s, bm in enumerate(allow):
+                if bm is None:
+                    arr[s] = None
+                else:
+                    b = np.ascontiguousarray(bm, dtype=np.uint32)
+                    keep.append(b)
+                    arr[s] = b.ctypes.data
+            ptrs = C.cast(arr, C.c_void_p)
+        check(self._lib.wdbx_b200_search_filtered_host(self._handle(), _np_ptr(q), B, k, _metric_code(metric),
+                                                       C.c_float(min_score), ptrs, _np_ptr(scores), _np_ptr(gids),
+                                                       _np_ptr(counts)))
+        return scores, gids, counts
+
     def search(self, q_dev, k: int, metric="cosine", segment: int = ALL_SEGMENTS, out: Optional[Dict] = None,
                stream=None) -> Dict:
         """Device-resident search: q_dev is a CUDA fp32 tensor [B, dim]; outputs are CUDA tensors

@@ -137,6 +137,9 @@ class VectorStore:
             raise ValueError(f"unknown GPU_METRIC {self.metric!r}")
         self.dtype = str(self.config.get("GPU_DTYPE", "fp32")).lower()
         self.strict = bool(self.config.get("GPU_STRICT", False))
+        self.prefilter = bool(self.config.get("GPU_PREFILTER", False))   # opt-in: changes filtered results
+        self._allow_cache: Dict[str, Any] = {}
+        self._version = 0                                                # bumped by every mutation
 
         self.dist = dist if dist is not None else DistContext.from_env(self.config.get("GPU_DEVICE", None))
         self.shard_map = ShardMap(self.num_shards, self.dist.world)
@@ -323,6 +326,7 @@ class VectorStore:
             self._bulk_dead = set(state["bulk_dead"])
             self._shard_count = list(state["shard_count"])
             self._shard_live = live
+            self._version += 1
             meta = self.data_dir / "metadata" / "metadata.json"
             if meta.exists():
                 self.metadata = json.loads(meta.read_text())
@@ -440,6 +444,7 @@ class VectorStore:
             else:
                 self._bulk_dead.add(gid)
             self._shard_live[s] -= 1
+            self._version += 1
             return True
 
     def _clear_shard(self, shard: int) -> bool:
@@ -450,6 +455,7 @@ class VectorStore:
                 self._gid_to_id[gid] = None
                 self.metadata.pop(vid, None)
             self._row_gids[shard] = []
+            self._version += 1
             self._shard_count[shard] = 0
             self._shard_live[shard] = 0
         return True
@@ -464,6 +470,7 @@ class VectorStore:
                 ok = self.indices[loc[0] if loc else shard].add(vector_id, vec)
                 if ok:
                     self.metadata[vector_id] = metadata or {}
+                    self._version += 1
             if ok and self.config.get("VECTOR_STORE_SAVE_IMMEDIATELY", False):
                 self._save_metadata()
             return bool(ok)
@@ -493,6 +500,7 @@ class VectorStore:
                     stored += len(vecs)
                     for vid in vecs:
                         self.metadata[vid] = metadata.get(vid, {})
+                    self._version += 1
         if self.config.get("VECTOR_STORE_SAVE_IMMEDIATELY", False):
             self._save_metadata()
         return stored
@@ -545,6 +553,7 @@ class VectorStore:
             self._bulk.append((g0, g0 + n, id_prefix))
             self._bulk_starts.append(g0)
             self._bulk_rows[g0] = tuple(base)
+            self._version += 1
         return n
 
     def delete(self, vector_id: str) -> bool:
@@ -567,6 +576,7 @@ class VectorStore:
             if self._locate(vector_id) is None:
                 return False
             self.metadata[vector_id] = metadata
+            self._version += 1
         if self.config.get("VECTOR_STORE_SAVE_IMMEDIATELY", False):
             self._save_metadata()
         return True
@@ -607,6 +617,7 @@ class VectorStore:
             self._shard_count = [0] * self.num_shards
             self._shard_live = [0] * self.num_shards
             self._row_gids = [[] for _ in range(self.num_shards)]
+            self._version += 1
         self._save_metadata()
         return count
 
@@ -697,6 +708,10 @@ class VectorStore:
                filter_metadata: Optional[Dict[str, Any]] = None) -> List[Tuple[str, float, Dict[str, Any]]]:
         """Reference: vector_store.py:301-353 (same result list, same filter / threshold order)."""
         query_np = np.array(query_vector, dtype=np.float32)
+        if filter_metadata and self.prefilter and self.dist.world == 1:
+            # opt-in (GPU_PREFILTER): exact top-`limit` AMONG the matching rows + threshold push-down
+            lists = self._guard([], self._search_prefiltered, query_np, limit, threshold, filter_metadata)
+            return [(vid, score, self.metadata.get(vid, {})) for vid, score in (lists[0] if lists else [])]
         sel = EACH if filter_metadata else ALL
         lists = self._guard([], self._search_lists, query_np, limit, sel)
         all_results: List[Tuple[str, float]] = []
@@ -710,6 +725,42 @@ class VectorStore:
             all_results = [r for r in all_results if self._matches_filter(r[0], filter_metadata)]
         all_results = all_results[:limit]
         return [(vid, score, self.metadata.get(vid, {})) for vid, score in all_results]
+
+    # ------------------------------------------------------------------ opt-in device-side pre-filter
+    def _allow_bitmaps(self, filter_metadata: Dict[str, Any]):
+        """Per-shard uint32 bitmaps over the rows of this rank's partitions: bit = metadata matches.
+        Cached per (filter, store version); evaluating the Mongo-style filter is host work over the
+        reference's own metadata dict (vector_store.py:414-463), the scan then only consults the
+        bitmap for rows that already beat the running top-k threshold."""
+        key = json.dumps(filter_metadata, sort_keys=True, default=str)
+        cached = self._allow_cache.get(key)
+        if cached is not None and cached[0] == self._version:
+            return cached[1]
+        maps = []
+        for s in range(self.num_shards):
+            order = np.concatenate(self._row_gids[s]) if self._row_gids[s] else np.empty(0, np.uint32)
+            ok = np.fromiter((self._matches_filter(self._id_of(int(g)), filter_metadata) for g in order),
+                             dtype=bool, count=order.shape[0])
+            pad = (-ok.shape[0]) % 32
+            bits = np.packbits(np.concatenate([ok, np.zeros(pad, bool)]), bitorder="little")
+            maps.append(bits.view(np.uint32) if bits.size else np.zeros(0, np.uint32))
+        if len(self._allow_cache) > 16:
+            self._allow_cache.clear()
+        self._allow_cache[key] = (self._version, maps)
+        return maps
+
+    def _search_prefiltered(self, q: np.ndarray, limit: int, threshold: float, filter_metadata: Dict[str, Any]):
+        if q.shape != (self.vector_dim,):
+            raise ValueError(f"Vector dimension mismatch: expected {self.vector_dim}, got {q.shape[-1]}")
+        k = min(int(limit), self.count(), _lib.MAX_K)
+        if k <= 0:
+            return [[]]
+        with self._lock:
+            maps = self._allow_bitmaps(filter_metadata)
+        floor = float(threshold) if threshold > 0 else float("-inf")
+        scores, gids, counts = self.engine.search_filtered_host(q[None, :], k, self.metric, floor, maps)
+        c = int(counts[0])
+        return [[(self._id_of(int(g)), float(s)) for g, s in zip(gids[0, :c], scores[0, :c])]]
 
     async def search_async(self, query_vector: List[float], limit: int = 10, threshold: float = 0.0,
                            filter_metadata: Optional[Dict[str, Any]] = None):
