@@ -166,6 +166,6 @@ def test_opt_in_prefilter_on_device(built_lib):
         assert [g[0] for g in got] == [f"r{r}" for r in rows]          # full k among the matching rows
         np.testing.assert_allclose([g[1] for g in got], sc, rtol=1e-5, atol=1e-6)
         assert len(ref.search(q.tolist(), limit=10, filter_metadata={"tag": "a"})) < 10   # reference semantics truncate
-        hi = pre.search(q.tolist(), limit=10, threshold=float(sc[4]), filter_metadata={"tag": "a"})
+        hi = pre.search(q.tolist(), limit=10, threshold=float(sc[4] + sc[5]) / 2, filter_metadata={"tag": "a"})
         assert [g[0] for g in hi] == [f"r{r}" for r in rows[:5]]       # threshold pushed into the kernel
     pre.close(); ref.close()

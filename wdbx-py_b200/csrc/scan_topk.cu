@@ -47,7 +47,7 @@ int scan_plan(int dim, int dpad, int elem_bytes, int k, int B, int sm_count, con
     };
     auto stage_bytes_for = [&](int u) { return static_cast<size_t>(u) * G * row_bytes; };
     auto total = [&](int w, int st, int u) {
-      return fixed(w, st) + std::max(stage_bytes_for(u) * w * st, static_cast<size_t>(w) * k * 8);
+      return fixed(w, st) + std::max(stage_bytes_for(u) * w * st, static_cast<size_t>(w) * std::max(k, 32) * 8);
     };
     int u = U;
     while (stages > 2 && total(warps, stages, u) > budget) --stages;

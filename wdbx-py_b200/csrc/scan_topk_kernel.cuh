@@ -105,6 +105,34 @@ __device__ __forceinline__ void emit_list(const uint64_t* list, int k, int lane,
   if (count_out && lane == 0) *count_out = cnt;
 }
 
+// ---- k <= 32: a list is one key per lane (descending, 0 = empty), merged in registers.
+// c[i] = max(a[i], b[31-i]) holds the 32 largest keys of the union and is bitonic; five
+// compare-exchange stages sort it descending.
+__device__ __forceinline__ uint64_t warp_merge32(uint64_t a, uint64_t b, int lane) {
+  const uint64_t br = __shfl_sync(FULL_MASK, b, 31 - lane);
+  uint64_t c = a > br ? a : br;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    const uint64_t o = __shfl_xor_sync(FULL_MASK, c, s);
+    const bool keep_max = (lane & s) == 0;
+    c = keep_max ? (c > o ? c : o) : (c < o ? c : o);
+  }
+  return c;
+}
+
+// Binary tree over the warps of the CTA through shared memory ([nwarps][32] keys); every thread of
+// the CTA must call it; the result is valid in warp 0.
+__device__ __forceinline__ uint64_t block_tree_merge32(uint64_t mine, uint64_t* scratch, int warp, int lane, int nwarps) {
+  for (int stride = 1; stride < nwarps; stride <<= 1) {
+    scratch[warp * 32 + lane] = mine;
+    __syncthreads();
+    if ((warp & (2 * stride - 1)) == 0 && warp + stride < nwarps)
+      mine = warp_merge32(mine, scratch[(warp + stride) * 32 + lane], lane);
+    __syncthreads();
+  }
+  return mine;
+}
+
 struct TileLoc {
   int seg;
   long long row0;
@@ -154,24 +182,13 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
   off += align128(static_cast<size_t>(nwarps) * QB * k * 8);
   unsigned char* stage_area = smem + off;  // nwarps * stages * stage_bytes, reused as merge scratch
 
-  for (int i = tid; i < QB * dpad; i += blockDim.x) {
-    const int b = i / dpad, c = i - b * dpad;
-    q_s[i] = (b < nq && c < p.dim) ? __ldg(p.q + static_cast<size_t>(qbase + b) * p.dim + c) : 0.0f;
-  }
-  for (int i = tid; i < nwarps * QB * k; i += blockDim.x) lists[i] = 0ull;
+  // every warp arms its own barriers and starts its TMA pipeline right away; the query staging
+  // below overlaps the first bulk copies
   if (lane == 0) {
     for (int s = 0; s < p.stages; ++s) mbar_init(smem_u32(mbar + warp * p.stages + s), 1);
   }
   fence_mbar_init();
-  __syncthreads();
-  for (int b = warp; b < QB; b += nwarps) {
-    float ss = 0.0f;
-    for (int i = lane; i < dpad; i += 32) ss = fmaf(q_s[b * dpad + i], q_s[b * dpad + i], ss);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, o);
-    if (lane == 0) qinv_s[b] = ss > 0.0f ? 1.0f / sqrtf(ss) : 0.0f;
-  }
-  __syncthreads();
+  __syncwarp();
   const bool cosine = (p.metric == kCosine);
 
   // ---- lane geometry.  lanes-per-row lpr >= V (scan_plan guarantees it): after the reduction every
@@ -186,7 +203,6 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
   const int my_b = my_v / U, my_u = my_v % U;
   const bool leader = (lig & ((lpr >> VLOG) - 1)) == 0;
   const int my_r = my_u * G + g;  // row (inside the tile) of the value this lane ends up with
-  const float my_qinv = qinv_s[my_b];
   // k-th score of list my_b; while the list is not full: the caller's score floor (threshold
   // push-down, -inf by default)
   float my_thr_f = p.min_score;
@@ -216,6 +232,23 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
   };
   for (int s = 0; s < p.stages; ++s)
     if (t_issue < total) issue(s);
+
+  // ---- stage the queries (zero padded), clear the running lists, 1/|q|
+  for (int i = tid; i < QB * dpad; i += blockDim.x) {
+    const int b = i / dpad, c = i - b * dpad;
+    q_s[i] = (b < nq && c < p.dim) ? __ldg(p.q + static_cast<size_t>(qbase + b) * p.dim + c) : 0.0f;
+  }
+  for (int i = tid; i < nwarps * QB * k; i += blockDim.x) lists[i] = 0ull;
+  __syncthreads();
+  for (int b = warp; b < QB; b += nwarps) {
+    float ss = 0.0f;
+    for (int i = lane; i < dpad; i += 32) ss = fmaf(q_s[b * dpad + i], q_s[b * dpad + i], ss);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, o);
+    if (lane == 0) qinv_s[b] = ss > 0.0f ? 1.0f / sqrtf(ss) : 0.0f;
+  }
+  __syncthreads();
+  const float my_qinv = qinv_s[my_b];
 
   // compute-side cursor runs one tile ahead so the inv-norm load of tile i+1 is in flight while
   // tile i is processed
@@ -362,17 +395,26 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
     }
   }
 
-  // ---- CTA merge: warp b folds the nwarps lists of query b and publishes k keys
+  // ---- CTA merge: fold the nwarps lists of every query and publish k keys per query
   __syncthreads();
-  uint64_t* scratch = reinterpret_cast<uint64_t*>(stage_area);  // [nwarps][k] (stage buffers are idle now)
-  for (int b = warp; b < nq; b += nwarps) {
-    uint64_t* dst = scratch + static_cast<size_t>(warp) * k;
-    list_clear(dst, k, lane);
-    uint64_t thr = 0ull;
-    for (int w = 0; w < nwarps; ++w)
-      absorb_keys<false>(dst, k, thr, lists + (static_cast<size_t>(w) * QB + b) * k, k, 0, 1, lane);
-    uint64_t* out = p.cand + (static_cast<size_t>(qbase + b) * gridDim.x + blockIdx.x) * k;
-    for (int i = lane; i < k; i += 32) out[i] = dst[i];
+  uint64_t* scratch = reinterpret_cast<uint64_t*>(stage_area);  // [nwarps][max(k,32)] (stage buffers are idle now)
+  const bool small_k = k <= 32;  // lists fit one key per lane: register bitonic merges + a warp tree
+  if (small_k) {
+    for (int b = 0; b < nq; ++b) {
+      uint64_t mine = lane < k ? my_lists[b * k + lane] : 0ull;
+      mine = block_tree_merge32(mine, scratch, warp, lane, nwarps);
+      if (warp == 0 && lane < k) p.cand[(static_cast<size_t>(qbase + b) * gridDim.x + blockIdx.x) * k + lane] = mine;
+    }
+  } else {
+    for (int b = warp; b < nq; b += nwarps) {
+      uint64_t* dst = scratch + static_cast<size_t>(warp) * k;
+      list_clear(dst, k, lane);
+      uint64_t thr = 0ull;
+      for (int w = 0; w < nwarps; ++w)
+        absorb_keys<false>(dst, k, thr, lists + (static_cast<size_t>(w) * QB + b) * k, k, 0, 1, lane);
+      uint64_t* out = p.cand + (static_cast<size_t>(qbase + b) * gridDim.x + blockIdx.x) * k;
+      for (int i = lane; i < k; i += 32) out[i] = dst[i];
+    }
   }
 
   // ---- last CTA to finish merges all CTA lists of these queries
@@ -388,7 +430,23 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
   uint64_t* final_list = lists;  // the running lists are dead: reuse the first k slots
   for (int b = 0; b < nq; ++b) {
     const uint64_t* cand_q = p.cand + static_cast<size_t>(qbase + b) * gridDim.x * k;
-    {
+    if (small_k) {
+      uint64_t acc = 0ull;
+      for (int c0 = warp; c0 < static_cast<int>(gridDim.x); c0 += 4 * nwarps) {
+        uint64_t v[4];  // four CTA lists in flight per warp
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c0 + j * nwarps;
+          v[j] = (c < static_cast<int>(gridDim.x) && lane < k)
+                     ? __ldcg(reinterpret_cast<const unsigned long long*>(cand_q + static_cast<size_t>(c) * k + lane))
+                     : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc = warp_merge32(acc, v[j], lane);
+      }
+      acc = block_tree_merge32(acc, scratch, warp, lane, nwarps);
+      if (warp == 0 && lane < k) final_list[lane] = acc;
+    } else {
       uint64_t* dst = scratch + static_cast<size_t>(warp) * k;
       list_clear(dst, k, lane);
       uint64_t thr = 0ull;
@@ -397,9 +455,12 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
     __syncthreads();
     if (warp == 0) {
       const int qi = qbase + b;
-      list_clear(final_list, k, lane);
-      uint64_t thr = 0ull;
-      absorb_keys<false>(final_list, k, thr, scratch, nwarps * k, 0, 1, lane);
+      if (!small_k) {
+        list_clear(final_list, k, lane);
+        uint64_t thr = 0ull;
+        absorb_keys<false>(final_list, k, thr, scratch, nwarps * k, 0, 1, lane);
+      }
+      __syncwarp();
       if (p.xchg_world > 1) {
         // push this rank's list for query b into every rank's exchange buffer (NVLink P2P stores)
         for (int r = 0; r < p.xchg_world; ++r) {
@@ -445,7 +506,20 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
       const int qi = qbase + b;
       list_clear(final_list, k, lane);
       uint64_t thr = 0ull;
-      if (ok) {
+      if (ok && small_k) {
+        uint64_t v[kMaxPeers];  // all peers' lists in flight, then register merges
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r) {
+          const uint64_t* src = p.xchg_peer[p.xchg_rank] +
+                                ((static_cast<size_t>(p.xchg_slot) * kMaxPeers + r) * kXchgMaxB + b) * kXchgMaxK;
+          v[r] = (r < p.xchg_world && lane < k) ? __ldcg(reinterpret_cast<const unsigned long long*>(src + lane)) : 0ull;
+        }
+        uint64_t acc = 0ull;
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r) acc = warp_merge32(acc, v[r], lane);
+        if (lane < k) final_list[lane] = acc;
+        __syncwarp();
+      } else if (ok) {
         for (int r = 0; r < p.xchg_world; ++r) {
           const uint64_t* src = p.xchg_peer[p.xchg_rank] +
                                 ((static_cast<size_t>(p.xchg_slot) * kMaxPeers + r) * kXchgMaxB + b) * kXchgMaxK;
