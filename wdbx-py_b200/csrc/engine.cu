@@ -93,6 +93,7 @@ struct wdbx_b200_engine {
   ScanTuning tune{0, 0, 0, 0, -1, 0};
   int gemm_min_batch = 16;  // B >= this => tcgen05 path (0 = never); measured crossover vs K1 (8 queries/pass) ~ 12-16
   int gemm_mode = 0;        // 0 = bf16 filter + exact refine (K2b), 1 = 3xTF32 with fused top-k (K2)
+  int pdl = 1;              // programmatic dependent launch for K1 (WDBX_B200_PDL=0 disables)
   cudaStream_t mstream = nullptr;  // mutations
   // staging for host-sourced appends
   float* stage_rows = nullptr;
@@ -314,6 +315,9 @@ int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B
     p.xchg_seq = e->xseq;
     p.xchg_slot = static_cast<int>(e->xseq & 1u);
   }
+  // back-to-back searches: let the next scan start on SMs that have finished while the last CTA still
+  // merges (programmatic dependent launch); never for the flag-gated re-run, which must see its flags
+  plan.pdl = (e->pdl && only_flag == nullptr) ? 1 : 0;
   CU_TRY(launch_scan_topk(p, plan, e->dtype == WDBX_B200_BF16, stream));
   e->launches.fetch_add(1, std::memory_order_relaxed);
   return WDBX_B200_OK;
@@ -556,6 +560,7 @@ int wdbx_b200_create(int device, int dim, int dtype, int num_segments, wdbx_b200
   e->tune.queries_per_pass = env_int("WDBX_B200_QUERIES_PER_PASS", 0);
   e->gemm_min_batch = env_int("WDBX_B200_GEMM_MIN_BATCH", e->gemm_min_batch);
   e->gemm_mode = env_int("WDBX_B200_GEMM_MODE", 0);
+  e->pdl = env_int("WDBX_B200_PDL", 1);
   ScanPlan plan;
   if (scan_plan(dim, e->dpad, e->elem_bytes, 10, 1, e->sm_count, e->tune, &plan) != 0) {
     delete e;

@@ -80,6 +80,7 @@ struct ScanPlan {
   int lpr_log2, nch, U, KS, tile_rows, stage_bytes, stages, warps, grid;
   size_t smem_bytes;
   int queries_per_block;
+  int pdl;  // launch with programmatic dependent launch: the scan of query i+1 overlaps the merge tail of query i
 };
 
 // Fill the derived fields (plan) for the given shape.  Returns 0 or a negative wdbx error code.

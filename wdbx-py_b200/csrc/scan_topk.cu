@@ -69,6 +69,7 @@ int scan_plan(int dim, int dpad, int elem_bytes, int k, int B, int sm_count, con
     plan->grid = tune.grid > 0 ? tune.grid : sm_count;
     plan->smem_bytes = total(warps, stages, u);
     plan->queries_per_block = QB;
+    plan->pdl = 0;
     return 0;
   }
 }

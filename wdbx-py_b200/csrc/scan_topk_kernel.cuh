@@ -182,6 +182,8 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
   off += align128(static_cast<size_t>(nwarps) * QB * k * 8);
   unsigned char* stage_area = smem + off;  // nwarps * stages * stage_bytes, reused as merge scratch
 
+  // let the next search on this stream start as soon as SMs free up (no-op without the PDL attribute)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // every warp arms its own barriers and starts its TMA pipeline right away; the query staging
   // below overlaps the first bulk copies
   if (lane == 0) {
@@ -395,6 +397,11 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
     }
   }
 
+  // Programmatic dependent launch: everything above only READS the store and the queries, so it may
+  // overlap the merge tail of the previous search on this stream; from here on we touch the
+  // workspace / outputs / exchange buffers that the previous grid may still be using.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
   // ---- CTA merge: fold the nwarps lists of every query and publish k keys per query
   __syncthreads();
   uint64_t* scratch = reinterpret_cast<uint64_t*>(stage_area);  // [nwarps][max(k,32)] (stage buffers are idle now)
@@ -546,8 +553,21 @@ cudaError_t launch_one(const ScanParams& p, const ScanPlan& plan, cudaStream_t s
   });
   if (attr_err != cudaSuccess) return attr_err;
   dim3 grid(plan.grid, (p.B + QB - 1) / QB, 1), block(plan.warps * 32, 1, 1);
-  kern<<<grid, block, plan.smem_bytes, stream>>>(p);
-  return cudaGetLastError();
+  if (!plan.pdl) {
+    kern<<<grid, block, plan.smem_bytes, stream>>>(p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = plan.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 // One translation unit per QB instantiates its kernels through this dispatcher.
