@@ -120,17 +120,125 @@ __device__ __forceinline__ uint64_t warp_merge32(uint64_t a, uint64_t b, int lan
   return c;
 }
 
-// Binary tree over the warps of the CTA through shared memory ([nwarps][32] keys); every thread of
+// ---- k <= 32*S: a list is S keys per lane, element e = slot*32 + lane, sorted descending.
+// Same bitonic scheme on 32*S elements: combine with the reversed second list, compare-exchange
+// across slots (strides 32*S/2 .. 32), then across lanes (16 .. 1).
+template <int S>
+__device__ __forceinline__ void warp_merge(uint64_t (&a)[S], const uint64_t (&b)[S], int lane) {
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const uint64_t br = __shfl_sync(FULL_MASK, b[S - 1 - s], 31 - lane);
+    a[s] = a[s] > br ? a[s] : br;
+  }
+#pragma unroll
+  for (int st = S / 2; st >= 1; st >>= 1) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      if ((s & st) == 0) {
+        const uint64_t hi = a[s] > a[s + st] ? a[s] : a[s + st];
+        const uint64_t lo = a[s] > a[s + st] ? a[s + st] : a[s];
+        a[s] = hi;
+        a[s + st] = lo;
+      }
+    }
+  }
+#pragma unroll
+  for (int st = 16; st > 0; st >>= 1) {
+    const bool keep_max = (lane & st) == 0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const uint64_t o = __shfl_xor_sync(FULL_MASK, a[s], st);
+      a[s] = keep_max ? (a[s] > o ? a[s] : o) : (a[s] < o ? a[s] : o);
+    }
+  }
+}
+
+template <int S, bool GLOBAL>
+__device__ __forceinline__ void load_list(uint64_t (&r)[S], const uint64_t* src, int k, int lane, bool valid = true) {
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int e = s * 32 + lane;
+    if (!valid || e >= k) r[s] = 0ull;
+    else r[s] = GLOBAL ? __ldcg(reinterpret_cast<const unsigned long long*>(src + e)) : src[e];
+  }
+}
+
+template <int S>
+__device__ __forceinline__ void store_list(uint64_t* dst, const uint64_t (&r)[S], int k, int lane) {
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int e = s * 32 + lane;
+    if (e < k) dst[e] = r[s];
+  }
+}
+
+// Binary tree over the warps of the CTA through shared memory ([nwarps][32*S] keys); every thread of
 // the CTA must call it; the result is valid in warp 0.
-__device__ __forceinline__ uint64_t block_tree_merge32(uint64_t mine, uint64_t* scratch, int warp, int lane, int nwarps) {
+template <int S>
+__device__ __forceinline__ void block_tree_merge(uint64_t (&mine)[S], uint64_t* scratch, int warp, int lane, int nwarps) {
   for (int stride = 1; stride < nwarps; stride <<= 1) {
-    scratch[warp * 32 + lane] = mine;
+#pragma unroll
+    for (int s = 0; s < S; ++s) scratch[(warp * S + s) * 32 + lane] = mine[s];
     __syncthreads();
-    if ((warp & (2 * stride - 1)) == 0 && warp + stride < nwarps)
-      mine = warp_merge32(mine, scratch[(warp + stride) * 32 + lane], lane);
+    if ((warp & (2 * stride - 1)) == 0 && warp + stride < nwarps) {
+      uint64_t other[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) other[s] = scratch[((warp + stride) * S + s) * 32 + lane];
+      warp_merge<S>(mine, other, lane);
+    }
     __syncthreads();
   }
-  return mine;
+}
+
+// fast epilogue pieces (k <= 32*S), shared by the CTA merge, the last-CTA merge and the exchange merge
+template <int S>
+__device__ __forceinline__ void cta_merge_fast(const uint64_t* my_list_b, uint64_t* scratch, uint64_t* out_global, int k,
+                                               int warp, int lane, int nwarps) {
+  uint64_t mine[S];
+  load_list<S, false>(mine, my_list_b, k, lane);
+  block_tree_merge<S>(mine, scratch, warp, lane, nwarps);
+  if (warp == 0) store_list<S>(out_global, mine, k, lane);
+}
+
+template <int S>
+__device__ __forceinline__ void grid_merge_fast(const uint64_t* cand_q, int n_lists, uint64_t* scratch, uint64_t* final_list,
+                                                int k, int warp, int lane, int nwarps) {
+  uint64_t acc[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) acc[s] = 0ull;
+  constexpr int INFLIGHT = S == 1 ? 4 : 2;  // CTA lists in flight per warp
+  for (int c0 = warp; c0 < n_lists; c0 += INFLIGHT * nwarps) {
+    uint64_t v[INFLIGHT][S];
+#pragma unroll
+    for (int j = 0; j < INFLIGHT; ++j) {
+      const int c = c0 + j * nwarps;
+      load_list<S, true>(v[j], cand_q + static_cast<size_t>(c < n_lists ? c : 0) * k, k, lane, c < n_lists);
+    }
+#pragma unroll
+    for (int j = 0; j < INFLIGHT; ++j) warp_merge<S>(acc, v[j], lane);
+  }
+  block_tree_merge<S>(acc, scratch, warp, lane, nwarps);
+  if (warp == 0) store_list<S>(final_list, acc, k, lane);
+}
+
+template <int S>
+__device__ __forceinline__ void peers_merge_fast(const uint64_t* my_xbuf_slot_b, int world, uint64_t* final_list, int k,
+                                                 int lane) {
+  // my_xbuf_slot_b: list of peer r for this query at my_xbuf_slot_b + r * kXchgMaxB * kXchgMaxK
+  uint64_t acc[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) acc[s] = 0ull;
+  for (int r0 = 0; r0 < world; r0 += 2) {
+    uint64_t v[2][S];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      load_list<S, true>(v[j], my_xbuf_slot_b + static_cast<size_t>(r0 + j < world ? r0 + j : 0) * kXchgMaxB * kXchgMaxK, k,
+                         lane, r0 + j < world);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) warp_merge<S>(acc, v[j], lane);
+  }
+  store_list<S>(final_list, acc, k, lane);
+  __syncwarp();
 }
 
 struct TileLoc {
@@ -405,12 +513,12 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
   // ---- CTA merge: fold the nwarps lists of every query and publish k keys per query
   __syncthreads();
   uint64_t* scratch = reinterpret_cast<uint64_t*>(stage_area);  // [nwarps][max(k,32)] (stage buffers are idle now)
-  const bool small_k = k <= 32;  // lists fit one key per lane: register bitonic merges + a warp tree
+  const bool small_k = k <= 128;  // lists fit 1 or 4 keys per lane: register bitonic merges + a warp tree
   if (small_k) {
     for (int b = 0; b < nq; ++b) {
-      uint64_t mine = lane < k ? my_lists[b * k + lane] : 0ull;
-      mine = block_tree_merge32(mine, scratch, warp, lane, nwarps);
-      if (warp == 0 && lane < k) p.cand[(static_cast<size_t>(qbase + b) * gridDim.x + blockIdx.x) * k + lane] = mine;
+      uint64_t* out = p.cand + (static_cast<size_t>(qbase + b) * gridDim.x + blockIdx.x) * k;
+      if (k <= 32) cta_merge_fast<1>(my_lists + b * k, scratch, out, k, warp, lane, nwarps);
+      else cta_merge_fast<4>(my_lists + b * k, scratch, out, k, warp, lane, nwarps);
     }
   } else {
     for (int b = warp; b < nq; b += nwarps) {
@@ -438,21 +546,8 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
   for (int b = 0; b < nq; ++b) {
     const uint64_t* cand_q = p.cand + static_cast<size_t>(qbase + b) * gridDim.x * k;
     if (small_k) {
-      uint64_t acc = 0ull;
-      for (int c0 = warp; c0 < static_cast<int>(gridDim.x); c0 += 4 * nwarps) {
-        uint64_t v[4];  // four CTA lists in flight per warp
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = c0 + j * nwarps;
-          v[j] = (c < static_cast<int>(gridDim.x) && lane < k)
-                     ? __ldcg(reinterpret_cast<const unsigned long long*>(cand_q + static_cast<size_t>(c) * k + lane))
-                     : 0ull;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc = warp_merge32(acc, v[j], lane);
-      }
-      acc = block_tree_merge32(acc, scratch, warp, lane, nwarps);
-      if (warp == 0 && lane < k) final_list[lane] = acc;
+      if (k <= 32) grid_merge_fast<1>(cand_q, static_cast<int>(gridDim.x), scratch, final_list, k, warp, lane, nwarps);
+      else grid_merge_fast<4>(cand_q, static_cast<int>(gridDim.x), scratch, final_list, k, warp, lane, nwarps);
     } else {
       uint64_t* dst = scratch + static_cast<size_t>(warp) * k;
       list_clear(dst, k, lane);
@@ -514,18 +609,10 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
       list_clear(final_list, k, lane);
       uint64_t thr = 0ull;
       if (ok && small_k) {
-        uint64_t v[kMaxPeers];  // all peers' lists in flight, then register merges
-#pragma unroll
-        for (int r = 0; r < kMaxPeers; ++r) {
-          const uint64_t* src = p.xchg_peer[p.xchg_rank] +
-                                ((static_cast<size_t>(p.xchg_slot) * kMaxPeers + r) * kXchgMaxB + b) * kXchgMaxK;
-          v[r] = (r < p.xchg_world && lane < k) ? __ldcg(reinterpret_cast<const unsigned long long*>(src + lane)) : 0ull;
-        }
-        uint64_t acc = 0ull;
-#pragma unroll
-        for (int r = 0; r < kMaxPeers; ++r) acc = warp_merge32(acc, v[r], lane);
-        if (lane < k) final_list[lane] = acc;
-        __syncwarp();
+        const uint64_t* base = p.xchg_peer[p.xchg_rank] +
+                               (static_cast<size_t>(p.xchg_slot) * kMaxPeers * kXchgMaxB + b) * kXchgMaxK;
+        if (k <= 32) peers_merge_fast<1>(base, p.xchg_world, final_list, k, lane);
+        else peers_merge_fast<4>(base, p.xchg_world, final_list, k, lane);
       } else if (ok) {
         for (int r = 0; r < p.xchg_world; ++r) {
           const uint64_t* src = p.xchg_peer[p.xchg_rank] +
