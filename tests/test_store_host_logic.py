@@ -209,3 +209,29 @@ def test_opt_in_prefilter_returns_full_k_among_matches():
     assert got[0][0] not in [g[0] for g in pre.search(q, limit=5, filter_metadata=flt)]
     pre.update_metadata(got[1][0], {"i": 0, "tag": "b"})
     assert got[1][0] not in [g[0] for g in pre.search(q, limit=5, filter_metadata=flt)]
+
+
+def test_data_feeders_csv_jsonl(tmp_path):
+    from wdbx_b200 import data_utils as du
+
+    assert du.parse_vector("[1, 2.5, -3]") == [1.0, 2.5, -3.0]
+    assert du.parse_vector("1, 2,3") == [1.0, 2.0, 3.0] and du.parse_vector("1 2 3") == [1.0, 2.0, 3.0]
+    assert du.parse_vector("array([1., 2.])") == [1.0, 2.0] and du.parse_vector({"embedding": [1, 2]}) == [1.0, 2.0]
+    with pytest.raises(ValueError):
+        du.parse_vector("not a vector")
+    csv_path = tmp_path / "v.csv"
+    csv_path.write_text('id,vec,lang\na,"[1,0,0,0]",en\nb,"0 1 0 0",de\nbad,"oops",xx\nc,"0,0,1,0",en\n')
+    vecs, meta = du.load_vectors_from_csv(str(csv_path), "vec", id_column="id", metadata_columns=["lang"])
+    assert list(vecs) == ["a", "b", "c"] and meta["b"] == {"lang": "de"} and vecs["c"] == [0.0, 0.0, 1.0, 0.0]
+    vecs_i, meta_i = du.load_vectors_from_csv(str(csv_path), 1, id_column=0, metadata_columns=[2])
+    assert vecs_i == vecs and meta_i["a"] == {"col_2 ": "en"}
+    jl = tmp_path / "v.jsonl"
+    jl.write_text('{"id": "x", "emb": [0, 0, 0, 1], "t": 1}\n{"id": "y", "emb": "1 1 0 0", "t": 2}\n{"id": "z", "t": 3}\n')
+    vj, mj = du.load_vectors_from_jsonl(str(jl), "emb", id_field="id")
+    assert list(vj) == ["x", "y"] and mj["y"] == {"id": "y", "t": 2}
+    st = make_store(4, 2)
+    assert du.ingest_csv(st, str(csv_path), "vec", id_column="id", metadata_columns=["lang"]) == 3
+    assert du.ingest_jsonl(st, str(jl), "emb", id_field="id") == 2
+    assert st.count() == 5 and st.search([0, 0, 0, 1], limit=1)[0][0] == "x"
+    assert [r[0] for r in st.search([1, 0, 0, 0], limit=5, filter_metadata={"lang": "en"})] == ["a", "c"]
+    st.close()
