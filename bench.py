@@ -3,8 +3,11 @@
 
 Workload (BASELINE.json metric / configs[2], "C3"): 10M x 768 fp32 cosine, top-10, query batch 1,
 rows striped over the N GPUs of one box (strong scaling: the total matrix is fixed).
-A "step" is one query over the whole matrix: every rank scans its rows with kernel K1, the ranks
-all-gather their packed top-10 keys (NCCL) and merge them (K3).
+A "step" is one query over the whole matrix: every rank filters its rows with the bf16 tensor-core
+filter over the 2-byte shadow of its fp32 rows (K2b: half the HBM bytes of a scan of the stored rows,
+rigorous error bound), re-scores the few hundred surviving rows from the fp32 rows with the streaming
+kernel's exact arithmetic (refine: results bit-identical to the fp32 scan K1), and the ranks exchange
+their packed top-10 keys over NVLink peer memory and merge them on the device.
 
 One JSON line on rank 0 (see the keys in main()).  `value` is measured with queries resident in
 HBM, `e2e` through the public host API (VectorStore.search: host query in, (id, score, metadata)
@@ -47,13 +50,13 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def _traffic_from_profile():
-    """DRAM bytes per launch of the scan kernel from the committed ncu capture, if any."""
-    p = ROOT / "profiles" / "scan_topk_c3_ncu_summary.json"
+def _traffic_from_profile(kernel_id: int):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    name = "gemm_filter_b1_ncu_summary.json" if kernel_id == 2 else "scan_topk_c3_ncu_summary.json"
     try:
-        return float(json.loads(p.read_text()).get("dram_bytes_per_launch"))
+        return float(json.loads((ROOT / "profiles" / name).read_text()).get("dram_bytes_per_launch")), f"profiles/{name}"
     except Exception:
-        return None
+        return None, None
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -267,26 +270,37 @@ def run_gpu(args):
     ms_per_step = ms_total / steps
     qps = 1e3 / ms_per_step
 
-    # ---- roofline of the dominant kernel (K1 scan): its own launches, timed alone on this rank
-    for i in range(3):
-        store.engine.search(qs[i], K, METRIC)
-    torch.cuda.synchronize()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- roofline of the dominant kernel: the engine brackets ITS launches with CUDA events on the search
+    # stream (wdbx_b200_set_kernel_timing); which kernel that is (K2b filter over the bf16 shadow, or the K1
+    # scan of the stored rows) is reported by the engine, not assumed here
+    store.engine.set_kernel_timing(True)
     kout = store.engine.search(qs[0], K, METRIC)
+    for i in range(3):
+        store.engine.search(qs[i], K, METRIC, out=kout)
     n_k = max(10, min(steps, 100))
-    k0.record()
+    k_ms, kernel_id = [], 0
     for i in range(n_k):
         store.engine.search(qs[i % N_QUERIES], K, METRIC, out=kout)
-    k1.record()
-    torch.cuda.synchronize()
-    kernel_ms = reduce_max(k0.elapsed_time(k1) / n_k)
-    algo_bytes = local_rows * DIM * 4 + local_rows * 4          # rows + 1/|x| per row
+        st = store.engine.stats()          # synchronises on the kernel's end event
+        k_ms.append(st["last_kernel_ms"])
+        kernel_id = st["last_kernel"]
+    store.engine.set_kernel_timing(False)
+    kernel_ms = reduce_max(sum(k_ms) / len(k_ms))
+    ld16 = (DIM + 7) // 8 * 8
+    if kernel_id == 2:
+        kernel_name = "gemm_filter_kernel (K2b filter over the bf16 shadow rows)"
+        algo_bytes = local_rows * ld16 * 2 + local_rows * 4     # 2-byte shadow rows + 1/|x| per row
+        algo_note = "rows x dim x 2 (bf16 shadow) + rows x 4 (1/|x|): the bytes THIS kernel must read"
+    else:
+        kernel_name = "scan_topk_kernel (K1)"
+        algo_bytes = local_rows * DIM * 4 + local_rows * 4      # rows + 1/|x| per row
+        algo_note = "rows x dim x 4 + rows x 4 (SURVEY.md 8d)"
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+    k1_bytes = local_rows * DIM * 4 + local_rows * 4
     peak, peak_src = _peaks()
-    traffic = _traffic_from_profile()   # ncu --set full capture of this kernel on the 10M-row matrix (N=1)
-    traffic_src = None
+    traffic, traffic_src = _traffic_from_profile(kernel_id)   # ncu --set full capture on the 10M-row matrix (N=1)
     if traffic is not None:
-        traffic_src = "profiles/scan_topk_c3_ncu_summary.json (dram read+write per launch, 10M rows on one GPU)"
+        traffic_src += " (dram read+write per launch, 10M rows on one GPU)"
         if local_rows != N_ROWS:
             traffic = traffic * local_rows / N_ROWS
             traffic_src += f", scaled by rows_per_gpu/{N_ROWS}"
@@ -344,8 +358,12 @@ def run_gpu(args):
                        "l2_policy": "inputs larger than L2 (>=3.8 GB per GPU streamed per step vs 126 MB L2); "
                                     "64 distinct queries cycled"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "scan_topk_kernel (K1)",
-                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src},
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name,
+                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                         "algorithmic_bytes_definition": algo_note, "peak_source": peak_src,
+                         # the same launch expressed in SURVEY.md 8d's K1 bytes (fp32 rows): what a scan of the
+                         # stored rows would have had to stream in this time
+                         "fp32_scan_equivalent_gbs": k1_bytes / (kernel_ms * 1e-3) / 1e9},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": DIM * 4,
                     "d2h_bytes_per_step": K * 20 + 4, "api": "VectorStore.search (host list in, tuples out)",

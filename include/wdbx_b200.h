@@ -63,7 +63,7 @@ typedef struct wdbx_b200_stats {
   int32_t dtype;
   int32_t num_segments;
   int32_t sm_count;
-  int32_t reserved0;
+  int32_t last_kernel;  /* dominant kernel of the last timed search: 0 none, 1 K1 streaming scan, 2 K2b bf16 filter */
   int64_t rows_total;     /* rows appended over all segments (tombstoned rows included) */
   int64_t rows_live;      /* rows_total minus tombstones */
   int64_t capacity_rows;  /* rows that fit without growing */
@@ -73,6 +73,8 @@ typedef struct wdbx_b200_stats {
   double last_search_ms;       /* device time of the last wdbx_b200_search_host call */
   int64_t seg_rows[WDBX_B200_MAX_SEGMENTS];
   int64_t seg_live[WDBX_B200_MAX_SEGMENTS];
+  double last_kernel_ms;       /* duration of that kernel's launches (CUDA events on its stream); 0 unless
+                                  wdbx_b200_set_kernel_timing(e, 1) was called */
 } wdbx_b200_stats;
 
 /* ABI version of the loaded library (== WDBX_B200_ABI_VERSION). */
@@ -201,6 +203,11 @@ int wdbx_b200_search_exchange(wdbx_b200_engine* e, const float* q_dev, int B, in
  * identical for every setting. */
 int wdbx_b200_set_tuning(wdbx_b200_engine* e, int warps, int stages, int rows_unroll, int grid,
                          int evict_first);
+
+/* Bracket the dominant kernel of every search (K1 scan, or the K2b filter launches) with CUDA events on
+ * the search stream; wdbx_b200_get_stats then reports its duration.  Measurement hook for bench.py's
+ * roofline (off by default); no reference counterpart. */
+int wdbx_b200_set_kernel_timing(wdbx_b200_engine* e, int enable);
 
 /* Fill *out.  Replaces: FaissIndex.get_stats / size (indexing.py:1161-1183). */
 int wdbx_b200_get_stats(wdbx_b200_engine* e, wdbx_b200_stats* out);

@@ -165,6 +165,9 @@ class FakeEngine:
     def set_tuning(self, *a, **kw):
         pass
 
+    def set_kernel_timing(self, enable=True):
+        pass
+
     def stats(self):
         return {"kernel_launches": self.launches, "rows_total": int(sum(r.shape[0] for r in self.rows)),
                 "rows_live": int(sum((~d).sum() for d in self.dead))}

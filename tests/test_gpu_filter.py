@@ -35,7 +35,10 @@ def _oracle_check(X, Q, k, metric, scores, gids, counts, dead=None, sample=16):
     (1000, 64, 128, 10, "ip", "fp32"), (1000, 64, 128, 10, "cosine", "fp32"), (1000, 64, 128, 10, "l2", "fp32"),
     (5000, 768, 200, 10, "cosine", "fp32"), (20011, 384, 64, 5, "cosine", "fp32"), (3000, 1536, 130, 10, "l2", "fp32"),
     (777, 100, 33, 32, "ip", "fp32"), (70000, 96, 512, 10, "cosine", "fp32"), (300, 20, 256, 10, "cosine", "fp32"),
-    (30000, 384, 96, 20, "ip", "bf16"), (9000, 200, 70, 10, "cosine", "bf16"), (150000, 128, 300, 10, "l2", "fp32")])
+    (30000, 384, 96, 20, "ip", "bf16"), (9000, 200, 70, 10, "cosine", "bf16"), (150000, 128, 300, 10, "l2", "fp32"),
+    # small batches: several refine CTAs per query + K3 merge of their partial lists
+    (200000, 256, 1, 10, "cosine", "fp32"), (50000, 768, 3, 16, "l2", "fp32"), (120000, 128, 8, 10, "ip", "fp32"),
+    (40000, 384, 2, 1, "cosine", "bf16")])
 def test_filter_refine_is_bit_identical_to_scan(built_lib, n, dim, B, k, metric, dtype):
     rng = np.random.default_rng(n + dim + B)
     X = rng.standard_normal((n, dim), dtype=np.float32)

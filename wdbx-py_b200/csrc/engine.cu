@@ -70,11 +70,10 @@ struct Workspace {
   size_t fws_bytes = 0;
   unsigned long long* fcand = nullptr;
   size_t fcand_n = 0;
-  unsigned int* fcount = nullptr;
-  unsigned int* flower = nullptr;
-  int* foverflow = nullptr;
-  int fper_query = 0;
-  size_t fregions = 0;
+  unsigned int* fzero = nullptr;  // per-search zeroed block (counts, flags, tickets, lower-bound lists)
+  size_t fzero_n = 0;
+  uint64_t* fpart = nullptr;  // refine partial lists [ctas_per_query][B][k]
+  size_t fpart_n = 0;
 };
 
 int env_int(const char* name, int dflt) {
@@ -91,6 +90,7 @@ struct wdbx_b200_engine {
   uint32_t next_gid = 0;
   std::vector<Workspace> ws;
   ScanTuning tune{0, 0, 0, 0, -1, 0};
+  long long shadow_min_bytes = 2ll << 30;  // small batches use the bf16-shadow filter from this many stored bytes on (<0: never)
   int gemm_min_batch = 16;  // B >= this => tcgen05 path (0 = never); measured crossover vs K1 (8 queries/pass) ~ 12-16
   int gemm_mode = 0;        // 0 = bf16 filter + exact refine (K2b), 1 = 3xTF32 with fused top-k (K2)
   int pdl = 1;              // programmatic dependent launch for K1 (WDBX_B200_PDL=0 disables)
@@ -116,9 +116,15 @@ struct wdbx_b200_engine {
   bool xopened[kMaxPeers] = {false};
   int xworld = 0, xrank = 0;
   unsigned int xseq = 0;
+  uint64_t* xkeys = nullptr;  // local [B][k] keys of the filter path before the stand-alone exchange
   // stats
   std::atomic<long long> launches{0}, searches{0};
   double last_search_ms = 0.0;
+  // optional timing of the dominant kernel (wdbx_b200_set_kernel_timing)
+  bool ktiming = false;
+  cudaEvent_t kev0 = nullptr, kev1 = nullptr;
+  int last_kernel = 0;      // 1 = K1 scan, 2 = K2b filter
+  bool kpending = false;    // events recorded, not read yet
 };
 
 namespace {
@@ -318,7 +324,14 @@ int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B
   // back-to-back searches: let the next scan start on SMs that have finished while the last CTA still
   // merges (programmatic dependent launch); never for the flag-gated re-run, which must see its flags
   plan.pdl = (e->pdl && only_flag == nullptr) ? 1 : 0;
+  const bool timed = e->ktiming && only_flag == nullptr;
+  if (timed) CU_TRY(cudaEventRecord(e->kev0, stream));
   CU_TRY(launch_scan_topk(p, plan, e->dtype == WDBX_B200_BF16, stream));
+  if (timed) {
+    CU_TRY(cudaEventRecord(e->kev1, stream));
+    e->last_kernel = 1;
+    e->kpending = true;
+  }
   e->launches.fetch_add(1, std::memory_order_relaxed);
   return WDBX_B200_OK;
 }
@@ -379,7 +392,11 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
       cudaFree(sg.shadow);
       sg.shadow = nullptr;
       sg.shadow_rows = sg.shadow_cap = 0;
-      CU_TRY(cudaMalloc(&sg.shadow, static_cast<size_t>(sg.cap_rows) * ld16 * 2));
+      if (cudaMalloc(&sg.shadow, static_cast<size_t>(sg.cap_rows) * ld16 * 2) != cudaSuccess) {
+        cudaGetLastError();
+        sg.shadow = nullptr;
+        return fail(WDBX_B200_ERR_OOM, "no device memory for the bf16 shadow of segment %d", s);
+      }
       sg.shadow_cap = sg.cap_rows;
     }
     if (sg.shadow_rows < sg.n_rows) {
@@ -406,7 +423,21 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   const int cap = 512;
   const size_t n_regions = static_cast<size_t>(B) * s_total;
   const size_t need_ws = filter_query_workspace_bytes(B, e->dim);
-  if (w->fws_bytes < need_ws || w->fcand_n < n_regions * cap || w->fper_query < B || w->fregions < n_regions) {
+  // small batches: several refine CTAs per query (each a share of the candidate regions), merged by K3
+  int refine_ctas = (2 * e->sm_count + B - 1) / B;
+  if (refine_ctas > 64) refine_ctas = 64;
+  if (refine_ctas > s_total) refine_ctas = s_total;
+  if (refine_ctas < 1) refine_ctas = 1;
+  const size_t need_part = refine_ctas > 1 ? static_cast<size_t>(refine_ctas) * B * k : 0;
+  // one zero-initialised block per search: [n_regions] candidate counts | [B] overflow flags | [B] refine
+  // tickets | [B][16] shared lower-bound lists (64-byte rows) | [B] published bounds  (0 = "no bound yet")
+  const size_t lk = static_cast<size_t>(filter_max_k());
+  const size_t off_over = (n_regions + 15) / 16 * 16;
+  const size_t off_ticket = off_over + static_cast<size_t>(B);
+  const size_t off_list = (off_ticket + static_cast<size_t>(B) + 15) / 16 * 16;
+  const size_t off_glob = off_list + static_cast<size_t>(B) * lk;
+  const size_t need_zero = off_glob + static_cast<size_t>(B);
+  if (w->fpart_n < need_part || w->fws_bytes < need_ws || w->fcand_n < n_regions * cap || w->fzero_n < need_zero) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(stream, &cs);
     if (cs != cudaStreamCaptureStatusNone)
@@ -422,23 +453,23 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
       CU_TRY(cudaMalloc(&w->fcand, n_regions * cap * 8));
       w->fcand_n = n_regions * cap;
     }
-    if (w->fregions < n_regions) {
-      cudaFree(w->fcount); w->fcount = nullptr; w->fregions = 0;
-      CU_TRY(cudaMalloc(&w->fcount, n_regions * 4));
-      w->fregions = n_regions;
+    if (w->fpart_n < need_part) {
+      cudaFree(w->fpart); w->fpart = nullptr; w->fpart_n = 0;
+      CU_TRY(cudaMalloc(&w->fpart, need_part * 8));
+      w->fpart_n = need_part;
     }
-    if (w->fper_query < B) {
-      cudaFree(w->flower); cudaFree(w->foverflow);
-      w->flower = nullptr; w->foverflow = nullptr; w->fper_query = 0;
-      CU_TRY(cudaMalloc(&w->flower, static_cast<size_t>(B) * 4));
-      CU_TRY(cudaMalloc(&w->foverflow, static_cast<size_t>(B) * 4));
-      w->fper_query = B;
+    if (w->fzero_n < need_zero) {
+      cudaFree(w->fzero); w->fzero = nullptr; w->fzero_n = 0;
+      CU_TRY(cudaMalloc(&w->fzero, need_zero * 4));
+      w->fzero_n = need_zero;
     }
   }
-  CU_TRY(cudaMemsetAsync(w->fcount, 0, n_regions * 4, stream));
-  CU_TRY(cudaMemsetAsync(w->foverflow, 0, static_cast<size_t>(B) * 4, stream));
-  CU_TRY(cudaMemsetAsync(w->flower, 0, static_cast<size_t>(B) * 4, stream));  // 0 < mono(-inf): "no bound yet"
-  CU_TRY(launch_prep_queries(q_dev, B, e->dim, w->fws, stream));
+  unsigned int* fcount = w->fzero;
+  int* foverflow = reinterpret_cast<int*>(w->fzero + off_over);
+  unsigned int* ftickets = w->fzero + off_ticket;
+  unsigned int* lower_list = w->fzero + off_list;
+  unsigned int* lower_glob = w->fzero + off_glob;
+  CU_TRY(launch_prep_queries(q_dev, B, e->dim, w->fws, w->fzero, need_zero, stream));  // also zeroes w->fzero
   e->launches.fetch_add(1, std::memory_order_relaxed);
   // rigorous rounding bound relative to |x||q|: bf16 RNE is 2^-9 relative per rounded operand; the
   // fp32 accumulation of the tensor core is bounded (very conservatively) by dim * 2^-23
@@ -446,6 +477,7 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   SegDesc descs[kMaxSeg];
   memset(descs, 0, sizeof(descs));
   int slice_base = 0;
+  if (e->ktiming) CU_TRY(cudaEventRecord(e->kev0, stream));
   for (int s = s0; s < s1; ++s) {
     const Segment& sg = e->seg[s];
     SegDesc& d = descs[s];
@@ -457,37 +489,56 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
     d.n_rows = sg.n_rows;
     if (sg.n_rows == 0) continue;
     CU_TRY(launch_gemm_filter(f32 ? sg.shadow : static_cast<const void*>(sg.rows), f32 ? ld16 : e->dpad, d, s, e->dim, w->fws,
-                              B, k, metric, eps_rel, slices[s], w->fcand, w->fcount, w->flower, cap, slice_base, s_total,
-                              stream));
+                              B, k, metric, eps_rel, slices[s], w->fcand, fcount, lower_glob, lower_list, cap, slice_base,
+                              s_total, stream));
     e->launches.fetch_add(1, std::memory_order_relaxed);
     slice_base += slices[s];
   }
+  if (e->ktiming) CU_TRY(cudaEventRecord(e->kev1, stream));
   ScanTuning t1 = e->tune;
   t1.queries_per_pass = 1;
   ScanPlan plan;
   if (scan_plan(e->dim, e->dpad, e->elem_bytes, k, 1, e->sm_count, t1, &plan) != 0)
     return fail(WDBX_B200_ERR_ARG, "invalid scan shape (dim=%d k=%d)", e->dim, k);
   CU_TRY(launch_refine_topk(descs, kMaxSeg, q_dev, B, e->dim, e->dpad, e->elem_bytes, plan.lpr_log2, plan.nch, k, metric,
-                            w->fcand, w->fcount, cap, s_total, w->foverflow, keys_out, scores_out, gids_out, counts_out,
-                            stream));
+                            w->fcand, fcount, cap, s_total, foverflow, refine_ctas, w->fpart, ftickets, keys_out, scores_out,
+                            gids_out, counts_out, stream));
   e->launches.fetch_add(1, std::memory_order_relaxed);
   // exact re-run (K1) of the queries whose candidate list overflowed; exits immediately otherwise
-  return scan_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream, false,
-                       w->foverflow);
+  const int rrc = scan_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream,
+                                false, foverflow);
+  if (e->ktiming) {
+    e->last_kernel = 2;
+    e->kpending = true;
+  }
+  return rrc;
 }
 
-bool use_gemm(const wdbx_b200_engine* e, int B, int k) {
-  if (e->gemm_min_batch <= 0 || B < e->gemm_min_batch) return false;
-  if (e->gemm_mode == 1) return e->dtype == WDBX_B200_F32 && k <= gemm_max_k();
-  return k <= filter_max_k();
+// Regime choice.  Tensor path (K2b filter + exact refine) for batches of gemm_min_batch queries or more;
+// for SMALLER batches on fp32 storage too once the segments are large (shadow_min_bytes): the filter
+// streams the 2-byte shadow rows instead of the 4-byte stored rows, i.e. half the HBM bytes per query, and
+// the refine restores the exact fp32 result -- below that size the extra launches cost more than they save.
+bool use_gemm(const wdbx_b200_engine* e, int s0, int s1, int B, int k) {
+  if (e->gemm_min_batch <= 0) return false;
+  if (e->gemm_mode == 1) return B >= e->gemm_min_batch && e->dtype == WDBX_B200_F32 && k <= gemm_max_k();
+  if (k > filter_max_k()) return false;
+  if (B >= e->gemm_min_batch) return true;
+  if (e->dtype != WDBX_B200_F32 || e->shadow_min_bytes < 0) return false;
+  long long bytes = 0;
+  for (int s = s0; s < s1; ++s) bytes += e->seg[s].n_rows * static_cast<long long>(row_bytes(e));
+  return bytes >= e->shadow_min_bytes;
 }
 
 int search_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B, int k, int metric,
                     uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream) {
-  if (use_gemm(e, B, k)) {
+  if (use_gemm(e, s0, s1, B, k)) {
     if (e->gemm_mode == 1)
       return gemm_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream);
-    return filter_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream);
+    const int rc = filter_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream);
+    if (rc != WDBX_B200_ERR_OOM) return rc;
+    // no room for the bf16 shadow: keep serving from the stored rows (K1) and stop trying for small batches
+    cudaGetLastError();
+    e->shadow_min_bytes = -1;
   }
   return scan_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream);
 }
@@ -559,6 +610,10 @@ int wdbx_b200_create(int device, int dim, int dtype, int num_segments, wdbx_b200
   e->tune.evict_first = env_int("WDBX_B200_EVICT_FIRST", -1);
   e->tune.queries_per_pass = env_int("WDBX_B200_QUERIES_PER_PASS", 0);
   e->gemm_min_batch = env_int("WDBX_B200_GEMM_MIN_BATCH", e->gemm_min_batch);
+  {
+    const int mb = env_int("WDBX_B200_SHADOW_MIN_MB", -2);  // -1 = never; >= 0: threshold in MiB of stored rows
+    if (mb >= -1) e->shadow_min_bytes = mb < 0 ? -1 : static_cast<long long>(mb) << 20;
+  }
   e->gemm_mode = env_int("WDBX_B200_GEMM_MODE", 0);
   e->pdl = env_int("WDBX_B200_PDL", 1);
   ScanPlan plan;
@@ -589,19 +644,21 @@ void wdbx_b200_destroy(wdbx_b200_engine* e) {
     cudaFree(w.qsplit);
     cudaFree(w.fws);
     cudaFree(w.fcand);
-    cudaFree(w.fcount);
-    cudaFree(w.flower);
-    cudaFree(w.foverflow);
+    cudaFree(w.fzero);
+    cudaFree(w.fpart);
   }
   for (int r = 0; r < kMaxPeers; ++r)
     if (e->xopened[r]) cudaIpcCloseMemHandle(e->xpeer[r]);
   cudaFree(e->xbuf);
+  cudaFree(e->xkeys);
   cudaFree(e->stage_rows);
   cudaFree(e->stage_gids);
   cudaFree(e->dq);
   cudaFree(e->dres);
   cudaFreeHost(e->hq_pinned);
   cudaFreeHost(e->hres_pinned);
+  if (e->kev0) cudaEventDestroy(e->kev0);
+  if (e->kev1) cudaEventDestroy(e->kev1);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->mstream) cudaStreamDestroy(e->mstream);
@@ -1021,16 +1078,57 @@ int wdbx_b200_search_exchange(wdbx_b200_engine* e, const float* q_dev, int B, in
   if (!q_dev) return fail(WDBX_B200_ERR_ARG, "q_dev is NULL");
   DeviceGuard guard(e->device);
   std::lock_guard<std::mutex> lk(e->mu);
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  if (e->xworld >= 2 && B <= kXchgMaxB && k <= kXchgMaxK && e->gemm_mode != 1 && use_gemm(e, 0, e->nseg, B, k)) {
+    // bf16-filter path: local exact top-k (filter + refine), then the stand-alone exchange + merge kernel.
+    // Ranks may take different routes for the same search: both speak the same exchange protocol.
+    if (!e->xkeys) CU_TRY(cudaMalloc(&e->xkeys, static_cast<size_t>(kXchgMaxB) * kXchgMaxK * 8));
+    rc = filter_segments(e, 0, e->nseg, q_dev, B, k, metric, e->xkeys, nullptr, nullptr, nullptr, stream);
+    if (rc == WDBX_B200_OK) {
+      e->xseq += 1;
+      CU_TRY(launch_exchange_merge(e->xpeer, e->xworld, e->xrank, e->xseq, e->xkeys, B, k, keys_out, scores_out,
+                                   reinterpret_cast<long long*>(gids_out), counts_out, stream));
+      e->launches.fetch_add(1, std::memory_order_relaxed);
+      e->searches.fetch_add(1, std::memory_order_relaxed);
+      return rc;
+    }
+    if (rc != WDBX_B200_ERR_OOM) return rc;
+    cudaGetLastError();
+    e->shadow_min_bytes = -1;
+  }
   rc = scan_segments(e, 0, e->nseg, q_dev, B, k, metric, keys_out, scores_out, reinterpret_cast<long long*>(gids_out),
-                     counts_out, static_cast<cudaStream_t>(cuda_stream), true);
+                     counts_out, stream, true);
   if (rc == WDBX_B200_OK) e->searches.fetch_add(1, std::memory_order_relaxed);
   return rc;
+}
+
+int wdbx_b200_set_kernel_timing(wdbx_b200_engine* e, int enable) {
+  if (!e) return fail(WDBX_B200_ERR_ARG, "NULL engine");
+  DeviceGuard guard(e->device);
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (enable && !e->kev0) {
+    CU_TRY(cudaEventCreate(&e->kev0));
+    CU_TRY(cudaEventCreate(&e->kev1));
+  }
+  e->ktiming = enable != 0;
+  e->kpending = false;
+  return WDBX_B200_OK;
 }
 
 int wdbx_b200_get_stats(wdbx_b200_engine* e, wdbx_b200_stats* out) {
   if (!e || !out) return fail(WDBX_B200_ERR_ARG, "NULL argument");
   std::lock_guard<std::mutex> lk(e->mu);
   memset(out, 0, sizeof(*out));
+  if (e->kpending && e->kev1) {
+    DeviceGuard guard(e->device);
+    float ms = 0.0f;
+    if (cudaEventSynchronize(e->kev1) == cudaSuccess && cudaEventElapsedTime(&ms, e->kev0, e->kev1) == cudaSuccess) {
+      out->last_kernel = e->last_kernel;
+      out->last_kernel_ms = ms;
+    } else {
+      cudaGetLastError();
+    }
+  }
   out->abi_version = WDBX_B200_ABI_VERSION;
   out->device = e->device;
   out->dim = e->dim;

@@ -39,13 +39,11 @@ using namespace tc05;
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;        // bf16 elements per K block = 128 bytes
-constexpr int STAGES = 4;
+constexpr int STAGES_SINGLE = 4; // single-CTA ring (48 KB / stage)
+constexpr int STAGES_PAIR = 6;   // CTA-pair ring (32 KB / stage per CTA)
 constexpr int kThreads = 384;   // 4 control warps + 8 epilogue warps
 constexpr int kMaxKFilter = 16;
-constexpr int LT = 2 * BM;       // lower-bound list slots: two epilogue threads per query
-constexpr uint32_t X_TILE_BYTES = BN * BK * 2;  // 32 KB
 constexpr uint32_t Q_TILE_BYTES = BM * BK * 2;  // 16 KB
-constexpr uint32_t STAGE_BYTES = X_TILE_BYTES + Q_TILE_BYTES;
 constexpr uint32_t TMEM_COLS = 2 * BN;
 
 struct FilterParams {
@@ -63,19 +61,27 @@ struct FilterParams {
   unsigned long long* cand;   // [B][s_total][cap]  (seg << 32 | row): one private region per (query, row slice)
   unsigned int* cand_count;   // [B][s_total]
   unsigned int* lower_glob;   // [B] monotone-mapped float: best known lower bound of the exact k-th score
+  unsigned int* lower_list;   // [B][kMaxKFilter] monotone-mapped lower bounds of the k best rows seen by ANY CTA
   int cap;                    // entries per (query, slice) region
   int slice_base, s_total;    // this launch fills slices [slice_base, slice_base + n_slices) of s_total
 };
 
 // ---------------------------------------------------------------- prep: queries -> bf16 + norms
-__global__ void prep_queries_kernel(const float* __restrict__ q, int B, int dim, int ld, __nv_bfloat16* __restrict__ qb,
-                                    float* __restrict__ q_inv, float* __restrict__ q_nrm, float* __restrict__ q_sq) {
+// (rows B .. Bpad-1 are zero padding up to a whole 128-query block, so that the TMA box of the query
+// tile never leaves the tensor: a mostly out-of-bounds box measurably slows the load pipeline)
+__global__ void prep_queries_kernel(const float* __restrict__ q, int B, int Bpad, int dim, int ld,
+                                    __nv_bfloat16* __restrict__ qb, float* __restrict__ q_inv, float* __restrict__ q_nrm,
+                                    float* __restrict__ q_sq, unsigned int* __restrict__ zero, size_t n_zero) {
+  // per-search state of the filter (candidate counts, flags, tickets, lower-bound lists) starts at zero
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_zero;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    zero[i] = 0u;
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= B) return;
+  if (b >= Bpad) return;
   float ss = 0.0f;
   for (int c = lane; c < ld; c += 32) {
-    const float v = c < dim ? q[static_cast<size_t>(b) * dim + c] : 0.0f;
+    const float v = (c < dim && b < B) ? q[static_cast<size_t>(b) * dim + c] : 0.0f;
     qb[static_cast<size_t>(b) * ld + c] = __float2bfloat16_rn(v);
     ss = fmaf(v, v, ss);
   }
@@ -100,29 +106,61 @@ __global__ void shadow_rows_kernel(const float* __restrict__ rows, long long n, 
 }
 
 // ---------------------------------------------------------------- filter kernel
-// thread-private sorted list (descending) of the k best LOWER bounds, column-major [k][BM]
-__device__ __forceinline__ float lower_push(float* lows, int k, int lt, float v) {
-  int i = k - 1;
-  while (i > 0) {
-    const float prev = lows[(i - 1) * LT + lt];
-    if (prev >= v) break;
-    lows[i * LT + lt] = prev;
-    --i;
+// Per-query list of the k largest LOWER bounds (s~ - eps) seen so far by any thread of any CTA, kept in
+// global memory and updated lock-free: a new bound replaces the current minimum by compare-and-swap.
+// Every slot always holds the lower bound of a distinct row (or 0 = empty) and slots only grow, so the
+// minimum over the k slots -- even over a stale snapshot -- never exceeds the exact k-th best score.
+// That minimum is published through lower_glob (atomicMax) for the per-tile refresh of every thread.
+// Sharing ONE list (instead of one list per thread, whose k-th best only reflects 1/36 of the rows)
+// cuts the candidates per query roughly by the number of threads that share the query.
+__device__ __forceinline__ float lower_insert(unsigned int* slots, unsigned int* glob, int k, float lo, float L) {
+  const unsigned int m = mono_u32(lo);
+  unsigned int result = 0u;
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    unsigned int vmin = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
+    int imin = 0;
+    for (int i4 = 0; i4 < k; i4 += 4) {
+      const uint4 v4 = __ldcg(reinterpret_cast<const uint4*>(slots + i4));
+      const unsigned int vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        if (i4 + jj < k) {
+          const unsigned int v = vv[jj];
+          if (v < vmin) { second = vmin; vmin = v; imin = i4 + jj; }
+          else if (v < second) second = v;
+        }
+      }
+    }
+    if (m <= vmin) { result = vmin; break; }           // not among the k best bounds (any more)
+    if (atomicCAS(slots + imin, vmin, m) == vmin) {
+      result = second < m ? second : m;                // minimum of my snapshot after the replacement
+      if (k == 1) result = m;
+      if (result > 0x007FFFFFu) atomicMax(glob, result);
+      break;
+    }
   }
-  lows[i * LT + lt] = v;
-  return lows[(k - 1) * LT + lt];
+  const float g = unmono_f32(max(result, 0x007FFFFFu));
+  return g > L ? g : L;
 }
 
-template <int METRIC>
+// NCTA = 1: one CTA per 128-query block.  NCTA = 2: a CTA PAIR (cluster of two SMs of one TPC, cta_group::2)
+// owns two adjacent query blocks and one row slice: each CTA stages its own 128 queries and HALF of the
+// 256-row X tile, the leader issues one M=256 MMA that reads both halves, each CTA's TMEM receives the
+// accumulator of its own queries -- the X operand crosses L2 -> shared memory once per pair instead of
+// once per CTA (2/3 of the single-CTA staging traffic per MAC).
+template <int METRIC, int NCTA>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_q,
                    const FilterParams p) {
+  constexpr int STAGES = (NCTA == 2) ? STAGES_PAIR : STAGES_SINGLE;
+  constexpr int X_ROWS = BN / NCTA;                      // X rows staged by this CTA per tile
+  constexpr uint32_t X_TILE_BYTES = X_ROWS * BK * 2;
+  constexpr uint32_t STAGE_BYTES = X_TILE_BYTES + Q_TILE_BYTES;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // keep the shared-memory address space visible to the compiler (LDS/STS instead of generic accesses)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* stage_base = smem;
-  float* lows = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);        // [k][LT]
-  float* colscale = lows + static_cast<size_t>(kMaxKFilter) * LT;             // [2][BN] score scale per column
+  float* colscale = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);    // [2][BN] score scale per column
   float* coleps = colscale + 2 * BN;                                          // [2][BN] eps scale per column
   uint64_t* bars = reinterpret_cast<uint64_t*>(coleps + 2 * BN);
   uint64_t* full_bar = bars;
@@ -133,6 +171,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x, slice = blockIdx.y;
+  const uint32_t cta_rank = (NCTA == 2) ? cluster_ctarank() : 0u;   // cluster = (2,1,1): rank == qb & 1
   const int k = p.k;
   const float NEG_INF = __int_as_float(0xff800000);
 
@@ -145,37 +184,51 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(tmem_full + a), 1);
-      mbar_init(smem_u32(tmem_empty + a), 8);
+      mbar_init(smem_u32(tmem_empty + a), 8 * NCTA);  // epilogue warps of the whole pair
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_ptr), TMEM_COLS);
+  if (warp == 2) {
+    if (NCTA == 2) tmem_alloc_pair(smem_u32(tmem_ptr), TMEM_COLS);
+    else tmem_alloc(smem_u32(tmem_ptr), TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();   // the peer's barriers must exist before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int my_tiles = (p.n_tiles - slice + p.n_slices - 1) / p.n_slices;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        const int row0 = (slice + t * p.n_slices) * BN;
-        for (int kb = 0; kb < p.n_kblocks; ++kb) {
-          mbar_wait(smem_u32(empty_bar + stage), phase ^ 1u);
-          unsigned char* sb = stage_base + static_cast<size_t>(stage) * STAGE_BYTES;
-          const uint32_t bar = smem_u32(full_bar + stage);
-          mbar_expect_tx(bar, STAGE_BYTES);
-          tma_load_2d(smem_u32(sb), &tm_x, kb * BK, row0, bar);
-          tma_load_2d(smem_u32(sb + X_TILE_BYTES), &tm_q, kb * BK, qb * BM, bar);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    // ===== TMA producer: the whole warp walks the ring (uniform control flow), one elected lane issues
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int row0 = (slice + t * p.n_slices) * BN;
+      for (int kb = 0; kb < p.n_kblocks; ++kb) {
+        mbar_wait(smem_u32(empty_bar + stage), phase ^ 1u);
+        const uint32_t sb = smem_u32(stage_base) + static_cast<uint32_t>(stage) * STAGE_BYTES;
+        const uint32_t bar = smem_u32(full_bar) + static_cast<uint32_t>(stage) * 8u;
+        if (elect_one()) {
+          if (NCTA == 2) {
+            // both CTAs' bytes are credited to the leader's barrier (the only one the MMA issuer waits on)
+            if (cta_rank == 0) mbar_expect_tx(bar, 2 * STAGE_BYTES);
+            tma_load_2d_pair(sb, &tm_x, kb * BK, row0 + static_cast<int>(cta_rank) * X_ROWS, bar);
+            tma_load_2d_pair(sb + X_TILE_BYTES, &tm_q, kb * BK, qb * BM, bar);
+          } else {
+            mbar_expect_tx(bar, STAGE_BYTES);
+            tma_load_2d(sb, &tm_x, kb * BK, row0, bar);
+            tma_load_2d(sb + X_TILE_BYTES, &tm_q, kb * BK, qb * BM, bar);
+          }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(BM, BN, 1u);  // BF16 x BF16 -> F32
+    // ===== MMA issuer (leader CTA only in pair mode): uniform loop, one elected lane issues
+    if (cta_rank == 0) {
+      const uint32_t idesc = make_idesc(BM * NCTA, BN, 1u);  // BF16 x BF16 -> F32
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < my_tiles; ++t) {
@@ -186,18 +239,28 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         for (int kb = 0; kb < p.n_kblocks; ++kb) {
           mbar_wait(smem_u32(full_bar + stage), phase);
           tc_fence_after();
-          const uint32_t sb = smem_u32(stage_base + static_cast<size_t>(stage) * STAGE_BYTES);
+          const uint32_t sb = smem_u32(stage_base) + static_cast<uint32_t>(stage) * STAGE_BYTES;
           const uint64_t d_x = make_desc_kmajor(sb, 128, 2);
           const uint64_t d_q = make_desc_kmajor(sb + X_TILE_BYTES, 128, 2);
+          const uint32_t ebar = smem_u32(empty_bar) + static_cast<uint32_t>(stage) * 8u;
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint64_t adv = static_cast<uint64_t>((kk * 16 * 2) >> 4);  // 32 bytes per K=16 step
-            umma_f16(d_tmem, d_q + adv, d_x + adv, idesc, (kb | kk) ? 1u : 0u);
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              const uint64_t adv = static_cast<uint64_t>((kk * 16 * 2) >> 4);  // 32 bytes per K=16 step
+              if (NCTA == 2) umma_f16_pair(d_tmem, d_q + adv, d_x + adv, idesc, (kb | kk) ? 1u : 0u);
+              else umma_f16(d_tmem, d_q + adv, d_x + adv, idesc, (kb | kk) ? 1u : 0u);
+            }
+            if (NCTA == 2) umma_commit_pair(ebar);   // frees the stage in both CTAs
+            else umma_commit(ebar);
           }
-          umma_commit(smem_u32(empty_bar + stage));
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(smem_u32(tmem_full + a));
+        if (elect_one()) {
+          if (NCTA == 2) umma_commit_pair(smem_u32(tmem_full + a));
+          else umma_commit(smem_u32(tmem_full + a));
+        }
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -206,7 +269,6 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     // lower bounds (both are valid bounds) and its own candidate region.
     const int et = (warp & 3) * 32 + lane;      // TMEM lane == query inside the block
     const int half = (warp - 4) >> 2;           // column half of the tile
-    const int lt = half * BM + et;              // slot of this thread in the lower-bound lists
     const int q = qb * BM + et;
     const bool q_valid = q < p.B;
     const float qinv = q_valid ? p.q_inv[q] : 0.0f;
@@ -214,13 +276,46 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const float qsq = q_valid ? p.q_sq[q] : 0.0f;
     // eps of this query: cosine eps_rel (norms cancel); ip eps_rel*|x||q|; l2 2*eps_rel*|x||q|
     const float qeps = (METRIC == kCosine) ? p.eps_rel : (METRIC == kL2 ? 2.0f * p.eps_rel * qnrm : p.eps_rel * qnrm);
-    for (int i = 0; i < k; ++i) lows[i * LT + lt] = NEG_INF;
-    float L = NEG_INF;  // k-th best lower bound seen by this thread / published by any CTA of this query
+    float L = NEG_INF;  // best known lower bound of this query's exact k-th best score (see lower_insert)
+    unsigned int* my_slots = p.lower_list + static_cast<size_t>(q_valid ? q : 0) * kMaxKFilter;
+    // FAST TEST.  "upper bound of the exact score >= L" is rewritten so that it costs one multiply (or one
+    // fma) and one compare per accumulator element, against a per-thread threshold T that only changes
+    // when L does:  cosine  d*inv|x| >= (L - eps)|q|;  ip  d + |x|eps >= L;  l2  2d + |x|eps - |x|^2 >= L + |q|^2.
+    // T carries a 1e-6 relative slack (and the staged |x|^2 is shrunk by 1e-6) so that the fast test can
+    // only ADMIT more elements than the reference form; admitted groups are re-tested below with the
+    // reference form, which alone decides what becomes a candidate.
+    auto fast_thr = [&](float l) -> float {
+      if (METRIC == kCosine) {
+        const float t = (l - qeps) * qnrm;
+        return t - 1e-6f * (fabsf(t) + qeps * qnrm);
+      }
+      if (METRIC == kL2) return (l + qsq) - 1e-6f * (fabsf(l) + 2.0f * qsq);
+      return l;
+    };
+    float T = fast_thr(L);
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     // private candidate region of this (query, slice, half): plain stores, no atomics on the hot path
     const size_t region = static_cast<size_t>(q_valid ? q : 0) * p.s_total + 2 * (p.slice_base + slice) + half;
     unsigned long long* my_cand = p.cand + region * p.cap;
     unsigned int n_cand = 0;
+    // per-column scale (cosine 1/|x|, l2 |x|^2 shrunk by 1e-6) and |x| for the eps term of column
+    // half*128 + et of tile t; columns past the end get |x| = -inf (upper bound -inf) and are rejected by the
+    // reference form anyway.  The loads for tile t+1 (and the shared bound) are issued BEFORE tile t is
+    // processed, so their latency never sits on the epilogue's critical path.
+    auto load_scale = [&](int t, float& sc, float& ep) {
+      const long long row = static_cast<long long>(slice + t * p.n_slices) * BN + half * 128 + et;
+      sc = 0.0f;
+      ep = NEG_INF;
+      if (t < my_tiles && row < p.n_rows) {
+        const float inx = __ldg(p.inv_norm + row);
+        const float sq = __ldg(p.sqnorm + row);
+        sc = (METRIC == kCosine) ? inx : (METRIC == kL2 ? sq * (1.0f - 1e-6f) : 0.0f);
+        ep = (METRIC == kCosine) ? 1.0f : sqrtf(sq);  // |x|
+      }
+    };
+    float sc_next, ep_next;
+    load_scale(0, sc_next, ep_next);
+    unsigned int glob_next = q_valid ? __ldcg(p.lower_glob + q) : 0u;
     for (int t = 0; t < my_tiles; ++t) {
       const int a = t & 1;
       const long long row0 = static_cast<long long>(slice + t * p.n_slices) * BN;
@@ -228,71 +323,82 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       const int valid = rem < BN ? static_cast<int>(rem) : BN;
       float* cs = colscale + a * BN;
       float* ce = coleps + a * BN;
-      {
-        // per-column score scale and eps scale; columns past the end get eps = -inf so that their
-        // upper bound is -inf (they only reach the slow path while L is still -inf, where they are dropped)
-        const int c = half * 128 + et;
-        float sc = 0.0f, ep = NEG_INF;
-        if (c < valid) {
-          const float inx = __ldg(p.inv_norm + row0 + c);
-          const float sq = __ldg(p.sqnorm + row0 + c);
-          sc = (METRIC == kCosine) ? inx : (METRIC == kL2 ? sq : 0.0f);
-          ep = (METRIC == kCosine) ? 1.0f : sqrtf(sq);  // |x|
-        }
-        cs[c] = sc;
-        ce[c] = ep;
-      }
+      cs[half * 128 + et] = sc_next;   // buffer a was last read for tile t-2: every thread has passed the
+      ce[half * 128 + et] = ep_next;   // barrier of tile t-1 since
       // share the bound: any thread's k-th best lower bound is a valid global lower bound
       if (q_valid) {
-        const float g = unmono_f32(max(__ldcg(p.lower_glob + q), 0x007FFFFFu));
-        L = g > L ? g : L;
+        const float g = unmono_f32(max(glob_next, 0x007FFFFFu));
+        if (g > L) { L = g; T = fast_thr(L); }
+        glob_next = __ldcg(p.lower_glob + q);
       }
+      load_scale(t + 1, sc_next, ep_next);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(smem_u32(tmem_full + a), (static_cast<uint32_t>(t) >> 1) & 1u);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+        if (c0 >= valid) break;                       // tile-uniform
         uint32_t r[32];
         __syncwarp();
         tmem_ld32(lane_base + static_cast<uint32_t>(a * BN + c0), r);
         tmem_ld_wait();
-        if (c0 < valid && q_valid) {
+        unsigned gmask = 0;                           // bit g: some column of group [4g, 4g+4) passed the fast test
+        if (q_valid) {
 #pragma unroll
-          for (int j4 = 0; j4 < 32; j4 += 4) {
-            const float4 c4 = *reinterpret_cast<const float4*>(cs + c0 + j4);
-            const float4 e4 = *reinterpret_cast<const float4*>(ce + c0 + j4);
+          for (int g4 = 0; g4 < 8; ++g4) {
+            const float4 c4 = *reinterpret_cast<const float4*>(cs + c0 + 4 * g4);
             const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
-            const float ee[4] = {e4.x, e4.y, e4.z, e4.w};
-            float sv[4], up[4];
+            float u[4];
+            if (METRIC == kCosine) {
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const float d = __uint_as_float(r[j4 + jj]);
-              if (METRIC == kCosine) sv[jj] = d * cc[jj] * qinv;
-              else if (METRIC == kL2) sv[jj] = -((cc[jj] - 2.0f * d) + qsq);
-              else sv[jj] = d;
-              up[jj] = fmaf(ee[jj], qeps, sv[jj]);  // upper bound of the exact score
-            }
-            // one branch per 4 columns; !(x < L) also lets NaN through (the refine ranks it like K1)
-            if (!(up[0] < L) || !(up[1] < L) || !(up[2] < L) || !(up[3] < L)) {
+              for (int jj = 0; jj < 4; ++jj) u[jj] = __uint_as_float(r[4 * g4 + jj]) * cc[jj];
+            } else {
+              const float4 e4 = *reinterpret_cast<const float4*>(ce + c0 + 4 * g4);
+              const float ee[4] = {e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {
-                const int j = j4 + jj;
-                if (!(up[jj] < L) && (c0 + j) < valid) {
-                  const long long row = row0 + c0 + j;
-                  bool dead = false;
-                  if (p.tomb != nullptr) dead = (__ldg(p.tomb + (row >> 5)) >> (row & 31)) & 1u;
-                  if (!dead) {
-                    if (n_cand < static_cast<unsigned int>(p.cap))
-                      my_cand[n_cand] = (static_cast<unsigned long long>(p.seg) << 32) | static_cast<unsigned long long>(row);
-                    ++n_cand;
-                    const float lo = sv[jj] - ee[jj] * qeps;  // NaN never enters the list of lower bounds
-                    if (lo > lows[(k - 1) * LT + lt]) {
-                      const float kth = lower_push(lows, k, lt, lo);
-                      if (kth > L) {
-                        L = kth;
-                        atomicMax(p.lower_glob + q, mono_u32(L));  // publish: valid for every CTA of this query
-                      }
-                    }
+                const float d = __uint_as_float(r[4 * g4 + jj]);
+                if (METRIC == kL2) u[jj] = fmaf(2.0f, d, fmaf(ee[jj], qeps, -cc[jj]));
+                else u[jj] = fmaf(ee[jj], qeps, d);
+              }
+            }
+            // !(x < T) also admits NaN (the refine ranks it like K1)
+            if (!(u[0] < T) || !(u[1] < T) || !(u[2] < T) || !(u[3] < T)) gmask |= 1u << g4;
+          }
+        }
+        // rare path, warp-uniform: groups admitted by any lane are re-read from TMEM (4 columns) and
+        // decided with the reference form of the bound
+        unsigned um = __reduce_or_sync(FULL_MASK, gmask);
+        while (um) {
+          const int g4 = __ffs(um) - 1;
+          um &= um - 1;
+          uint32_t v[4];
+          tmem_ld4(lane_base + static_cast<uint32_t>(a * BN + c0 + 4 * g4), v);
+          tmem_ld_wait();
+          if ((gmask >> g4) & 1u) {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int col = c0 + 4 * g4 + jj;
+              if (col >= valid) continue;
+              const long long row = row0 + col;
+              const float d = __uint_as_float(v[jj]);
+              const float ej = ce[col];
+              float sv;
+              if (METRIC == kCosine) sv = d * cs[col] * qinv;
+              else if (METRIC == kL2) sv = -((__ldg(p.sqnorm + row) - 2.0f * d) + qsq);
+              else sv = d;
+              const float up = fmaf(ej, qeps, sv);  // upper bound of the exact score
+              if (!(up < L)) {
+                bool dead = false;
+                if (p.tomb != nullptr) dead = (__ldg(p.tomb + (row >> 5)) >> (row & 31)) & 1u;
+                if (!dead) {
+                  if (n_cand < static_cast<unsigned int>(p.cap))
+                    my_cand[n_cand] = (static_cast<unsigned long long>(p.seg) << 32) | static_cast<unsigned long long>(row);
+                  ++n_cand;
+                  const float lo = sv - ej * qeps;  // NaN never enters the list of lower bounds
+                  if (lo > L) {
+                    const float nl = lower_insert(my_slots, p.lower_glob + q, k, lo, L);
+                    if (nl > L) { L = nl; T = fast_thr(L); }
                   }
                 }
               }
@@ -302,24 +408,33 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(tmem_empty + a));
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_cluster(smem_u32(tmem_empty + a), 0u);   // the leader's MMA issuer waits
+        else mbar_arrive(smem_u32(tmem_empty + a));
+      }
     }
     if (q_valid) p.cand_count[region] = n_cand;
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();   // the peer may still be reading TMEM / signalling our barriers
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (NCTA == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-constexpr size_t kFilterSmem = 1024 + static_cast<size_t>(STAGES) * STAGE_BYTES + static_cast<size_t>(kMaxKFilter) * LT * 4 +
-                               4 * BN * 4 + (2 * STAGES + 4) * 8 + 16;
+constexpr size_t filter_smem(int ncta) {
+  const size_t stages = ncta == 2 ? STAGES_PAIR : STAGES_SINGLE;
+  const size_t stage_bytes = static_cast<size_t>(BN / ncta) * BK * 2 + Q_TILE_BYTES;
+  return 1024 + stages * stage_bytes + 4 * BN * 4 + (2 * stages + 4) * 8 + 16;
+}
 
 // ---------------------------------------------------------------- refine kernel
-// One CTA per query.  Candidates are re-scored from the stored rows with K1's arithmetic: lanes-per-row
+// gridDim.y CTAs per query (one when the batch alone fills the GPU; more for small batches, each taking a
+// share of the candidate regions and writing a partial list that K3 merges).  Candidates are re-scored from the stored rows with K1's arithmetic: lanes-per-row
 // lpr, chunk c = lig + j*lpr accumulated in j order with the x,y,z,w fmaf chain, xor-butterfly over
 // lpr lanes, then the same score formula -- so keys are bit-identical to scan_topk_kernel's.
 struct RefineParams {
@@ -329,6 +444,8 @@ struct RefineParams {
   const unsigned int* cand_count;   // [B][s_total]
   int s_total;
   int* overflow;                    // [B] set to 1 when the candidate list overflowed
+  uint64_t* part;                   // [B][gridDim.y][k] partial lists when gridDim.y > 1
+  unsigned int* tickets;            // [B] zeroed per search: the last CTA of a query merges the partial lists
   int B, dim, dpad, row_bytes, cpr, lpr_log2, nch, k, metric, cap;
   uint64_t* keys_out;
   float* scores_out;
@@ -344,8 +461,8 @@ __global__ void __launch_bounds__(256, 2) refine_topk_kernel(const __grid_consta
   const int k = p.k, dpad = p.dpad;
   float* q_s = reinterpret_cast<float*>(smem);                                   // [dpad]
   float* misc = reinterpret_cast<float*>(smem + scan::align128(static_cast<size_t>(dpad) * 4));
-  uint64_t* lists = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(misc) + 128);  // [nwarps][k]
-  uint64_t* final_list = lists + static_cast<size_t>(nwarps) * k;                // [k]
+  uint64_t* scratch = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(misc) + 128);  // [nwarps][32]
+  uint64_t* final_list = scratch + static_cast<size_t>(nwarps) * 32;                                // [32]
 
   // any (query, slice) region that overflowed => adversarial data: let K1 redo this query exactly
   {
@@ -353,7 +470,7 @@ __global__ void __launch_bounds__(256, 2) refine_topk_kernel(const __grid_consta
     for (int sl = tid; sl < p.s_total; sl += blockDim.x)
       over |= p.cand_count[static_cast<size_t>(q) * p.s_total + sl] > static_cast<unsigned int>(p.cap);
     if (__syncthreads_or(over)) {
-      if (tid == 0) {
+      if (tid == 0 && blockIdx.y == 0) {
         p.overflow[q] = 1;
         if (p.counts_out) p.counts_out[q] = 0;
       }
@@ -361,7 +478,6 @@ __global__ void __launch_bounds__(256, 2) refine_topk_kernel(const __grid_consta
     }
   }
   for (int i = tid; i < dpad; i += blockDim.x) q_s[i] = (i < p.dim) ? __ldg(p.q + static_cast<size_t>(q) * p.dim + i) : 0.0f;
-  for (int i = tid; i < nwarps * k + k; i += blockDim.x) lists[i] = 0ull;
   __syncthreads();
   if (warp == 0) {  // 1/|q| exactly as K1 computes it
     float ss = 0.0f;
@@ -375,69 +491,142 @@ __global__ void __launch_bounds__(256, 2) refine_topk_kernel(const __grid_consta
   const bool cosine = p.metric == kCosine;
   const int lpr_log2 = p.lpr_log2, lpr = 1 << lpr_log2, G = 32 >> lpr_log2;
   const int g = lane >> lpr_log2, lig = lane & (lpr - 1);
-  uint64_t* my_list = lists + static_cast<size_t>(warp) * k;
-  uint64_t thr = 0ull;
-  for (int sl = warp; sl < p.s_total; sl += nwarps) {
+  // k <= 32: a best-first list is one key per lane.  Scored keys are parked one per lane (`batch`); a
+  // full batch is sorted (bitonic network over the lanes) and merged into `acc` in registers.
+  uint64_t acc = 0ull, batch = 0ull;
+  int nb = 0;
+  auto flush = [&]() {
+    batch = scan::warp_sort32_desc(batch, lane);
+    acc = scan::warp_merge32(acc, batch, lane);
+    batch = 0ull;
+    nb = 0;
+  };
+  // Work unit = (candidate region, SUB-th part of it): a region's candidates are dealt round-robin to SUB
+  // warps, so the ~300 regions of a small batch spread over every warp of every CTA of the query.
+  // CU candidates per lane group are in flight at once: entry -> row chunks + norm + id -> score.
+  constexpr int SUB = 4, CU = 2;
+  const int n_units = p.s_total * SUB;
+  for (int unit = blockIdx.y * nwarps + warp; unit < n_units; unit += gridDim.y * nwarps) {
+   const int sl = unit / SUB, sub = unit - sl * SUB;
    const int cnt = static_cast<int>(p.cand_count[static_cast<size_t>(q) * p.s_total + sl]);
    const unsigned long long* cand = p.cand + (static_cast<size_t>(q) * p.s_total + sl) * p.cap;
-   for (int base = 0; base < cnt; base += G) {
-    const int ci = base + g;
-    const bool have = ci < cnt;
-    const unsigned long long ent = have ? cand[ci] : cand[0];
-    const int sg = static_cast<int>(ent >> 32);
-    const long long row = static_cast<long long>(ent & 0xFFFFFFFFull);
-    const unsigned char* rp = p.seg[sg].rows + static_cast<size_t>(row) * p.row_bytes;
-    float acc = 0.0f;
-    for (int j = 0; j < p.nch; ++j) {
-      const int c = lig + (j << lpr_log2);
-      if (c < p.cpr) {
-        if (!BF16) {
-          const float4 x = __ldg(reinterpret_cast<const float4*>(rp + c * 16));
-          const float4 qv = lds128(q_s + c * 4);
-          if (L2) {
-            const float d0 = x.x - qv.x, d1 = x.y - qv.y, d2 = x.z - qv.z, d3 = x.w - qv.w;
-            acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc); acc = fmaf(d2, d2, acc); acc = fmaf(d3, d3, acc);
-          } else {
-            acc = fmaf(x.x, qv.x, acc); acc = fmaf(x.y, qv.y, acc); acc = fmaf(x.z, qv.z, acc); acc = fmaf(x.w, qv.w, acc);
-          }
-        } else {
-          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(rp + c * 16));
-          const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-          const float4 qa = lds128(q_s + c * 8);
-          const float4 qb = lds128(q_s + c * 8 + 4);
-          const float qq[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+   for (int base = sub * G * CU; base < cnt; base += SUB * G * CU) {
+    bool have[CU];
+    long long row[CU];
+    int sg[CU];
+    const unsigned char* rp[CU];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xFFFF0000u);
-            if (L2) {
-              const float d0 = lo - qq[2 * i], d1 = hi - qq[2 * i + 1];
-              acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc);
+    for (int u = 0; u < CU; ++u) {
+      const int ci = base + u * G + g;
+      have[u] = ci < cnt;
+      const unsigned long long ent = have[u] ? cand[ci] : cand[0];
+      sg[u] = static_cast<int>(ent >> 32);
+      row[u] = static_cast<long long>(ent & 0xFFFFFFFFull);
+      rp[u] = p.seg[sg[u]].rows + static_cast<size_t>(row[u]) * p.row_bytes;
+    }
+    float inx[CU];
+    uint32_t gid[CU];
+#pragma unroll
+    for (int u = 0; u < CU; ++u) {   // requested together with the row chunks, consumed after the reduction
+      inx[u] = cosine ? __ldg(p.seg[sg[u]].inv_norm + row[u]) : 1.0f;
+      gid[u] = __ldg(p.seg[sg[u]].gids + row[u]);
+    }
+    float dot[CU];
+#pragma unroll
+    for (int u = 0; u < CU; ++u) dot[u] = 0.0f;
+    // the row chunks of a lane are requested 4 x CU at a time before the first one is consumed (one dependent
+    // DRAM round trip per chunk made the refine latency-bound); per candidate the fma order is K1's
+    for (int j0 = 0; j0 < p.nch; j0 += 4) {
+      uint4 raw[CU][4];
+#pragma unroll
+      for (int u = 0; u < CU; ++u) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int c = lig + ((j0 + v) << lpr_log2);
+          raw[u][v] = (j0 + v < p.nch && c < p.cpr) ? __ldg(reinterpret_cast<const uint4*>(rp[u] + c * 16))
+                                                    : make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < CU; ++u) {
+        float acc1 = dot[u];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int c = lig + ((j0 + v) << lpr_log2);
+          if (j0 + v < p.nch && c < p.cpr) {
+            if (!BF16) {
+              const float4 x = make_float4(__uint_as_float(raw[u][v].x), __uint_as_float(raw[u][v].y),
+                                           __uint_as_float(raw[u][v].z), __uint_as_float(raw[u][v].w));
+              const float4 qv = lds128(q_s + c * 4);
+              if (L2) {
+                const float d0 = x.x - qv.x, d1 = x.y - qv.y, d2 = x.z - qv.z, d3 = x.w - qv.w;
+                acc1 = fmaf(d0, d0, acc1); acc1 = fmaf(d1, d1, acc1); acc1 = fmaf(d2, d2, acc1); acc1 = fmaf(d3, d3, acc1);
+              } else {
+                acc1 = fmaf(x.x, qv.x, acc1); acc1 = fmaf(x.y, qv.y, acc1); acc1 = fmaf(x.z, qv.z, acc1); acc1 = fmaf(x.w, qv.w, acc1);
+              }
             } else {
-              acc = fmaf(lo, qq[2 * i], acc); acc = fmaf(hi, qq[2 * i + 1], acc);
+              const uint32_t w[4] = {raw[u][v].x, raw[u][v].y, raw[u][v].z, raw[u][v].w};
+              const float4 qa = lds128(q_s + c * 8);
+              const float4 qb = lds128(q_s + c * 8 + 4);
+              const float qq[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xFFFF0000u);
+                if (L2) {
+                  const float d0 = lo - qq[2 * i], d1 = hi - qq[2 * i + 1];
+                  acc1 = fmaf(d0, d0, acc1); acc1 = fmaf(d1, d1, acc1);
+                } else {
+                  acc1 = fmaf(lo, qq[2 * i], acc1); acc1 = fmaf(hi, qq[2 * i + 1], acc1);
+                }
+              }
             }
           }
         }
+        dot[u] = acc1;
       }
     }
-    for (int o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, o);
-    float s = acc;
-    if (L2) s = -s;
-    else if (cosine) s = s * __ldg(p.seg[sg].inv_norm + row) * qinv;
-    s = (s != s) ? __int_as_float(0xff800000) : s;
-    const uint64_t key = have ? pack_key(s, __ldg(p.seg[sg].gids + row)) : 0ull;
-    unsigned m = __ballot_sync(FULL_MASK, lig == 0 && have && key > thr);
-    while (m) {
-      const int src_lane = __ffs(m) - 1;
-      m &= m - 1;
-      const uint64_t kk = __shfl_sync(FULL_MASK, key, src_lane);
-      if (kk > thr) thr = scan::list_insert(my_list, k, kk, lane);
+#pragma unroll
+    for (int u = 0; u < CU; ++u) {
+      float d = dot[u];
+      for (int o = lpr >> 1; o > 0; o >>= 1) d += __shfl_xor_sync(FULL_MASK, d, o);
+      float sc = d;
+      if (L2) sc = -sc;
+      else if (cosine) sc = sc * inx[u] * qinv;
+      sc = (sc != sc) ? __int_as_float(0xff800000) : sc;
+      const uint64_t key = have[u] ? pack_key(sc, gid[u]) : 0ull;
+      unsigned m = __ballot_sync(FULL_MASK, lig == 0 && have[u]);
+      while (m) {
+        const int src_lane = __ffs(m) - 1;
+        m &= m - 1;
+        const uint64_t kk = __shfl_sync(FULL_MASK, key, src_lane);
+        if (lane == nb) batch = kk;
+        if (++nb == 32) flush();
+      }
     }
    }
   }
-  __syncthreads();
+  if (nb > 0) flush();
+  // CTA list: binary tree over the warps (registers + shared memory), then -- several CTAs per query --
+  // partial list -> global and the last CTA of this query (atomic ticket) folds all of them the same way
+  uint64_t mine[1] = {acc};
+  scan::block_tree_merge<1>(mine, scratch, warp, lane, nwarps);
+  if (gridDim.y > 1) {
+    if (warp == 0) {
+      scan::store_list<1>(p.part + (static_cast<size_t>(q) * gridDim.y + blockIdx.y) * k, mine, k, lane);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) misc[1] = __uint_as_float(atomicAdd(p.tickets + q, 1u));
+    }
+    __syncthreads();
+    if (__float_as_uint(misc[1]) != gridDim.y - 1) return;
+    __threadfence();
+    scan::grid_merge_fast<1>(p.part + static_cast<size_t>(q) * gridDim.y * k, static_cast<int>(gridDim.y), scratch,
+                             final_list, k, warp, lane, nwarps);
+  } else if (warp == 0) {
+    scan::store_list<1>(final_list, mine, k, lane);
+  }
   if (warp == 0) {
-    uint64_t t2 = 0ull;
-    scan::absorb_keys<false>(final_list, k, t2, lists, nwarps * k, 0, 1, lane);
+    __syncwarp();
     scan::emit_list(final_list, k, lane, p.keys_out ? p.keys_out + static_cast<size_t>(q) * k : nullptr,
                     p.scores_out ? p.scores_out + static_cast<size_t>(q) * k : nullptr,
                     p.gids_out ? p.gids_out + static_cast<size_t>(q) * k : nullptr, p.counts_out ? p.counts_out + q : nullptr);
@@ -470,14 +659,26 @@ bool encode_map_bf16(CUtensorMap* map, const void* base, long long rows, int col
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// WDBX_B200_FILTER_PAIR=0 forces the single-CTA kernel (A/B comparisons, fallback)
+bool pair_mode() {
+  static const bool on = [] {
+    const char* v = getenv("WDBX_B200_FILTER_PAIR");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
+
 }  // namespace
 
 int filter_max_k() { return kMaxKFilter; }
+
 int filter_ld16(int dim) { return (dim + 7) / 8 * 8; }
 
-// workspace layout (bytes): qb16 [B][ld16] bf16 | q_inv, q_nrm, q_sq [B] f32 each
+// workspace layout (bytes): qb16 [Bpad][ld16] bf16 | q_inv, q_nrm, q_sq [Bpad] f32 each; Bpad = B rounded up to 128
+static int filter_bpad(int B) { return (B + BM - 1) / BM * BM; }
 size_t filter_query_workspace_bytes(int B, int dim) {
-  return (static_cast<size_t>(B) * filter_ld16(dim) * 2 + 15) / 16 * 16 + 3 * static_cast<size_t>(B) * 4;
+  const size_t bp = filter_bpad(B);
+  return (bp * filter_ld16(dim) * 2 + 15) / 16 * 16 + 3 * bp * 4;
 }
 
 int filter_slices_for(long long n_rows, int B, int sm_count) {
@@ -498,44 +699,51 @@ cudaError_t launch_shadow_rows(const float* rows, long long n, int dpad, int ld1
   return cudaGetLastError();
 }
 
-cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace, cudaStream_t stream) {
+cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace, unsigned int* zero, size_t n_zero,
+                                cudaStream_t stream) {
   const int ld = filter_ld16(dim);
+  const int bp = filter_bpad(B);
   __nv_bfloat16* qb = static_cast<__nv_bfloat16*>(workspace);
-  float* f = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + (static_cast<size_t>(B) * ld * 2 + 15) / 16 * 16);
+  float* f = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + (static_cast<size_t>(bp) * ld * 2 + 15) / 16 * 16);
   const int wpb = 8;
-  prep_queries_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, stream>>>(q, B, dim, ld, qb, f, f + B, f + 2 * B);
+  prep_queries_kernel<<<(bp + wpb - 1) / wpb, wpb * 32, 0, stream>>>(q, B, bp, dim, ld, qb, f, f + bp, f + 2 * bp, zero, n_zero);
   return cudaGetLastError();
 }
 
 // One launch per segment.  xb = bf16 matrix [n_rows][ld_x] (shadow, or the stored rows of a bf16 engine).
 cudaError_t launch_gemm_filter(const void* xb, int ld_x, const SegDesc& seg, int seg_index, int dim, const void* workspace,
                                int B, int k, int metric, float eps_rel, int n_slices, unsigned long long* cand,
-                               unsigned int* cand_count, unsigned int* lower_glob, int cap, int slice_base, int s_total,
-                               cudaStream_t stream) {
+                               unsigned int* cand_count, unsigned int* lower_glob, unsigned int* lower_list, int cap,
+                               int slice_base, int s_total, cudaStream_t stream) {
   if (seg.n_rows <= 0 || n_slices <= 0) return cudaSuccess;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(gemm_filter_kernel<kCosine>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFilterSmem));
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(gemm_filter_kernel<kIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFilterSmem));
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(gemm_filter_kernel<kL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFilterSmem));
+    auto set = [&](auto kern, int ncta) {
+      if (attr_err == cudaSuccess)
+        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(filter_smem(ncta)));
+    };
+    set(gemm_filter_kernel<kCosine, 1>, 1); set(gemm_filter_kernel<kIP, 1>, 1); set(gemm_filter_kernel<kL2, 1>, 1);
+    set(gemm_filter_kernel<kCosine, 2>, 2); set(gemm_filter_kernel<kIP, 2>, 2); set(gemm_filter_kernel<kL2, 2>, 2);
   });
   if (attr_err != cudaSuccess) return attr_err;
   const int ld = filter_ld16(dim);
   const unsigned char* ws = static_cast<const unsigned char*>(workspace);
-  const float* f = reinterpret_cast<const float*>(ws + (static_cast<size_t>(B) * ld * 2 + 15) / 16 * 16);
+  const int bp = filter_bpad(B);
+  const float* f = reinterpret_cast<const float*>(ws + (static_cast<size_t>(bp) * ld * 2 + 15) / 16 * 16);
+  // CTA pairs need an even number of query blocks (the pair = two adjacent blocks on one row slice)
+  const int n_qblocks = (B + BM - 1) / BM;
+  const int ncta = (pair_mode() && (n_qblocks % 2) == 0) ? 2 : 1;
   CUtensorMap tm_x, tm_q;
-  if (!encode_map_bf16(&tm_x, xb, seg.n_rows, dim, ld_x, BN) || !encode_map_bf16(&tm_q, ws, B, dim, ld, BM))
+  if (!encode_map_bf16(&tm_x, xb, seg.n_rows, dim, ld_x, BN / ncta) || !encode_map_bf16(&tm_q, ws, bp, dim, ld, BM))
     return cudaErrorInvalidValue;
   FilterParams p;
   p.inv_norm = seg.inv_norm;
   p.sqnorm = seg.sqnorm;
   p.tomb = seg.tomb;
   p.q_inv = f;
-  p.q_nrm = f + B;
-  p.q_sq = f + 2 * B;
+  p.q_nrm = f + bp;
+  p.q_sq = f + 2 * bp;
   p.n_rows = seg.n_rows;
   p.B = B;
   p.k = k;
@@ -547,20 +755,39 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const SegDesc& seg, int
   p.cand = cand;
   p.cand_count = cand_count;
   p.lower_glob = lower_glob;
+  p.lower_list = lower_list;
   p.cap = cap;
   p.slice_base = slice_base;
   p.s_total = s_total;
-  dim3 grid((B + BM - 1) / BM, n_slices, 1), block(kThreads, 1, 1);
-  if (metric == kCosine) gemm_filter_kernel<kCosine><<<grid, block, kFilterSmem, stream>>>(tm_x, tm_q, p);
-  else if (metric == kL2) gemm_filter_kernel<kL2><<<grid, block, kFilterSmem, stream>>>(tm_x, tm_q, p);
-  else gemm_filter_kernel<kIP><<<grid, block, kFilterSmem, stream>>>(tm_x, tm_q, p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(n_qblocks, n_slices, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = filter_smem(ncta);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ncta == 2 ? 1 : 0;
+  auto go = [&](auto kern) { return cudaLaunchKernelEx(&cfg, kern, tm_x, tm_q, p); };
+  if (ncta == 2) {
+    if (metric == kCosine) return go(gemm_filter_kernel<kCosine, 2>);
+    if (metric == kL2) return go(gemm_filter_kernel<kL2, 2>);
+    return go(gemm_filter_kernel<kIP, 2>);
+  }
+  if (metric == kCosine) return go(gemm_filter_kernel<kCosine, 1>);
+  if (metric == kL2) return go(gemm_filter_kernel<kL2, 1>);
+  return go(gemm_filter_kernel<kIP, 1>);
 }
 
 cudaError_t launch_refine_topk(const SegDesc* segs, int n_seg, const float* q, int B, int dim, int dpad, int elem_bytes,
                                int lpr_log2, int nch, int k, int metric, const unsigned long long* cand,
-                               const unsigned int* cand_count, int cap, int s_total, int* overflow, uint64_t* keys_out,
-                               float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream) {
+                               const unsigned int* cand_count, int cap, int s_total, int* overflow, int ctas_per_query,
+                               uint64_t* part, unsigned int* tickets, uint64_t* keys_out, float* scores_out,
+                               long long* gids_out, int* counts_out, cudaStream_t stream) {
   RefineParams p;
   memset(&p, 0, sizeof(p));
   for (int s = 0; s < n_seg; ++s) p.seg[s] = segs[s];
@@ -568,6 +795,8 @@ cudaError_t launch_refine_topk(const SegDesc* segs, int n_seg, const float* q, i
   p.cand = cand;
   p.cand_count = cand_count;
   p.overflow = overflow;
+  p.part = part;
+  p.tickets = tickets;
   p.B = B;
   p.dim = dim;
   p.dpad = dpad;
@@ -585,11 +814,11 @@ cudaError_t launch_refine_topk(const SegDesc* segs, int n_seg, const float* q, i
   p.counts_out = counts_out;
   const int warps = 8;
   const size_t smem = ((static_cast<size_t>(dpad) * 4 + 127) & ~static_cast<size_t>(127)) + 128 +
-                      (static_cast<size_t>(warps) * k + k) * 8;
+                      (static_cast<size_t>(warps) * 32 + 32) * 8;
   const bool bf16 = elem_bytes == 2, l2 = metric == kL2;
   auto go = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    kern<<<B, warps * 32, smem, stream>>>(p);
+    kern<<<dim3(B, ctas_per_query > 1 ? ctas_per_query : 1, 1), warps * 32, smem, stream>>>(p);
   };
   if (bf16) { if (l2) go(refine_topk_kernel<true, true>); else go(refine_topk_kernel<true, false>); }
   else { if (l2) go(refine_topk_kernel<false, true>); else go(refine_topk_kernel<false, false>); }

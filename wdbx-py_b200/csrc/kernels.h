@@ -103,19 +103,26 @@ int filter_ld16(int dim);
 size_t filter_query_workspace_bytes(int B, int dim);
 int filter_slices_for(long long n_rows, int B, int sm_count);
 cudaError_t launch_shadow_rows(const float* rows, long long n, int dpad, int ld16, void* dst, cudaStream_t stream);
-cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace, cudaStream_t stream);
+cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace, unsigned int* zero, size_t n_zero,
+                                cudaStream_t stream);
 cudaError_t launch_gemm_filter(const void* xb, int ld_x, const SegDesc& seg, int seg_index, int dim, const void* workspace,
                                int B, int k, int metric, float eps_rel, int n_slices, unsigned long long* cand,
-                               unsigned int* cand_count, unsigned int* lower_glob, int cap, int slice_base, int s_total,
-                               cudaStream_t stream);
+                               unsigned int* cand_count, unsigned int* lower_glob, unsigned int* lower_list, int cap,
+                               int slice_base, int s_total, cudaStream_t stream);
 cudaError_t launch_refine_topk(const SegDesc* segs, int n_seg, const float* q, int B, int dim, int dpad, int elem_bytes,
                                int lpr_log2, int nch, int k, int metric, const unsigned long long* cand,
-                               const unsigned int* cand_count, int cap, int s_total, int* overflow, uint64_t* keys_out,
-                               float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream);
+                               const unsigned int* cand_count, int cap, int s_total, int* overflow, int ctas_per_query,
+                               uint64_t* part, unsigned int* tickets, uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out,
+                               cudaStream_t stream);
 
 // K3: merge G best-first lists per query.
 cudaError_t launch_merge_topk(const uint64_t* keys, int G, int B, int k, uint64_t* keys_out, float* scores_out,
                               long long* gids_out, int* counts_out, cudaStream_t stream);
+
+// Stand-alone NVLink key exchange + merge (same protocol as the one fused into K1's last CTA); see exchange.cu.
+cudaError_t launch_exchange_merge(uint64_t* const* peers, int world, int rank, unsigned int seq, const uint64_t* keys_in,
+                                  int B, int k, uint64_t* keys_out, float* scores_out, long long* gids_out,
+                                  int* counts_out, cudaStream_t stream);
 
 // K4: ingest rows (fp32 source) into the stored layout + norms.
 cudaError_t launch_append_rows(const float* src, long long n, int dim, int dpad, bool bf16, unsigned char* dst_rows,

@@ -120,6 +120,22 @@ __device__ __forceinline__ uint64_t warp_merge32(uint64_t a, uint64_t b, int lan
   return c;
 }
 
+// full bitonic sort (descending) of one key per lane
+__device__ __forceinline__ uint64_t warp_sort32_desc(uint64_t v, int lane) {
+#pragma unroll
+  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      const uint64_t o = __shfl_xor_sync(FULL_MASK, v, j);
+      const bool desc_block = (lane & k2) == 0;   // the last stage (k2 == 32) is one descending block
+      const bool low_lane = (lane & j) == 0;
+      const bool keep_max = desc_block == low_lane;
+      v = keep_max ? (v > o ? v : o) : (v < o ? v : o);
+    }
+  }
+  return v;
+}
+
 // ---- k <= 32*S: a list is S keys per lane, element e = slot*32 + lane, sorted descending.
 // Same bitonic scheme on 32*S elements: combine with the reversed second list, compare-exchange
 // across slots (strides 32*S/2 .. 32), then across lanes (16 .. 1).

@@ -25,11 +25,12 @@ DTYPES = {"fp32": F32, "float32": F32, "f32": F32, "bf16": BF16, "bfloat16": BF1
 class Stats(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("device", C.c_int32), ("dim", C.c_int32), ("dim_padded", C.c_int32),
-        ("dtype", C.c_int32), ("num_segments", C.c_int32), ("sm_count", C.c_int32), ("reserved0", C.c_int32),
+        ("dtype", C.c_int32), ("num_segments", C.c_int32), ("sm_count", C.c_int32), ("last_kernel", C.c_int32),
         ("rows_total", C.c_int64), ("rows_live", C.c_int64), ("capacity_rows", C.c_int64),
         ("bytes_resident", C.c_int64), ("kernel_launches", C.c_int64), ("searches", C.c_int64),
         ("last_search_ms", C.c_double),
         ("seg_rows", C.c_int64 * MAX_SEGMENTS), ("seg_live", C.c_int64 * MAX_SEGMENTS),
+        ("last_kernel_ms", C.c_double),
     ]
 
 
@@ -56,6 +57,7 @@ SIGNATURES = {
     "wdbx_b200_exchange_attach": (C.c_int, [_P, C.c_int, _P]),
     "wdbx_b200_search_exchange": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "wdbx_b200_set_tuning": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "wdbx_b200_set_kernel_timing": (C.c_int, [_P, C.c_int]),
     "wdbx_b200_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
 }
 

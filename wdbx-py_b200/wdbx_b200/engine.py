@@ -288,6 +288,11 @@ class Engine:
     def set_tuning(self, warps: int = 0, stages: int = 0, rows_unroll: int = 0, grid: int = 0, evict_first: int = -1):
         check(self._lib.wdbx_b200_set_tuning(self._handle(), warps, stages, rows_unroll, grid, evict_first))
 
+    def set_kernel_timing(self, enable: bool = True):
+        """Bracket the dominant kernel of every search with CUDA events; `stats()` then carries
+        `last_kernel` (1 = K1 scan, 2 = K2b filter) and `last_kernel_ms`.  Measurement hook."""
+        check(self._lib.wdbx_b200_set_kernel_timing(self._handle(), 1 if enable else 0))
+
     def stats(self) -> Dict:
         st = _lib.Stats()
         check(self._lib.wdbx_b200_get_stats(self._handle(), C.byref(st)))
