@@ -38,7 +38,7 @@ def _oracle_check(X, Q, k, metric, scores, gids, counts, dead=None, sample=16):
     (30000, 384, 96, 20, "ip", "bf16"), (9000, 200, 70, 10, "cosine", "bf16"), (150000, 128, 300, 10, "l2", "fp32"),
     # small batches: several refine CTAs per query + K3 merge of their partial lists
     (200000, 256, 1, 10, "cosine", "fp32"), (50000, 768, 3, 16, "l2", "fp32"), (120000, 128, 8, 10, "ip", "fp32"),
-    (40000, 384, 2, 1, "cosine", "bf16")])
+    (40000, 384, 2, 1, "cosine", "bf16"), (60000, 256, 4, 25, "cosine", "fp32"), (20000, 96, 300, 32, "l2", "fp32")])
 def test_filter_refine_is_bit_identical_to_scan(built_lib, n, dim, B, k, metric, dtype):
     rng = np.random.default_rng(n + dim + B)
     X = rng.standard_normal((n, dim), dtype=np.float32)
@@ -127,3 +127,30 @@ def test_small_k_larger_than_rows_and_empty(built_lib):
     assert np.all(c == 7) and np.all(g[:, 7:] == -1)
     _oracle_check(X, Q, 10, "cosine", s, g, c)
     e2.close()
+
+
+def test_small_batches_route_by_size_and_report_the_dominant_kernel(built_lib):
+    """fp32 segments above the size threshold serve even single queries through the bf16-shadow filter
+    (half the HBM bytes, bit-identical results); wdbx_b200_set_kernel_timing reports which kernel ran."""
+    import wdbx_b200
+
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((50000, 128), dtype=np.float32)
+    q = rng.standard_normal((1, 128), dtype=np.float32)
+    got = {}
+    for name, mb in (("filter", "0"), ("scan", "-1")):
+        os.environ["WDBX_B200_SHADOW_MIN_MB"] = mb
+        try:
+            e = wdbx_b200.Engine(device=0, dim=128, dtype="fp32", num_segments=1)
+        finally:
+            os.environ.pop("WDBX_B200_SHADOW_MIN_MB", None)
+        e.append(0, X)
+        e.set_kernel_timing(True)
+        got[name] = e.search_host(q, 10, metric="cosine")
+        st = e.stats()
+        assert st["last_kernel"] == (2 if name == "filter" else 1) and st["last_kernel_ms"] > 0.0
+        e.set_kernel_timing(False)
+        e.close()
+    for a, b in zip(got["filter"], got["scan"]):
+        np.testing.assert_array_equal(np.asarray(a).view(np.uint32) if a.dtype == np.float32 else a,
+                                      np.asarray(b).view(np.uint32) if b.dtype == np.float32 else b)

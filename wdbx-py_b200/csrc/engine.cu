@@ -90,7 +90,9 @@ struct wdbx_b200_engine {
   uint32_t next_gid = 0;
   std::vector<Workspace> ws;
   ScanTuning tune{0, 0, 0, 0, -1, 0};
-  long long shadow_min_bytes = 2ll << 30;  // small batches use the bf16-shadow filter from this many stored bytes on (<0: never)
+  // small batches use the bf16-shadow filter from this many stored bytes on (<0: never).  Measured: at 1.5 GB
+  // (1M x 384) the filter path already wins (195 vs 222 us per query); below ~1 GB its extra launches cost more
+  long long shadow_min_bytes = 1ll << 30;
   int gemm_min_batch = 16;  // B >= this => tcgen05 path (0 = never); measured crossover vs K1 (8 queries/pass) ~ 12-16
   int gemm_mode = 0;        // 0 = bf16 filter + exact refine (K2b), 1 = 3xTF32 with fused top-k (K2)
   int pdl = 1;              // programmatic dependent launch for K1 (WDBX_B200_PDL=0 disables)
@@ -415,18 +417,18 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   // one private candidate region per (query, row slice); B * slices is ~ (#SMs x 128) whatever B is
   int slices[kMaxSeg];
   int s_total = 0;
+  const int rps = filter_regions_per_slice(B);
   for (int s = s0; s < s1; ++s) {
     slices[s] = e->seg[s].n_rows > 0 ? filter_slices_for(e->seg[s].n_rows, B, e->sm_count) : 0;
-    s_total += 2 * slices[s];  // two candidate regions per (query, slice): one per epilogue column half
+    s_total += rps * slices[s];  // candidate regions per (query, slice): one per epilogue column half / warp
   }
-  if (s_total == 0) s_total = 2;
-  const int cap = 512;
+  if (s_total == 0) s_total = rps;
+  const int cap = rps == 2 ? 512 : 1024;
   const size_t n_regions = static_cast<size_t>(B) * s_total;
   const size_t need_ws = filter_query_workspace_bytes(B, e->dim);
   // small batches: several refine CTAs per query (each a share of the candidate regions), merged by K3
-  int refine_ctas = (2 * e->sm_count + B - 1) / B;
-  if (refine_ctas > 64) refine_ctas = 64;
-  if (refine_ctas > s_total) refine_ctas = s_total;
+  int refine_ctas = (2 * e->sm_count + B - 1) / B;   // two 256-thread CTAs per SM
+  if (refine_ctas > 8 * s_total) refine_ctas = 8 * s_total;
   if (refine_ctas < 1) refine_ctas = 1;
   const size_t need_part = refine_ctas > 1 ? static_cast<size_t>(refine_ctas) * B * k : 0;
   // one zero-initialised block per search: [n_regions] candidate counts | [B] overflow flags | [B] refine

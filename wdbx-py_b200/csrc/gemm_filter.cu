@@ -42,7 +42,7 @@ constexpr int BK = 64;        // bf16 elements per K block = 128 bytes
 constexpr int STAGES_SINGLE = 4; // single-CTA ring (48 KB / stage)
 constexpr int STAGES_PAIR = 6;   // CTA-pair ring (32 KB / stage per CTA)
 constexpr int kThreads = 384;   // 4 control warps + 8 epilogue warps
-constexpr int kMaxKFilter = 16;
+constexpr int kMaxKFilter = 32;   // shared lower-bound list = one 128-byte line per query; refine lists = one key per lane
 constexpr uint32_t Q_TILE_BYTES = BM * BK * 2;  // 16 KB
 constexpr uint32_t TMEM_COLS = 2 * BN;
 
@@ -56,6 +56,7 @@ struct FilterParams {
   long long n_rows;
   int B, k;
   int n_kblocks, n_tiles, n_slices;
+  // (cap / slice_base / s_total below are shared by both filter kernels; the region index differs)
   int seg;                 // segment index stored with each candidate
   float eps_rel;           // rounding bound relative to |x||q|
   unsigned long long* cand;   // [B][s_total][cap]  (seg << 32 | row): one private region per (query, row slice)
@@ -426,6 +427,293 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------- filter kernel, small batches (B <= 16)
+// Same filter with the operands swapped: the X tile is the M side (two 128-row MMAs per 256-row tile), the
+// queries are the N = 16 side.  For a handful of queries the 128-query tile above spends 8x the tensor work
+// (and, at ~7 TB/s of HBM streaming, enough power to trip the board's power cap) on zero padding; here a
+// tile costs 2 x 4 MMAs of 128x16x16, the query tile is 2 KB per stage (6 stages of 34 KB), an accumulator
+// tile is 32 TMEM columns, and the epilogue is one X row per thread: one multiply + compare per query.
+constexpr int SQ = 16;                                 // query columns per MMA
+constexpr int S_STAGES = 6;
+constexpr uint32_t SX_BYTES = BN * BK * 2;             // 32 KB: 256 rows x 64 dims
+constexpr uint32_t SQ_BYTES = SQ * BK * 2;             // 2 KB
+constexpr uint32_t S_STAGE_BYTES = SX_BYTES + SQ_BYTES;
+constexpr uint32_t S_TMEM_COLS = 64;                   // 2 buffers x 2 sub-tiles x 16 columns
+constexpr int kSmallWarpRegions = 1;                   // candidate regions per (query, slice): one, shared by the CTA
+
+template <int METRIC>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_q,
+                         const FilterParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* stage_base = smem;
+  unsigned int* Lq = reinterpret_cast<unsigned int*>(smem + S_STAGES * S_STAGE_BYTES);  // [SQ] mono(best known bound)
+  float* Tq = reinterpret_cast<float*>(Lq + SQ);                                        // [SQ] fast-test threshold
+  float* q_inv_s = Tq + SQ;
+  float* q_nrm_s = q_inv_s + SQ;
+  float* q_sq_s = q_nrm_s + SQ;
+  unsigned int* wcount = reinterpret_cast<unsigned int*>(q_sq_s + SQ);                  // [SQ] candidates of this CTA per query
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wcount + SQ);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + S_STAGES;
+  uint64_t* tmem_full = bars + 2 * S_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.y;
+  const int k = p.k;
+  const float NEG_INF = __int_as_float(0xff800000);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_x);
+    prefetch_tmap(&tm_q);
+    for (int s = 0; s < S_STAGES; ++s) {
+      mbar_init(smem_u32(full_bar + s), 1);
+      mbar_init(smem_u32(empty_bar + s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(tmem_full + a), 1);
+      mbar_init(smem_u32(tmem_empty + a), 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_ptr), S_TMEM_COLS);
+  if (warp == 3) {
+    for (int j = lane; j < SQ; j += 32) {
+      const bool v = j < p.B;
+      Lq[j] = 0u;
+      Tq[j] = NEG_INF;
+      q_inv_s[j] = v ? p.q_inv[j] : 0.0f;
+      q_nrm_s[j] = v ? p.q_nrm[j] : 0.0f;
+      q_sq_s[j] = v ? p.q_sq[j] : 0.0f;
+    }
+    for (int i = lane; i < SQ; i += 32) wcount[i] = 0u;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int my_tiles = (p.n_tiles - slice + p.n_slices - 1) / p.n_slices;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int row0 = (slice + t * p.n_slices) * BN;
+      for (int kb = 0; kb < p.n_kblocks; ++kb) {
+        mbar_wait(smem_u32(empty_bar + stage), phase ^ 1u);
+        const uint32_t sb = smem_u32(stage_base) + static_cast<uint32_t>(stage) * S_STAGE_BYTES;
+        const uint32_t bar = smem_u32(full_bar) + static_cast<uint32_t>(stage) * 8u;
+        if (elect_one()) {
+          mbar_expect_tx(bar, S_STAGE_BYTES);
+          tma_load_2d(sb, &tm_x, kb * BK, row0, bar);
+          tma_load_2d(sb + SX_BYTES, &tm_q, kb * BK, 0, bar);
+        }
+        __syncwarp();
+        if (++stage == S_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(128, SQ, 1u);  // M = 128 X rows, N = 16 queries, BF16 x BF16 -> F32
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int a = t & 1;
+      mbar_wait(smem_u32(tmem_empty + a), ((static_cast<uint32_t>(t) >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(a * 2 * SQ);
+      for (int kb = 0; kb < p.n_kblocks; ++kb) {
+        mbar_wait(smem_u32(full_bar + stage), phase);
+        tc_fence_after();
+        const uint32_t sb = smem_u32(stage_base) + static_cast<uint32_t>(stage) * S_STAGE_BYTES;
+        const uint64_t d_x0 = make_desc_kmajor(sb, 128, 2);
+        const uint64_t d_x1 = make_desc_kmajor(sb + SX_BYTES / 2, 128, 2);
+        const uint64_t d_q = make_desc_kmajor(sb + SX_BYTES, 128, 2);
+        const uint32_t ebar = smem_u32(empty_bar) + static_cast<uint32_t>(stage) * 8u;
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t adv = static_cast<uint64_t>((kk * 16 * 2) >> 4);
+            umma_f16(d_tmem, d_x0 + adv, d_q + adv, idesc, (kb | kk) ? 1u : 0u);
+            umma_f16(d_tmem + SQ, d_x1 + adv, d_q + adv, idesc, (kb | kk) ? 1u : 0u);
+          }
+          umma_commit(ebar);
+        }
+        __syncwarp();
+        if (++stage == S_STAGES) { stage = 0; phase ^= 1u; }
+      }
+      if (elect_one()) umma_commit(smem_u32(tmem_full + a));
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: 8 warps, one X row of the tile per thread (TMEM lane = row inside the 128-row sub-tile)
+    const int ew = warp - 4;
+    const int quarter = warp & 3, sub = ew >> 2;
+    const int row_in_tile = sub * 128 + quarter * 32 + lane;
+    const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(sub * SQ);
+    // fast test per (row, query), see gemm_filter_kernel:  cosine d/|x| >= (L - eps)|q|;  ip d + |x|eps >= L;
+    // l2 2d + |x|eps - |x|^2 >= L + |q|^2, thresholds with 1e-6 slack; admitted pairs are decided by the
+    // reference form below.  L / T live in shared memory per query and are shared by the whole CTA.
+    auto qeps_of = [&](int j) -> float {
+      return (METRIC == kCosine) ? p.eps_rel : (METRIC == kL2 ? 2.0f * p.eps_rel * q_nrm_s[j] : p.eps_rel * q_nrm_s[j]);
+    };
+    auto fast_thr = [&](float l, int j) -> float {
+      if (METRIC == kCosine) {
+        const float t = (l - p.eps_rel) * q_nrm_s[j];
+        return t - 1e-6f * (fabsf(t) + p.eps_rel * q_nrm_s[j]);
+      }
+      if (METRIC == kL2) return (l + q_sq_s[j]) - 1e-6f * (fabsf(l) + 2.0f * q_sq_s[j]);
+      return l;
+    };
+    auto raise_bound = [&](int j, float nl) {   // any thread: publish a better bound of query j to the CTA
+      const unsigned int m = mono_u32(nl);
+      if (atomicMax(Lq + j, m) < m) Tq[j] = fast_thr(nl, j);
+    };
+    auto load_row = [&](int t, float& inx, float& sq) {
+      const long long row = static_cast<long long>(slice + t * p.n_slices) * BN + row_in_tile;
+      inx = 0.0f;
+      sq = 0.0f;
+      if (t < my_tiles && row < p.n_rows) {
+        if (METRIC == kCosine) inx = __ldg(p.inv_norm + row);
+        else sq = __ldg(p.sqnorm + row);
+      }
+    };
+    float inx_next, sq_next;
+    load_row(0, inx_next, sq_next);
+    unsigned int glob_next = (ew == 0 && lane < p.B) ? __ldcg(p.lower_glob + lane) : 0u;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int a = t & 1;
+      const long long row = static_cast<long long>(slice + t * p.n_slices) * BN + row_in_tile;
+      const bool row_valid = row < p.n_rows;
+      const float inx = inx_next, sq = sq_next;
+      const float ex = (METRIC == kCosine) ? 1.0f : sqrtf(sq);   // |x|
+      const float sqs = sq * (1.0f - 1e-6f);
+      if (ew == 0 && lane < p.B) {   // bounds published by other CTAs (one tile stale: prefetched)
+        if (glob_next > 0x007FFFFFu) raise_bound(lane, unmono_f32(glob_next));
+        glob_next = __ldcg(p.lower_glob + lane);
+      }
+      load_row(t + 1, inx_next, sq_next);
+      mbar_wait(smem_u32(tmem_full + a), (static_cast<uint32_t>(t) >> 1) & 1u);
+      tc_fence_after();
+      uint32_t r[SQ];
+      __syncwarp();
+      tmem_ld16(taddr0 + static_cast<uint32_t>(a * 2 * SQ), r);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tmem_empty + a));   // the accumulator is in registers: free it now
+      // fast test: one multiply (or fma) + compare per (row, query); `any` = queries with an admitted row
+      unsigned any = 0u;
+#pragma unroll
+      for (int j = 0; j < SQ; ++j) {
+        if (j < p.B) {   // uniform
+          const float d = __uint_as_float(r[j]);
+          float u;
+          if (METRIC == kCosine) u = d * inx;
+          else if (METRIC == kL2) u = fmaf(2.0f, d, fmaf(ex, qeps_of(j), -sqs));
+          else u = fmaf(ex, qeps_of(j), d);
+          if (__any_sync(FULL_MASK, row_valid && !(u < Tq[j]))) any |= 1u << j;
+        }
+      }
+      if (any) {
+        // rare path (warp-uniform).  Reference form of the bound per admitted query; the row with the best
+        // lower bound of the warp is offered to the shared list -- one lane per QUERY inserts, all queries
+        // in parallel, so a cold start costs one round trip instead of a chain of them -- then the rows
+        // that still pass against the updated bound are appended (warp-aggregated, no atomics).
+        bool dead = false;
+        if (p.tomb != nullptr && row_valid) dead = (__ldg(p.tomb + (row >> 5)) >> (row & 31)) & 1u;
+        float my_best = NEG_INF;       // lane j: best lower bound of this warp's rows for query j
+        unsigned rem = any;
+        while (rem) {
+          const int j = __ffs(rem) - 1;
+          rem &= rem - 1;
+          float d = 0.0f;
+#pragma unroll
+          for (int jj = 0; jj < SQ; ++jj) d = (jj == j) ? __uint_as_float(r[jj]) : d;   // r[] stays in registers
+          float sv;
+          if (METRIC == kCosine) sv = d * inx * q_inv_s[j];
+          else if (METRIC == kL2) sv = -((sq - 2.0f * d) + q_sq_s[j]);
+          else sv = d;
+          const float lo = (row_valid && !dead) ? sv - ex * qeps_of(j) : NEG_INF;   // NaN: mono_u32 ranks it as -inf
+          const unsigned int wbest = __reduce_max_sync(FULL_MASK, mono_u32(lo));
+          if (lane == j) my_best = unmono_f32(max(wbest, 0x007FFFFFu));
+        }
+        if (lane < p.B && ((any >> lane) & 1u)) {
+          const float L = unmono_f32(max(*reinterpret_cast<volatile unsigned int*>(Lq + lane), 0x007FFFFFu));
+          if (my_best > L) {
+            const float nl = lower_insert(p.lower_list + static_cast<size_t>(lane) * kMaxKFilter, p.lower_glob + lane, k,
+                                          my_best, L);
+            if (nl > L) raise_bound(lane, nl);
+          }
+          // cold start: every warp of the grid meets its first tile with "no bound" at the same moment, and
+          // an insert that lands while the shared list still has empty slots returns none either.  Appending
+          // all 32 rows of every warp then (~38k candidates per query) costs far more than waiting the few
+          // microseconds until k rows have been offered by anyone (bounded: tiny stores may never get there).
+          if (Lq[lane] <= 0x007FFFFFu) {
+            for (int spin = 0; spin < 48; ++spin) {
+              const unsigned int g = __ldcg(p.lower_glob + lane);
+              if (g > 0x007FFFFFu) { raise_bound(lane, unmono_f32(g)); break; }
+              __nanosleep(200);
+            }
+          }
+          // ... and the first finite bound is only the weakest of the first k offers: on the first tile give
+          // the other ~1200 warps' offers (already in flight) a moment to land, then take the settled bound
+          if (t == 0) {
+            __nanosleep(3000);
+            const unsigned int g = __ldcg(p.lower_glob + lane);
+            if (g > 0x007FFFFFu) raise_bound(lane, unmono_f32(g));
+          }
+        }
+        __syncwarp();
+        rem = any;
+        while (rem) {
+          const int j = __ffs(rem) - 1;
+          rem &= rem - 1;
+          float d = 0.0f;
+#pragma unroll
+          for (int jj = 0; jj < SQ; ++jj) d = (jj == j) ? __uint_as_float(r[jj]) : d;
+          float sv;
+          if (METRIC == kCosine) sv = d * inx * q_inv_s[j];
+          else if (METRIC == kL2) sv = -((sq - 2.0f * d) + q_sq_s[j]);
+          else sv = d;
+          const float up = fmaf(ex, qeps_of(j), sv);   // upper bound of the exact score (reference form)
+          const float L = unmono_f32(max(*reinterpret_cast<volatile unsigned int*>(Lq + j), 0x007FFFFFu));
+          const bool take = row_valid && !dead && !(up < L);   // !(x < L) keeps NaN (the refine ranks it like K1)
+          const unsigned tm = __ballot_sync(FULL_MASK, take);
+          if (tm) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(wcount + j, static_cast<unsigned int>(__popc(tm)));   // shared memory
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (take) {
+              const unsigned int idx = base + __popc(tm & ((1u << lane) - 1u));
+              if (idx < static_cast<unsigned int>(p.cap)) {
+                const size_t region = static_cast<size_t>(j) * p.s_total + static_cast<size_t>(p.slice_base + slice);
+                p.cand[region * p.cap + idx] = (static_cast<unsigned long long>(p.seg) << 32) | static_cast<unsigned long long>(row);
+              }
+            }
+          }
+        }
+      }
+    }
+    // all epilogue warps done -> one thread per query publishes the CTA's candidate count
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (ew == 0 && lane < p.B)
+      p.cand_count[static_cast<size_t>(lane) * p.s_total + static_cast<size_t>(p.slice_base + slice)] = wcount[lane];
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, S_TMEM_COLS);
+  }
+}
+
+constexpr size_t kFilterSmallSmem = 1024 + static_cast<size_t>(S_STAGES) * S_STAGE_BYTES + (5 * SQ + SQ) * 4 +
+                                    (2 * S_STAGES + 4) * 8 + 16;
+
 constexpr size_t filter_smem(int ncta) {
   const size_t stages = ncta == 2 ? STAGES_PAIR : STAGES_SINGLE;
   const size_t stage_bytes = static_cast<size_t>(BN / ncta) * BK * 2 + Q_TILE_BYTES;
@@ -446,6 +734,7 @@ struct RefineParams {
   int* overflow;                    // [B] set to 1 when the candidate list overflowed
   uint64_t* part;                   // [B][gridDim.y][k] partial lists when gridDim.y > 1
   unsigned int* tickets;            // [B] zeroed per search: the last CTA of a query merges the partial lists
+  int sub;                          // warps sharing one candidate region (work units per region)
   int B, dim, dpad, row_bytes, cpr, lpr_log2, nch, k, metric, cap;
   uint64_t* keys_out;
   float* scores_out;
@@ -504,7 +793,8 @@ __global__ void __launch_bounds__(256, 2) refine_topk_kernel(const __grid_consta
   // Work unit = (candidate region, SUB-th part of it): a region's candidates are dealt round-robin to SUB
   // warps, so the ~300 regions of a small batch spread over every warp of every CTA of the query.
   // CU candidates per lane group are in flight at once: entry -> row chunks + norm + id -> score.
-  constexpr int SUB = 4, CU = 2;
+  constexpr int CU = 2;
+  const int SUB = p.sub;
   const int n_units = p.s_total * SUB;
   for (int unit = blockIdx.y * nwarps + warp; unit < n_units; unit += gridDim.y * nwarps) {
    const int sl = unit / SUB, sub = unit - sl * SUB;
@@ -659,16 +949,33 @@ bool encode_map_bf16(CUtensorMap* map, const void* base, long long rows, int col
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// WDBX_B200_FILTER_PAIR=0 forces the single-CTA kernel (A/B comparisons, fallback)
-bool pair_mode() {
-  static const bool on = [] {
+// CTA pairs (cta_group::2) halve the L2 -> shared-memory traffic of the X operand but couple the two
+// epilogues; measured on B200 (10M x 768): faster for 2-4 query blocks (B 129..512: 72k vs 64k QPS at
+// B=256), equal at 8 blocks, slower beyond (power-capped either way).  WDBX_B200_FILTER_PAIR=0 / 1
+// forces never / whenever the block count is even.
+bool pair_mode(int n_qblocks) {
+  static const int forced = [] {
     const char* v = getenv("WDBX_B200_FILTER_PAIR");
+    return v ? (v[0] == '0' ? 0 : 1) : -1;
+  }();
+  if ((n_qblocks & 1) != 0 || forced == 0) return false;
+  return forced == 1 || n_qblocks <= 4;
+}
+
+// WDBX_B200_FILTER_SMALL=0 routes small batches through the 128-query kernel (A/B comparisons)
+bool small_batch_mode(int B) {
+  static const bool on = [] {
+    const char* v = getenv("WDBX_B200_FILTER_SMALL");
     return !(v && v[0] == '0');
   }();
-  return on;
+  return on && B <= SQ;
 }
 
 }  // namespace
+
+// candidate regions per (query, row slice): one per epilogue warp in the small-batch kernel, one per column
+// half in the 128-query kernel
+int filter_regions_per_slice(int B) { return small_batch_mode(B) ? kSmallWarpRegions : 2; }
 
 int filter_max_k() { return kMaxKFilter; }
 
@@ -725,6 +1032,11 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const SegDesc& seg, int
     };
     set(gemm_filter_kernel<kCosine, 1>, 1); set(gemm_filter_kernel<kIP, 1>, 1); set(gemm_filter_kernel<kL2, 1>, 1);
     set(gemm_filter_kernel<kCosine, 2>, 2); set(gemm_filter_kernel<kIP, 2>, 2); set(gemm_filter_kernel<kL2, 2>, 2);
+    auto set_small = [&](auto kern) {
+      if (attr_err == cudaSuccess)
+        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFilterSmallSmem));
+    };
+    set_small(gemm_filter_small_kernel<kCosine>); set_small(gemm_filter_small_kernel<kIP>); set_small(gemm_filter_small_kernel<kL2>);
   });
   if (attr_err != cudaSuccess) return attr_err;
   const int ld = filter_ld16(dim);
@@ -733,9 +1045,11 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const SegDesc& seg, int
   const float* f = reinterpret_cast<const float*>(ws + (static_cast<size_t>(bp) * ld * 2 + 15) / 16 * 16);
   // CTA pairs need an even number of query blocks (the pair = two adjacent blocks on one row slice)
   const int n_qblocks = (B + BM - 1) / BM;
-  const int ncta = (pair_mode() && (n_qblocks % 2) == 0) ? 2 : 1;
+  const bool small = small_batch_mode(B);
+  const int ncta = (!small && pair_mode(n_qblocks)) ? 2 : 1;
   CUtensorMap tm_x, tm_q;
-  if (!encode_map_bf16(&tm_x, xb, seg.n_rows, dim, ld_x, BN / ncta) || !encode_map_bf16(&tm_q, ws, bp, dim, ld, BM))
+  if (!encode_map_bf16(&tm_x, xb, seg.n_rows, dim, ld_x, BN / ncta) ||
+      !encode_map_bf16(&tm_q, ws, bp, dim, ld, small ? SQ : BM))
     return cudaErrorInvalidValue;
   FilterParams p;
   p.inv_norm = seg.inv_norm;
@@ -763,7 +1077,7 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const SegDesc& seg, int
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(n_qblocks, n_slices, 1);
   cfg.blockDim = dim3(kThreads, 1, 1);
-  cfg.dynamicSmemBytes = filter_smem(ncta);
+  cfg.dynamicSmemBytes = small ? kFilterSmallSmem : filter_smem(ncta);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -773,6 +1087,11 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const SegDesc& seg, int
   cfg.attrs = attr;
   cfg.numAttrs = ncta == 2 ? 1 : 0;
   auto go = [&](auto kern) { return cudaLaunchKernelEx(&cfg, kern, tm_x, tm_q, p); };
+  if (small) {
+    if (metric == kCosine) return go(gemm_filter_small_kernel<kCosine>);
+    if (metric == kL2) return go(gemm_filter_small_kernel<kL2>);
+    return go(gemm_filter_small_kernel<kIP>);
+  }
   if (ncta == 2) {
     if (metric == kCosine) return go(gemm_filter_kernel<kCosine, 2>);
     if (metric == kL2) return go(gemm_filter_kernel<kL2, 2>);
@@ -782,6 +1101,8 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const SegDesc& seg, int
   if (metric == kL2) return go(gemm_filter_kernel<kL2, 1>);
   return go(gemm_filter_kernel<kIP, 1>);
 }
+
+static int warps_per_cta_refine() { return 8; }
 
 cudaError_t launch_refine_topk(const SegDesc* segs, int n_seg, const float* q, int B, int dim, int dpad, int elem_bytes,
                                int lpr_log2, int nch, int k, int metric, const unsigned long long* cand,
@@ -797,6 +1118,12 @@ cudaError_t launch_refine_topk(const SegDesc* segs, int n_seg, const float* q, i
   p.overflow = overflow;
   p.part = part;
   p.tickets = tickets;
+  {
+    // enough work units that every warp of the launch gets one, whatever the number of regions
+    const int total_warps = warps_per_cta_refine() * (ctas_per_query > 1 ? ctas_per_query : 1);
+    int sub = (total_warps + s_total - 1) / (s_total > 0 ? s_total : 1);
+    p.sub = sub < 4 ? 4 : (sub > 32 ? 32 : sub);
+  }
   p.B = B;
   p.dim = dim;
   p.dpad = dpad;
@@ -812,7 +1139,7 @@ cudaError_t launch_refine_topk(const SegDesc* segs, int n_seg, const float* q, i
   p.scores_out = scores_out;
   p.gids_out = gids_out;
   p.counts_out = counts_out;
-  const int warps = 8;
+  const int warps = warps_per_cta_refine();
   const size_t smem = ((static_cast<size_t>(dpad) * 4 + 127) & ~static_cast<size_t>(127)) + 128 +
                       (static_cast<size_t>(warps) * 32 + 32) * 8;
   const bool bf16 = elem_bytes == 2, l2 = metric == kL2;

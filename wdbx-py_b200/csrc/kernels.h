@@ -102,6 +102,7 @@ int filter_max_k();
 int filter_ld16(int dim);
 size_t filter_query_workspace_bytes(int B, int dim);
 int filter_slices_for(long long n_rows, int B, int sm_count);
+int filter_regions_per_slice(int B);
 cudaError_t launch_shadow_rows(const float* rows, long long n, int dpad, int ld16, void* dst, cudaStream_t stream);
 cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace, unsigned int* zero, size_t n_zero,
                                 cudaStream_t stream);
