@@ -288,7 +288,7 @@ def run_gpu(args):
     kernel_ms = reduce_max(sum(k_ms) / len(k_ms))
     ld16 = (DIM + 7) // 8 * 8
     if kernel_id == 2:
-        kernel_name = "gemm_filter_kernel (K2b filter over the bf16 shadow rows)"
+        kernel_name = "gemm_filter_small_kernel (K2b bf16 tcgen05 filter, B<=16 variant, over the 2-byte shadow rows)"
         algo_bytes = local_rows * ld16 * 2 + local_rows * 4     # 2-byte shadow rows + 1/|x| per row
         algo_note = "rows x dim x 2 (bf16 shadow) + rows x 4 (1/|x|): the bytes THIS kernel must read"
     else:

@@ -41,7 +41,10 @@ def _worker(rank, world, port, outdir):
     ctx = wdbx_b200.DistContext.from_env(rank)
     X, Q = _data()
     out = {}
-    for fused in (True, False):
+    # route: "filter" = bf16-shadow filter + refine + stand-alone NVLink exchange kernel (what large stores use),
+    # "scan" = K1 with the exchange fused into its last CTA; both must agree with one GPU
+    for route, fused in (("filter", True), ("filter", False), ("scan", True), ("scan", False)):
+        os.environ["WDBX_B200_SHADOW_MIN_MB"] = "0" if route == "filter" else "-1"
         st = wdbx_b200.VectorStore(384, tempfile.mkdtemp(), num_shards=2, dist=ctx,
                                    config=wdbx_b200.WDBXConfig({"GPU_STRICT": True, "GPU_FUSED_EXCHANGE": fused}))
         assert st._fused == fused
@@ -53,10 +56,11 @@ def _worker(rank, world, port, outdir):
         qd = st.engine.upload(Q)
         dev = st.search_device(qd, 10)
         torch.cuda.synchronize()
-        out["fused" if fused else "nccl"] = {"res": res, "dev_gids": dev["gids"].cpu().tolist(),
+        out[route + ("_fused" if fused else "_nccl")] = {"res": res, "dev_gids": dev["gids"].cpu().tolist(),
                                               "filtered": [(i, s) for i, s, _ in st.search(Q[1].tolist(), limit=5, filter_metadata={"x": 1})],
                                               "tie": [i for i, _, _ in st.search(X[77].tolist(), limit=2)]}
         st.close()
+    os.environ.pop("WDBX_B200_SHADOW_MIN_MB", None)
     Path(outdir, f"rank{rank}.json").write_text(json.dumps(out))
     dist.barrier()
     dist.destroy_process_group()
@@ -81,7 +85,7 @@ def test_two_gpus_match_one(built_lib):
         mp.spawn(_worker, args=(2, _free_port(), outdir), nprocs=2, join=True)
         got = [json.loads(Path(outdir, f"rank{r}.json").read_text()) for r in range(2)]
     for r in range(2):
-        for mode in ("fused", "nccl"):
+        for mode in ("filter_fused", "filter_nccl", "scan_fused", "scan_nccl"):
             assert got[r][mode]["res"] == want, (r, mode)
             assert got[r][mode]["tie"] == ["v77", "v123"]
             assert got[r][mode]["filtered"] == []
