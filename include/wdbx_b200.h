@@ -196,6 +196,14 @@ int wdbx_b200_search_exchange(wdbx_b200_engine* e, const float* q_dev, int B, in
                               uint64_t* keys_out, float* scores_out, int64_t* gids_out,
                               int32_t* counts_out, void* cuda_stream);
 
+/* Host-buffer form of wdbx_b200_search_exchange: pinned H2D of the queries -> collective search + on-device
+ * exchange -> ONE D2H of the packed result -> synchronise.  Every rank must call it with the same queries.
+ * Replaces: VectorStore.search's shard loop + merge (vector_store.py:323-330, :345) when the shards live on
+ * several GPUs. */
+int wdbx_b200_search_exchange_host(wdbx_b200_engine* e, const float* q_host, int B, int k, int metric,
+                                   float* scores_host, int64_t* gids_host, uint64_t* keys_host,
+                                   int32_t* counts_host);
+
 /* Override the scan kernel's launch geometry (0 / -1 = automatic): consumer warps per CTA,
  * TMA pipeline stages per warp, rows held per lane group (1, 2, 4), CTAs, L2 evict-first hint.
  * Benchmark / profiling hook; the counterpart of the reference's HNSW_EF_SEARCH / FAISS_NPROBE

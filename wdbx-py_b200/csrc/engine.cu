@@ -1073,14 +1073,14 @@ int wdbx_b200_exchange_attach(wdbx_b200_engine* e, int world, const void* ipc_ha
   return WDBX_B200_OK;
 }
 
-int wdbx_b200_search_exchange(wdbx_b200_engine* e, const float* q_dev, int B, int k, int metric, uint64_t* keys_out,
-                              float* scores_out, int64_t* gids_out, int32_t* counts_out, void* cuda_stream) {
-  int rc = check_search_args(e, B, k, metric);
-  if (rc != WDBX_B200_OK) return rc;
-  if (!q_dev) return fail(WDBX_B200_ERR_ARG, "q_dev is NULL");
-  DeviceGuard guard(e->device);
-  std::lock_guard<std::mutex> lk(e->mu);
-  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+}  // extern "C"
+
+namespace {
+
+// Collective search of all segments + on-device key exchange with the peer ranks.  Caller holds e->mu.
+int exchange_search_locked(wdbx_b200_engine* e, const float* q_dev, int B, int k, int metric, uint64_t* keys_out,
+                           float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream) {
+  int rc;
   if (e->xworld >= 2 && B <= kXchgMaxB && k <= kXchgMaxK && e->gemm_mode != 1 && use_gemm(e, 0, e->nseg, B, k)) {
     // bf16-filter path: local exact top-k (filter + refine), then the stand-alone exchange + merge kernel.
     // Ranks may take different routes for the same search: both speak the same exchange protocol.
@@ -1089,19 +1089,85 @@ int wdbx_b200_search_exchange(wdbx_b200_engine* e, const float* q_dev, int B, in
     if (rc == WDBX_B200_OK) {
       e->xseq += 1;
       CU_TRY(launch_exchange_merge(e->xpeer, e->xworld, e->xrank, e->xseq, e->xkeys, B, k, keys_out, scores_out,
-                                   reinterpret_cast<long long*>(gids_out), counts_out, stream));
+                                   gids_out, counts_out, stream));
       e->launches.fetch_add(1, std::memory_order_relaxed);
-      e->searches.fetch_add(1, std::memory_order_relaxed);
       return rc;
     }
     if (rc != WDBX_B200_ERR_OOM) return rc;
     cudaGetLastError();
     e->shadow_min_bytes = -1;
   }
-  rc = scan_segments(e, 0, e->nseg, q_dev, B, k, metric, keys_out, scores_out, reinterpret_cast<long long*>(gids_out),
-                     counts_out, stream, true);
+  return scan_segments(e, 0, e->nseg, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream, true);
+}
+
+}  // namespace
+
+extern "C" {
+
+int wdbx_b200_search_exchange(wdbx_b200_engine* e, const float* q_dev, int B, int k, int metric, uint64_t* keys_out,
+                              float* scores_out, int64_t* gids_out, int32_t* counts_out, void* cuda_stream) {
+  int rc = check_search_args(e, B, k, metric);
+  if (rc != WDBX_B200_OK) return rc;
+  if (!q_dev) return fail(WDBX_B200_ERR_ARG, "q_dev is NULL");
+  DeviceGuard guard(e->device);
+  std::lock_guard<std::mutex> lk(e->mu);
+  rc = exchange_search_locked(e, q_dev, B, k, metric, keys_out, scores_out, reinterpret_cast<long long*>(gids_out),
+                              counts_out, static_cast<cudaStream_t>(cuda_stream));
   if (rc == WDBX_B200_OK) e->searches.fetch_add(1, std::memory_order_relaxed);
   return rc;
+}
+
+int wdbx_b200_search_exchange_host(wdbx_b200_engine* e, const float* q_host, int B, int k, int metric,
+                                   float* scores_host, int64_t* gids_host, uint64_t* keys_host, int32_t* counts_host) {
+  int rc = check_search_args(e, B, k, metric);
+  if (rc != WDBX_B200_OK) return rc;
+  if (!q_host) return fail(WDBX_B200_ERR_ARG, "q_host is NULL");
+  DeviceGuard guard(e->device);
+  std::lock_guard<std::mutex> hlk(e->host_mu);
+  const size_t nq = static_cast<size_t>(B) * e->dim;
+  const size_t nres = static_cast<size_t>(B) * k;
+  // result block layout: keys[nres] u64 | gids[nres] i64 | scores[nres] f32 | counts[B] i32
+  const size_t off_keys = 0, off_gids = nres * 8, off_scores = nres * 16, off_counts = nres * 20;
+  const size_t bytes = off_counts + static_cast<size_t>(B) * 4;
+  if (e->q_floats < nq) {
+    cudaFreeHost(e->hq_pinned); e->hq_pinned = nullptr;
+    cudaFree(e->dq); e->dq = nullptr;
+    e->q_floats = 0;
+    CU_TRY(cudaMallocHost(&e->hq_pinned, nq * 4));
+    CU_TRY(cudaMalloc(&e->dq, nq * 4));
+    e->q_floats = nq;
+  }
+  if (e->res_bytes < bytes) {
+    cudaFreeHost(e->hres_pinned); e->hres_pinned = nullptr;
+    cudaFree(e->dres); e->dres = nullptr;
+    e->res_bytes = 0;
+    CU_TRY(cudaMallocHost(&e->hres_pinned, bytes));
+    CU_TRY(cudaMalloc(&e->dres, bytes));
+    e->res_bytes = bytes;
+  }
+  memcpy(e->hq_pinned, q_host, nq * 4);
+  cudaStream_t st = e->hstream;
+  CU_TRY(cudaMemcpyAsync(e->dq, e->hq_pinned, nq * 4, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaEventRecord(e->ev0, st));
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    rc = exchange_search_locked(e, e->dq, B, k, metric, reinterpret_cast<uint64_t*>(e->dres + off_keys),
+                                reinterpret_cast<float*>(e->dres + off_scores),
+                                reinterpret_cast<long long*>(e->dres + off_gids),
+                                reinterpret_cast<int*>(e->dres + off_counts), st);
+    if (rc != WDBX_B200_OK) return rc;
+  }
+  CU_TRY(cudaEventRecord(e->ev1, st));
+  CU_TRY(cudaMemcpyAsync(e->hres_pinned, e->dres, bytes, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  float ms = 0.0f;
+  if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_search_ms = ms;
+  if (keys_host) memcpy(keys_host, e->hres_pinned + off_keys, nres * 8);
+  if (gids_host) memcpy(gids_host, e->hres_pinned + off_gids, nres * 8);
+  if (scores_host) memcpy(scores_host, e->hres_pinned + off_scores, nres * 4);
+  if (counts_host) memcpy(counts_host, e->hres_pinned + off_counts, static_cast<size_t>(B) * 4);
+  e->searches.fetch_add(1, std::memory_order_relaxed);
+  return WDBX_B200_OK;
 }
 
 int wdbx_b200_set_kernel_timing(wdbx_b200_engine* e, int enable) {

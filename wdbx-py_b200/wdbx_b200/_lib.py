@@ -58,6 +58,7 @@ SIGNATURES = {
     "wdbx_b200_search_exchange": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "wdbx_b200_set_tuning": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "wdbx_b200_set_kernel_timing": (C.c_int, [_P, C.c_int]),
+    "wdbx_b200_search_exchange_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "wdbx_b200_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
 }
 

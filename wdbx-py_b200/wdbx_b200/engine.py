@@ -178,6 +178,23 @@ class Engine:
                                               _np_ptr(counts)))
         return (scores, gids, counts, keys) if want_keys else (scores, gids, counts)
 
+    def search_exchange_host(self, queries, k: int, metric="cosine"):
+        """Collective host-buffer search (every rank, same queries): pinned H2D -> local exact top-k ->
+        on-device NVLink exchange + merge -> one D2H.  Returns (scores, gids, counts) of the GLOBAL top-k;
+        counts == -1 means a peer did not join in time."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"Vector dimension mismatch: expected {self.dim}, got {q.shape[-1]}")
+        B = q.shape[0]
+        scores = np.empty((B, k), dtype=np.float32)
+        gids = np.empty((B, k), dtype=np.int64)
+        counts = np.empty((B,), dtype=np.int32)
+        check(self._lib.wdbx_b200_search_exchange_host(self._handle(), _np_ptr(q), B, k, _metric_code(metric),
+                                                       _np_ptr(scores), _np_ptr(gids), None, _np_ptr(counts)))
+        return scores, gids, counts
+
     def search_filtered_host(self, queries, k: int, metric="cosine", min_score: float = float("-inf"), allow=None):
         """Opt-in pre-filtered search: ``allow`` is a list (one entry per segment) of uint32 bitmaps over the
         segment's rows (bit 1 = row may be returned; None = all rows), ``min_score`` a score floor.

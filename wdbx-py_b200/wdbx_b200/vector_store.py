@@ -637,14 +637,13 @@ class VectorStore:
         if self.dist.world == 1:
             return self.engine.search_host(Q, k, metric=metric, per_segment=(sel == EACH),
                                            segment=(sel if sel >= 0 else ALL))
-        # SPMD: local top-k on every rank -> all-gather packed keys -> merge kernel
-        qd = self.engine.upload(Q)
+        # SPMD: local top-k on every rank -> on-device NVLink exchange, or all-gather of packed keys + merge kernel
         if sel == ALL and self._fused and Q.shape[0] <= self.engine.XCHG_MAX_B and k <= self.engine.XCHG_MAX_K:
-            merged = self.engine.search_exchange(qd, k, metric)
-            scores, gids, counts = self._unpack(merged, Q.shape[0], k)
+            scores, gids, counts = self.engine.search_exchange_host(Q, k, metric)   # one C call: H2D, kernels, D2H
             if (counts < 0).any():
                 raise RuntimeError("fused exchange timed out: a peer rank did not join the collective search")
             return scores, gids, counts
+        qd = self.engine.upload(Q)
         if sel == EACH:
             import torch
 
