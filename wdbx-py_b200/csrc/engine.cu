@@ -377,10 +377,9 @@ int gemm_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B
   return WDBX_B200_OK;
 }
 
-// Regime choice (north star): small batches stream X once per QB queries on CUDA cores (K1, HBM
-// bound); from gemm_min_batch queries on, the scan is a dense contraction and runs on tcgen05 (K2).
-// K2b path: bf16 tensor-core filter over the shadow matrix + exact refine with K1's arithmetic; queries
-// whose candidate list overflowed are re-run by K1 (only_flag).  Caller holds e->mu, device is set.
+// K2b path: (lazily built / extended) bf16 shadow -> prep -> one filter launch per segment -> refine ->
+// flag-gated K1 re-run of the queries whose candidate region overflowed.  Returns WDBX_B200_ERR_OOM when the
+// shadow cannot be allocated (the caller then serves from the stored rows).  Caller holds e->mu, device is set.
 int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B, int k, int metric,
                     uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream) {
   const int ld16 = filter_ld16(e->dim);

@@ -1,26 +1,29 @@
 // gemm_filter.cu -- K2b: single-pass bf16 tensor-core FILTER + exact fp32 REFINE (sm_100a only).
 //
-// The batched regime of the exact search (option c).  Replaces, for a
-// batch of queries, FaissIndex.search (wdbx/core/indexing.py:1002-1024) + the shard merge of
-// VectorStore.search (wdbx/core/vector_store.py:323-330); results are BIT-IDENTICAL to the
+// The default search path (option c): every batch >= 16 and, on fp32 stores of
+// 1 GB or more, every batch size.  Replaces FaissIndex.search (wdbx/core/indexing.py:1002-1024) + the shard
+// merge of VectorStore.search (wdbx/core/vector_store.py:323-330); results are BIT-IDENTICAL to the
 // streaming kernel K1 because the final scores are recomputed with K1's own fp32 arithmetic.
 //
-//   1. prep:    q -> bf16 (RNE), 1/|q|, |q|, |q|^2                                  (prep_queries_kernel)
+//   1. prep:    q -> bf16 (RNE), 1/|q|, |q|, |q|^2, padded to whole 128-query blocks; zeroes the per-search
+//               state                                                              (prep_queries_kernel)
 //   2. filter:  S~ = Qb . Xb^T on tcgen05 (kind::f16, bf16 operands, fp32 TMEM accumulators) over a
-//               bf16 SHADOW of the stored matrix (built lazily, half the HBM bytes of the fp32 rows).
-//               |s~ - s| <= eps is a rigorous rounding bound (2^-9 relative per bf16 operand), so with
-//               L = k-th best (s~ - eps) seen so far -- a lower bound on the exact k-th best score, shared
-//               between CTAs through a global atomicMax -- every row with s~ + eps >= L is appended to the
-//               query's candidate list; everything else provably cannot be in the exact top-k.
-//   3. refine:  one CTA per query re-scores its candidates (a few hundred) from the fp32 rows with K1's
-//               lane mapping, summation order and score formula, keeps the top-k with K1's list code.
-//   4. queries whose candidate list overflowed (adversarial data) are flagged and re-run by K1 itself.
+//               bf16 SHADOW of the stored matrix (half the HBM bytes of the fp32 rows).
+//               |s~ - s| <= eps is a rigorous rounding bound (2^-9 relative per bf16 operand).  Per query
+//               ONE list of the k largest lower bounds (s~ - eps) seen by any thread of any CTA lives in
+//               global memory (lock-free, see lower_insert); its minimum L never exceeds the exact k-th
+//               best score, so every row with s~ + eps >= L is appended to a candidate region and
+//               everything else provably cannot be in the exact top-k.
+//               gemm_filter_small_kernel: B <= 16, X rows on the M side of the MMA, 16 queries on N;
+//               gemm_filter_kernel<METRIC, NCTA>: 128-query tiles, NCTA = 2 = CTA pairs (cta_group::2).
+//   3. refine:  candidates (a few hundred to a few thousand per query) are re-scored from the fp32 rows
+//               with K1's lane mapping, summation order and score formula; register bitonic lists; several
+//               CTAs per query for small batches, the last one folds the partial lists (refine_topk_kernel).
+//   4. queries whose candidate region overflowed (adversarial data) are flagged and re-run by K1 itself.
 //
-// Filter CTA = 12 warps: 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 idle | 4-11 epilogue
-// (two threads per query, one per half of the tile's columns: a single warp per scheduler could not
-// drain a 128x256 accumulator as fast as the bf16 MMAs produce it).
-// Tile 128 queries x 256 rows x 64 dims (one 128-byte swizzle atom per row), 4-stage mbarrier ring
-// (48 KB / stage), two accumulator tiles in TMEM (512 columns).
+// Filter CTA = 12 warps: 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 idle | 4-11 epilogue;
+// mbarrier ring of TMA stages, two accumulator tiles in TMEM so that the epilogue of tile t overlaps the
+// MMAs of tile t+1.  DESIGN.md section 4 has the measurements behind every choice.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
