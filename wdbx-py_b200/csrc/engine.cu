@@ -1209,7 +1209,8 @@ int wdbx_b200_get_stats(wdbx_b200_engine* e, wdbx_b200_stats* out) {
     out->rows_total += sg.n_rows;
     out->rows_live += sg.n_rows - sg.n_dead;
     out->capacity_rows += sg.cap_rows;
-    out->bytes_resident += sg.cap_rows * per_row + (sg.tomb ? sg.cap_rows / 8 : 0);
+    out->bytes_resident += sg.cap_rows * per_row + (sg.tomb ? sg.cap_rows / 8 : 0) +
+                           (sg.shadow ? sg.shadow_cap * static_cast<int64_t>(filter_ld16(e->dim)) * 2 : 0);
     out->seg_rows[s] = sg.n_rows;
     out->seg_live[s] = sg.n_rows - sg.n_dead;
   }
