@@ -364,9 +364,9 @@ def run_gpu(args):
                          # the same launch expressed in SURVEY.md 8d's K1 bytes (fp32 rows): what a scan of the
                          # stored rows would have had to stream in this time
                          "fp32_scan_equivalent_gbs": k1_bytes / (kernel_ms * 1e-3) / 1e9,
-                         "note": "achieved/frac use the bytes this kernel must read; with SURVEY.md 8d's K1 bytes "
-                                 "(fp32 rows, which this path no longer streams) the same launch would read as "
-                                 f"frac {k1_bytes / (kernel_ms * 1e-3) / 1e9 / peak:.2f}"},
+                         "note": ("achieved/frac use the bytes this kernel must read; with SURVEY.md 8d's K1 bytes "
+                                  "(fp32 rows, which this path no longer streams) the same launch would read as "
+                                  f"frac {k1_bytes / (kernel_ms * 1e-3) / 1e9 / peak:.2f}") if kernel_id == 2 else None},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": DIM * 4,
                     "d2h_bytes_per_step": K * 20 + 4, "api": "VectorStore.search (host list in, tuples out)",
