@@ -154,3 +154,28 @@ def test_small_batches_route_by_size_and_report_the_dominant_kernel(built_lib):
     for a, b in zip(got["filter"], got["scan"]):
         np.testing.assert_array_equal(np.asarray(a).view(np.uint32) if a.dtype == np.float32 else a,
                                       np.asarray(b).view(np.uint32) if b.dtype == np.float32 else b)
+
+
+@pytest.mark.parametrize("B", [1, 20])
+def test_ascending_scores_worst_case_for_a_running_bound(built_lib, B):
+    """Rows arrive in ascending score order: every row beats the bound known when it is seen, so (almost)
+    every row is a candidate -- the regions overflow and the flagged queries are re-run by the exact scan.
+    The answer must not change."""
+    rng = np.random.default_rng(99)
+    n, dim, k = 60000, 64, 10
+    u = rng.standard_normal(dim).astype(np.float32)
+    u /= np.linalg.norm(u)
+    ramp = (np.arange(1, n + 1, dtype=np.float32) / n)[:, None]
+    X = (ramp * u[None, :] + 1e-4 * rng.standard_normal((n, dim), dtype=np.float32)).astype(np.float32)
+    Q = (u[None, :] + 0.01 * rng.standard_normal((B, dim), dtype=np.float32)).astype(np.float32)
+    e2, e1 = _engine(dim, gemm_min_batch=1), _engine(dim, gemm_min_batch=0)
+    for e in (e2, e1):
+        e.append(0, X)
+    for metric in ("ip", "l2"):
+        s2, g2, c2 = e2.search_host(Q, k, metric=metric)
+        s1, g1, c1 = e1.search_host(Q, k, metric=metric)
+        np.testing.assert_array_equal(c2, c1)
+        np.testing.assert_array_equal(g2, g1)
+        np.testing.assert_array_equal(s2.view(np.uint32), s1.view(np.uint32))
+        _oracle_check(X, Q, k, metric, s2, g2, c2, sample=3)
+    e2.close(); e1.close()
