@@ -829,6 +829,14 @@ class VectorStore:
             for i, ix in enumerate(self.indices)
         ]
         est = self.engine.stats() if self.engine is not None else {}
+        # observability: what the last host search streamed, as an effective rate
+        # over the STORED row bytes (the bf16-shadow filter path reads half of them, so this can exceed the
+        # HBM peak; the kernel's own rate is in last_kernel_ms when kernel timing is on)
+        ms = est.get("last_search_ms") or 0.0
+        if ms > 0 and est.get("rows_total"):
+            elem = 2 if self.dtype == "bf16" else 4
+            stored = est["rows_total"] * est.get("dim_padded", self.vector_dim) * elem
+            est["last_search_stored_gbs"] = stored / (ms * 1e-3) / 1e9
         return {
             "vector_count": self.count(),
             "metadata_count": len(self.metadata),
