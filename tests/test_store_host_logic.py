@@ -235,3 +235,24 @@ def test_data_feeders_csv_jsonl(tmp_path):
     assert st.count() == 5 and st.search([0, 0, 0, 1], limit=1)[0][0] == "x"
     assert [r[0] for r in st.search([1, 0, 0, 0], limit=5, filter_metadata={"lang": "en"})] == ["a", "c"]
     st.close()
+
+
+def test_list_query_conversion_matches_numpy():
+    """The public API takes lists of Python floats (reference: vector_store.py:301); the fast struct-based
+    conversion must produce exactly numpy's fp32 rounding and fall back to numpy for everything else."""
+    st = wdbx_b200.VectorStore(8, tempfile.mkdtemp(), num_shards=1, dist=wdbx_b200.DistContext(0, 1, 0),
+                               _engine_factory=FakeEngine)
+    rng = np.random.default_rng(3)
+    cases = [rng.standard_normal(8).tolist(), [0.1] * 8, [1, 2, 3, 4, 5, 6, 7, 8], [float("nan")] + [0.0] * 7,
+             [1e-46] * 8, [np.float32(1.5)] * 8, [3.4028235677973366e38] * 8]
+    for lst in cases:
+        got, want = st._query_array(lst), np.array(lst, dtype=np.float32)
+        assert got.dtype == np.float32 and got.shape == (8,)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), lst
+    with np.errstate(over="ignore"):
+        assert np.array_equal(st._query_array([1e39] * 8), np.array([1e39] * 8, dtype=np.float32))   # overflow -> inf via numpy
+    assert st._query_array(np.arange(8)).dtype == np.float32                  # non-list input
+    assert st._query_array([0.0] * 3).shape == (3,)                           # wrong length: numpy path, search() raises
+    with pytest.raises(ValueError, match="dimension mismatch"):
+        st.search([0.0] * 3)
+    st.close()
