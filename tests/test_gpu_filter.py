@@ -179,3 +179,27 @@ def test_ascending_scores_worst_case_for_a_running_bound(built_lib, B):
         np.testing.assert_array_equal(s2.view(np.uint32), s1.view(np.uint32))
         _oracle_check(X, Q, k, metric, s2, g2, c2, sample=3)
     e2.close(); e1.close()
+
+
+@pytest.mark.parametrize("B", [3, 40])
+def test_zero_query_and_zero_rows_on_the_filter_path(built_lib, B):
+    """A zero query scores every row 0 (cosine / ip): the bound never separates anything, every row is a
+    candidate, and the answer is the k lowest gids -- exactly what the scan returns."""
+    rng = np.random.default_rng(17)
+    n, dim, k = 5000, 32, 10
+    X = rng.standard_normal((n, dim), dtype=np.float32)
+    X[11] = 0.0
+    Q = rng.standard_normal((B, dim), dtype=np.float32)
+    Q[1] = 0.0
+    e2, e1 = _engine(dim, gemm_min_batch=1), _engine(dim, gemm_min_batch=0)
+    for e in (e2, e1):
+        e.append(0, X)
+    for metric in ("cosine", "ip", "l2"):
+        s2, g2, c2 = e2.search_host(Q, k, metric=metric)
+        s1, g1, c1 = e1.search_host(Q, k, metric=metric)
+        np.testing.assert_array_equal(c2, c1)
+        np.testing.assert_array_equal(g2, g1)
+        np.testing.assert_array_equal(s2.view(np.uint32), s1.view(np.uint32))
+        if metric != "l2":
+            assert g2[1].tolist() == list(range(k)) and not s2[1].any()
+    e2.close(); e1.close()
