@@ -56,9 +56,10 @@ def test_filter_refine_is_bit_identical_to_scan(built_lib, n, dim, B, k, metric,
     e2.close(); e1.close()
 
 
-def test_filter_segments_tombstones_edge_rows(built_lib):
+@pytest.mark.parametrize("B", [160, 6])   # 128-query kernel (CTA pair) / small-batch kernel
+def test_filter_segments_tombstones_edge_rows(built_lib, B):
     rng = np.random.default_rng(78)
-    n, dim, B, k = 9000, 384, 160, 10
+    n, dim, k = 9000, 384, 10
     X = rng.standard_normal((n, dim), dtype=np.float32)
     X[100] = 0.0
     X[4000] = X[17]
