@@ -83,3 +83,64 @@ def test_world2_matches_single_rank():
     assert sum(rows) == 301 and abs(rows[0] - rows[1]) <= 3  # striped: balanced within one row per shard
     assert got[0] == got[1] == want
     assert [i for i, _ in want["tie"][:2]] == ["id7", "id40"]
+
+
+# ---------------------------------------------------------------------------------------------- persistence
+def _probe(store):
+    X, Q = _dataset()
+    return {"plain": [[(i, s) for i, s, _ in store.search(Q[b].tolist(), limit=10)] for b in range(Q.shape[0])],
+            "tie": [(i, s) for i, s, _ in store.search(X[7].tolist(), limit=3)],
+            "get": store.get("id40")[0], "count": store.count()}
+
+
+def _restripe_worker(rank, world, port, data_dir, outdir):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "wdbx-py_b200"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    import wdbx_b200
+    from tests.fake_engine import FakeEngine
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = wdbx_b200.WDBXConfig({"GPU_STRICT": True})
+    store = wdbx_b200.VectorStore(16, data_dir, num_shards=3, dist=wdbx_b200.DistContext(rank, world, rank), config=cfg,
+                                  _engine_factory=FakeEngine)     # saved by ONE rank: re-striped over two
+    out = {"loaded": _probe(store), "local_rows": store.engine.stats()["rows_total"]}
+    X, _ = _dataset()
+    store.store("late", (X[3] * 2.0).tolist(), {"late": True})
+    store.delete("id12")
+    out["after"] = _probe(store)
+    assert store.save()
+    Path(outdir, f"rank{rank}.json").write_text(json.dumps(out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_saved_store_is_restriped_across_world_sizes():
+    """A store saved by W ranks loads on W' ranks (rows re-striped from the saved partitions) and back."""
+    import wdbx_b200
+    from tests.fake_engine import FakeEngine
+
+    cfg = wdbx_b200.WDBXConfig({"GPU_STRICT": True})
+    one = lambda d: wdbx_b200.VectorStore(16, d, num_shards=3, dist=wdbx_b200.DistContext(0, 1, 0), config=cfg,
+                                          _engine_factory=FakeEngine)
+    with tempfile.TemporaryDirectory() as data_dir, tempfile.TemporaryDirectory() as outdir:
+        st = one(data_dir)
+        _run_store(st)
+        want_loaded = json.loads(json.dumps(_probe(st)))
+        assert st.save()
+        st.close()
+        mp.spawn(_restripe_worker, args=(2, _free_port(), data_dir, outdir), nprocs=2, join=True)
+        got = [json.loads(Path(outdir, f"rank{r}.json").read_text()) for r in range(2)]
+        rows = [g.pop("local_rows") for g in got]
+        assert sum(rows) == 301 and abs(rows[0] - rows[1]) <= 3
+        assert got[0] == got[1] and got[0]["loaded"] == want_loaded
+        assert not list(Path(data_dir).glob("shard_*/rows.rank*of1.npy"))      # superseded partitions removed
+        back = one(data_dir)                                                      # two ranks -> one rank
+        assert json.loads(json.dumps(_probe(back))) == got[0]["after"]
+        assert back.count() == want_loaded["count"]                              # +late, -id12
+        # "late" = 2 * id3: same cosine, so the tie rule (lower insertion id first) orders them
+        assert [r[0] for r in back.search(_dataset()[0][3].tolist(), limit=2)] == ["id3", "late"]
+        back.close()

@@ -272,12 +272,35 @@ class VectorStore:
                     tmp.write_text(json.dumps(state))
                     tmp.replace(self.data_dir / "vectors" / "state.json")
             self.dist.barrier()
+            if rank == 0:   # partitions of an earlier run with another rank count are superseded now
+                for s in range(self.num_shards):
+                    for f in (self.data_dir / f"shard_{s}").glob("rows.rank*of*.npy"):
+                        if not f.name.endswith(f"of{world}.npy"):
+                            f.unlink(missing_ok=True)
             return True
         except Exception as e:
             logger.error(f"Error saving vectors: {e}")
             if self.strict:
                 raise
             return False
+
+    def _load_partition(self, shard: int, count: int, rank: int, world: int, saved_world: int) -> np.ndarray:
+        """This rank's rows of a shard, in local order.  Position n of the shard lives on rank n % world at
+        local row n // world; a store saved by a different number of ranks is RE-STRIPED: position n is
+        fetched from the saved file of rank n % saved_world, row n // saved_world (memory-mapped, so a rank
+        only touches the rows it keeps)."""
+        d = self.data_dir / f"shard_{shard}"
+        if saved_world == world:
+            return np.load(d / f"rows.rank{rank}of{world}.npy")
+        pos = np.arange(rank, count, world, dtype=np.int64)
+        rows = np.empty((pos.shape[0], self.vector_dim), dtype=np.float32)
+        src_rank, src_row = pos % saved_world, pos // saved_world
+        for r in range(saved_world):
+            m = src_rank == r
+            if m.any():
+                part = np.load(d / f"rows.rank{r}of{saved_world}.npy", mmap_mode="r")
+                rows[m] = part[src_row[m]]
+        return rows
 
     def _load_data(self) -> int:
         """Start-up load (reference: vector_store.py:136-156): rebuild the device partitions from disk."""
@@ -288,9 +311,10 @@ class VectorStore:
             state = json.loads(path.read_text())
             rank, world = self.dist.rank, self.dist.world
             for key, have in (("version", self.STATE_VERSION), ("dim", self.vector_dim), ("dtype", self.dtype),
-                              ("num_shards", self.num_shards), ("world", world)):
+                              ("num_shards", self.num_shards)):
                 if state.get(key) != have:
                     raise ValueError(f"saved store has {key}={state.get(key)!r}, this instance {have!r}")
+            saved_world = int(state.get("world", world))   # may differ: partitions are re-striped below
             n_gid = int(state["next_gid"])
             gid_to_id = _GidMap.restore(n_gid, state["ids"])
             bulk = [(g0, g1, p) for g0, g1, p, _ in state["bulk"]]
@@ -307,7 +331,7 @@ class VectorStore:
                 order = np.load(self.data_dir / f"shard_{s}" / "row_gids.npy")
                 if order.shape[0] != state["shard_count"][s]:
                     raise ValueError(f"shard {s}: row_gids.npy does not match state.json")
-                rows = np.load(self.data_dir / f"shard_{s}" / f"rows.rank{rank}of{world}.npy")
+                rows = self._load_partition(s, order.shape[0], rank, world, saved_world)
                 mine = order[rank::world]
                 if rows.shape != (mine.shape[0], self.vector_dim):
                     raise ValueError(f"shard {s}: partition file has shape {rows.shape}")
@@ -712,7 +736,7 @@ class VectorStore:
         visible next to a 370 us search on 8 GPUs); anything it rejects goes through numpy as before."""
         if type(query_vector) is list and len(query_vector) == self.vector_dim:
             try:
-                return np.frombuffer(self._qstruct.pack(*query_vector), dtype=np.float32)
+                return np.frombuffer(bytearray(self._qstruct.pack(*query_vector)), dtype=np.float32)   # writable
             except (struct.error, OverflowError, TypeError):
                 pass
         return np.array(query_vector, dtype=np.float32)
