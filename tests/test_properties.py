@@ -71,3 +71,26 @@ def test_oracle_fp32_ranking_matches_fp64_outside_tie_window(n, dim, k, metric, 
     rows, sc = oracle.topk_desc(oracle.scores_fp32(X, q, metric), k)
     rep = oracle.check_topk(X, q, metric, k, rows, sc)
     assert rep["hard_mismatch"] == 0 and rep["max_err_over_tol"] <= 1.0 and rep["sorted"]
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(0, 90), st.integers(1, 8), st.integers(1, 8), st.integers(0, 2**31 - 1))
+def test_restriping_saved_partitions_preserves_every_row(count, saved_world, world, seed):
+    """Position n of a shard lives on rank n % W at local row n // W; loading W-rank partitions on W' ranks
+    (VectorStore._load_partition) must hand every rank exactly its positions, in order."""
+    import tempfile
+    from pathlib import Path
+    from types import SimpleNamespace
+
+    from wdbx_b200.vector_store import VectorStore
+
+    dim = 3
+    full = np.random.default_rng(seed).standard_normal((count, dim)).astype(np.float32)
+    with tempfile.TemporaryDirectory() as d:
+        (Path(d) / "shard_0").mkdir()
+        for r in range(saved_world):
+            np.save(Path(d) / "shard_0" / f"rows.rank{r}of{saved_world}.npy", full[r::saved_world])
+        me = SimpleNamespace(data_dir=Path(d), vector_dim=dim)
+        got = [VectorStore._load_partition(me, 0, count, r, world, saved_world) for r in range(world)]
+    for r in range(world):
+        assert got[r].dtype == np.float32 and np.array_equal(got[r], full[r::world])
