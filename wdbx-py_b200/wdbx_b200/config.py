@@ -21,7 +21,8 @@ DEFAULTS: Dict[str, Any] = {
     "GPU_PREFILTER": False,     # opt-in: filter_metadata becomes a device-side PRE-filter (full k among matches)
     "GPU_FUSED_EXCHANGE": True,  # multi-GPU: fuse the cross-GPU merge into the scan kernel (NVLink P2P)
     "GPU_BATCH_WINDOW_US": 200,  # micro-batching window of vector_search_async
-    "GPU_BATCH_MAX": 8,          # queries coalesced into one launch by the async front-end
+    "GPU_BATCH_MAX": 64,         # queries coalesced into one pass by the async front-end (10M x 768: 64 queries
+                                 # cost 2.46 ms on the filter path, one query 2.24 ms)
 }
 
 

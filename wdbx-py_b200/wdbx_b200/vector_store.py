@@ -184,7 +184,7 @@ class VectorStore:
         # async front-end: coalesce concurrent single-query requests (single process only: under SPMD
         # every rank would have to form identical batches)
         self._batcher = None
-        bmax = int(self.config.get("GPU_BATCH_MAX", 8) or 0)
+        bmax = int(self.config.get("GPU_BATCH_MAX", 64) or 0)
         if self.dist.world == 1 and bmax > 1:
             from .batcher import MicroBatcher
 
