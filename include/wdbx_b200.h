@@ -75,6 +75,8 @@ typedef struct wdbx_b200_stats {
   int64_t seg_live[WDBX_B200_MAX_SEGMENTS];
   double last_kernel_ms;       /* duration of that kernel's launches (CUDA events on its stream); 0 unless
                                   wdbx_b200_set_kernel_timing(e, 1) was called */
+  int64_t last_candidates;     /* K2b, kernel timing on: rows the filter of the last search handed to the exact
+                                  refine, summed over its queries (0 otherwise) */
 } wdbx_b200_stats;
 
 /* ABI version of the loaded library (== WDBX_B200_ABI_VERSION). */

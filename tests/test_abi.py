@@ -29,7 +29,7 @@ def test_header_symbols_exported(built_lib):
 def test_stats_struct_layout():
     from wdbx_b200 import _lib
 
-    assert C.sizeof(_lib.Stats) == 8 * 4 + 6 * 8 + 8 + 2 * 64 * 8 + 8   # ... + last_kernel_ms
+    assert C.sizeof(_lib.Stats) == 8 * 4 + 6 * 8 + 8 + 2 * 64 * 8 + 8 + 8   # ... + last_kernel_ms + last_candidates
 
 
 def test_argument_errors_need_no_device(built_lib):

@@ -68,38 +68,55 @@ def _assert_match(got_s, got_g, want_s, want_i, metric, dim, scale=1.0):
         assert np.all(np.diff(got_s[b]) <= 0)
 
 
-@pytest.mark.parametrize("name,n,dim,dtype,metric,k,B,gemm", [
-    ("C2", 1_000_000, 384, "fp32", "cosine", 10, 1, 0),
-    ("C3-B1", 10_000_000, 768, "fp32", "cosine", 10, 1, 0),
-    ("C3-B1024", 10_000_000, 768, "fp32", "cosine", 10, 1024, 48),
-    ("C4-shard", 12_500_000, 384, "bf16", "ip", 100, 1, 0),
-    ("C5", 5_000_000, 1536, "fp32", "l2", 10, 4096, 48),
+# route "default" = the engine's own regime choice (K2b bf16 filter + exact refine for every fp32 config here, the
+# headline path); "scan" forces the streaming kernel K1 over the stored rows.  `kernel` is what must have run
+# (engine-reported: 1 = K1 scan, 2 = K2b filter).
+@pytest.mark.parametrize("name,n,dim,dtype,metric,k,B,route,kernel", [
+    ("C2", 1_000_000, 384, "fp32", "cosine", 10, 16, "default", 2),
+    ("C2-scan", 1_000_000, 384, "fp32", "cosine", 10, 12, "scan", 1),
+    ("C3-B1", 10_000_000, 768, "fp32", "cosine", 10, 16, "default", 2),
+    ("C3-B1-scan", 10_000_000, 768, "fp32", "cosine", 10, 4, "scan", 1),
+    ("C3-B1024", 10_000_000, 768, "fp32", "cosine", 10, 1024, "default", 2),
+    ("C4-shard", 12_500_000, 384, "bf16", "ip", 100, 2, "default", 0),
+    ("C5", 5_000_000, 1536, "fp32", "l2", 10, 4096, "default", 2),
 ])
-def test_full_size_config(built_lib, name, n, dim, dtype, metric, k, B, gemm):
+def test_full_size_config(built_lib, name, n, dim, dtype, metric, k, B, route, kernel):
     import torch
     import wdbx_b200
 
     dev = torch.device("cuda", 0)
     seed = 9000 + dim
-    os.environ["WDBX_B200_GEMM_MIN_BATCH"] = str(gemm)
+    if route == "scan":
+        os.environ["WDBX_B200_GEMM_MIN_BATCH"] = "0"
+        os.environ["WDBX_B200_SHADOW_MIN_MB"] = "-1"
     try:
         eng = wdbx_b200.Engine(0, dim, dtype, 1)
     finally:
         os.environ.pop("WDBX_B200_GEMM_MIN_BATCH", None)
+        os.environ.pop("WDBX_B200_SHADOW_MIN_MB", None)
     _fill(eng, n, dim, seed, dev)
     Q = torch.randn((B, dim), generator=torch.Generator(device=dev).manual_seed(77), device=dev)
-    out = eng.search(Q, k, metric)
+    eng.set_kernel_timing(True)
+    if B <= 16:
+        # the single-query configs: every query is its own batch-1 search (the benchmarked call), 12+ of them
+        outs = [eng.search(Q[b:b + 1], k, metric) for b in range(B)]
+        out = {key: torch.cat([o[key] for o in outs]) for key in ("scores", "gids", "counts")}
+    else:
+        out = eng.search(Q, k, metric)
     torch.cuda.synchronize()
+    if kernel:
+        assert eng.stats()["last_kernel"] == kernel, (name, eng.stats()["last_kernel"])
+    eng.set_kernel_timing(False)
     got_s, got_g, cnt = out["scores"].cpu().numpy(), out["gids"].cpu().numpy(), out["counts"].cpu().numpy()
     assert np.all(cnt == k)
     assert np.all(np.diff(got_s, axis=1) <= 0)           # sorted, all B queries
     assert np.all((got_g >= 0) & (got_g < n))
-    sel = np.unique(np.linspace(0, B - 1, min(B, 12)).astype(int))   # fp64 check on a spread of queries
+    sel = np.unique(np.linspace(0, B - 1, min(B, 16)).astype(int))   # fp64 check on a spread of queries
     want_s, want_i = _checker_topk(n, dim, seed, dev, Q[sel], k, metric, dtype == "bf16")
     scale = 1.0 if metric == "cosine" else float(dim) * (2.0 if metric == "l2" else 1.0)
     _assert_match(got_s[sel], got_g[sel], want_s, want_i, metric, dim, scale)
     # the device checker itself is pinned to the numpy oracle on a prefix
-    if name == "C2":
+    if name == "C2-scan":
         x0 = next(_chunks(n, dim, seed, dev))[1][:50000]
         rows, sc = oracle.topk_desc(oracle.scores_fp64(x0.cpu().numpy(), Q[0].cpu().numpy(), metric), k)
         ws, wi = _checker_topk(50000, dim, seed, dev, Q[:1], k, metric, False)

@@ -52,6 +52,7 @@ struct Segment {
   uint32_t* allow = nullptr; // device copy of a per-search "allowed rows" bitmap (metadata pre-filter)
   size_t allow_words = 0;
   void* shadow = nullptr;    // bf16 copy of the fp32 rows for the tensor-core filter (K2b), built lazily
+  float* rres = nullptr;     // per-row bound of |x - bf16(x)| (same capacity as the shadow): the data-derived filter bound
   int64_t shadow_rows = 0, shadow_cap = 0;
   std::vector<uint32_t> tomb_host;
   int64_t n_rows = 0, cap_rows = 0, n_dead = 0;
@@ -127,6 +128,8 @@ struct wdbx_b200_engine {
   cudaEvent_t kev0 = nullptr, kev1 = nullptr;
   int last_kernel = 0;      // 1 = K1 scan, 2 = K2b filter
   bool kpending = false;    // events recorded, not read yet
+  const unsigned int* last_fcount = nullptr;  // K2b: candidate counts of the last timed search (device) ...
+  size_t last_fregions = 0;                   // ... one per (query, region)
 };
 
 namespace {
@@ -150,6 +153,7 @@ int64_t round_cap(int64_t rows) { return (rows + 127) / 128 * 128; }
 void free_segment(Segment& s) {
   cudaFree(s.allow);
   cudaFree(s.shadow);
+  cudaFree(s.rres);
   cudaFree(s.rows);
   cudaFree(s.inv_norm);
   cudaFree(s.sqnorm);
@@ -201,7 +205,9 @@ int ensure_capacity(wdbx_b200_engine* e, Segment& s, int64_t rows) {
   CU_TRY(cudaDeviceSynchronize());
   cudaFree(s.rows); cudaFree(s.inv_norm); cudaFree(s.sqnorm); cudaFree(s.gids); cudaFree(s.tomb);
   cudaFree(s.shadow);  // rebuilt lazily by the next batched search
+  cudaFree(s.rres);
   s.shadow = nullptr;
+  s.rres = nullptr;
   s.shadow_rows = s.shadow_cap = 0;
   s.rows = nrows; s.inv_norm = ninv; s.sqnorm = nsq; s.gids = ngid; s.tomb = ntomb;
   s.cap_rows = cap;
@@ -391,10 +397,14 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
     if (!sg.shadow || sg.shadow_cap < sg.n_rows) {
       CU_TRY(cudaStreamSynchronize(stream));
       cudaFree(sg.shadow);
+      cudaFree(sg.rres);
       sg.shadow = nullptr;
+      sg.rres = nullptr;
       sg.shadow_rows = sg.shadow_cap = 0;
-      if (cudaMalloc(&sg.shadow, static_cast<size_t>(sg.cap_rows) * ld16 * 2) != cudaSuccess) {
+      if (cudaMalloc(&sg.shadow, static_cast<size_t>(sg.cap_rows) * ld16 * 2) != cudaSuccess ||
+          cudaMalloc(&sg.rres, static_cast<size_t>(sg.cap_rows) * 4) != cudaSuccess) {
         cudaGetLastError();
+        cudaFree(sg.shadow);
         sg.shadow = nullptr;
         return fail(WDBX_B200_ERR_OOM, "no device memory for the bf16 shadow of segment %d", s);
       }
@@ -403,7 +413,8 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
     if (sg.shadow_rows < sg.n_rows) {
       CU_TRY(launch_shadow_rows(reinterpret_cast<const float*>(sg.rows + static_cast<size_t>(sg.shadow_rows) * row_bytes(e)),
                                 sg.n_rows - sg.shadow_rows, e->dpad, ld16,
-                                static_cast<unsigned char*>(sg.shadow) + static_cast<size_t>(sg.shadow_rows) * ld16 * 2, stream));
+                                static_cast<unsigned char*>(sg.shadow) + static_cast<size_t>(sg.shadow_rows) * ld16 * 2,
+                                sg.rres + sg.shadow_rows, stream));
       e->launches.fetch_add(1, std::memory_order_relaxed);
       sg.shadow_rows = sg.n_rows;
       built = true;
@@ -472,9 +483,10 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   unsigned int* lower_glob = w->fzero + off_glob;
   CU_TRY(launch_prep_queries(q_dev, B, e->dim, w->fws, w->fzero, need_zero, stream));  // also zeroes w->fzero
   e->launches.fetch_add(1, std::memory_order_relaxed);
-  // rigorous rounding bound relative to |x||q|: bf16 RNE is 2^-9 relative per rounded operand; the
-  // fp32 accumulation of the tensor core is bounded (very conservatively) by dim * 2^-23
-  const float eps_rel = (f32 ? 0.00390625f : 0.001953125f) * 1.002f + static_cast<float>(e->dim) * 1.2e-7f + 1e-6f;
+  // the operand-rounding part of the filter's error bound is derived from the data (per-row |x - bf16(x)|,
+  // per-query |q - bf16(q)|); these are the accumulation terms on top (gemm_filter.cu, "error bound")
+  const float acc_rel = filter_acc_rel(e->dim, e->dpad);
+  const float c_l2 = filter_c_l2(e->dpad);
   SegDesc descs[kMaxSeg];
   memset(descs, 0, sizeof(descs));
   int slice_base = 0;
@@ -489,9 +501,9 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
     d.tomb = sg.n_dead > 0 ? sg.tomb : nullptr;
     d.n_rows = sg.n_rows;
     if (sg.n_rows == 0) continue;
-    CU_TRY(launch_gemm_filter(f32 ? sg.shadow : static_cast<const void*>(sg.rows), f32 ? ld16 : e->dpad, d, s, e->dim, w->fws,
-                              B, k, metric, eps_rel, slices[s], w->fcand, fcount, lower_glob, lower_list, cap, slice_base,
-                              s_total, stream));
+    CU_TRY(launch_gemm_filter(f32 ? sg.shadow : static_cast<const void*>(sg.rows), f32 ? ld16 : e->dpad,
+                              f32 ? sg.rres : nullptr, d, s, e->dim, w->fws, B, k, metric, acc_rel, c_l2, slices[s], w->fcand,
+                              fcount, lower_glob, lower_list, cap, slice_base, s_total, stream));
     e->launches.fetch_add(1, std::memory_order_relaxed);
     slice_base += slices[s];
   }
@@ -511,6 +523,8 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   if (e->ktiming) {
     e->last_kernel = 2;
     e->kpending = true;
+    e->last_fcount = fcount;
+    e->last_fregions = n_regions;
   }
   return rrc;
 }
@@ -775,7 +789,8 @@ int wdbx_b200_overwrite(wdbx_b200_engine* e, int segment, int64_t row, const flo
   if (s.shadow && row < s.shadow_rows) {
     const int ld16 = filter_ld16(e->dim);
     CU_TRY(launch_shadow_rows(reinterpret_cast<const float*>(s.rows + static_cast<size_t>(row) * row_bytes(e)), 1, e->dpad,
-                              ld16, static_cast<unsigned char*>(s.shadow) + static_cast<size_t>(row) * ld16 * 2, e->mstream));
+                              ld16, static_cast<unsigned char*>(s.shadow) + static_cast<size_t>(row) * ld16 * 2, s.rres + row,
+                              e->mstream));
     e->launches.fetch_add(1, std::memory_order_relaxed);
   }
   if (s.tomb && ((s.tomb_host[row >> 5] >> (row & 31)) & 1u)) {
@@ -1192,6 +1207,17 @@ int wdbx_b200_get_stats(wdbx_b200_engine* e, wdbx_b200_stats* out) {
     if (cudaEventSynchronize(e->kev1) == cudaSuccess && cudaEventElapsedTime(&ms, e->kev0, e->kev1) == cudaSuccess) {
       out->last_kernel = e->last_kernel;
       out->last_kernel_ms = ms;
+      if (e->last_kernel == 2 && e->last_fcount && e->last_fregions > 0) {
+        // measurement hook only: rows the filter passed on to the exact refine (summed over queries)
+        std::vector<unsigned int> h(e->last_fregions);
+        if (cudaMemcpy(h.data(), e->last_fcount, h.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess) {
+          long long sum = 0;
+          for (unsigned int v : h) sum += v;
+          out->last_candidates = sum;
+        } else {
+          cudaGetLastError();
+        }
+      }
     } else {
       cudaGetLastError();
     }
@@ -1210,7 +1236,7 @@ int wdbx_b200_get_stats(wdbx_b200_engine* e, wdbx_b200_stats* out) {
     out->rows_live += sg.n_rows - sg.n_dead;
     out->capacity_rows += sg.cap_rows;
     out->bytes_resident += sg.cap_rows * per_row + (sg.tomb ? sg.cap_rows / 8 : 0) +
-                           (sg.shadow ? sg.shadow_cap * static_cast<int64_t>(filter_ld16(e->dim)) * 2 : 0);
+                           (sg.shadow ? sg.shadow_cap * (static_cast<int64_t>(filter_ld16(e->dim)) * 2 + 4) : 0);
     out->seg_rows[s] = sg.n_rows;
     out->seg_live[s] = sg.n_rows - sg.n_dead;
   }

@@ -9,7 +9,9 @@
 //               state                                                              (prep_queries_kernel)
 //   2. filter:  S~ = Qb . Xb^T on tcgen05 (kind::f16, bf16 operands, fp32 TMEM accumulators) over a
 //               bf16 SHADOW of the stored matrix (half the HBM bytes of the fp32 rows).
-//               |s~ - s| <= eps is a rigorous rounding bound (2^-9 relative per bf16 operand).  Per query
+//               |s~ - s| <= eps(row, query) is a RIGOROUS bound derived from the data (see "error bound"
+//               below): eps = |r||q_b| + |x||t| + accumulation terms, r = x - bf16(x) and t = q - bf16(q) the
+//               actual rounding residuals (|r| is stored per row next to the shadow).  Per query
 //               ONE list of the k largest lower bounds (s~ - eps) seen by any thread of any CTA lives in
 //               global memory (lock-free, see lower_insert); its minimum L never exceeds the exact k-th
 //               best score, so every row with s~ + eps >= L is appended to a candidate region and
@@ -53,15 +55,19 @@ struct FilterParams {
   const float* inv_norm;   // [n_rows] 1/|x|  (exact, of the stored rows)
   const float* sqnorm;     // [n_rows] |x|^2
   const uint32_t* tomb;    // bitmap or NULL
+  const float* rres;       // [n_rows] upper bound of |x - bf16(x)| (NULL for bf16 stores: the rows ARE the filter operand)
   const float* q_inv;      // [B]
   const float* q_nrm;      // [B]
   const float* q_sq;       // [B]
+  const float* q_bn;       // [B] upper bound of |bf16(q)|
+  const float* q_tn;       // [B] upper bound of |q - bf16(q)|
   long long n_rows;
   int B, k;
   int n_kblocks, n_tiles, n_slices;
   // (cap / slice_base / s_total below are shared by both filter kernels; the region index differs)
   int seg;                 // segment index stored with each candidate
-  float eps_rel;           // rounding bound relative to |x||q|
+  float acc_rel;           // accumulation terms of the bound, relative to |x||q| (see "error bound")
+  float c_l2;              // l2 only: rounding of |x|^2, |q|^2 and of the expanded form, relative to |x|^2 + |q|^2
   unsigned long long* cand;   // [B][s_total][cap]  (seg << 32 | row): one private region per (query, row slice)
   unsigned int* cand_count;   // [B][s_total]
   unsigned int* lower_glob;   // [B] monotone-mapped float: best known lower bound of the exact k-th score
@@ -70,12 +76,74 @@ struct FilterParams {
   int slice_base, s_total;    // this launch fills slices [slice_base, slice_base + n_slices) of s_total
 };
 
+// ---------------------------------------------------------------- error bound
+// The filter must never drop a row that the exact path (K1's fp32 arithmetic) would rank in the top-k, so
+// every filter score s~ carries eps(row, query) with |s~ - s_K1| <= eps.  With x_b = bf16(x) (RNE), q_b =
+// bf16(q) and the ACTUAL residuals r = x - x_b, t = q - q_b (both exact in fp32):
+//     x.q = x_b.q_b + r.q_b + x.t      =>      |x.q - x_b.q_b| <= |r||q_b| + |x||t|          (Cauchy-Schwarz)
+// which holds for ANY data -- coherent rounding (every element rounding the same way, few-level /
+// quantised embeddings) simply shows up as a larger |r| -- and is ~3.5x tighter on ordinary data than the
+// worst-case 2 * 2^-8 |x||q| (bf16 has 8 significand bits: unit round-off 2^-8 per rounded operand).
+// |r| is computed once per row when the shadow is built (shadow_rows_kernel, `rres`), |q_b| and |t| per
+// query by prep_queries_kernel; all three are inflated by 1e-4, and A / C below by another 1e-3, which
+// covers the fp32 rounding of the norms themselves.  On top of that:
+//   * the tensor core accumulates the (exact) bf16 x bf16 products in fp32, possibly truncating: at most
+//     dim * 2^-23 relative to sum|x_b,i q_b,i| <= 1.01 |x||q|;
+//   * K1's own fp32 dot product (what the final ranking uses) is within (dpad/32 + 40) * 2^-24 |x||q| of the
+//     exact one (fma chain per lane + butterfly), its score formula adds two roundings;
+// both folded into acc_rel (host: filter_acc_rel).  Per metric, relative quantities for cosine:
+//     cosine  eps = rho_x * A_q + C_q,            rho_x = |r|/|x|,  A_q = 1.001 |q_b|/|q|,  C_q = 1.001 |t|/|q| + acc_rel
+//     ip      eps = |r| A'_q + |x| C'_q,          A'_q = 1.001 |q_b|,  C'_q = 1.001 (|t| + acc_rel |q|)
+//     l2      eps = 2 (|r| A'_q + |x| C'_q) + c_l2 (|x|^2 + |q|^2)      (expanded form -(|x|^2 - 2 x.q + |q|^2):
+//             c_l2 covers the fp32 rounding of the stored |x|^2, of |q|^2, of the three additions, and of K1's
+//             direct sum of squared differences)
+// bf16 stores: the stored rows are the filter operand, r = 0.  tests/test_gpu_filter.py::test_bound_is_rigorous
+// holds the adversarial cases (all elements just above a bf16 midpoint, etc.).
+struct QueryBound {
+  float A, C;           // see above (cosine: relative; ip / l2: absolute)
+  float qinv, qnrm, qsq;
+};
+template <int METRIC>
+__device__ __forceinline__ QueryBound make_query_bound(float qinv, float qnrm, float qsq, float qbn, float qtn, float acc_rel) {
+  QueryBound b;
+  b.qinv = qinv; b.qnrm = qnrm; b.qsq = qsq;
+  if (METRIC == kCosine) {
+    b.A = 1.001f * qbn * qinv;
+    b.C = fmaf(1.001f * qtn, qinv, acc_rel);
+  } else {
+    b.A = 1.001f * qbn;
+    b.C = 1.001f * fmaf(acc_rel, qnrm, qtn);
+  }
+  return b;
+}
+// exact-form score estimate sv and its error bound eps for one (row, query): d = bf16 dot from TMEM,
+// inx = 1/|x| (cosine), sq = |x|^2 (ip / l2), rr = |r| bound of the row
+template <int METRIC>
+__device__ __forceinline__ void bound_eval(float d, float inx, float sq, float rr, const QueryBound& b, float c_l2,
+                                           float& sv, float& eps) {
+  if (METRIC == kCosine) {
+    sv = d * inx * b.qinv;
+    eps = fmaf(rr * inx, b.A, b.C);
+  } else {
+    const float xn = sqrtf(sq) * 1.00001f;
+    const float e = fmaf(rr, b.A, xn * b.C);
+    if (METRIC == kL2) {
+      sv = -((sq - 2.0f * d) + b.qsq);
+      eps = fmaf(2.0f, e, c_l2 * (sq + b.qsq));
+    } else {
+      sv = d;
+      eps = e;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- prep: queries -> bf16 + norms
 // (rows B .. Bpad-1 are zero padding up to a whole 128-query block, so that the TMA box of the query
 // tile never leaves the tensor: a mostly out-of-bounds box measurably slows the load pipeline)
 __global__ void prep_queries_kernel(const float* __restrict__ q, int B, int Bpad, int dim, int ld,
                                     __nv_bfloat16* __restrict__ qb, float* __restrict__ q_inv, float* __restrict__ q_nrm,
-                                    float* __restrict__ q_sq, unsigned int* __restrict__ zero, size_t n_zero) {
+                                    float* __restrict__ q_sq, float* __restrict__ q_bn, float* __restrict__ q_tn,
+                                    unsigned int* __restrict__ zero, size_t n_zero) {
   // per-search state of the filter (candidate counts, flags, tickets, lower-bound lists) starts at zero
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_zero;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
@@ -83,30 +151,52 @@ __global__ void prep_queries_kernel(const float* __restrict__ q, int B, int Bpad
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= Bpad) return;
-  float ss = 0.0f;
+  float ss = 0.0f, sb = 0.0f, st = 0.0f;
   for (int c = lane; c < ld; c += 32) {
     const float v = (c < dim && b < B) ? q[static_cast<size_t>(b) * dim + c] : 0.0f;
-    qb[static_cast<size_t>(b) * ld + c] = __float2bfloat16_rn(v);
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    qb[static_cast<size_t>(b) * ld + c] = h;
+    const float hb = __bfloat162float(h);
+    const float t = v - hb;              // exact
     ss = fmaf(v, v, ss);
+    sb = fmaf(hb, hb, sb);
+    st = fmaf(t, t, st);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, o);
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(FULL_MASK, ss, o);
+    sb += __shfl_xor_sync(FULL_MASK, sb, o);
+    st += __shfl_xor_sync(FULL_MASK, st, o);
+  }
   if (lane == 0) {
     q_sq[b] = ss;
     q_nrm[b] = sqrtf(ss);
     q_inv[b] = ss > 0.0f ? 1.0f / sqrtf(ss) : 0.0f;
+    q_bn[b] = sqrtf(sb) * 1.0001f;
+    q_tn[b] = sqrtf(st) * 1.0001f;
   }
 }
 
-// fp32 stored rows -> bf16 shadow rows (RNE), one warp per row
+// fp32 stored rows -> bf16 shadow rows (RNE) + the norm of the rounding residual |x - bf16(x)| (inflated by
+// 1e-4: an upper bound whatever the fp32 summation does), one warp per row
 __global__ void shadow_rows_kernel(const float* __restrict__ rows, long long n, int dpad, int ld16,
-                                   __nv_bfloat16* __restrict__ dst) {
+                                   __nv_bfloat16* __restrict__ dst, float* __restrict__ rres) {
   const int lane = threadIdx.x & 31;
   const long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n) return;
   const float* s = rows + r * dpad;
   __nv_bfloat16* d = dst + r * ld16;
-  for (int c = lane; c < ld16; c += 32) d[c] = __float2bfloat16_rn(c < dpad ? s[c] : 0.0f);
+  float sr = 0.0f;
+  for (int c = lane; c < ld16; c += 32) {
+    const float v = c < dpad ? s[c] : 0.0f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    d[c] = h;
+    const float t = v - __bfloat162float(h);   // exact (NaN / inf rows give NaN: such a row is always a candidate)
+    sr = fmaf(t, t, sr);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sr += __shfl_xor_sync(FULL_MASK, sr, o);
+  if (lane == 0) rres[r] = sqrtf(sr) * 1.0001f;
 }
 
 // ---------------------------------------------------------------- filter kernel
@@ -165,8 +255,9 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* stage_base = smem;
   float* colscale = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);    // [2][BN] score scale per column
-  float* coleps = colscale + 2 * BN;                                          // [2][BN] eps scale per column
-  uint64_t* bars = reinterpret_cast<uint64_t*>(coleps + 2 * BN);
+  float* coleps = colscale + 2 * BN;                                          // [2][BN] |x| term of eps per column
+  float* colres = coleps + 2 * BN;                                            // [2][BN] residual term of eps per column
+  uint64_t* bars = reinterpret_cast<uint64_t*>(colres + 2 * BN);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
@@ -275,26 +366,31 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const int half = (warp - 4) >> 2;           // column half of the tile
     const int q = qb * BM + et;
     const bool q_valid = q < p.B;
-    const float qinv = q_valid ? p.q_inv[q] : 0.0f;
-    const float qnrm = q_valid ? p.q_nrm[q] : 0.0f;
-    const float qsq = q_valid ? p.q_sq[q] : 0.0f;
-    // eps of this query: cosine eps_rel (norms cancel); ip eps_rel*|x||q|; l2 2*eps_rel*|x||q|
-    const float qeps = (METRIC == kCosine) ? p.eps_rel : (METRIC == kL2 ? 2.0f * p.eps_rel * qnrm : p.eps_rel * qnrm);
+    const QueryBound qb_ = make_query_bound<METRIC>(q_valid ? p.q_inv[q] : 0.0f, q_valid ? p.q_nrm[q] : 0.0f,
+                                                    q_valid ? p.q_sq[q] : 0.0f, q_valid ? p.q_bn[q] : 0.0f,
+                                                    q_valid ? p.q_tn[q] : 0.0f, p.acc_rel);
+    const float qnrm = qb_.qnrm, qsq = qb_.qsq;
+    const float c_l2 = p.c_l2;
     float L = NEG_INF;  // best known lower bound of this query's exact k-th best score (see lower_insert)
     unsigned int* my_slots = p.lower_list + static_cast<size_t>(q_valid ? q : 0) * kMaxKFilter;
-    // FAST TEST.  "upper bound of the exact score >= L" is rewritten so that it costs one multiply (or one
-    // fma) and one compare per accumulator element, against a per-thread threshold T that only changes
-    // when L does:  cosine  d*inv|x| >= (L - eps)|q|;  ip  d + |x|eps >= L;  l2  2d + |x|eps - |x|^2 >= L + |q|^2.
+    // FAST TEST.  "upper bound of the exact score >= L" (bound_eval: sv + eps >= L) is rewritten so that it costs
+    // two or three fused multiply-adds and one compare per accumulator element, against a per-thread
+    // threshold T that only changes when L does:
+    //   cosine  d/|x| + rho_x (A_q |q|) >= (L - C_q)|q|        (the inequality multiplied by |q|: no division)
+    //   ip      d + |r| A'_q + |x| C'_q >= L
+    //   l2      2d + 2|r| A'_q + 2|x| C'_q - (1 - c_l2)|x|^2 >= L + (1 - c_l2)|q|^2
     // T carries a 1e-6 relative slack (and the staged |x|^2 is shrunk by 1e-6) so that the fast test can
     // only ADMIT more elements than the reference form; admitted groups are re-tested below with the
-    // reference form, which alone decides what becomes a candidate.
+    // reference form (bound_eval), which alone decides what becomes a candidate.
+    const float fA = (METRIC == kCosine) ? qb_.A * qnrm : qb_.A;
+    const float fC = qb_.C;
     auto fast_thr = [&](float l) -> float {
       if (METRIC == kCosine) {
-        const float t = (l - qeps) * qnrm;
-        return t - 1e-6f * (fabsf(t) + qeps * qnrm);
+        const float t = (l - qb_.C) * qnrm;
+        return t - 1e-6f * (fabsf(t) + qnrm);
       }
-      if (METRIC == kL2) return (l + qsq) - 1e-6f * (fabsf(l) + 2.0f * qsq);
-      return l;
+      if (METRIC == kL2) return (l + qsq * (1.0f - c_l2)) - 1e-6f * (fabsf(l) + 2.0f * qsq);
+      return l - 1e-6f * fabsf(l);
     };
     float T = fast_thr(L);
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
@@ -302,23 +398,35 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const size_t region = static_cast<size_t>(q_valid ? q : 0) * p.s_total + 2 * (p.slice_base + slice) + half;
     unsigned long long* my_cand = p.cand + region * p.cap;
     unsigned int n_cand = 0;
-    // per-column scale (cosine 1/|x|, l2 |x|^2 shrunk by 1e-6) and |x| for the eps term of column
-    // half*128 + et of tile t; columns past the end get |x| = -inf (upper bound -inf) and are rejected by the
-    // reference form anyway.  The loads for tile t+1 (and the shared bound) are issued BEFORE tile t is
-    // processed, so their latency never sits on the epilogue's critical path.
-    auto load_scale = [&](int t, float& sc, float& ep) {
+    // per-column terms of column half*128 + et of tile t, staged for the fast test:
+    //   cosine  cs = 1/|x|                       cr = rho_x = |r|/|x|
+    //   ip      ce = |x|                         cr = |r|
+    //   l2      cs = (1 - c_l2)(1 - 1e-6)|x|^2   ce = 2|x|    cr = 2|r|
+    // columns past the end get ce = -inf (cosine: all zero) and are rejected by the reference path's range
+    // check anyway.  The loads for tile t+1 (and the shared bound) are issued BEFORE tile t is processed, so
+    // their latency never sits on the epilogue's critical path.
+    auto load_scale = [&](int t, float& sc, float& ep, float& rs) {
       const long long row = static_cast<long long>(slice + t * p.n_slices) * BN + half * 128 + et;
       sc = 0.0f;
-      ep = NEG_INF;
+      ep = (METRIC == kCosine) ? 0.0f : NEG_INF;
+      rs = 0.0f;
       if (t < my_tiles && row < p.n_rows) {
-        const float inx = __ldg(p.inv_norm + row);
-        const float sq = __ldg(p.sqnorm + row);
-        sc = (METRIC == kCosine) ? inx : (METRIC == kL2 ? sq * (1.0f - 1e-6f) : 0.0f);
-        ep = (METRIC == kCosine) ? 1.0f : sqrtf(sq);  // |x|
+        const float rr = p.rres != nullptr ? __ldg(p.rres + row) : 0.0f;
+        if (METRIC == kCosine) {
+          const float inx = __ldg(p.inv_norm + row);
+          sc = inx;
+          rs = rr * inx;
+        } else {
+          const float sq = __ldg(p.sqnorm + row);
+          const float xn = sqrtf(sq) * 1.00001f;
+          sc = (METRIC == kL2) ? sq * ((1.0f - c_l2) * (1.0f - 1e-6f)) : 0.0f;
+          ep = (METRIC == kL2) ? 2.0f * xn : xn;
+          rs = (METRIC == kL2) ? 2.0f * rr : rr;
+        }
       }
     };
-    float sc_next, ep_next;
-    load_scale(0, sc_next, ep_next);
+    float sc_next, ep_next, rs_next;
+    load_scale(0, sc_next, ep_next, rs_next);
     unsigned int glob_next = q_valid ? __ldcg(p.lower_glob + q) : 0u;
     for (int t = 0; t < my_tiles; ++t) {
       const int a = t & 1;
@@ -327,15 +435,17 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       const int valid = rem < BN ? static_cast<int>(rem) : BN;
       float* cs = colscale + a * BN;
       float* ce = coleps + a * BN;
+      float* cr = colres + a * BN;
       cs[half * 128 + et] = sc_next;   // buffer a was last read for tile t-2: every thread has passed the
       ce[half * 128 + et] = ep_next;   // barrier of tile t-1 since
+      cr[half * 128 + et] = rs_next;
       // share the bound: any thread's k-th best lower bound is a valid global lower bound
       if (q_valid) {
         const float g = unmono_f32(max(glob_next, 0x007FFFFFu));
         if (g > L) { L = g; T = fast_thr(L); }
         glob_next = __ldcg(p.lower_glob + q);
       }
-      load_scale(t + 1, sc_next, ep_next);
+      load_scale(t + 1, sc_next, ep_next, rs_next);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(smem_u32(tmem_full + a), (static_cast<uint32_t>(t) >> 1) & 1u);
       tc_fence_after();
@@ -351,19 +461,22 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 #pragma unroll
           for (int g4 = 0; g4 < 8; ++g4) {
             const float4 c4 = *reinterpret_cast<const float4*>(cs + c0 + 4 * g4);
+            const float4 r4 = *reinterpret_cast<const float4*>(cr + c0 + 4 * g4);
             const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+            const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
             float u[4];
             if (METRIC == kCosine) {
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) u[jj] = __uint_as_float(r[4 * g4 + jj]) * cc[jj];
+              for (int jj = 0; jj < 4; ++jj) u[jj] = fmaf(rr[jj], fA, __uint_as_float(r[4 * g4 + jj]) * cc[jj]);
             } else {
               const float4 e4 = *reinterpret_cast<const float4*>(ce + c0 + 4 * g4);
               const float ee[4] = {e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {
                 const float d = __uint_as_float(r[4 * g4 + jj]);
-                if (METRIC == kL2) u[jj] = fmaf(2.0f, d, fmaf(ee[jj], qeps, -cc[jj]));
-                else u[jj] = fmaf(ee[jj], qeps, d);
+                const float e = fmaf(rr[jj], fA, ee[jj] * fC);
+                if (METRIC == kL2) u[jj] = fmaf(2.0f, d, e - cc[jj]);
+                else u[jj] = d + e;
               }
             }
             // !(x < T) also admits NaN (the refine ranks it like K1)
@@ -386,12 +499,11 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
               if (col >= valid) continue;
               const long long row = row0 + col;
               const float d = __uint_as_float(v[jj]);
-              const float ej = ce[col];
-              float sv;
-              if (METRIC == kCosine) sv = d * cs[col] * qinv;
-              else if (METRIC == kL2) sv = -((__ldg(p.sqnorm + row) - 2.0f * d) + qsq);
-              else sv = d;
-              const float up = fmaf(ej, qeps, sv);  // upper bound of the exact score
+              const float rrow = p.rres != nullptr ? __ldg(p.rres + row) : 0.0f;
+              float sv, ej;
+              bound_eval<METRIC>(d, METRIC == kCosine ? cs[col] : 0.0f, METRIC == kCosine ? 0.0f : __ldg(p.sqnorm + row),
+                                 rrow, qb_, c_l2, sv, ej);
+              const float up = sv + ej;  // upper bound of the exact score
               if (!(up < L)) {
                 bool dead = false;
                 if (p.tomb != nullptr) dead = (__ldg(p.tomb + (row >> 5)) >> (row & 31)) & 1u;
@@ -399,7 +511,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                   if (n_cand < static_cast<unsigned int>(p.cap))
                     my_cand[n_cand] = (static_cast<unsigned long long>(p.seg) << 32) | static_cast<unsigned long long>(row);
                   ++n_cand;
-                  const float lo = sv - ej * qeps;  // NaN never enters the list of lower bounds
+                  const float lo = sv - ej;  // NaN never enters the list of lower bounds
                   if (lo > L) {
                     const float nl = lower_insert(my_slots, p.lower_glob + q, k, lo, L);
                     if (nl > L) { L = nl; T = fast_thr(L); }
@@ -456,7 +568,10 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
   float* q_inv_s = Tq + SQ;
   float* q_nrm_s = q_inv_s + SQ;
   float* q_sq_s = q_nrm_s + SQ;
-  unsigned int* wcount = reinterpret_cast<unsigned int*>(q_sq_s + SQ);                  // [SQ] candidates of this CTA per query
+  float* q_A_s = q_sq_s + SQ;                                                           // [SQ] QueryBound::A
+  float* q_C_s = q_A_s + SQ;                                                            // [SQ] QueryBound::C
+  float* q_fA_s = q_C_s + SQ;                                                           // [SQ] fast-test form of A
+  unsigned int* wcount = reinterpret_cast<unsigned int*>(q_fA_s + SQ);                  // [SQ] candidates of this CTA per query
   uint64_t* bars = reinterpret_cast<uint64_t*>(wcount + SQ);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + S_STAGES;
@@ -486,11 +601,16 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
   if (warp == 3) {
     for (int j = lane; j < SQ; j += 32) {
       const bool v = j < p.B;
+      const QueryBound b = make_query_bound<METRIC>(v ? p.q_inv[j] : 0.0f, v ? p.q_nrm[j] : 0.0f, v ? p.q_sq[j] : 0.0f,
+                                                    v ? p.q_bn[j] : 0.0f, v ? p.q_tn[j] : 0.0f, p.acc_rel);
       Lq[j] = 0u;
       Tq[j] = NEG_INF;
-      q_inv_s[j] = v ? p.q_inv[j] : 0.0f;
-      q_nrm_s[j] = v ? p.q_nrm[j] : 0.0f;
-      q_sq_s[j] = v ? p.q_sq[j] : 0.0f;
+      q_inv_s[j] = b.qinv;
+      q_nrm_s[j] = b.qnrm;
+      q_sq_s[j] = b.qsq;
+      q_A_s[j] = b.A;
+      q_C_s[j] = b.C;
+      q_fA_s[j] = (METRIC == kCosine) ? b.A * b.qnrm : b.A;
     }
     for (int i = lane; i < SQ; i += 32) wcount[i] = 0u;
   }
@@ -556,48 +676,56 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
     const int quarter = warp & 3, sub = ew >> 2;
     const int row_in_tile = sub * 128 + quarter * 32 + lane;
     const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(sub * SQ);
-    // fast test per (row, query), see gemm_filter_kernel:  cosine d/|x| >= (L - eps)|q|;  ip d + |x|eps >= L;
-    // l2 2d + |x|eps - |x|^2 >= L + |q|^2, thresholds with 1e-6 slack; admitted pairs are decided by the
-    // reference form below.  L / T live in shared memory per query and are shared by the whole CTA.
-    auto qeps_of = [&](int j) -> float {
-      return (METRIC == kCosine) ? p.eps_rel : (METRIC == kL2 ? 2.0f * p.eps_rel * q_nrm_s[j] : p.eps_rel * q_nrm_s[j]);
+    // fast test per (row, query), see gemm_filter_kernel (same inequalities, thresholds with 1e-6 slack); admitted
+    // pairs are decided by the reference form (bound_eval) below.  L / T live in shared memory per query and are
+    // shared by the whole CTA.
+    const float c_l2 = p.c_l2;
+    auto qbound = [&](int j) -> QueryBound {
+      QueryBound b;
+      b.A = q_A_s[j]; b.C = q_C_s[j]; b.qinv = q_inv_s[j]; b.qnrm = q_nrm_s[j]; b.qsq = q_sq_s[j];
+      return b;
     };
     auto fast_thr = [&](float l, int j) -> float {
       if (METRIC == kCosine) {
-        const float t = (l - p.eps_rel) * q_nrm_s[j];
-        return t - 1e-6f * (fabsf(t) + p.eps_rel * q_nrm_s[j]);
+        const float t = (l - q_C_s[j]) * q_nrm_s[j];
+        return t - 1e-6f * (fabsf(t) + q_nrm_s[j]);
       }
-      if (METRIC == kL2) return (l + q_sq_s[j]) - 1e-6f * (fabsf(l) + 2.0f * q_sq_s[j]);
-      return l;
+      if (METRIC == kL2) return (l + q_sq_s[j] * (1.0f - c_l2)) - 1e-6f * (fabsf(l) + 2.0f * q_sq_s[j]);
+      return l - 1e-6f * fabsf(l);
     };
     auto raise_bound = [&](int j, float nl) {   // any thread: publish a better bound of query j to the CTA
       const unsigned int m = mono_u32(nl);
       if (atomicMax(Lq + j, m) < m) Tq[j] = fast_thr(nl, j);
     };
-    auto load_row = [&](int t, float& inx, float& sq) {
+    auto load_row = [&](int t, float& inx, float& sq, float& rr) {
       const long long row = static_cast<long long>(slice + t * p.n_slices) * BN + row_in_tile;
       inx = 0.0f;
       sq = 0.0f;
+      rr = 0.0f;
       if (t < my_tiles && row < p.n_rows) {
         if (METRIC == kCosine) inx = __ldg(p.inv_norm + row);
         else sq = __ldg(p.sqnorm + row);
+        if (p.rres != nullptr) rr = __ldg(p.rres + row);
       }
     };
-    float inx_next, sq_next;
-    load_row(0, inx_next, sq_next);
+    float inx_next, sq_next, rr_next;
+    load_row(0, inx_next, sq_next, rr_next);
     unsigned int glob_next = (ew == 0 && lane < p.B) ? __ldcg(p.lower_glob + lane) : 0u;
     for (int t = 0; t < my_tiles; ++t) {
       const int a = t & 1;
       const long long row = static_cast<long long>(slice + t * p.n_slices) * BN + row_in_tile;
       const bool row_valid = row < p.n_rows;
-      const float inx = inx_next, sq = sq_next;
-      const float ex = (METRIC == kCosine) ? 1.0f : sqrtf(sq);   // |x|
-      const float sqs = sq * (1.0f - 1e-6f);
+      const float inx = inx_next, sq = sq_next, rr = rr_next;
+      // per-row terms of the fast test: cosine fr = rho_x; ip fe = |x|, fr = |r|; l2 fe = 2|x|, fr = 2|r|, sqs = shrunk |x|^2
+      const float xn = sqrtf(sq) * 1.00001f;
+      const float fe = (METRIC == kL2) ? 2.0f * xn : xn;
+      const float fr = (METRIC == kCosine) ? rr * inx : ((METRIC == kL2) ? 2.0f * rr : rr);
+      const float sqs = sq * ((1.0f - c_l2) * (1.0f - 1e-6f));
       if (ew == 0 && lane < p.B) {   // bounds published by other CTAs (one tile stale: prefetched)
         if (glob_next > 0x007FFFFFu) raise_bound(lane, unmono_f32(glob_next));
         glob_next = __ldcg(p.lower_glob + lane);
       }
-      load_row(t + 1, inx_next, sq_next);
+      load_row(t + 1, inx_next, sq_next, rr_next);
       mbar_wait(smem_u32(tmem_full + a), (static_cast<uint32_t>(t) >> 1) & 1u);
       tc_fence_after();
       uint32_t r[SQ];
@@ -614,9 +742,9 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
         if (j < p.B) {   // uniform
           const float d = __uint_as_float(r[j]);
           float u;
-          if (METRIC == kCosine) u = d * inx;
-          else if (METRIC == kL2) u = fmaf(2.0f, d, fmaf(ex, qeps_of(j), -sqs));
-          else u = fmaf(ex, qeps_of(j), d);
+          if (METRIC == kCosine) u = fmaf(fr, q_fA_s[j], d * inx);
+          else if (METRIC == kL2) u = fmaf(2.0f, d, fmaf(fr, q_fA_s[j], fe * q_C_s[j]) - sqs);
+          else u = d + fmaf(fr, q_fA_s[j], fe * q_C_s[j]);
           if (__any_sync(FULL_MASK, row_valid && !(u < Tq[j]))) any |= 1u << j;
         }
       }
@@ -635,11 +763,9 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
           float d = 0.0f;
 #pragma unroll
           for (int jj = 0; jj < SQ; ++jj) d = (jj == j) ? __uint_as_float(r[jj]) : d;   // r[] stays in registers
-          float sv;
-          if (METRIC == kCosine) sv = d * inx * q_inv_s[j];
-          else if (METRIC == kL2) sv = -((sq - 2.0f * d) + q_sq_s[j]);
-          else sv = d;
-          const float lo = (row_valid && !dead) ? sv - ex * qeps_of(j) : NEG_INF;   // NaN: mono_u32 ranks it as -inf
+          float sv, ej;
+          bound_eval<METRIC>(d, inx, sq, rr, qbound(j), c_l2, sv, ej);
+          const float lo = (row_valid && !dead) ? sv - ej : NEG_INF;   // NaN: mono_u32 ranks it as -inf
           const unsigned int wbest = __reduce_max_sync(FULL_MASK, mono_u32(lo));
           if (lane == j) my_best = unmono_f32(max(wbest, 0x007FFFFFu));
         }
@@ -677,11 +803,9 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
           float d = 0.0f;
 #pragma unroll
           for (int jj = 0; jj < SQ; ++jj) d = (jj == j) ? __uint_as_float(r[jj]) : d;
-          float sv;
-          if (METRIC == kCosine) sv = d * inx * q_inv_s[j];
-          else if (METRIC == kL2) sv = -((sq - 2.0f * d) + q_sq_s[j]);
-          else sv = d;
-          const float up = fmaf(ex, qeps_of(j), sv);   // upper bound of the exact score (reference form)
+          float sv, ej;
+          bound_eval<METRIC>(d, inx, sq, rr, qbound(j), c_l2, sv, ej);
+          const float up = sv + ej;   // upper bound of the exact score (reference form)
           const float L = unmono_f32(max(*reinterpret_cast<volatile unsigned int*>(Lq + j), 0x007FFFFFu));
           const bool take = row_valid && !dead && !(up < L);   // !(x < L) keeps NaN (the refine ranks it like K1)
           const unsigned tm = __ballot_sync(FULL_MASK, take);
@@ -714,13 +838,13 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
   }
 }
 
-constexpr size_t kFilterSmallSmem = 1024 + static_cast<size_t>(S_STAGES) * S_STAGE_BYTES + (5 * SQ + SQ) * 4 +
+constexpr size_t kFilterSmallSmem = 1024 + static_cast<size_t>(S_STAGES) * S_STAGE_BYTES + (8 * SQ + SQ) * 4 +
                                     (2 * S_STAGES + 4) * 8 + 16;
 
 constexpr size_t filter_smem(int ncta) {
   const size_t stages = ncta == 2 ? STAGES_PAIR : STAGES_SINGLE;
   const size_t stage_bytes = static_cast<size_t>(BN / ncta) * BK * 2 + Q_TILE_BYTES;
-  return 1024 + stages * stage_bytes + 4 * BN * 4 + (2 * stages + 4) * 8 + 16;
+  return 1024 + stages * stage_bytes + 6 * BN * 4 + (2 * stages + 4) * 8 + 16;
 }
 
 // ---------------------------------------------------------------- refine kernel
@@ -984,11 +1108,23 @@ int filter_max_k() { return kMaxKFilter; }
 
 int filter_ld16(int dim) { return (dim + 7) / 8 * 8; }
 
-// workspace layout (bytes): qb16 [Bpad][ld16] bf16 | q_inv, q_nrm, q_sq [Bpad] f32 each; Bpad = B rounded up to 128
+// workspace layout (bytes): qb16 [Bpad][ld16] bf16 | q_inv, q_nrm, q_sq, q_bn, q_tn [Bpad] f32 each; Bpad = B rounded up to 128
 static int filter_bpad(int B) { return (B + BM - 1) / BM * BM; }
 size_t filter_query_workspace_bytes(int B, int dim) {
   const size_t bp = filter_bpad(B);
-  return (bp * filter_ld16(dim) * 2 + 15) / 16 * 16 + 3 * bp * 4;
+  return (bp * filter_ld16(dim) * 2 + 15) / 16 * 16 + 5 * bp * 4;
+}
+
+// accumulation terms of the error bound (see "error bound" above), relative to |x||q|: tensor-core fp32
+// accumulation (dim * 2^-23 * 1.01, truncation allowed) + K1's fp32 dot and score formula + slack
+float filter_acc_rel(int dim, int dpad) {
+  return static_cast<float>(dim) * 1.21e-7f + (static_cast<float>(dpad) / 32.0f + 40.0f) * 6e-8f + 1e-6f;
+}
+// l2: relative to |x|^2 + |q|^2 -- rounding of the stored |x|^2 and of |q|^2 (one lane sums dpad/32 squares, then
+// a 5-level butterfly), the three additions of the expanded form, K1's direct sum of squared differences
+// (2 x (fma chain + butterfly + the rounding of each difference)) and slack
+float filter_c_l2(int dpad) {
+  return (3.0f * static_cast<float>(dpad) / 32.0f + 64.0f) * 6e-8f + 1e-6f;
 }
 
 int filter_slices_for(long long n_rows, int B, int sm_count) {
@@ -1001,11 +1137,12 @@ int filter_slices_for(long long n_rows, int B, int sm_count) {
   return static_cast<int>(s);
 }
 
-cudaError_t launch_shadow_rows(const float* rows, long long n, int dpad, int ld16, void* dst, cudaStream_t stream) {
+cudaError_t launch_shadow_rows(const float* rows, long long n, int dpad, int ld16, void* dst, float* rres,
+                               cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   const int wpb = 8;
   shadow_rows_kernel<<<static_cast<unsigned>((n + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
-      rows, n, dpad, ld16, static_cast<__nv_bfloat16*>(dst));
+      rows, n, dpad, ld16, static_cast<__nv_bfloat16*>(dst), rres);
   return cudaGetLastError();
 }
 
@@ -1016,13 +1153,15 @@ cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace,
   __nv_bfloat16* qb = static_cast<__nv_bfloat16*>(workspace);
   float* f = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + (static_cast<size_t>(bp) * ld * 2 + 15) / 16 * 16);
   const int wpb = 8;
-  prep_queries_kernel<<<(bp + wpb - 1) / wpb, wpb * 32, 0, stream>>>(q, B, bp, dim, ld, qb, f, f + bp, f + 2 * bp, zero, n_zero);
+  prep_queries_kernel<<<(bp + wpb - 1) / wpb, wpb * 32, 0, stream>>>(q, B, bp, dim, ld, qb, f, f + bp, f + 2 * bp, f + 3 * bp,
+                                                                     f + 4 * bp, zero, n_zero);
   return cudaGetLastError();
 }
 
 // One launch per segment.  xb = bf16 matrix [n_rows][ld_x] (shadow, or the stored rows of a bf16 engine).
-cudaError_t launch_gemm_filter(const void* xb, int ld_x, const SegDesc& seg, int seg_index, int dim, const void* workspace,
-                               int B, int k, int metric, float eps_rel, int n_slices, unsigned long long* cand,
+cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, const SegDesc& seg, int seg_index, int dim,
+                               const void* workspace, int B, int k, int metric, float acc_rel, float c_l2, int n_slices,
+                               unsigned long long* cand,
                                unsigned int* cand_count, unsigned int* lower_glob, unsigned int* lower_list, int cap,
                                int slice_base, int s_total, cudaStream_t stream) {
   if (seg.n_rows <= 0 || n_slices <= 0) return cudaSuccess;
@@ -1061,6 +1200,9 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const SegDesc& seg, int
   p.q_inv = f;
   p.q_nrm = f + bp;
   p.q_sq = f + 2 * bp;
+  p.q_bn = f + 3 * bp;
+  p.q_tn = f + 4 * bp;
+  p.rres = rres;
   p.n_rows = seg.n_rows;
   p.B = B;
   p.k = k;
@@ -1068,7 +1210,8 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const SegDesc& seg, int
   p.n_tiles = static_cast<int>((seg.n_rows + BN - 1) / BN);
   p.n_slices = n_slices;
   p.seg = seg_index;
-  p.eps_rel = eps_rel;
+  p.acc_rel = acc_rel;
+  p.c_l2 = c_l2;
   p.cand = cand;
   p.cand_count = cand_count;
   p.lower_glob = lower_glob;

@@ -103,11 +103,15 @@ int filter_ld16(int dim);
 size_t filter_query_workspace_bytes(int B, int dim);
 int filter_slices_for(long long n_rows, int B, int sm_count);
 int filter_regions_per_slice(int B);
-cudaError_t launch_shadow_rows(const float* rows, long long n, int dpad, int ld16, void* dst, cudaStream_t stream);
+float filter_acc_rel(int dim, int dpad);
+float filter_c_l2(int dpad);
+// bf16 shadow rows + per-row upper bound of |x - bf16(x)| (rres)
+cudaError_t launch_shadow_rows(const float* rows, long long n, int dpad, int ld16, void* dst, float* rres, cudaStream_t stream);
 cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace, unsigned int* zero, size_t n_zero,
                                 cudaStream_t stream);
-cudaError_t launch_gemm_filter(const void* xb, int ld_x, const SegDesc& seg, int seg_index, int dim, const void* workspace,
-                               int B, int k, int metric, float eps_rel, int n_slices, unsigned long long* cand,
+cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, const SegDesc& seg, int seg_index, int dim,
+                               const void* workspace, int B, int k, int metric, float acc_rel, float c_l2, int n_slices,
+                               unsigned long long* cand,
                                unsigned int* cand_count, unsigned int* lower_glob, unsigned int* lower_list, int cap,
                                int slice_base, int s_total, cudaStream_t stream);
 cudaError_t launch_refine_topk(const SegDesc* segs, int n_seg, const float* q, int B, int dim, int dpad, int elem_bytes,

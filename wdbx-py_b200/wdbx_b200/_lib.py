@@ -30,7 +30,7 @@ class Stats(C.Structure):
         ("bytes_resident", C.c_int64), ("kernel_launches", C.c_int64), ("searches", C.c_int64),
         ("last_search_ms", C.c_double),
         ("seg_rows", C.c_int64 * MAX_SEGMENTS), ("seg_live", C.c_int64 * MAX_SEGMENTS),
-        ("last_kernel_ms", C.c_double),
+        ("last_kernel_ms", C.c_double), ("last_candidates", C.c_int64),
     ]
 
 
