@@ -257,3 +257,36 @@ def test_list_query_conversion_matches_numpy():
     with pytest.raises(ValueError, match="dimension mismatch"):
         st.search([0.0] * 3)
     st.close()
+
+
+def test_shard_clear_drops_bulk_ids_of_that_shard():
+    """bulk ids of a cleared shard must not resolve to the (reused) row positions."""
+    st = make_store(4, 2)
+    X = np.eye(4, dtype=np.float32)[[0, 1, 2, 3, 0, 1]]
+    assert st.bulk_load(X, id_prefix="v") == 6
+    st.update_metadata("v0", {"m": 1})
+    assert st.indices[0].clear()
+    assert st.get("v0") is None and st.get("v2") is None and not st.delete("v0")
+    assert st.get("v1")[0] == X[1].tolist()
+    assert st.count() == 3 and "v0" not in st.metadata
+    # a new id landing in shard 0 reuses row 0 of the shard: the stale bulk id must stay dead
+    new = next(f"n{i}" for i in range(100) if st._get_shard_for_id(f"n{i}") == 0)
+    assert st.store(new, [0, 0, 0, 1])
+    assert st.get("v0") is None and not st.delete("v0") and st.get(new)[0] == [0.0, 0.0, 0.0, 1.0]
+    assert st.count() == 4
+    # the id can be stored again explicitly
+    assert st.store("v0", [1, 0, 0, 0]) and st.get("v0")[0] == [1.0, 0.0, 0.0, 0.0]
+
+
+def test_bulk_ids_are_canonical_and_prefix_collisions_rejected():
+    """'v01' / unicode digits must not alias bulk row 1; explicit ids may not shadow bulk rows."""
+    st = make_store(4, 1)
+    X = np.eye(4, dtype=np.float32)
+    st.bulk_load(X, id_prefix="v")
+    assert st.get("v1") is not None
+    assert st.get("v01") is None and not st.delete("v01") and st.get("v²") is None and st.get("v") is None
+    assert st.store("v²", [1, 1, 0, 0]) and st.count() == 5
+    st.store("w2", [0, 0, 1, 1])
+    with pytest.raises(ValueError):
+        st.bulk_load(X, id_prefix="w")
+    assert st.bulk_load(X[:2], id_prefix="w") == 2      # w2 is outside the new range: no collision

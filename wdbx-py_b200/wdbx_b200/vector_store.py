@@ -154,6 +154,7 @@ class VectorStore:
         self._bulk_starts: List[int] = []
         self._bulk_rows: Dict[int, Tuple[int, int]] = {}     # gid0 -> (first n per shard base, n rows) for lookups
         self._bulk_dead: set = set()
+        self._bulk_cleared: Dict[int, set] = {}              # gid0 -> shards cleared since that bulk_load
         self._row_gids: List[List[np.ndarray]] = [[] for _ in range(self.num_shards)]  # gid of every row, per shard
         self._shard_count = [0] * self.num_shards            # rows ever appended per shard (all ranks)
         self._shard_live = [0] * self.num_shards
@@ -267,6 +268,7 @@ class VectorStore:
                         "ids": [[g, v] for g, v in self._gid_to_id.items()],
                         "bulk": [[g0, g1, p, list(self._bulk_rows[g0])] for g0, g1, p in self._bulk],
                         "bulk_dead": sorted(self._bulk_dead),
+                        "bulk_cleared": [[g0, sorted(v)] for g0, v in self._bulk_cleared.items()],
                     }
                     tmp = self.data_dir / "vectors" / "state.json.tmp"
                     tmp.write_text(json.dumps(state))
@@ -350,6 +352,7 @@ class VectorStore:
             self._bulk_starts = [g0 for g0, _, _ in bulk]
             self._bulk_rows = {g0: tuple(base) for g0, _, _, base in state["bulk"]}
             self._bulk_dead = set(state["bulk_dead"])
+            self._bulk_cleared = {int(g0): set(v) for g0, v in state.get("bulk_cleared", [])}
             self._shard_count = list(state["shard_count"])
             self._shard_live = live
             self._version += 1
@@ -406,12 +409,15 @@ class VectorStore:
         for g0, g1, prefix in self._bulk:
             if vector_id.startswith(prefix):
                 tail = vector_id[len(prefix):]
-                if tail.isdigit():
+                # canonical decimal only: "v01" or a unicode digit must not alias row 1
+                if tail.isascii() and tail.isdigit() and (tail == "0" or tail[0] != "0"):
                     gid = g0 + int(tail)
                     if gid < g1 and gid not in self._bulk_dead:
                         i = gid - g0
                         base = self._bulk_rows[g0]
                         shard = i % self.num_shards
+                        if shard in self._bulk_cleared.get(g0, ()):
+                            return None
                         return shard, base[shard] + i // self.num_shards, gid
         return None
 
@@ -480,6 +486,12 @@ class VectorStore:
                 gid = self._loc.pop(vid)[2]
                 self._gid_to_id[gid] = None
                 self.metadata.pop(vid, None)
+            # bulk rows of this shard are gone too: their ids must stop resolving to (reused) row positions
+            for g0, g1, prefix in self._bulk:
+                self._bulk_cleared.setdefault(g0, set()).add(shard)
+                if self.metadata:
+                    for i in range(shard, g1 - g0, self.num_shards):
+                        self.metadata.pop(f"{prefix}{i}", None)
             self._row_gids[shard] = []
             self._version += 1
             self._shard_count[shard] = 0
@@ -553,6 +565,11 @@ class VectorStore:
             for g0_, g1_, p_ in self._bulk:
                 if p_ == id_prefix:
                     raise ValueError(f"id_prefix {id_prefix!r} already used by a bulk_load")
+            for vid in self._loc:   # an explicit id "v5" would shadow bulk row 5 of prefix "v"
+                if vid.startswith(id_prefix):
+                    tail = vid[len(id_prefix):]
+                    if tail.isascii() and tail.isdigit() and (tail == "0" or tail[0] != "0") and int(tail) < n:
+                        raise ValueError(f"id_prefix {id_prefix!r} collides with the existing id {vid!r}")
             g0 = len(self._gid_to_id)
             base = list(self._shard_count)
             for s in range(S):
@@ -640,6 +657,7 @@ class VectorStore:
             self._loc = {}
             self._gid_to_id.drop_all()  # gids keep growing: keys stay unique
             self._bulk, self._bulk_starts, self._bulk_rows, self._bulk_dead = [], [], {}, set()
+            self._bulk_cleared = {}
             self._shard_count = [0] * self.num_shards
             self._shard_live = [0] * self.num_shards
             self._row_gids = [[] for _ in range(self.num_shards)]
