@@ -96,7 +96,8 @@ struct wdbx_b200_engine {
   long long shadow_min_bytes = 1ll << 30;
   int gemm_min_batch = 16;  // B >= this => tcgen05 path (0 = never); measured crossover vs K1 (8 queries/pass) ~ 12-16
   int gemm_mode = 0;        // 0 = bf16 filter + exact refine (K2b), 1 = 3xTF32 with fused top-k (K2)
-  int pdl = 1;              // programmatic dependent launch for K1 (WDBX_B200_PDL=0 disables)
+  int pdl = 1;              // programmatic dependent launch between the launches of a search (WDBX_B200_PDL=0 disables)
+  bool shadow_warned = false;
   cudaStream_t mstream = nullptr;  // mutations
   // staging for host-sourced appends
   float* stage_rows = nullptr;
@@ -262,8 +263,10 @@ int get_workspace(wdbx_b200_engine* e, cudaStream_t stream, size_t cand_keys, in
 // Launch one K1 scan over segments [s0, s1).  Caller holds e->mu and has set the device.
 int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B, int k, int metric,
                   uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream,
-                  bool exchange = false, const int* only_flag = nullptr, float min_score = -INFINITY,
+                  unsigned int xseq = 0u, const int* only_flag = nullptr, float min_score = -INFINITY,
                   bool use_allow = false) {
+  // xseq != 0: collective search, the last CTA exchanges its lists with the peer ranks under this sequence number
+  const bool exchange = xseq != 0u;
   ScanPlan plan;
   const int rc = scan_plan(e->dim, e->dpad, e->elem_bytes, k, B, e->sm_count, e->tune, &plan);
   if (rc == -4) return fail(WDBX_B200_ERR_LIMIT, "dimension %d too large for the scan kernel's shared-memory stage", e->dim);
@@ -322,16 +325,15 @@ int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B
     if (e->xworld < 2) return fail(WDBX_B200_ERR_ARG, "exchange not attached (call wdbx_b200_exchange_init/attach first)");
     if (B > plan.queries_per_block || B > kXchgMaxB || k > kXchgMaxK)
       return fail(WDBX_B200_ERR_LIMIT, "fused exchange supports B <= %d queries in one pass and k <= %d", kXchgMaxB, kXchgMaxK);
-    e->xseq += 1;
     for (int r = 0; r < e->xworld; ++r) p.xchg_peer[r] = e->xpeer[r];
     p.xchg_world = e->xworld;
     p.xchg_rank = e->xrank;
-    p.xchg_seq = e->xseq;
-    p.xchg_slot = static_cast<int>(e->xseq & 1u);
+    p.xchg_seq = xseq;
+    p.xchg_slot = static_cast<int>(xseq & 1u);
   }
-  // back-to-back searches: let the next scan start on SMs that have finished while the last CTA still
-  // merges (programmatic dependent launch); never for the flag-gated re-run, which must see its flags
-  plan.pdl = (e->pdl && only_flag == nullptr) ? 1 : 0;
+  // back-to-back launches: let this one start on SMs that have finished while the last CTA of the previous launch
+  // still merges (programmatic dependent launch; the flag-gated re-run waits for its flags inside the kernel)
+  plan.pdl = e->pdl ? 1 : 0;
   const bool timed = e->ktiming && only_flag == nullptr;
   if (timed) CU_TRY(cudaEventRecord(e->kev0, stream));
   CU_TRY(launch_scan_topk(p, plan, e->dtype == WDBX_B200_BF16, stream));
@@ -383,13 +385,25 @@ int gemm_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B
   return WDBX_B200_OK;
 }
 
-// K2b path: (lazily built / extended) bf16 shadow -> prep -> one filter launch per segment -> refine ->
-// flag-gated K1 re-run of the queries whose candidate region overflowed.  Returns WDBX_B200_ERR_OOM when the
-// shadow cannot be allocated (the caller then serves from the stored rows).  Caller holds e->mu, device is set.
+// K2b path: (lazily built / extended) bf16 shadow -> prep -> one filter launch per segment (small batches: the
+// filter kernel re-scores its own candidates and its last CTA merges / exchanges / emits; larger batches: a
+// refine launch) -> flag-gated K1 re-run of the queries whose candidate region overflowed.  Returns
+// WDBX_B200_ERR_OOM when the shadow cannot be allocated (the caller then serves from the stored rows).
+// xseq != 0 (fused small-batch kernel only): collective search with the on-device key exchange.
+// Caller holds e->mu, device is set.
 int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B, int k, int metric,
-                    uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream) {
+                    uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream,
+                    unsigned int xseq = 0u, float min_score = -INFINITY, bool use_allow = false) {
   const int ld16 = filter_ld16(e->dim);
   const bool f32 = e->dtype == WDBX_B200_F32;
+  const bool fused = filter_fused_tail(B);
+  if (!fused && (xseq != 0u || use_allow || min_score > -INFINITY))
+    return fail(WDBX_B200_ERR_ARG, "exchange / pre-filter on the filter path need the small-batch kernel");
+  long long total_rows = 0;
+  for (int s = s0; s < s1; ++s) total_rows += e->seg[s].n_rows;
+  if (total_rows == 0)   // nothing to filter: K1 emits the empty lists (and joins the exchange)
+    return scan_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream, xseq, nullptr,
+                         min_score, use_allow);
   bool built = false;
   for (int s = s0; s < s1; ++s) {
     Segment& sg = e->seg[s];
@@ -430,25 +444,27 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   const int rps = filter_regions_per_slice(B);
   for (int s = s0; s < s1; ++s) {
     slices[s] = e->seg[s].n_rows > 0 ? filter_slices_for(e->seg[s].n_rows, B, e->sm_count) : 0;
-    s_total += rps * slices[s];  // candidate regions per (query, slice): one per epilogue column half / warp
+    s_total += rps * slices[s];  // candidate regions per (query, slice): one per epilogue column half / CTA
   }
-  if (s_total == 0) s_total = rps;
   const int cap = rps == 2 ? 512 : 1024;
   const size_t n_regions = static_cast<size_t>(B) * s_total;
   const size_t need_ws = filter_query_workspace_bytes(B, e->dim);
-  // small batches: several refine CTAs per query (each a share of the candidate regions), merged by K3
+  // refine launch (larger batches): several CTAs per query (each a share of the candidate regions), the last one merges
   int refine_ctas = (2 * e->sm_count + B - 1) / B;   // two 256-thread CTAs per SM
   if (refine_ctas > 8 * s_total) refine_ctas = 8 * s_total;
   if (refine_ctas < 1) refine_ctas = 1;
-  const size_t need_part = refine_ctas > 1 ? static_cast<size_t>(refine_ctas) * B * k : 0;
-  // one zero-initialised block per search: [n_regions] candidate counts | [B] overflow flags | [B] refine
-  // tickets | [B][16] shared lower-bound lists (64-byte rows) | [B] published bounds  (0 = "no bound yet")
+  // partial lists: fused tail [B][s_total][k] (one per filter CTA), refine launch [refine_ctas][B][k]
+  const size_t need_part = fused ? n_regions * k : (refine_ctas > 1 ? static_cast<size_t>(refine_ctas) * B * k : 0);
+  // one zero-initialised block per search: [n_regions] candidate counts | [B] overflow flags | [B] tickets
+  // (fused tail: [0] = the search's ticket) | [B][filter_max_k] shared lower-bound lists | [B] published
+  // bounds  (0 = "no bound yet")
   const size_t lk = static_cast<size_t>(filter_max_k());
   const size_t off_over = (n_regions + 15) / 16 * 16;
   const size_t off_ticket = off_over + static_cast<size_t>(B);
   const size_t off_list = (off_ticket + static_cast<size_t>(B) + 15) / 16 * 16;
   const size_t off_glob = off_list + static_cast<size_t>(B) * lk;
-  const size_t need_zero = off_glob + static_cast<size_t>(B);
+  const size_t off_ctr = off_glob + static_cast<size_t>(B);   // [kMaxSeg] dynamic tile counters (fused small-batch kernel)
+  const size_t need_zero = off_ctr + static_cast<size_t>(kMaxSeg);
   if (w->fpart_n < need_part || w->fws_bytes < need_ws || w->fcand_n < n_regions * cap || w->fzero_n < need_zero) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(stream, &cs);
@@ -481,12 +497,43 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   unsigned int* ftickets = w->fzero + off_ticket;
   unsigned int* lower_list = w->fzero + off_list;
   unsigned int* lower_glob = w->fzero + off_glob;
-  CU_TRY(launch_prep_queries(q_dev, B, e->dim, w->fws, w->fzero, need_zero, stream));  // also zeroes w->fzero
+  const bool pdl = e->pdl != 0;
+  CU_TRY(launch_prep_queries(q_dev, B, e->dim, w->fws, w->fzero, need_zero, pdl, stream));  // also zeroes w->fzero
   e->launches.fetch_add(1, std::memory_order_relaxed);
   // the operand-rounding part of the filter's error bound is derived from the data (per-row |x - bf16(x)|,
   // per-query |q - bf16(q)|); these are the accumulation terms on top (gemm_filter.cu, "error bound")
   const float acc_rel = filter_acc_rel(e->dim, e->dpad);
   const float c_l2 = filter_c_l2(e->dpad);
+  ScanTuning t1 = e->tune;
+  t1.queries_per_pass = 1;
+  ScanPlan plan;
+  if (scan_plan(e->dim, e->dpad, e->elem_bytes, k, 1, e->sm_count, t1, &plan) != 0)
+    return fail(WDBX_B200_ERR_ARG, "invalid scan shape (dim=%d k=%d)", e->dim, k);
+  FilterTail tail;
+  memset(&tail, 0, sizeof(tail));
+  if (fused) {
+    tail.q = q_dev;
+    tail.dpad = e->dpad;
+    tail.elem_bytes = e->elem_bytes;
+    tail.lpr_log2 = plan.lpr_log2;
+    tail.nch = plan.nch;
+    tail.min_score = min_score;
+    tail.overflow = foverflow;
+    tail.part = w->fpart;
+    tail.ticket = ftickets;
+    tail.tile_ctr = w->fzero + off_ctr;
+    if (xseq != 0u) {
+      for (int r = 0; r < e->xworld; ++r) tail.xchg.peer[r] = e->xpeer[r];
+      tail.xchg.world = e->xworld;
+      tail.xchg.rank = e->xrank;
+      tail.xchg.seq = xseq;
+      tail.xchg.slot = static_cast<int>(xseq & 1u);
+    }
+    tail.keys_out = keys_out;
+    tail.scores_out = scores_out;
+    tail.gids_out = gids_out;
+    tail.counts_out = counts_out;
+  }
   SegDesc descs[kMaxSeg];
   memset(descs, 0, sizeof(descs));
   int slice_base = 0;
@@ -499,27 +546,26 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
     d.sqnorm = sg.sqnorm;
     d.gids = sg.gids;
     d.tomb = sg.n_dead > 0 ? sg.tomb : nullptr;
+    d.allow = use_allow ? sg.allow : nullptr;
     d.n_rows = sg.n_rows;
     if (sg.n_rows == 0) continue;
     CU_TRY(launch_gemm_filter(f32 ? sg.shadow : static_cast<const void*>(sg.rows), f32 ? ld16 : e->dpad,
                               f32 ? sg.rres : nullptr, d, s, e->dim, w->fws, B, k, metric, acc_rel, c_l2, slices[s], w->fcand,
-                              fcount, lower_glob, lower_list, cap, slice_base, s_total, stream));
+                              fcount, lower_glob, lower_list, cap, slice_base, s_total, fused ? &tail : nullptr, pdl, stream));
     e->launches.fetch_add(1, std::memory_order_relaxed);
     slice_base += slices[s];
   }
   if (e->ktiming) CU_TRY(cudaEventRecord(e->kev1, stream));
-  ScanTuning t1 = e->tune;
-  t1.queries_per_pass = 1;
-  ScanPlan plan;
-  if (scan_plan(e->dim, e->dpad, e->elem_bytes, k, 1, e->sm_count, t1, &plan) != 0)
-    return fail(WDBX_B200_ERR_ARG, "invalid scan shape (dim=%d k=%d)", e->dim, k);
-  CU_TRY(launch_refine_topk(descs, kMaxSeg, q_dev, B, e->dim, e->dpad, e->elem_bytes, plan.lpr_log2, plan.nch, k, metric,
-                            w->fcand, fcount, cap, s_total, foverflow, refine_ctas, w->fpart, ftickets, keys_out, scores_out,
-                            gids_out, counts_out, stream));
-  e->launches.fetch_add(1, std::memory_order_relaxed);
-  // exact re-run (K1) of the queries whose candidate list overflowed; exits immediately otherwise
+  if (!fused) {
+    CU_TRY(launch_refine_topk(descs, kMaxSeg, q_dev, B, e->dim, e->dpad, e->elem_bytes, plan.lpr_log2, plan.nch, k, metric,
+                              w->fcand, fcount, cap, s_total, foverflow, refine_ctas, w->fpart, ftickets, keys_out, scores_out,
+                              gids_out, counts_out, stream));
+    e->launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  // exact re-run (K1) of the queries whose candidate list overflowed; exits immediately otherwise.  Collective
+  // searches: a flagged query makes the filter's last CTA skip the exchange and K1 redo all B queries with it.
   const int rrc = scan_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream,
-                                false, foverflow);
+                                xseq, foverflow, min_score, use_allow);
   if (e->ktiming) {
     e->last_kernel = 2;
     e->kpending = true;
@@ -537,6 +583,7 @@ bool use_gemm(const wdbx_b200_engine* e, int s0, int s1, int B, int k) {
   if (e->gemm_min_batch <= 0) return false;
   if (e->gemm_mode == 1) return B >= e->gemm_min_batch && e->dtype == WDBX_B200_F32 && k <= gemm_max_k();
   if (k > filter_max_k()) return false;
+  if (static_cast<size_t>(e->dpad) * 4 > 160 * 1024) return false;   // the fused tail stages fp32 queries in shared memory
   if (B >= e->gemm_min_batch) return true;
   if (e->dtype != WDBX_B200_F32 || e->shadow_min_bytes < 0) return false;
   long long bytes = 0;
@@ -554,6 +601,11 @@ int search_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
     // no room for the bf16 shadow: keep serving from the stored rows (K1) and stop trying for small batches
     cudaGetLastError();
     e->shadow_min_bytes = -1;
+    if (!e->shadow_warned) {
+      e->shadow_warned = true;
+      fprintf(stderr, "[wdbx_b200] device %d: no memory for the bf16 shadow; small batches are served by the fp32 scan "
+                      "(about half the queries/s)\n", e->device);
+    }
   }
   return scan_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream);
 }
@@ -1015,10 +1067,22 @@ int wdbx_b200_search_filtered_host(wdbx_b200_engine* e, const float* q_host, int
         else CU_TRY(cudaMemsetAsync(sg.allow, 0xFF, words * 4, st));  // NULL entry = every row allowed
       }
     }
-    // filtered searches always take the streaming kernel (the bitmap is only consulted for candidates)
-    rc = scan_segments(e, 0, e->nseg, e->dq, B, k, metric, nullptr, reinterpret_cast<float*>(e->dres + off_scores),
-                       reinterpret_cast<long long*>(e->dres + off_gids), reinterpret_cast<int*>(e->dres + off_counts), st,
-                       false, nullptr, min_score, use_allow);
+    // small batches on the filter path consult the bitmap / floor in the fused filter kernel (candidates only);
+    // everything else takes the streaming kernel
+    rc = WDBX_B200_ERR_OOM;
+    if (e->gemm_mode != 1 && use_gemm(e, 0, e->nseg, B, k) && filter_fused_tail(B)) {
+      rc = filter_segments(e, 0, e->nseg, e->dq, B, k, metric, nullptr, reinterpret_cast<float*>(e->dres + off_scores),
+                           reinterpret_cast<long long*>(e->dres + off_gids), reinterpret_cast<int*>(e->dres + off_counts), st,
+                           0u, min_score, use_allow);
+      if (rc == WDBX_B200_ERR_OOM) {
+        cudaGetLastError();
+        e->shadow_min_bytes = -1;
+      }
+    }
+    if (rc == WDBX_B200_ERR_OOM)
+      rc = scan_segments(e, 0, e->nseg, e->dq, B, k, metric, nullptr, reinterpret_cast<float*>(e->dres + off_scores),
+                         reinterpret_cast<long long*>(e->dres + off_gids), reinterpret_cast<int*>(e->dres + off_counts), st,
+                         0u, nullptr, min_score, use_allow);
     if (rc != WDBX_B200_OK) return rc;
   }
   CU_TRY(cudaMemcpyAsync(e->hres_pinned, e->dres, bytes, cudaMemcpyDeviceToHost, st));
@@ -1092,26 +1156,59 @@ int wdbx_b200_exchange_attach(wdbx_b200_engine* e, int world, const void* ipc_ha
 namespace {
 
 // Collective search of all segments + on-device key exchange with the peer ranks.  Caller holds e->mu.
+// Every rank takes the same decisions here (they depend on B, k, dim only -- never on the rank's own rows), and
+// the routes a rank may take for one search (fused filter kernel, K1 scan, stand-alone exchange kernel) all
+// speak the same exchange protocol under the same sequence number.
 int exchange_search_locked(wdbx_b200_engine* e, const float* q_dev, int B, int k, int metric, uint64_t* keys_out,
                            float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream) {
+  if (e->xworld < 2) return fail(WDBX_B200_ERR_ARG, "exchange not attached (call wdbx_b200_exchange_init/attach first)");
+  if (B > kXchgMaxB || k > kXchgMaxK)
+    return fail(WDBX_B200_ERR_LIMIT, "fused exchange supports B <= %d queries and k <= %d", kXchgMaxB, kXchgMaxK);
+  // the K1 scan (and the flag-gated re-run behind the filter) exchanges from ONE query block: batches larger
+  // than the block the plan allows for this shape (e.g. 1 query for dim 64) run as consecutive collective passes
+  ScanPlan plan;
+  const int prc = scan_plan(e->dim, e->dpad, e->elem_bytes, k, B, e->sm_count, e->tune, &plan);
+  if (prc != 0) return fail(prc == -4 ? WDBX_B200_ERR_LIMIT : WDBX_B200_ERR_ARG, "invalid scan shape (dim=%d k=%d)", e->dim, k);
+  if (B > plan.queries_per_block) {
+    const int qb = plan.queries_per_block;
+    for (int b0 = 0; b0 < B; b0 += qb) {
+      const int nb = std::min(qb, B - b0);
+      const size_t o = static_cast<size_t>(b0) * k;
+      const int rc = exchange_search_locked(e, q_dev + static_cast<size_t>(b0) * e->dim, nb, k, metric,
+                                            keys_out ? keys_out + o : nullptr, scores_out ? scores_out + o : nullptr,
+                                            gids_out ? gids_out + o : nullptr, counts_out ? counts_out + b0 : nullptr, stream);
+      if (rc != WDBX_B200_OK) return rc;
+    }
+    return WDBX_B200_OK;
+  }
+  e->xseq += 1;
+  if (e->xseq == 0u) e->xseq = 1u;   // 0 means "no exchange"
+  const unsigned int seq = e->xseq;
   int rc;
-  if (e->xworld >= 2 && B <= kXchgMaxB && k <= kXchgMaxK && e->gemm_mode != 1 && use_gemm(e, 0, e->nseg, B, k)) {
-    // bf16-filter path: local exact top-k (filter + refine), then the stand-alone exchange + merge kernel.
-    // Ranks may take different routes for the same search: both speak the same exchange protocol.
-    if (!e->xkeys) CU_TRY(cudaMalloc(&e->xkeys, static_cast<size_t>(kXchgMaxB) * kXchgMaxK * 8));
-    rc = filter_segments(e, 0, e->nseg, q_dev, B, k, metric, e->xkeys, nullptr, nullptr, nullptr, stream);
-    if (rc == WDBX_B200_OK) {
-      e->xseq += 1;
-      CU_TRY(launch_exchange_merge(e->xpeer, e->xworld, e->xrank, e->xseq, e->xkeys, B, k, keys_out, scores_out,
-                                   gids_out, counts_out, stream));
-      e->launches.fetch_add(1, std::memory_order_relaxed);
-      return rc;
+  if (e->gemm_mode != 1 && use_gemm(e, 0, e->nseg, B, k)) {
+    if (filter_fused_tail(B)) {
+      // bf16-filter path, ONE launch: filter + in-kernel refine; its last CTA pushes / awaits / merges the keys
+      rc = filter_segments(e, 0, e->nseg, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream, seq);
+    } else {
+      // 128-query filter kernel (WDBX_B200_FILTER_SMALL=0): local exact top-k, then the stand-alone exchange kernel
+      if (!e->xkeys) CU_TRY(cudaMalloc(&e->xkeys, static_cast<size_t>(kXchgMaxB) * kXchgMaxK * 8));
+      rc = filter_segments(e, 0, e->nseg, q_dev, B, k, metric, e->xkeys, nullptr, nullptr, nullptr, stream);
+      if (rc == WDBX_B200_OK) {
+        CU_TRY(launch_exchange_merge(e->xpeer, e->xworld, e->xrank, seq, e->xkeys, B, k, keys_out, scores_out, gids_out,
+                                     counts_out, stream));
+        e->launches.fetch_add(1, std::memory_order_relaxed);
+      }
     }
     if (rc != WDBX_B200_ERR_OOM) return rc;
     cudaGetLastError();
     e->shadow_min_bytes = -1;
+    if (!e->shadow_warned) {
+      e->shadow_warned = true;
+      fprintf(stderr, "[wdbx_b200] device %d: no memory for the bf16 shadow; small batches are served by the fp32 scan "
+                      "(about half the queries/s)\n", e->device);
+    }
   }
-  return scan_segments(e, 0, e->nseg, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream, true);
+  return scan_segments(e, 0, e->nseg, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream, seq);
 }
 
 }  // namespace

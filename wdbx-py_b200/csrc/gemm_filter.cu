@@ -30,6 +30,8 @@
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "scan_topk_kernel.cuh"
@@ -74,7 +76,15 @@ struct FilterParams {
   unsigned int* lower_list;   // [B][kMaxKFilter] monotone-mapped lower bounds of the k best rows seen by ANY CTA
   int cap;                    // entries per (query, slice) region
   int slice_base, s_total;    // this launch fills slices [slice_base, slice_base + n_slices) of s_total
+  unsigned int* tile_ctr;     // small-batch kernel: the launch's dynamic tile counter (zero at launch)
+  int trace;                  // WDBX_B200_FILTER_TRACE=1: every CTA prints its phase timestamps (small-batch kernel)
 };
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 // ---------------------------------------------------------------- error bound
 // The filter must never drop a row that the exact path (K1's fp32 arithmetic) would rank in the top-k, so
@@ -144,6 +154,10 @@ __global__ void prep_queries_kernel(const float* __restrict__ q, int B, int Bpad
                                     __nv_bfloat16* __restrict__ qb, float* __restrict__ q_inv, float* __restrict__ q_nrm,
                                     float* __restrict__ q_sq, float* __restrict__ q_bn, float* __restrict__ q_tn,
                                     unsigned int* __restrict__ zero, size_t n_zero) {
+  // programmatic dependent launch: the filter kernel behind us may start its set-up now; we wait for the previous
+  // search on this stream (it still reads the state and the query workspace that we rewrite below)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // per-search state of the filter (candidate counts, flags, tickets, lower-bound lists) starts at zero
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_zero;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
@@ -548,6 +562,14 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 // (and, at ~7 TB/s of HBM streaming, enough power to trip the board's power cap) on zero padding; here a
 // tile costs 2 x 4 MMAs of 128x16x16, the query tile is 2 KB per stage (6 stages of 34 KB), an accumulator
 // tile is 32 TMEM columns, and the epilogue is one X row per thread: one multiply + compare per query.
+//
+// ONE launch per search (per segment): after its last tile the CTA re-scores ITS OWN candidates from the stored
+// rows with K1's arithmetic (small_tail), publishes one k-key list per query, and the last CTA of the search
+// (atomic ticket over all segment launches) merges the lists, runs the cross-GPU key exchange and emits --
+// what used to be refine_topk_kernel + exchange_merge_kernel (3 launches and ~40 us per search, which capped
+// 8-GPU scaling at 0.71).  The CTA's first tile is PARKED: its accumulators stay in registers, its rows only
+// OFFER their lower bounds to the shared list, and the tile is decided after the last one -- no thread ever
+// waits for a first bound (the earlier spin stalled the TMA ring for ~13 us at every launch).
 constexpr int SQ = 16;                                 // query columns per MMA
 constexpr int S_STAGES = 6;
 constexpr uint32_t SX_BYTES = BN * BK * 2;             // 32 KB: 256 rows x 64 dims
@@ -555,11 +577,300 @@ constexpr uint32_t SQ_BYTES = SQ * BK * 2;             // 2 KB
 constexpr uint32_t S_STAGE_BYTES = SX_BYTES + SQ_BYTES;
 constexpr uint32_t S_TMEM_COLS = 64;                   // 2 buffers x 2 sub-tiles x 16 columns
 constexpr int kSmallWarpRegions = 1;                   // candidate regions per (query, slice): one, shared by the CTA
+constexpr int kTailWarps = kThreads / 32;
+
+struct SmallTail {
+  const float* q;              // [B][dim] fp32 queries
+  const unsigned char* rows;   // stored rows of this segment
+  const uint32_t* gids;
+  const uint32_t* allow;       // per-search "allowed rows" bitmap or NULL
+  int dim, dpad, row_bytes, cpr, lpr_log2, nch, bf16;
+  float min_score;
+  int* overflow;
+  uint64_t* part;
+  unsigned int* ticket;
+  XchgCtx xchg;
+  uint64_t* keys_out;
+  float* scores_out;
+  long long* gids_out;
+  int* counts_out;
+};
+
+// Re-score CU x G candidates of one query exactly as K1 does: lanes-per-row lpr, chunk c = lig + j*lpr
+// accumulated in j order with the x,y,z,w fmaf chain, xor-butterfly over the lpr lanes, K1's score formula.
+// The exact ranking key replaces the candidate entry in place.
+template <bool BF16, bool L2>
+__device__ __forceinline__ void rescore_unit(const SmallTail& tp, const float* q_s, float qinv, bool cosine,
+                                             unsigned long long* cand, int cnt, int base, const float* inv_norm, int lane) {
+  constexpr int CU = 2;
+  const int lpr_log2 = tp.lpr_log2, lpr = 1 << lpr_log2, G = 32 >> lpr_log2;
+  const int g = lane >> lpr_log2, lig = lane & (lpr - 1);
+  bool have[CU];
+  long long row[CU];
+  const unsigned char* rp[CU];
+#pragma unroll
+  for (int u = 0; u < CU; ++u) {
+    const int ci = base + u * G + g;
+    have[u] = ci < cnt;
+    // (entries outside the unit may already hold another warp's re-scored key: never read them)
+    row[u] = have[u] ? static_cast<long long>(__ldcg(cand + ci) & 0xFFFFFFFFull) : 0ll;
+    rp[u] = tp.rows + static_cast<size_t>(row[u]) * tp.row_bytes;
+  }
+  float inx[CU];
+  uint32_t gid[CU];
+#pragma unroll
+  for (int u = 0; u < CU; ++u) {
+    inx[u] = cosine ? __ldg(inv_norm + row[u]) : 1.0f;
+    gid[u] = __ldg(tp.gids + row[u]);
+  }
+  float dot[CU];
+#pragma unroll
+  for (int u = 0; u < CU; ++u) dot[u] = 0.0f;
+  for (int j0 = 0; j0 < tp.nch; j0 += 4) {
+    uint4 raw[CU][4];
+#pragma unroll
+    for (int u = 0; u < CU; ++u) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int c = lig + ((j0 + v) << lpr_log2);
+        raw[u][v] = (j0 + v < tp.nch && c < tp.cpr) ? __ldg(reinterpret_cast<const uint4*>(rp[u] + c * 16))
+                                                    : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < CU; ++u) {
+      float acc1 = dot[u];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int c = lig + ((j0 + v) << lpr_log2);
+        if (j0 + v < tp.nch && c < tp.cpr) {
+          if (!BF16) {
+            const float4 x = make_float4(__uint_as_float(raw[u][v].x), __uint_as_float(raw[u][v].y),
+                                         __uint_as_float(raw[u][v].z), __uint_as_float(raw[u][v].w));
+            const float4 qv = lds128(q_s + c * 4);
+            if (L2) {
+              const float d0 = x.x - qv.x, d1 = x.y - qv.y, d2 = x.z - qv.z, d3 = x.w - qv.w;
+              acc1 = fmaf(d0, d0, acc1); acc1 = fmaf(d1, d1, acc1); acc1 = fmaf(d2, d2, acc1); acc1 = fmaf(d3, d3, acc1);
+            } else {
+              acc1 = fmaf(x.x, qv.x, acc1); acc1 = fmaf(x.y, qv.y, acc1); acc1 = fmaf(x.z, qv.z, acc1); acc1 = fmaf(x.w, qv.w, acc1);
+            }
+          } else {
+            const uint32_t w[4] = {raw[u][v].x, raw[u][v].y, raw[u][v].z, raw[u][v].w};
+            const float4 qa = lds128(q_s + c * 8);
+            const float4 qb = lds128(q_s + c * 8 + 4);
+            const float qq[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xFFFF0000u);
+              if (L2) {
+                const float d0 = lo - qq[2 * i], d1 = hi - qq[2 * i + 1];
+                acc1 = fmaf(d0, d0, acc1); acc1 = fmaf(d1, d1, acc1);
+              } else {
+                acc1 = fmaf(lo, qq[2 * i], acc1); acc1 = fmaf(hi, qq[2 * i + 1], acc1);
+              }
+            }
+          }
+        }
+      }
+      dot[u] = acc1;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < CU; ++u) {
+    float d = dot[u];
+    for (int o = lpr >> 1; o > 0; o >>= 1) d += __shfl_xor_sync(FULL_MASK, d, o);
+    float sc = d;
+    if (L2) sc = -sc;
+    else if (cosine) sc = sc * inx[u] * qinv;
+    sc = (sc != sc) ? __int_as_float(0xff800000) : sc;
+    // score floor exactly as K1 applies it (a row passes when s >= min_score)
+    const uint64_t key = (sc >= tp.min_score) ? pack_key(sc, gid[u]) : 0ull;
+    if (have[u] && lig == 0) cand[base + u * G + g] = key;
+  }
+}
+
+// Last-CTA fold of all per-CTA lists of one query: the [n_lists][k] keys are read as ONE flat array, 32 keys per
+// warp step and four steps in flight (a single L2 round trip for 148 lists of 10), each chunk sorted in registers
+// and merged into the warp's list, then a tree over the warps.  (Merging list by list -- grid_merge_fast -- paid
+// one dependent round trip per 48 lists: 12 us of a 300 us launch.)
+template <int S>
+__device__ __forceinline__ void grid_merge_flat(const uint64_t* keys, int n_keys, uint64_t* scratch, uint64_t* final_list,
+                                                int k, int warp, int lane, int nwarps) {
+  uint64_t acc[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) acc[s] = 0ull;
+  const int nchunks = (n_keys + 31) >> 5;
+  for (int c0 = warp; c0 < nchunks; c0 += 4 * nwarps) {
+    uint64_t v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = (c0 + j * nwarps) * 32 + lane;
+      v[j] = idx < n_keys ? __ldcg(reinterpret_cast<const unsigned long long*>(keys + idx)) : 0ull;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (c0 + j * nwarps < nchunks) {   // warp-uniform
+        uint64_t b4[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) b4[s] = 0ull;
+        b4[0] = scan::warp_sort32_desc(v[j], lane);
+        scan::warp_merge<S>(acc, b4, lane);
+      }
+    }
+  }
+  scan::block_tree_merge<S>(acc, scratch, warp, lane, nwarps);
+  if (warp == 0) scan::store_list<S>(final_list, acc, k, lane);
+}
+
+// Everything after the CTA's last tile (all kThreads threads call it; `ring` = the idle TMA stage ring).
+template <int METRIC, int S>
+__device__ __forceinline__ void small_tail(const FilterParams& p, const SmallTail& tp, unsigned char* ring,
+                                           const unsigned int* wcount, int slice, unsigned long long t_entry,
+                                           unsigned long long t_loop) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned long long ts[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) ts[i] = 0ull;
+  auto stamp = [&](int i) { if (p.trace) ts[i] = gtime_ns() - t_entry; };
+  stamp(0);
+  const int k = p.k, B = p.B, dpad = tp.dpad;
+  uint64_t* scratch = reinterpret_cast<uint64_t*>(ring);                 // [kTailWarps][32 * S] merge scratch
+  uint64_t* final_list = scratch + kTailWarps * 32 * S;                  // [32 * S]
+  float* qinv_s = reinterpret_cast<float*>(final_list + 32 * S);         // [SQ] 1/|q| as K1 computes it
+  int* cnt_s = reinterpret_cast<int*>(qinv_s + SQ);                      // [SQ] candidates of this CTA per query
+  int* flag_s = cnt_s + SQ;                                              // [SQ + 2] last-CTA flag | any overflow | per query
+  const size_t q_off = scan::align128(static_cast<size_t>(kTailWarps + 1) * 32 * S * 8 + (3 * SQ + 2) * 4);
+  float* q_s = reinterpret_cast<float*>(ring + q_off);                   // [QG][dpad] fp32 queries, zero padded
+  int QG = static_cast<int>((static_cast<size_t>(S_STAGES) * S_STAGE_BYTES - q_off) / (static_cast<size_t>(dpad) * 4));
+  QG = QG < B ? QG : B;                                                  // >= 1: the host routes larger rows to K1
+  const size_t my_slice = static_cast<size_t>(p.slice_base + slice);
+  if (tid < SQ) {
+    int c = tid < B ? static_cast<int>(wcount[tid]) : 0;
+    if (c > p.cap) {   // adversarial data: thousands of near-identical rows -> the flag-gated K1 launch re-runs the query
+      tp.overflow[tid] = 1;
+      c = 0;
+    }
+    cnt_s[tid] = c;
+    if (tid < B) p.cand_count[static_cast<size_t>(tid) * p.s_total + my_slice] = wcount[tid];   // statistics only
+  }
+  __syncthreads();
+  const bool cosine = METRIC == kCosine;
+  const int G = 32 >> tp.lpr_log2;
+  const int upc = 2 * G;   // candidates per work unit (rescore_unit: CU = 2)
+  for (int j0 = 0; j0 < B; j0 += QG) {
+    const int nqg = (B - j0) < QG ? (B - j0) : QG;
+    for (int i = tid; i < nqg * dpad; i += kThreads) {
+      const int b = i / dpad, c = i - b * dpad;
+      q_s[i] = c < tp.dim ? __ldg(tp.q + static_cast<size_t>(j0 + b) * tp.dim + c) : 0.0f;
+    }
+    __syncthreads();
+    for (int b = warp; b < nqg; b += kTailWarps) {
+      float ss = 0.0f;
+      for (int i = lane; i < dpad; i += 32) ss = fmaf(q_s[b * dpad + i], q_s[b * dpad + i], ss);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, o);
+      if (lane == 0) qinv_s[j0 + b] = ss > 0.0f ? 1.0f / sqrtf(ss) : 0.0f;
+    }
+    __syncthreads();
+    stamp(1);
+    // work units (query, chunk of `upc` candidates) dealt round-robin over the 12 warps
+    const int myu = lane < nqg ? (cnt_s[j0 + lane] + upc - 1) / upc : 0;
+    int incl = myu;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(FULL_MASK, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(FULL_MASK, incl, 31);
+    for (int u = warp; u < total; u += kTailWarps) {
+      const int jl = __ffs(__ballot_sync(FULL_MASK, incl > u)) - 1;
+      const int c = u - __shfl_sync(FULL_MASK, incl - myu, jl);
+      const int j = j0 + jl;
+      unsigned long long* cand = p.cand + (static_cast<size_t>(j) * p.s_total + my_slice) * p.cap;
+      if (tp.bf16) rescore_unit<true, METRIC == kL2>(tp, q_s + jl * dpad, qinv_s[j], cosine, cand, cnt_s[j], c * upc, p.inv_norm, lane);
+      else rescore_unit<false, METRIC == kL2>(tp, q_s + jl * dpad, qinv_s[j], cosine, cand, cnt_s[j], c * upc, p.inv_norm, lane);
+    }
+    __syncthreads();
+  }
+  stamp(2);
+  // per query: the CTA's exact keys -> one sorted k-list (register bitonic sort + merge), published for the last CTA
+  for (int j = warp; j < B; j += kTailWarps) {
+    const unsigned long long* cand = p.cand + (static_cast<size_t>(j) * p.s_total + my_slice) * p.cap;
+    const int cnt = cnt_s[j];
+    uint64_t acc[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) acc[s] = 0ull;
+    for (int base = 0; base < cnt; base += 32) {
+      uint64_t b4[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) b4[s] = 0ull;
+      b4[0] = scan::warp_sort32_desc(base + lane < cnt ? __ldcg(cand + base + lane) : 0ull, lane);
+      scan::warp_merge<S>(acc, b4, lane);
+    }
+    scan::store_list<S>(tp.part + (static_cast<size_t>(j) * p.s_total + my_slice) * k, acc, k, lane);
+  }
+  stamp(3);
+  __threadfence();
+  __syncthreads();
+  stamp(4);
+  if (tid == 0) flag_s[0] = (atomicAdd(tp.ticket, 1u) == static_cast<unsigned int>(p.s_total) - 1u) ? 1 : 0;
+  __syncthreads();
+  stamp(5);
+  if (p.trace && tid == 128 && flag_s[0] == 0)
+    printf("TRACE cta %d cand %d entry %llu loop_end %llu tail_in %llu q_ready %llu rescored %llu listed %llu fenced %llu ticket %llu\n",
+           slice, cnt_s[0], t_entry, t_loop - t_entry, ts[0], ts[1], ts[2], ts[3], ts[4], ts[5]);
+  if (flag_s[0] == 0) return;
+  // ---- last CTA of the search: fold the s_total lists of every query, exchange across GPUs, emit
+  __threadfence();
+  if (tid == 0) {
+    int any = 0;
+    for (int j = 0; j < B; ++j) {
+      const int o = *reinterpret_cast<volatile int*>(tp.overflow + j);
+      flag_s[2 + j] = o;
+      any |= o;
+    }
+    flag_s[1] = any;
+  }
+  __syncthreads();
+  stamp(6);
+  const bool xchg = tp.xchg.world > 1;
+  if (xchg && flag_s[1]) return;   // a query overflowed: the flag-gated K1 launch redoes the whole collective search
+  for (int j = 0; j < B; ++j) {
+    const bool over = flag_s[2 + j] != 0;   // CTA-uniform
+    if (!over) grid_merge_flat<S>(tp.part + static_cast<size_t>(j) * p.s_total * k, p.s_total * k, scratch, final_list, k,
+                                  warp, lane, kTailWarps);
+    stamp(7);
+    if (warp == 0) {
+      __syncwarp();
+      if (over) {
+        if (tp.counts_out && lane == 0) tp.counts_out[j] = 0;
+      } else if (xchg) {
+        scan::xchg_push(tp.xchg, j, final_list, k, lane);
+      } else {
+        scan::emit_list(final_list, k, lane, tp.keys_out ? tp.keys_out + static_cast<size_t>(j) * k : nullptr,
+                        tp.scores_out ? tp.scores_out + static_cast<size_t>(j) * k : nullptr,
+                        tp.gids_out ? tp.gids_out + static_cast<size_t>(j) * k : nullptr, tp.counts_out ? tp.counts_out + j : nullptr);
+      }
+    }
+    __syncthreads();
+  }
+  if (xchg && warp == 0) {
+    const bool ok = scan::xchg_publish_wait(tp.xchg, lane);
+    for (int j = 0; j < B; ++j)
+      scan::xchg_merge_emit(tp.xchg, j, final_list, k, ok, lane, tp.keys_out ? tp.keys_out + static_cast<size_t>(j) * k : nullptr,
+                            tp.scores_out ? tp.scores_out + static_cast<size_t>(j) * k : nullptr,
+                            tp.gids_out ? tp.gids_out + static_cast<size_t>(j) * k : nullptr, tp.counts_out ? tp.counts_out + j : nullptr);
+  }
+  stamp(8);
+  if (p.trace && tid == 128)
+    printf("TRACE LAST cta %d cand %d entry %llu loop_end %llu tail_in %llu q_ready %llu rescored %llu listed %llu fenced %llu ticket %llu flags %llu merged %llu done %llu\n",
+           slice, cnt_s[0], t_entry, t_loop - t_entry, ts[0], ts[1], ts[2], ts[3], ts[4], ts[5], ts[6], ts[7], ts[8]);
+}
 
 template <int METRIC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_q,
-                         const FilterParams p) {
+                         const __grid_constant__ FilterParams p, const __grid_constant__ SmallTail tp) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* stage_base = smem;
@@ -577,13 +888,20 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
   uint64_t* empty_bar = bars + S_STAGES;
   uint64_t* tmem_full = bars + 2 * S_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* sched_full = tmem_empty + 2;     // [4] tile-index ring: producer -> MMA warp + epilogue warps
+  uint64_t* sched_empty = sched_full + 4;    // [4]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sched_empty + 4);
+  int* tile_ring = reinterpret_cast<int*>(tmem_ptr + 4);   // [4] tile index per ring slot, -1 = no more tiles
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.y;
   const int k = p.k;
   const float NEG_INF = __int_as_float(0xff800000);
+  const unsigned long long t_entry = p.trace ? gtime_ns() : 0ull;
 
+  // programmatic dependent launch: the flag-gated K1 launch behind us may become resident as SMs free up; our
+  // own set-up below overlaps the tail of the launch before us (prep), whose results we wait for right after
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_x);
     prefetch_tmap(&tm_q);
@@ -595,22 +913,41 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
       mbar_init(smem_u32(tmem_full + a), 1);
       mbar_init(smem_u32(tmem_empty + a), 8);
     }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(smem_u32(sched_full + s), 1);
+      mbar_init(smem_u32(sched_empty + s), 9);   // MMA warp + 8 epilogue warps
+    }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_ptr), S_TMEM_COLS);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (warp == 3) {
     for (int j = lane; j < SQ; j += 32) {
       const bool v = j < p.B;
       const QueryBound b = make_query_bound<METRIC>(v ? p.q_inv[j] : 0.0f, v ? p.q_nrm[j] : 0.0f, v ? p.q_sq[j] : 0.0f,
                                                     v ? p.q_bn[j] : 0.0f, v ? p.q_tn[j] : 0.0f, p.acc_rel);
-      Lq[j] = 0u;
-      Tq[j] = NEG_INF;
       q_inv_s[j] = b.qinv;
       q_nrm_s[j] = b.qnrm;
       q_sq_s[j] = b.qsq;
       q_A_s[j] = b.A;
       q_C_s[j] = b.C;
       q_fA_s[j] = (METRIC == kCosine) ? b.A * b.qnrm : b.A;
+      // the caller's score floor is a valid lower bound of every RETURNED score from the start
+      float t0 = NEG_INF;
+      unsigned int l0 = 0u;
+      if (tp.min_score > NEG_INF) {
+        l0 = mono_u32(tp.min_score);
+        if (METRIC == kCosine) {
+          const float t = (tp.min_score - b.C) * b.qnrm;
+          t0 = t - 1e-6f * (fabsf(t) + b.qnrm);
+        } else if (METRIC == kL2) {
+          t0 = (tp.min_score + b.qsq * (1.0f - p.c_l2)) - 1e-6f * (fabsf(tp.min_score) + 2.0f * b.qsq);
+        } else {
+          t0 = tp.min_score - 1e-6f * fabsf(tp.min_score);
+        }
+      }
+      Lq[j] = l0;
+      Tq[j] = t0;
     }
     for (int i = lane; i < SQ; i += 32) wcount[i] = 0u;
   }
@@ -618,13 +955,47 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const int my_tiles = (p.n_tiles - slice + p.n_slices - 1) / p.n_slices;
+  // DYNAMIC TILE SCHEDULE.  Tiles are 256 consecutive rows; the producer draws the next tile index from a
+  // per-launch atomic counter and hands it to the MMA warp and the epilogue warps through a 4-slot ring in
+  // shared memory (mbarrier pipeline: sched_full / sched_empty).  A static round-robin split left the CTAs
+  // finishing up to 54 us apart on a 281 us launch (SMs do not get equal shares of the HBM stream); with the
+  // counter every CTA ends within one tile (~8 us) of the others.
+  // consumers: wait for the ring slot of tile number `sq` of this CTA, read it, release the slot
+  auto fetch_tile = [&](int sq) -> int {
+    const int slot = sq & 3;
+    mbar_wait(smem_u32(sched_full + slot), (static_cast<uint32_t>(sq) >> 2) & 1u);
+    const int t = *reinterpret_cast<volatile int*>(tile_ring + slot);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(sched_empty + slot));
+    return t;
+  };
 
   if (warp == 0) {
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = 0; t < my_tiles; ++t) {
-      const int row0 = (slice + t * p.n_slices) * BN;
+    // the draw of tile sq+1 (a global atomic: a microsecond or two under a saturated HBM stream) is issued
+    // before the loads of tile sq and only consumed after them, so the producer never sits on its latency
+    auto publish = [&](int sq, int t) {
+      const int slot = sq & 3;
+      mbar_wait(smem_u32(sched_empty + slot), ((static_cast<uint32_t>(sq) >> 2) & 1u) ^ 1u);
+      if (lane == 0) {
+        tile_ring[slot] = t;
+        mbar_arrive(smem_u32(sched_full + slot));
+      }
+      __syncwarp();
+    };
+    auto draw = [&]() -> int {   // lane 0 holds the raw ticket
+      return lane == 0 ? static_cast<int>(atomicAdd(p.tile_ctr, 1u)) : 0;
+    };
+    auto settle = [&](int raw) -> int {
+      const int t = __shfl_sync(FULL_MASK, raw, 0);
+      return t < p.n_tiles ? t : -1;
+    };
+    int t_cur = settle(draw());
+    publish(0, t_cur);
+    for (int sq = 0; t_cur >= 0; ++sq) {
+      const int raw_nxt = draw();
+      const int row0 = t_cur * BN;
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
         mbar_wait(smem_u32(empty_bar + stage), phase ^ 1u);
         const uint32_t sb = smem_u32(stage_base) + static_cast<uint32_t>(stage) * S_STAGE_BYTES;
@@ -637,14 +1008,17 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
         __syncwarp();
         if (++stage == S_STAGES) { stage = 0; phase ^= 1u; }
       }
+      t_cur = settle(raw_nxt);
+      publish(sq + 1, t_cur);
     }
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc(128, SQ, 1u);  // M = 128 X rows, N = 16 queries, BF16 x BF16 -> F32
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = 0; t < my_tiles; ++t) {
-      const int a = t & 1;
-      mbar_wait(smem_u32(tmem_empty + a), ((static_cast<uint32_t>(t) >> 1) & 1u) ^ 1u);
+    for (int sq = 0;; ++sq) {
+      if (fetch_tile(sq) < 0) break;
+      const int a = sq & 1;
+      mbar_wait(smem_u32(tmem_empty + a), ((static_cast<uint32_t>(sq) >> 1) & 1u) ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(a * 2 * SQ);
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
@@ -698,22 +1072,30 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
       if (atomicMax(Lq + j, m) < m) Tq[j] = fast_thr(nl, j);
     };
     auto load_row = [&](int t, float& inx, float& sq, float& rr) {
-      const long long row = static_cast<long long>(slice + t * p.n_slices) * BN + row_in_tile;
+      const long long row = static_cast<long long>(t) * BN + row_in_tile;
       inx = 0.0f;
       sq = 0.0f;
       rr = 0.0f;
-      if (t < my_tiles && row < p.n_rows) {
+      if (t >= 0 && row < p.n_rows) {
         if (METRIC == kCosine) inx = __ldg(p.inv_norm + row);
         else sq = __ldg(p.sqnorm + row);
         if (p.rres != nullptr) rr = __ldg(p.rres + row);
       }
     };
+    int t_nxt = fetch_tile(0);
+    const int t_first = t_nxt;   // the CTA's first tile is parked (decided last)
     float inx_next, sq_next, rr_next;
-    load_row(0, inx_next, sq_next, rr_next);
-    unsigned int glob_next = (ew == 0 && lane < p.B) ? __ldcg(p.lower_glob + lane) : 0u;
-    for (int t = 0; t < my_tiles; ++t) {
-      const int a = t & 1;
-      const long long row = static_cast<long long>(slice + t * p.n_slices) * BN + row_in_tile;
+    load_row(t_nxt, inx_next, sq_next, rr_next);
+    unsigned int glob_next = 0u;
+    uint32_t r0[SQ];   // the parked accumulators of this thread's row of the first tile
+#pragma unroll
+    for (int j = 0; j < SQ; ++j) r0[j] = 0u;
+    // iterations 0, 1, ... are the CTA's tiles in the order it drew them; one more iteration decides the parked tile
+    for (int it = 0; t_first >= 0; ++it) {
+      const bool parked = t_nxt < 0;
+      const int t = parked ? t_first : t_nxt;
+      const int a = it & 1;
+      const long long row = static_cast<long long>(t) * BN + row_in_tile;
       const bool row_valid = row < p.n_rows;
       const float inx = inx_next, sq = sq_next, rr = rr_next;
       // per-row terms of the fast test: cosine fr = rho_x; ip fe = |x|, fr = |r|; l2 fe = 2|x|, fr = 2|r|, sqs = shrunk |x|^2
@@ -721,20 +1103,35 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
       const float fe = (METRIC == kL2) ? 2.0f * xn : xn;
       const float fr = (METRIC == kCosine) ? rr * inx : ((METRIC == kL2) ? 2.0f * rr : rr);
       const float sqs = sq * ((1.0f - c_l2) * (1.0f - 1e-6f));
-      if (ew == 0 && lane < p.B) {   // bounds published by other CTAs (one tile stale: prefetched)
-        if (glob_next > 0x007FFFFFu) raise_bound(lane, unmono_f32(glob_next));
+      if (ew == 0 && lane < p.B) {
+        // bounds published by other CTAs: prefetched one tile ahead, except right after the parked tile, whose
+        // offers (every CTA's, all at the same moment) are exactly what tile 1 needs to see
+        const unsigned int gl = (it <= 1) ? __ldcg(p.lower_glob + lane) : glob_next;
+        if (gl > 0x007FFFFFu) raise_bound(lane, unmono_f32(gl));
         glob_next = __ldcg(p.lower_glob + lane);
       }
-      load_row(t + 1, inx_next, sq_next, rr_next);
-      mbar_wait(smem_u32(tmem_full + a), (static_cast<uint32_t>(t) >> 1) & 1u);
-      tc_fence_after();
+      if (!parked) {
+        t_nxt = fetch_tile(it + 1);
+        load_row(t_nxt >= 0 ? t_nxt : t_first, inx_next, sq_next, rr_next);
+      }
       uint32_t r[SQ];
-      __syncwarp();
-      tmem_ld16(taddr0 + static_cast<uint32_t>(a * 2 * SQ), r);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(tmem_empty + a));   // the accumulator is in registers: free it now
+      if (!parked) {
+        mbar_wait(smem_u32(tmem_full + a), (static_cast<uint32_t>(it) >> 1) & 1u);
+        tc_fence_after();
+        __syncwarp();
+        tmem_ld16(taddr0 + static_cast<uint32_t>(a * 2 * SQ), r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(tmem_empty + a));   // the accumulator is in registers: free it now
+        if (it == 0) {
+#pragma unroll
+          for (int j = 0; j < SQ; ++j) r0[j] = r[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < SQ; ++j) r[j] = r0[j];
+      }
       // fast test: one multiply (or fma) + compare per (row, query); `any` = queries with an admitted row
       unsigned any = 0u;
 #pragma unroll
@@ -751,95 +1148,85 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
       if (any) {
         // rare path (warp-uniform).  Reference form of the bound per admitted query; the row with the best
         // lower bound of the warp is offered to the shared list -- one lane per QUERY inserts, all queries
-        // in parallel, so a cold start costs one round trip instead of a chain of them -- then the rows
-        // that still pass against the updated bound are appended (warp-aggregated, no atomics).
+        // in parallel -- then the rows that still pass against the updated bound are appended
+        // (warp-aggregated, one shared-memory atomic per warp and query).
         bool dead = false;
-        if (p.tomb != nullptr && row_valid) dead = (__ldg(p.tomb + (row >> 5)) >> (row & 31)) & 1u;
-        float my_best = NEG_INF;       // lane j: best lower bound of this warp's rows for query j
-        unsigned rem = any;
-        while (rem) {
-          const int j = __ffs(rem) - 1;
-          rem &= rem - 1;
-          float d = 0.0f;
-#pragma unroll
-          for (int jj = 0; jj < SQ; ++jj) d = (jj == j) ? __uint_as_float(r[jj]) : d;   // r[] stays in registers
-          float sv, ej;
-          bound_eval<METRIC>(d, inx, sq, rr, qbound(j), c_l2, sv, ej);
-          const float lo = (row_valid && !dead) ? sv - ej : NEG_INF;   // NaN: mono_u32 ranks it as -inf
-          const unsigned int wbest = __reduce_max_sync(FULL_MASK, mono_u32(lo));
-          if (lane == j) my_best = unmono_f32(max(wbest, 0x007FFFFFu));
+        if (row_valid) {
+          if (p.tomb != nullptr) dead = (__ldg(p.tomb + (row >> 5)) >> (row & 31)) & 1u;
+          if (tp.allow != nullptr) dead = dead || !((__ldg(tp.allow + (row >> 5)) >> (row & 31)) & 1u);
         }
-        if (lane < p.B && ((any >> lane) & 1u)) {
-          const float L = unmono_f32(max(*reinterpret_cast<volatile unsigned int*>(Lq + lane), 0x007FFFFFu));
-          if (my_best > L) {
-            const float nl = lower_insert(p.lower_list + static_cast<size_t>(lane) * kMaxKFilter, p.lower_glob + lane, k,
-                                          my_best, L);
-            if (nl > L) raise_bound(lane, nl);
+        if (!parked) {
+          float my_best = NEG_INF;       // lane j: best lower bound of this warp's rows for query j
+          unsigned rem = any;
+          while (rem) {
+            const int j = __ffs(rem) - 1;
+            rem &= rem - 1;
+            float d = 0.0f;
+#pragma unroll
+            for (int jj = 0; jj < SQ; ++jj) d = (jj == j) ? __uint_as_float(r[jj]) : d;   // r[] stays in registers
+            float sv, ej;
+            bound_eval<METRIC>(d, inx, sq, rr, qbound(j), c_l2, sv, ej);
+            const float lo = (row_valid && !dead) ? sv - ej : NEG_INF;   // NaN: mono_u32 ranks it as -inf
+            const unsigned int wbest = __reduce_max_sync(FULL_MASK, mono_u32(lo));
+            if (lane == j) my_best = unmono_f32(max(wbest, 0x007FFFFFu));
           }
-          // cold start: every warp of the grid meets its first tile with "no bound" at the same moment, and
-          // an insert that lands while the shared list still has empty slots returns none either.  Appending
-          // all 32 rows of every warp then (~38k candidates per query) costs far more than waiting the few
-          // microseconds until k rows have been offered by anyone (bounded: tiny stores may never get there).
-          if (Lq[lane] <= 0x007FFFFFu) {
-            for (int spin = 0; spin < 48; ++spin) {
-              const unsigned int g = __ldcg(p.lower_glob + lane);
-              if (g > 0x007FFFFFu) { raise_bound(lane, unmono_f32(g)); break; }
-              __nanosleep(200);
+          if (lane < p.B && ((any >> lane) & 1u)) {
+            const float L = unmono_f32(max(*reinterpret_cast<volatile unsigned int*>(Lq + lane), 0x007FFFFFu));
+            if (my_best > L) {
+              const float nl = lower_insert(p.lower_list + static_cast<size_t>(lane) * kMaxKFilter, p.lower_glob + lane, k,
+                                            my_best, L);
+              if (nl > L) raise_bound(lane, nl);
             }
           }
-          // ... and the first finite bound is only the weakest of the first k offers: on the first tile give
-          // the other ~1200 warps' offers (already in flight) a moment to land, then take the settled bound
-          if (t == 0) {
-            __nanosleep(3000);
-            const unsigned int g = __ldcg(p.lower_glob + lane);
-            if (g > 0x007FFFFFu) raise_bound(lane, unmono_f32(g));
-          }
+          __syncwarp();
         }
-        __syncwarp();
-        rem = any;
-        while (rem) {
-          const int j = __ffs(rem) - 1;
-          rem &= rem - 1;
-          float d = 0.0f;
+        if (it != 0) {   // tile 0 only offers; it is decided in the parked iteration against the settled bound
+          unsigned rem = any;
+          while (rem) {
+            const int j = __ffs(rem) - 1;
+            rem &= rem - 1;
+            float d = 0.0f;
 #pragma unroll
-          for (int jj = 0; jj < SQ; ++jj) d = (jj == j) ? __uint_as_float(r[jj]) : d;
-          float sv, ej;
-          bound_eval<METRIC>(d, inx, sq, rr, qbound(j), c_l2, sv, ej);
-          const float up = sv + ej;   // upper bound of the exact score (reference form)
-          const float L = unmono_f32(max(*reinterpret_cast<volatile unsigned int*>(Lq + j), 0x007FFFFFu));
-          const bool take = row_valid && !dead && !(up < L);   // !(x < L) keeps NaN (the refine ranks it like K1)
-          const unsigned tm = __ballot_sync(FULL_MASK, take);
-          if (tm) {
-            unsigned int base = 0;
-            if (lane == 0) base = atomicAdd(wcount + j, static_cast<unsigned int>(__popc(tm)));   // shared memory
-            base = __shfl_sync(FULL_MASK, base, 0);
-            if (take) {
-              const unsigned int idx = base + __popc(tm & ((1u << lane) - 1u));
-              if (idx < static_cast<unsigned int>(p.cap)) {
-                const size_t region = static_cast<size_t>(j) * p.s_total + static_cast<size_t>(p.slice_base + slice);
-                p.cand[region * p.cap + idx] = (static_cast<unsigned long long>(p.seg) << 32) | static_cast<unsigned long long>(row);
+            for (int jj = 0; jj < SQ; ++jj) d = (jj == j) ? __uint_as_float(r[jj]) : d;
+            float sv, ej;
+            bound_eval<METRIC>(d, inx, sq, rr, qbound(j), c_l2, sv, ej);
+            const float up = sv + ej;   // upper bound of the exact score (reference form)
+            const float L = unmono_f32(max(*reinterpret_cast<volatile unsigned int*>(Lq + j), 0x007FFFFFu));
+            const bool take = row_valid && !dead && !(up < L);   // !(x < L) keeps NaN (the refine ranks it like K1)
+            const unsigned tm = __ballot_sync(FULL_MASK, take);
+            if (tm) {
+              unsigned int base = 0;
+              if (lane == 0) base = atomicAdd(wcount + j, static_cast<unsigned int>(__popc(tm)));   // shared memory
+              base = __shfl_sync(FULL_MASK, base, 0);
+              if (take) {
+                const unsigned int idx = base + __popc(tm & ((1u << lane) - 1u));
+                if (idx < static_cast<unsigned int>(p.cap)) {
+                  const size_t region = static_cast<size_t>(j) * p.s_total + static_cast<size_t>(p.slice_base + slice);
+                  p.cand[region * p.cap + idx] = (static_cast<unsigned long long>(p.seg) << 32) | static_cast<unsigned long long>(row);
+                }
               }
             }
           }
         }
       }
+      if (parked) break;
     }
-    // all epilogue warps done -> one thread per query publishes the CTA's candidate count
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (ew == 0 && lane < p.B)
-      p.cand_count[static_cast<size_t>(lane) * p.s_total + static_cast<size_t>(p.slice_base + slice)] = wcount[lane];
   }
 
+  const unsigned long long t_loop = p.trace ? gtime_ns() : 0ull;
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, S_TMEM_COLS);
   }
+  // the TMA ring is idle (every load was consumed by an MMA that an epilogue warp has waited for): reuse it
+  if (k <= 32) small_tail<METRIC, 1>(p, tp, stage_base, wcount, slice, t_entry, t_loop);
+  else small_tail<METRIC, 4>(p, tp, stage_base, wcount, slice, t_entry, t_loop);
 }
 
 constexpr size_t kFilterSmallSmem = 1024 + static_cast<size_t>(S_STAGES) * S_STAGE_BYTES + (8 * SQ + SQ) * 4 +
-                                    (2 * S_STAGES + 4) * 8 + 16;
+                                    (2 * S_STAGES + 12) * 8 + 16 + 16;
 
 constexpr size_t filter_smem(int ncta) {
   const size_t stages = ncta == 2 ? STAGES_PAIR : STAGES_SINGLE;
@@ -1147,24 +1534,36 @@ cudaError_t launch_shadow_rows(const float* rows, long long n, int dpad, int ld1
 }
 
 cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace, unsigned int* zero, size_t n_zero,
-                                cudaStream_t stream) {
+                                bool pdl, cudaStream_t stream) {
   const int ld = filter_ld16(dim);
   const int bp = filter_bpad(B);
   __nv_bfloat16* qb = static_cast<__nv_bfloat16*>(workspace);
   float* f = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + (static_cast<size_t>(bp) * ld * 2 + 15) / 16 * 16);
   const int wpb = 8;
-  prep_queries_kernel<<<(bp + wpb - 1) / wpb, wpb * 32, 0, stream>>>(q, B, bp, dim, ld, qb, f, f + bp, f + 2 * bp, f + 3 * bp,
-                                                                     f + 4 * bp, zero, n_zero);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((bp + wpb - 1) / wpb, 1, 1);
+  cfg.blockDim = dim3(wpb * 32, 1, 1);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, prep_queries_kernel, q, B, bp, dim, ld, qb, f, f + bp, f + 2 * bp, f + 3 * bp, f + 4 * bp,
+                            zero, n_zero);
 }
+
+bool filter_fused_tail(int B) { return small_batch_mode(B); }
 
 // One launch per segment.  xb = bf16 matrix [n_rows][ld_x] (shadow, or the stored rows of a bf16 engine).
 cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, const SegDesc& seg, int seg_index, int dim,
                                const void* workspace, int B, int k, int metric, float acc_rel, float c_l2, int n_slices,
                                unsigned long long* cand,
                                unsigned int* cand_count, unsigned int* lower_glob, unsigned int* lower_list, int cap,
-                               int slice_base, int s_total, cudaStream_t stream) {
+                               int slice_base, int s_total, const FilterTail* tail, bool pdl, cudaStream_t stream) {
   if (seg.n_rows <= 0 || n_slices <= 0) return cudaSuccess;
+  if (tail != nullptr && tail->tile_ctr == nullptr) return cudaErrorInvalidValue;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -1188,6 +1587,7 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, cons
   // CTA pairs need an even number of query blocks (the pair = two adjacent blocks on one row slice)
   const int n_qblocks = (B + BM - 1) / BM;
   const bool small = small_batch_mode(B);
+  if (small && tail == nullptr) return cudaErrorInvalidValue;
   const int ncta = (!small && pair_mode(n_qblocks)) ? 2 : 1;
   CUtensorMap tm_x, tm_q;
   if (!encode_map_bf16(&tm_x, xb, seg.n_rows, dim, ld_x, BN / ncta) ||
@@ -1219,6 +1619,11 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, cons
   p.cap = cap;
   p.slice_base = slice_base;
   p.s_total = s_total;
+  p.tile_ctr = tail != nullptr ? tail->tile_ctr + seg_index : nullptr;
+  {
+    const char* tv = getenv("WDBX_B200_FILTER_TRACE");
+    p.trace = (tv && tv[0] == '1') ? 1 : 0;
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(n_qblocks, n_slices, 1);
@@ -1226,18 +1631,44 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, cons
   cfg.dynamicSmemBytes = small ? kFilterSmallSmem : filter_smem(ncta);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = ncta == 2 ? 1 : 0;
-  auto go = [&](auto kern) { return cudaLaunchKernelEx(&cfg, kern, tm_x, tm_q, p); };
   if (small) {
+    SmallTail tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.q = tail->q;
+    tp.rows = seg.rows;
+    tp.gids = seg.gids;
+    tp.allow = seg.allow;
+    tp.dim = dim;
+    tp.dpad = tail->dpad;
+    tp.row_bytes = tail->dpad * tail->elem_bytes;
+    tp.cpr = tp.row_bytes / 16;
+    tp.lpr_log2 = tail->lpr_log2;
+    tp.nch = tail->nch;
+    tp.bf16 = tail->elem_bytes == 2 ? 1 : 0;
+    tp.min_score = tail->min_score;
+    tp.overflow = tail->overflow;
+    tp.part = tail->part;
+    tp.ticket = tail->ticket;
+    tp.xchg = tail->xchg;
+    tp.keys_out = tail->keys_out;
+    tp.scores_out = tail->scores_out;
+    tp.gids_out = tail->gids_out;
+    tp.counts_out = tail->counts_out;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = pdl ? 1 : 0;
+    auto go = [&](auto kern) { return cudaLaunchKernelEx(&cfg, kern, tm_x, tm_q, p, tp); };
     if (metric == kCosine) return go(gemm_filter_small_kernel<kCosine>);
     if (metric == kL2) return go(gemm_filter_small_kernel<kL2>);
     return go(gemm_filter_small_kernel<kIP>);
   }
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.numAttrs = ncta == 2 ? 1 : 0;
+  auto go = [&](auto kern) { return cudaLaunchKernelEx(&cfg, kern, tm_x, tm_q, p); };
   if (ncta == 2) {
     if (metric == kCosine) return go(gemm_filter_kernel<kCosine, 2>);
     if (metric == kL2) return go(gemm_filter_kernel<kL2, 2>);

@@ -18,6 +18,13 @@ constexpr int kXchgMaxK = 128;
 constexpr size_t kXchgKeyCount = 2ull * kMaxPeers * kXchgMaxB * kXchgMaxK;
 constexpr size_t kXchgBytes = kXchgKeyCount * 8 + 2 * kMaxPeers * 4 + 64;
 
+// One collective key exchange (world <= 1: none).  peer[r] = base of rank r's exchange buffer (own rank included).
+struct XchgCtx {
+  uint64_t* peer[kMaxPeers];
+  int world, rank, slot;   // slot = seq & 1
+  unsigned int seq;        // collective sequence number (same on all ranks)
+};
+
 struct SegDesc {
   const unsigned char* rows;  // [n_rows][row_bytes]
   const float* inv_norm;      // [n_rows] 1/|x| (0 for zero rows)
@@ -108,12 +115,30 @@ float filter_c_l2(int dpad);
 // bf16 shadow rows + per-row upper bound of |x - bf16(x)| (rres)
 cudaError_t launch_shadow_rows(const float* rows, long long n, int dpad, int ld16, void* dst, float* rres, cudaStream_t stream);
 cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace, unsigned int* zero, size_t n_zero,
-                                cudaStream_t stream);
+                                bool pdl, cudaStream_t stream);
+// Small batches (filter_fused_tail(B)): the filter kernel itself re-scores its candidates, and the last CTA of
+// the search merges all CTA lists, runs the cross-GPU exchange and emits -- no refine / exchange launch.
+struct FilterTail {
+  const float* q;            // [B][dim] fp32 queries
+  int dpad, elem_bytes;      // stored row layout
+  int lpr_log2, nch;         // K1's lane mapping (scan_plan): the re-scored keys are bit-identical to K1's
+  float min_score;           // score floor (-inf = none)
+  int* overflow;             // [B] set when a candidate region overflowed (the flag-gated K1 launch re-runs the query)
+  uint64_t* part;            // [B][s_total][k] per-CTA partial lists
+  unsigned int* ticket;      // zero at launch; the CTA that draws s_total - 1 finishes the search
+  unsigned int* tile_ctr;    // [kMaxSeg] zero at launch: dynamic tile counter of every segment's launch
+  XchgCtx xchg;
+  uint64_t* keys_out;
+  float* scores_out;
+  long long* gids_out;
+  int* counts_out;
+};
+bool filter_fused_tail(int B);
 cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, const SegDesc& seg, int seg_index, int dim,
                                const void* workspace, int B, int k, int metric, float acc_rel, float c_l2, int n_slices,
                                unsigned long long* cand,
                                unsigned int* cand_count, unsigned int* lower_glob, unsigned int* lower_list, int cap,
-                               int slice_base, int s_total, cudaStream_t stream);
+                               int slice_base, int s_total, const FilterTail* tail, bool pdl, cudaStream_t stream);
 cudaError_t launch_refine_topk(const SegDesc* segs, int n_seg, const float* q, int B, int dim, int dpad, int elem_bytes,
                                int lpr_log2, int nch, int k, int metric, const unsigned long long* cand,
                                const unsigned int* cand_count, int cap, int s_total, int* overflow, int ctas_per_query,

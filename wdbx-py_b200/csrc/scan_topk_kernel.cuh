@@ -257,6 +257,54 @@ __device__ __forceinline__ void peers_merge_fast(const uint64_t* my_xbuf_slot_b,
   __syncwarp();
 }
 
+// ---- NVLink key exchange, stand-alone pieces (same buffers / flags / sequence protocol as the exchange
+// fused into this file's kernel; used by the small-batch filter kernel's last CTA and by exchange.cu).
+// Warp-level: every rank stores its k best keys of query b into EVERY rank's peer-mapped buffer ...
+__device__ __forceinline__ void xchg_push(const XchgCtx& x, int b, const uint64_t* list, int k, int lane) {
+  for (int r = 0; r < x.world; ++r) {
+    uint64_t* dst = x.peer[r] + ((static_cast<size_t>(x.slot) * kMaxPeers + x.rank) * kXchgMaxB + b) * kXchgMaxK;
+    for (int i = lane; i < k; i += 32) dst[i] = list[i];
+  }
+}
+// ... then ONE warp (after every push of this rank is ordered before it: same warp or a CTA barrier)
+// release-stores the sequence number into the peers' flag slots and acquire-spins on its own flags
+// (bounded ~3 s: a missing peer must not hang the GPU).  Returns false on timeout.
+__device__ __forceinline__ bool xchg_publish_wait(const XchgCtx& x, int lane) {
+  __threadfence_system();
+  __syncwarp();
+  if (lane < x.world) {
+    unsigned int* flag = reinterpret_cast<unsigned int*>(x.peer[lane] + kXchgKeyCount) + x.slot * kMaxPeers + x.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(x.seq) : "memory");
+  }
+  const unsigned int* my_flags = reinterpret_cast<const unsigned int*>(x.peer[x.rank] + kXchgKeyCount) + x.slot * kMaxPeers;
+  bool ok = true;
+  if (lane < x.world) {
+    const long long t0 = clock64();
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(my_flags + lane) : "memory");
+      if (v == x.seq) break;
+      if (clock64() - t0 > 6000000000ll) { ok = false; break; }
+      __nanosleep(100);
+    } while (true);
+  }
+  ok = __all_sync(FULL_MASK, ok);
+  __threadfence_system();
+  return ok;
+}
+// ... and merges the G lists of query b that arrived in its own buffer (k <= kXchgMaxK) and emits them.
+__device__ __forceinline__ void xchg_merge_emit(const XchgCtx& x, int b, uint64_t* final_list, int k, bool ok, int lane,
+                                                uint64_t* keys_out, float* scores_out, long long* gids_out, int* count_out) {
+  list_clear(final_list, k, lane);
+  if (ok) {
+    const uint64_t* base = x.peer[x.rank] + (static_cast<size_t>(x.slot) * kMaxPeers * kXchgMaxB + b) * kXchgMaxK;
+    if (k <= 32) peers_merge_fast<1>(base, x.world, final_list, k, lane);
+    else peers_merge_fast<4>(base, x.world, final_list, k, lane);
+  }
+  emit_list(final_list, k, lane, keys_out, scores_out, gids_out, count_out);
+  if (!ok && count_out && lane == 0) *count_out = -1;  // exchange timed out
+}
+
 struct TileLoc {
   int seg;
   long long row0;
@@ -288,7 +336,10 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
   const int nq = (p.B - qbase) < QB ? (p.B - qbase) : QB;
   const int k = p.k;
   const int dpad = p.dpad;
+  // let the next launch on this stream start as soon as SMs free up (no-op without the PDL attribute)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (p.only_flag != nullptr) {  // uniform over the whole query block (all CTAs of this blockIdx.y)
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // the flags are written by the launch before us
     bool any = false;
     for (int b = 0; b < nq; ++b) any = any || (p.only_flag[qbase + b] != 0);
     if (!any) return;
@@ -306,8 +357,6 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
   off += align128(static_cast<size_t>(nwarps) * QB * k * 8);
   unsigned char* stage_area = smem + off;  // nwarps * stages * stage_bytes, reused as merge scratch
 
-  // let the next search on this stream start as soon as SMs free up (no-op without the PDL attribute)
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // every warp arms its own barriers and starts its TMA pipeline right away; the query staging
   // below overlaps the first bulk copies
   if (lane == 0) {
