@@ -35,7 +35,8 @@ K = 10
 METRIC = "cosine"
 CHUNK = 1_000_000          # generation chunk (global rows); a multiple of every supported N
 N_QUERIES = 64             # distinct queries cycled through the steps
-CPU_SAMPLE_ROWS = 1_000_000
+CPU_SAMPLE_ROWS = 1_000_000    # rows of the cpu_baseline leg inside the GPU arm (bounded: ~1 s of CPU work)
+PARITY_QUERIES = 16
 METRIC_NAME = "exact top-10 queries/sec, 10Mx768 fp32 cosine, batch 1"
 WORKLOAD = "C3: 10M x 768 fp32 cosine, top-10, query batch 1, rows striped over N GPUs"
 
@@ -52,11 +53,35 @@ def _peaks():
 
 def _traffic_from_profile(kernel_id: int):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
-    name = "gemm_filter_b1_ncu_summary.json" if kernel_id == 2 else "scan_topk_c3_ncu_summary.json"
-    try:
-        return float(json.loads((ROOT / "profiles" / name).read_text()).get("dram_bytes_per_launch")), f"profiles/{name}"
-    except Exception:
-        return None, None
+    names = (["r02_gemm_filter_small_c3_ncu_summary.json", "gemm_filter_b1_ncu_summary.json"] if kernel_id == 2
+             else ["scan_topk_c3_ncu_summary.json"])
+    for name in names:
+        try:
+            return float(json.loads((ROOT / "profiles" / name).read_text()).get("dram_bytes_per_launch")), f"profiles/{name}"
+        except Exception:
+            continue
+    return None, None
+
+
+# ------------------------------------------------------------------------------------------ synthetic data
+def _chunk_seed(c: int) -> int:
+    return 1234 + 1000 * 3 + c
+
+
+def _gen_chunk(dev, c: int, m: int):
+    """Chunk c (rows c*CHUNK ...) of the benchmark matrix: iid N(0,1) fp32 from a per-chunk seed, generated on the
+    GPU -- BOTH arms call this, so the reference arm scans exactly the matrix the GPU arm holds."""
+    import torch
+
+    g = torch.Generator(device=dev).manual_seed(_chunk_seed(c))
+    return torch.randn((m, DIM), generator=g, device=dev, dtype=torch.float32)
+
+
+def _gen_queries(dev):
+    import torch
+
+    gq = torch.Generator(device=dev).manual_seed(4321 + 3)
+    return torch.randn((N_QUERIES, DIM), generator=gq, device=dev, dtype=torch.float32)
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -160,23 +185,73 @@ def _cpu_scan_qps(steps: int, warmup: int, rows: int = CPU_SAMPLE_ROWS, X=None, 
     return steps / dt, cores, dt, results
 
 
+def _host_ram_bytes() -> int:
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    try:
+        return os.sysconf("SC_PHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        return 0
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU search path on the box's host cores."""
+    """--impl reference: the reference's CPU search path (oracle/flat_ip.c, all host threads) on the box's host
+    cores, over the SAME seeded matrix and queries as the GPU arm, exactly --steps / --warmup steps.  The full
+    10M x 768 matrix (30.7 GB) when the host has >= 48 GB available, else a prefix sample with QPS scaled."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = min(args.steps, 40)
-    warmup = min(args.warmup, 3)
-    qps_sample, cores, dt, _ = _cpu_scan_qps(steps, warmup)
-    scale = CPU_SAMPLE_ROWS / N_ROWS
+    import numpy as np
+
+    steps, warmup = args.steps, args.warmup
+    n_rows = args.rows
+    full = _host_ram_bytes() >= 48 * (1 << 30) and not args.cpu_sample
+    rows = n_rows if full else min(n_rows, CPU_SAMPLE_ROWS)
+    same_data = False
+    X = np.empty((rows, DIM), dtype=np.float32)
+    try:
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device for the shared generator")
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        for c in range((rows + CHUNK - 1) // CHUNK):
+            m = min(CHUNK, n_rows - c * CHUNK)          # generate the chunk exactly as the GPU arm does ...
+            take = min(m, rows - c * CHUNK)             # ... and keep the part inside the sample
+            X[c * CHUNK: c * CHUNK + take] = _gen_chunk(dev, c, m)[:take].cpu().numpy()
+        Q = _gen_queries(dev).cpu().numpy()
+        same_data = True
+        del dev
+        torch.cuda.empty_cache()
+    except Exception:
+        rng = np.random.default_rng(1234)
+        for c in range((rows + CHUNK - 1) // CHUNK):
+            take = min(CHUNK, rows - c * CHUNK)
+            X[c * CHUNK: c * CHUNK + take] = rng.standard_normal((take, DIM), dtype=np.float32)
+        Q = np.random.default_rng(4321).standard_normal((N_QUERIES, DIM), dtype=np.float32)
+    qps_sample, cores, dt, _ = _cpu_scan_qps(steps, warmup, rows=rows, X=X, Q=Q)
+    scale = rows / n_rows
     value = qps_sample * scale
-    sample = (f"{CPU_SAMPLE_ROWS} of {N_ROWS} rows x {DIM} (same distribution), {steps} single-query steps, "
-              f"QPS scaled by {scale:g} (the scan is O(N*D))")
+    if full:
+        sample = f"the full {n_rows} x {DIM} matrix, {steps} single-query steps ({dt:.1f} s)"
+    else:
+        sample = (f"first {rows} of {n_rows} rows x {DIM}, {steps} single-query steps ({dt:.1f} s), QPS scaled by "
+                  f"{scale:g} (the scan is O(N*D)); host RAM available {_host_ram_bytes() / 2**30:.0f} GiB < 48 GiB"
+                  if not args.cpu_sample else f"first {rows} of {n_rows} rows (--cpu-sample), QPS scaled by {scale:g}")
     line = {
         "impl": "reference", "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rows": N_ROWS, "dim": DIM, "k": K, "metric": METRIC, "batch": 1},
+        "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic" + (" (the GPU arm's seeded matrix and queries)" if same_data else " (numpy generator: no CUDA device)"),
+        "config": {"workload": WORKLOAD if n_rows == N_ROWS else f"REDUCED {n_rows} x {DIM} (not the named config)",
+                   "rows": n_rows, "dim": DIM, "k": K, "metric": METRIC, "batch": 1,
+                   "rows_per_gpu": n_rows // max(args.gpus, 1), "parallelism": f"row-striped x{args.gpus}",
+                   "l2_policy": "host arm: the matrix (30.7 GB) is far larger than any CPU cache; 64 distinct queries cycled"},
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -220,16 +295,14 @@ def run_gpu(args):
     cpu_prefix = []
     for c in range((n_rows + CHUNK - 1) // CHUNK):
         m = min(CHUNK, n_rows - c * CHUNK)
-        g = torch.Generator(device=dev).manual_seed(1234 + 1000 * 3 + c)
-        x = torch.randn((m, DIM), generator=g, device=dev, dtype=torch.float32)
+        x = _gen_chunk(dev, c, m)
         if rank == 0 and c * CHUNK < CPU_SAMPLE_ROWS and not args.no_cpu_baseline:
             take = min(m, CPU_SAMPLE_ROWS - c * CHUNK)
             cpu_prefix.append(x[:take].cpu().numpy())
         mine = x[rank::world].contiguous() if world > 1 else x
         store.bulk_load({"local": mine, "total": m}, id_prefix=f"c{c}_")
         del x, mine
-    gq = torch.Generator(device=dev).manual_seed(4321 + 3)
-    Qd = torch.randn((N_QUERIES, DIM), generator=gq, device=dev, dtype=torch.float32)
+    Qd = _gen_queries(dev)
     Qh = Qd.cpu().numpy()
     Qlists = [Qh[i].tolist() for i in range(N_QUERIES)]
     torch.cuda.synchronize()
@@ -253,7 +326,8 @@ def run_gpu(args):
 
     # ---- value: device-resident queries, K steps, CUDA events on the launching (current) stream
     qs = [Qd[i:i + 1] for i in range(N_QUERIES)]
-    for i in range(max(warmup, 3)):
+    warmup = max(warmup, 3)
+    for i in range(warmup):
         store.search_device(qs[i % N_QUERIES], K)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -288,7 +362,8 @@ def run_gpu(args):
     kernel_ms = reduce_max(sum(k_ms) / len(k_ms))
     ld16 = (DIM + 7) // 8 * 8
     if kernel_id == 2:
-        kernel_name = "gemm_filter_small_kernel (K2b bf16 tcgen05 filter, B<=16 variant, over the 2-byte shadow rows)"
+        kernel_name = ("gemm_filter_small_kernel (K2b, B<=16: bf16 tcgen05 filter over the 2-byte shadow rows + in-kernel exact "
+                       "re-score, last-CTA merge and cross-GPU exchange -- the whole search is this one launch)")
         algo_bytes = local_rows * ld16 * 2 + local_rows * 4     # 2-byte shadow rows + 1/|x| per row
         algo_note = "rows x dim x 2 (bf16 shadow) + rows x 4 (1/|x|): the bytes THIS kernel must read"
     else:
@@ -300,7 +375,7 @@ def run_gpu(args):
     peak, peak_src = _peaks()
     traffic, traffic_src = _traffic_from_profile(kernel_id)   # ncu --set full capture on the 10M-row matrix (N=1)
     if traffic is not None:
-        traffic_src += " (dram read+write per launch, 10M rows on one GPU)"
+        traffic_src += " (ncu --set full capture, not this run: dram read+write per launch, 10M rows on one GPU)"
         if local_rows != N_ROWS:
             traffic = traffic * local_rows / N_ROWS
             traffic_src += f", scaled by rows_per_gpu/{N_ROWS}"
@@ -332,24 +407,35 @@ def run_gpu(args):
         e2e_detail["device_ms_last_call"] = store.engine.stats().get("last_search_ms")
     sampler.stop()
 
-    # ---- parity gate on the timed data: exact fp64 re-score of the returned rows' neighbourhood
-    parity = None
-    if rank == 0 or world > 1:
-        parity = _parity_check(store, Qd, out_check_queries=2, world=world, rank=rank, dev=dev, n_rows=n_rows)
+    # ---- parity gate on the timed data: fp64 checker over the whole matrix, PARITY_QUERIES queries, through every
+    # route the store can take at this N (device exchange / NCCL all-gather + merge kernel)
+    checker = _Fp64Checker(Qd, world, rank, dev, n_rows)
+    routes = {"default": lambda q: store.search_device(q, K)}
+    if world > 1:
+        routes["nccl_allgather_merge"] = lambda q: store.engine.merge(
+            store.dist.all_gather_keys(store.engine.search(q, K, METRIC)["keys"]))
+    parity = {"checked_queries": PARITY_QUERIES}
+    for name, fn in routes.items():
+        parity[name] = checker.check(fn, range(PARITY_QUERIES))
+    parity["ids_match"] = all(v["ids_match_fp64_checker"] for v in parity.values() if isinstance(v, dict))
+
+    # ---- extra (not the headline): the other regimes on the same resident matrix, each with its own parity flag
+    extra = None if args.no_extra else _extra_regimes(store, Qd, qs, checker, local_rows, n_rows, world, dev, barrier,
+                                                      reduce_max, peak)
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         Xs = np.concatenate(cpu_prefix) if cpu_prefix else None
         sample_rows = Xs.shape[0]
-        qps_s, cores, dt, cres = _cpu_scan_qps(12, 2, rows=sample_rows, X=Xs, Q=Qh)
+        qps_s, cores, dt, cres = _cpu_scan_qps(40, 3, rows=sample_rows, X=Xs, Q=Qh)
         scale = sample_rows / n_rows
         cpu = {"value": qps_s * scale, "unit": "queries/s", "cores": cores, "kind": "port",
-               "sample": f"first {sample_rows} of {n_rows} rows of the same matrix, 12 single-query steps "
+               "sample": f"first {sample_rows} of {n_rows} rows of the same matrix, 40 single-query steps "
                          f"({dt:.1f} s), QPS scaled by {scale:g}"}
 
     if rank == 0:
         line = {
-            "metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
+            "metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD if n_rows == N_ROWS else f"REDUCED {n_rows} x {DIM} (not the named config)",
@@ -358,6 +444,9 @@ def run_gpu(args):
                        "l2_policy": "inputs larger than L2 (>=3.8 GB per GPU streamed per step vs 126 MB L2); "
                                     "64 distinct queries cycled"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         # the same launch in SURVEY.md 8d's bytes (fp32 rows + 1/|x|): > 1 means "faster than any scan of
+                         # the stored fp32 rows could be" -- the gain is algorithmic (2-byte shadow), not bandwidth
+                         "frac_8d_bytes": k1_bytes / (kernel_ms * 1e-3) / 1e9 / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name,
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes,
                          "algorithmic_bytes_definition": algo_note, "peak_source": peak_src,
@@ -374,6 +463,7 @@ def run_gpu(args):
             "gpu_launches": int(gpu_launches),
             "clocks": sampler.summary(),
             "parity": parity,
+            "extra": extra,
         }
         print(json.dumps(line), flush=True)
     store.close()
@@ -382,45 +472,171 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def _parity_check(store, Qd, out_check_queries, world, rank, dev, n_rows):
-    """Checker only (not the product path): torch fp32 chunked scores on this rank's rows -> global
-    top-k via all-gather on the host, compared with the engine's ids."""
-    import torch
-    import torch.distributed as dist
+class _Fp64Checker:
+    """Checker only (never the product path): exact fp64 cosine of EVERY row against a set of queries (chunk by chunk,
+    the rows are re-generated from their seeds), global top-k via all-gather; cached per query index."""
 
-    ok = True
-    worst = 0.0
-    for b in range(out_check_queries):
-        q = Qd[b:b + 1]
-        got = store.search_device(q, K)
-        got_g = got["gids"][0].cpu()
-        got_s = got["scores"][0].cpu()
-        # device rows are not exposed as tensors; re-generate this rank's stripe chunk by chunk
+    def __init__(self, Qd, world, rank, dev, n_rows):
+        self.Qd, self.world, self.rank, self.dev, self.n_rows = Qd, world, rank, dev, n_rows
+        self.want = {}
+
+    def _compute(self, idx):
+        import torch
+        import torch.distributed as dist
+
+        idx = [i for i in idx if i not in self.want]
+        if not idx:
+            return
+        q = self.Qd[idx].double()
+        qn = q / q.norm(dim=1, keepdim=True)
         best_s, best_g = [], []
-        for c in range((n_rows + CHUNK - 1) // CHUNK):
-            m = min(CHUNK, n_rows - c * CHUNK)
-            g = torch.Generator(device=dev).manual_seed(1234 + 1000 * 3 + c)
-            x = torch.randn((m, DIM), generator=g, device=dev, dtype=torch.float32)
-            xs = x[rank::world] if world > 1 else x
-            s = (xs.double() @ q[0].double()) / (xs.double().norm(dim=1) * q[0].double().norm())
-            v, i = torch.topk(s, min(K, s.numel()))
+        for c in range((self.n_rows + CHUNK - 1) // CHUNK):
+            m = min(CHUNK, self.n_rows - c * CHUNK)
+            x = _gen_chunk(self.dev, c, m)
+            xs = (x[self.rank::self.world] if self.world > 1 else x).double()
+            s = (xs @ qn.T) / xs.norm(dim=1, keepdim=True)          # [rows, nq]
+            v, i = torch.topk(s, min(K, s.shape[0]), dim=0)
             best_s.append(v)
-            best_g.append(c * CHUNK + rank + i * world)
+            best_g.append(c * CHUNK + self.rank + i * self.world)
             del x, xs, s
-        v = torch.cat(best_s)
-        gsel = torch.cat(best_g)
-        if world > 1:
-            vs = [torch.empty_like(v) for _ in range(world)]
-            gs = [torch.empty_like(gsel) for _ in range(world)]
+        v, g = torch.cat(best_s), torch.cat(best_g)
+        if self.world > 1:
+            vs = [torch.empty_like(v) for _ in range(self.world)]
+            gs = [torch.empty_like(g) for _ in range(self.world)]
             dist.all_gather(vs, v)
-            dist.all_gather(gs, gsel)
-            v, gsel = torch.cat(vs), torch.cat(gs)
-        top = torch.topk(v, K)
-        want_g = gsel[top.indices].cpu()
-        want_s = top.values.cpu()
-        ok = ok and bool((want_g == got_g).all())
-        worst = max(worst, float((got_s.double() - want_s).abs().max()))
-    return {"checked_queries": out_check_queries, "ids_match_fp64_checker": ok, "max_abs_score_err": worst}
+            dist.all_gather(gs, g)
+            v, g = torch.cat(vs), torch.cat(gs)
+        top = torch.topk(v, K, dim=0)
+        for j, i in enumerate(idx):
+            self.want[i] = (g[:, j][top.indices[:, j]].cpu(), top.values[:, j].cpu())
+
+    def check(self, search_fn, idx, batch=None):
+        """search_fn(q [B, dim]) -> result dict; idx: query indices (rows of Qd) or, with `batch`, rows of `batch`
+        whose first len(idx) rows are Qd[idx]."""
+        import torch
+
+        idx = list(idx)
+        self._compute(idx)
+        ok, worst = True, 0.0
+        if batch is not None:
+            out = search_fn(batch)
+            got = [(out["gids"][j].cpu(), out["scores"][j].cpu()) for j in range(len(idx))]
+        else:
+            got = []
+            for i in idx:
+                out = search_fn(self.Qd[i:i + 1])
+                got.append((out["gids"][0].cpu(), out["scores"][0].cpu()))
+        torch.cuda.synchronize()
+        for i, (gg, gs) in zip(idx, got):
+            wg, ws = self.want[i]
+            ok = ok and bool((wg == gg).all())
+            worst = max(worst, float((gs.double() - ws).abs().max()))
+        return {"ids_match_fp64_checker": ok, "max_abs_score_err": worst, "queries": len(idx)}
+
+
+def _tf32_peak_tflops(dev):
+    """Measured dense TF32 throughput (torch.matmul, 8192^3, best of 5): the denominator for the 3xTF32 kernel K2."""
+    import torch
+
+    try:
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn((8192, 8192), device=dev)
+        b = torch.randn((8192, 8192), device=dev)
+        best = 1e9
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        torch.backends.cuda.matmul.allow_tf32 = prev
+        del a, b
+        return 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
+
+
+def _extra_regimes(store, Qd, qs, checker, local_rows, n_rows, world, dev, barrier, reduce_max, peak):
+    """(i) the fp32 streaming scan K1 forced on the same matrix -- SURVEY.md 8d's bytes, the north star's ">= 80 % of
+    the HBM roofline" claim; (ii) C3 with a batch of 1024 queries (tensor-core regime) as useful TFLOP/s against the
+    measured bf16 peaks.  Device-timed like `value`; every number carries its own parity flag."""
+    import torch
+
+    extra = {}
+    eng = store.engine
+    # ---- (i) K1 forced
+    try:
+        eng.set_option("shadow_min_mb", -1)
+        for i in range(3):
+            store.search_device(qs[i], K)
+        barrier()
+        n = 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            store.search_device(qs[i % N_QUERIES], K)
+        e1.record()
+        barrier()
+        step_ms = reduce_max(e0.elapsed_time(e1)) / n
+        eng.set_kernel_timing(True)
+        kms = []
+        kout = eng.search(qs[0], K, METRIC)
+        for i in range(10):
+            eng.search(qs[i], K, METRIC, out=kout)
+            st = eng.stats()
+            kms.append(st["last_kernel_ms"])
+            kid = st["last_kernel"]
+        eng.set_kernel_timing(False)
+        kernel_ms = reduce_max(sum(kms) / len(kms))
+        bytes_8d = local_rows * DIM * 4 + local_rows * 4
+        par = checker.check(lambda q: store.search_device(q, K), range(PARITY_QUERIES))
+        extra["k1_fp32_scan_forced"] = {
+            "kernel": "scan_topk_kernel (K1)" if kid == 1 else f"unexpected kernel id {kid}", "ms_per_step": step_ms,
+            "queries_per_s": 1e3 / step_ms, "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_8d,
+            "achieved_gbs": bytes_8d / (kernel_ms * 1e-3) / 1e9, "frac_of_hbm_peak": bytes_8d / (kernel_ms * 1e-3) / 1e9 / peak,
+            "bytes_definition": "rows x dim x 4 + rows x 4 (SURVEY.md 8d)", "parity": par}
+    except Exception as e:  # never lose the headline line to an extra
+        extra["k1_fp32_scan_forced"] = {"error": repr(e)}
+    finally:
+        eng.set_option("shadow_min_mb", 1024)
+    # ---- (ii) batch of 1024 queries
+    try:
+        B = 1024
+        g = torch.Generator(device=dev).manual_seed(99)
+        Qb = torch.randn((B, DIM), generator=g, device=dev, dtype=torch.float32)
+        Qb[:PARITY_QUERIES] = Qd[:PARITY_QUERIES]
+        for _ in range(2):
+            store.search_device(Qb, K)
+        barrier()
+        n = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            store.search_device(Qb, K)
+        e1.record()
+        barrier()
+        ms = reduce_max(e0.elapsed_time(e1)) / n
+        tflops = 2.0 * n_rows * DIM * B / (ms * 1e-3) / 1e12
+        burst = sustained = None
+        try:
+            pk = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+            burst, sustained = float(pk["bf16_tflops"]), float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"]))
+        except Exception:
+            pass
+        par = checker.check(lambda q: store.search_device(q, K), range(PARITY_QUERIES), batch=Qb)
+        extra["c3_batch_1024"] = {
+            "kernel": "gemm_filter_kernel (K2b, 128-query tcgen05 tiles) + refine_topk_kernel", "ms_per_batch": ms,
+            "queries_per_s": B / ms * 1e3, "useful_tflops_all_gpus": tflops, "useful_tflops_per_gpu": tflops / world,
+            "bf16_peak_burst": burst, "bf16_peak_sustained": sustained,
+            "frac_of_burst": (tflops / world / burst) if burst else None,
+            "frac_of_sustained": (tflops / world / sustained) if sustained else None, "parity": par}
+    except Exception as e:
+        extra["c3_batch_1024"] = {"error": repr(e)}
+    extra["tf32_tflops_measured"] = _tf32_peak_tflops(dev)
+    extra["tf32_note"] = "dense TF32 torch.matmul 8192^3, best of 6: the measured denominator for the optional 3xTF32 kernel K2"
+    return extra
 
 
 def main():
@@ -431,6 +647,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=N_ROWS, help="debug only: a reduced matrix is flagged in config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the K1-forced / batch-1024 extra measurements")
+    ap.add_argument("--cpu-sample", action="store_true", help="reference arm: scan a 1M-row sample even if RAM allows 10M")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

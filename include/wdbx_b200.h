@@ -206,6 +206,39 @@ int wdbx_b200_search_exchange_host(wdbx_b200_engine* e, const float* q_host, int
                                    float* scores_host, int64_t* gids_host, uint64_t* keys_host,
                                    int32_t* counts_host);
 
+/* wdbx_b200_search_exchange_host with the opt-in pre-filter of wdbx_b200_search_filtered_host: every rank passes the
+ * bitmaps of ITS rows (and the same min_score); the result is the exact top-k among the allowed rows of all ranks.
+ * Replaces: the metadata post-filter of VectorStore.search (vector_store.py:333-342, :414-463) on a store
+ * whose shards live on several GPUs. */
+int wdbx_b200_search_exchange_filtered_host(wdbx_b200_engine* e, const float* q_host, int B, int k, int metric,
+                                            float min_score, const uint32_t* const* allow_bitmaps,
+                                            float* scores_host, int64_t* gids_host, int32_t* counts_host);
+
+/* SINGLE PROCESS, SEVERAL GPUs.  A group ties n engines (2..8, one per device of one box, same dim / dtype /
+ * num_segments) together so that an ordinary process -- the reference's REST server (wdbx/api/server.py:141-152)
+ * or CLI (wdbx/cli.py:541) behind WDBX.vector_search -- uses all GPUs without torchrun: peer access is enabled
+ * directly, every group search is launched on all devices from the calling thread and the devices merge their
+ * top-k over NVLink (the same on-device exchange as wdbx_b200_search_exchange for B <= 8 and k <= 128, peer
+ * copies of the packed keys to device 0 + the merge kernel otherwise).  The host layer stripes the rows of every
+ * segment over the engines (row n -> engine n % n_engines) with the per-engine calls above.
+ * Replaces: ShardManager._allocate_shards (wdbx/core/distributed.py:547-654) + the shard loop and merge of
+ * VectorStore.search (vector_store.py:323-330, :345).  The group does not own the engines: destroy it first. */
+typedef struct wdbx_b200_group wdbx_b200_group;
+int wdbx_b200_group_create(wdbx_b200_engine* const* engines, int n, wdbx_b200_group** out);
+void wdbx_b200_group_destroy(wdbx_b200_group* g);
+
+/* Host-buffer search over the whole group; `segment`, outputs and semantics as wdbx_b200_search_host.
+ * min_score / allow_bitmaps as wdbx_b200_search_filtered_host (-INFINITY / NULL = unfiltered); allow_bitmaps is
+ * engine-major: [n_engines * num_segments] pointers to bitmaps over each engine's OWN rows of each segment. */
+int wdbx_b200_group_search_host(wdbx_b200_group* g, int segment, const float* q_host, int B, int k, int metric,
+                                float min_score, const uint32_t* const* allow_bitmaps, float* scores_host,
+                                int64_t* gids_host, uint64_t* keys_host, int32_t* counts_host);
+
+/* Device-resident group search: q_dev0 [B, dim] fp32 and the outputs live on the FIRST engine's device;
+ * asynchronous with respect to the host, ordered after / before `cuda_stream` (a stream of that device). */
+int wdbx_b200_group_search(wdbx_b200_group* g, const float* q_dev0, int B, int k, int metric, uint64_t* keys_out,
+                           float* scores_out, int64_t* gids_out, int32_t* counts_out, void* cuda_stream);
+
 /* Override the scan kernel's launch geometry (0 / -1 = automatic): consumer warps per CTA,
  * TMA pipeline stages per warp, rows held per lane group (1, 2, 4), CTAs, L2 evict-first hint.
  * Benchmark / profiling hook; the counterpart of the reference's HNSW_EF_SEARCH / FAISS_NPROBE
@@ -213,6 +246,13 @@ int wdbx_b200_search_exchange_host(wdbx_b200_engine* e, const float* q_host, int
  * identical for every setting. */
 int wdbx_b200_set_tuning(wdbx_b200_engine* e, int warps, int stages, int rows_unroll, int grid,
                          int evict_first);
+
+/* Change a routing knob of a live engine (the WDBX_B200_* environment variables read at creation):
+ * "shadow_min_mb" (-1 = never use the bf16-shadow filter for small batches, else the store size in MiB from which
+ * it is used), "gemm_min_batch" (0 = never use the tensor-core path), "gemm_mode", "pdl", "queries_per_pass".
+ * Results are identical for every setting; benchmark hook (bench.py times the fp32 streaming scan and the
+ * filter path on the same resident matrix).  No reference counterpart. */
+int wdbx_b200_set_option(wdbx_b200_engine* e, const char* name, long long value);
 
 /* Bracket the dominant kernel of every search (K1 scan, or the K2b filter launches) with CUDA events on
  * the search stream; wdbx_b200_get_stats then reports its duration.  Measurement hook for bench.py's

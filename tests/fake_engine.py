@@ -174,3 +174,47 @@ class FakeEngine:
 
     def close(self):
         pass
+
+
+class FakeGroup:
+    """Numpy double of the C group (wdbx_b200_group_*): every fake engine answers for its stripe, the packed keys
+    are merged on the host exactly as the merge kernel / the on-device exchange would."""
+
+    NAMES = {0: "cosine", 1: "ip", 2: "l2"}
+
+    def __init__(self, engines):
+        self.engines = list(engines)
+        self.calls = 0
+
+    def close(self):
+        pass
+
+    @staticmethod
+    def _merge(keys_per_engine, k):
+        kk = np.concatenate(keys_per_engine, axis=-1)
+        merged = np.sort(kk, axis=-1)[..., ::-1][..., :k].copy()
+        scores, gids = unpack_keys(merged)
+        return scores, gids, (merged != 0).sum(-1).astype(np.int32), merged
+
+    def search_host(self, q, k, metric, segment, min_score, allow, want_keys):
+        name = self.NAMES[int(metric)]
+        self.calls += 1
+        per = []
+        for i, e in enumerate(self.engines):
+            if allow is not None or min_score > float("-inf"):
+                s, g, c = e.search_filtered_host(q, k, name, min_score, None if allow is None else allow[i])
+                keys = np.where(np.arange(k)[None, :] < c[:, None], pack_keys(s, np.maximum(g, 0)), np.uint64(0))
+            else:
+                keys = e.search_host(q, k, name, per_segment=(segment == -2), want_keys=True,
+                                     segment=(segment if segment >= 0 else -1))[3]
+            per.append(keys)
+        scores, gids, counts, merged = self._merge(per, k)
+        return (scores, gids, counts, merged) if want_keys else (scores, gids, counts)
+
+    def search_device(self, q_dev, k, metric, out, stream):
+        scores, gids, counts, merged = self.search_host(q_dev.numpy(), k, metric, -1, float("-inf"), None, True)
+        return {"keys": torch.from_numpy(merged.view(np.int64)), "scores": torch.from_numpy(scores),
+                "gids": torch.from_numpy(gids), "counts": torch.from_numpy(counts)}
+
+
+FakeEngine.group_factory = FakeGroup

@@ -38,7 +38,11 @@ def _oracle_check(X, Q, k, metric, scores, gids, counts, dead=None, sample=16):
     (30000, 384, 96, 20, "ip", "bf16"), (9000, 200, 70, 10, "cosine", "bf16"), (150000, 128, 300, 10, "l2", "fp32"),
     # small batches: several refine CTAs per query + K3 merge of their partial lists
     (200000, 256, 1, 10, "cosine", "fp32"), (50000, 768, 3, 16, "l2", "fp32"), (120000, 128, 8, 10, "ip", "fp32"),
-    (40000, 384, 2, 1, "cosine", "bf16"), (60000, 256, 4, 25, "cosine", "fp32"), (20000, 96, 300, 32, "l2", "fp32")])
+    (40000, 384, 2, 1, "cosine", "bf16"), (60000, 256, 4, 25, "cosine", "fp32"), (20000, 96, 300, 32, "l2", "fp32"),
+    # 32 < k <= 128: four keys per lane in every register list, shared lower-bound list of up to 128 slots
+    (90000, 384, 1, 100, "cosine", "fp32"), (50000, 256, 5, 128, "ip", "fp32"), (30000, 768, 12, 33, "l2", "fp32"),
+    (40000, 384, 40, 100, "cosine", "fp32"), (25000, 128, 200, 64, "l2", "fp32"), (30000, 384, 3, 100, "ip", "bf16"),
+    (60, 32, 2, 100, "cosine", "fp32"), (20000, 384, 160, 128, "ip", "bf16")])
 def test_filter_refine_is_bit_identical_to_scan(built_lib, n, dim, B, k, metric, dtype):
     rng = np.random.default_rng(n + dim + B)
     X = rng.standard_normal((n, dim), dtype=np.float32)

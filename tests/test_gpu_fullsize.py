@@ -77,6 +77,7 @@ def _assert_match(got_s, got_g, want_s, want_i, metric, dim, scale=1.0):
     ("C3-B1", 10_000_000, 768, "fp32", "cosine", 10, 16, "default", 2),
     ("C3-B1-scan", 10_000_000, 768, "fp32", "cosine", 10, 4, "scan", 1),
     ("C3-B1024", 10_000_000, 768, "fp32", "cosine", 10, 1024, "default", 2),
+    ("C3-k100", 10_000_000, 768, "fp32", "cosine", 100, 4, "default", 2),      # 32 < k <= 128 runs at filter speed too
     ("C4-shard", 12_500_000, 384, "bf16", "ip", 100, 2, "default", 0),
     ("C5", 5_000_000, 1536, "fp32", "l2", 10, 4096, "default", 2),
 ])

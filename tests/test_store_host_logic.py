@@ -290,3 +290,75 @@ def test_bulk_ids_are_canonical_and_prefix_collisions_rejected():
     with pytest.raises(ValueError):
         st.bulk_load(X, id_prefix="w")
     assert st.bulk_load(X[:2], id_prefix="w") == 2      # w2 is outside the new range: no collision
+
+
+def _multi_probe(st, X, Q):
+    return {
+        "plain": [[(i, s) for i, s, _ in st.search(Q[b].tolist(), limit=6)] for b in range(Q.shape[0])],
+        "filtered": [(i, s) for i, s, _ in st.search(Q[0].tolist(), limit=4, filter_metadata={"even": True})],
+        "batch": st.search_batch(Q, 5).as_lists(),
+        "tie": [i for i, _, _ in st.search(X[7].tolist(), limit=2)],
+        "get": st.get("v9")[0], "count": st.count(),
+    }
+
+
+def test_single_process_multi_device_store_matches_one_device(tmp_path):
+    """GPU_DEVICES: one ordinary process, rows striped over G engines (multi_engine.py); every answer must equal
+    the one-device store's, through CRUD, filters, the micro-batcher and persistence."""
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((157, 8), dtype=np.float32)
+    X[40] = X[7]
+    Q = rng.standard_normal((3, 8), dtype=np.float32)
+
+    def build(path, **cfg):
+        st = wdbx_b200.VectorStore(8, path, num_shards=3, config=wdbx_b200.WDBXConfig(dict(GPU_STRICT=True, **cfg)),
+                                   dist=wdbx_b200.DistContext(0, 1, 0), _engine_factory=FakeEngine)
+        return st
+
+    def fill(st):
+        st.bulk_load(X[:100], id_prefix="v")
+        st.batch_store({f"m{i}": X[100 + i] for i in range(57)}, {f"m{i}": {"even": i % 2 == 0} for i in range(57)})
+        st.delete("v3")
+        st.delete("m10")
+        st.store("m2", (X[5] * 3).tolist(), {"even": True})   # overwrite in place on whichever device owns the row
+
+    one = build(tmp_path / "one")
+    fill(one)
+    want = _multi_probe(one, X, Q)
+    multi = build(tmp_path / "multi", GPU_DEVICES="0-2")
+    assert multi.devices == [0, 1, 2] and multi._batcher is not None
+    fill(multi)
+    rows = multi.engine.stats()["rows_per_device"]
+    assert sum(rows) == 157 and max(rows) - min(rows) <= 3        # striped: balanced within one row per shard
+    assert _multi_probe(multi, X, Q) == want
+
+    async def burst():
+        return await asyncio.gather(*[multi.search_async(Q[b % 3].tolist(), limit=6) for b in range(12)])
+    got = asyncio.run(burst())
+    assert [[(i, s) for i, s, _ in r] for r in got] == [want["plain"][b % 3] for b in range(12)]
+    assert multi._batcher.batches < 12                              # requests were coalesced
+    # opt-in device pre-filter: the position bitmaps are split per device
+    pre = build(tmp_path / "pre", GPU_DEVICES=[0, 1], GPU_PREFILTER=True)
+    one_pre = build(tmp_path / "one_pre", GPU_PREFILTER=True)
+    fill(pre)
+    fill(one_pre)
+    f = {"even": True}
+    assert pre.search(Q[1].tolist(), limit=9, filter_metadata=f) == one_pre.search(Q[1].tolist(), limit=9, filter_metadata=f)
+    assert len(pre.search(Q[1].tolist(), limit=9, filter_metadata=f)) == 9
+    # persistence: saved by the 3-device store, loaded on one device and on two
+    assert multi.save()
+    multi.close()
+    for cfg in ({}, {"GPU_DEVICES": "0,1"}):
+        back = build(tmp_path / "multi", **cfg)
+        assert _multi_probe(back, X, Q) == want
+        back.close()
+
+
+def test_gpu_devices_spec_parsing():
+    from wdbx_b200.multi_engine import parse_devices
+
+    assert parse_devices(None) is None and parse_devices("") is None
+    assert parse_devices("0-3") == [0, 1, 2, 3] and parse_devices("0,2, 5") == [0, 2, 5]
+    assert parse_devices([1, 0]) == [1, 0] and parse_devices(2) == [0, 1] and parse_devices("1-2,4") == [1, 2, 4]
+    with pytest.raises(ValueError):
+        parse_devices("0,0")

@@ -37,6 +37,14 @@ for line in txt.splitlines():
         d = dict(zip(re.findall(r"([a-z_]+) \d+", line), map(int, re.findall(r"[a-z_]+ (\d+)", line))))
         d["last"] = "LAST" in line
         rows.append(d)
+tiles = {}
+for line in txt.splitlines():
+    if line.startswith("TILE"):
+        _, _, c, _, it, _, at, _, tl = line.split()
+        tiles.setdefault(int(it), []).append(int(at))
+for it in sorted(tiles):
+    v = sorted(tiles[it])
+    print(f"accumulator of the CTA's tile #{it:2d} ready: min {v[0]/1e3:7.1f}  median {v[len(v)//2]/1e3:7.1f}  max {v[-1]/1e3:7.1f} us after the CTA's entry")
 if not rows:
     print(txt[-2000:])
     sys.exit(1)
@@ -47,10 +55,10 @@ def col(name, fn=lambda r, v: v):
 print(f"{len(rows)} CTAs, {n} x {dim}; times since the first CTA's entry")
 ent = sorted(r["entry"] - t0 for r in rows)
 print(f"    entry: min {ent[0]/1e3:7.1f}  median {ent[len(ent)//2]/1e3:7.1f}  max {ent[-1]/1e3:7.1f} us")
-for name in ("loop_end", "tail_in", "q_ready", "rescored", "listed", "fenced", "ticket"):
+for name in ("loop_end", "tail_in", "q_ready", "rescored", "fenced", "ticket"):
     print(col(name))
 last = [r for r in rows if r["last"]][0]
 print(f"last CTA {last['cta']}: " + "  ".join(f"{n} {(last['entry'] - t0 + last[n]) / 1e3:.1f}" for n in
-      ("loop_end", "tail_in", "q_ready", "rescored", "listed", "fenced", "ticket", "flags", "merged", "done")) + " us")
+      ("loop_end", "tail_in", "q_ready", "rescored", "fenced", "ticket", "flags", "merged", "done")) + f" us; final keys {last['keys']}")
 c = sorted(r["cand"] for r in rows)
 print(f"candidates per CTA: min {c[0]} median {c[len(c)//2]} max {c[-1]} sum {sum(c)}")

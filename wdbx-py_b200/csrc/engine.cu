@@ -13,8 +13,11 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <new>
+#include <thread>
+#include <string>
 #include <vector>
 
 #include "kernels.h"
@@ -133,7 +136,45 @@ struct wdbx_b200_engine {
   size_t last_fregions = 0;                   // ... one per (query, region)
 };
 
+struct GroupJob {   // one group search, as seen by the launcher threads
+  int segment = 0, B = 0, k = 0, metric = 0;
+  const float* q_dev0 = nullptr;
+  cudaEvent_t ev_in = nullptr;
+  float min_score = 0.0f;
+  const uint32_t* const* allow = nullptr;
+  bool exchange = false;
+  uint64_t* out0_keys = nullptr;
+  float* out0_scores = nullptr;
+  long long* out0_gids = nullptr;
+  int* out0_counts = nullptr;
+};
+
+struct wdbx_b200_group {
+  std::vector<wdbx_b200_engine*> eng;   // engine i = rank i of the exchange; not owned
+  std::mutex mu;                        // one group search at a time
+  float* hq = nullptr;                  // portable pinned staging: queries in, packed result out
+  size_t hq_floats = 0;
+  unsigned char* hres = nullptr;
+  size_t hres_bytes = 0;
+  uint64_t* gkeys = nullptr;            // device 0: [lists][G][B][k] gathered keys (batches beyond the exchange's limits)
+  size_t gkeys_n = 0;
+  std::vector<cudaEvent_t> ev;          // per engine: "its keys have arrived on device 0"
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;   // device-resident searches: hand-over with the caller's stream
+  // launcher threads (one per engine > 0), see group_worker
+  std::vector<std::thread> workers;
+  std::mutex wmu;
+  std::condition_variable wcv;
+  std::atomic<uint64_t> gen{0};
+  std::atomic<int> done{0}, sleepers{0};
+  std::atomic<bool> stop{false};
+  GroupJob job;
+  std::vector<int> rcs;
+  std::vector<std::string> errs;
+};
+
 namespace {
+
+void group_worker(wdbx_b200_group* g, int i);
 
 struct DeviceGuard {
   int prev = -1;
@@ -453,8 +494,9 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   int refine_ctas = (2 * e->sm_count + B - 1) / B;   // two 256-thread CTAs per SM
   if (refine_ctas > 8 * s_total) refine_ctas = 8 * s_total;
   if (refine_ctas < 1) refine_ctas = 1;
-  // partial lists: fused tail [B][s_total][k] (one per filter CTA), refine launch [refine_ctas][B][k]
-  const size_t need_part = fused ? n_regions * k : (refine_ctas > 1 ? static_cast<size_t>(refine_ctas) * B * k : 0);
+  // fused tail: the queries' final key lists [B][filter_final_cap()]; refine launch: partial lists [refine_ctas][B][k]
+  const size_t need_part = fused ? static_cast<size_t>(B) * filter_final_cap()
+                                 : (refine_ctas > 1 ? static_cast<size_t>(refine_ctas) * B * k : 0);
   // one zero-initialised block per search: [n_regions] candidate counts | [B] overflow flags | [B] tickets
   // (fused tail: [0] = the search's ticket) | [B][filter_max_k] shared lower-bound lists | [B] published
   // bounds  (0 = "no bound yet")
@@ -464,7 +506,8 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   const size_t off_list = (off_ticket + static_cast<size_t>(B) + 15) / 16 * 16;
   const size_t off_glob = off_list + static_cast<size_t>(B) * lk;
   const size_t off_ctr = off_glob + static_cast<size_t>(B);   // [kMaxSeg] dynamic tile counters (fused small-batch kernel)
-  const size_t need_zero = off_ctr + static_cast<size_t>(kMaxSeg);
+  const size_t off_fin = off_ctr + static_cast<size_t>(kMaxSeg);   // [B] final-list counts (fused small-batch kernel)
+  const size_t need_zero = off_fin + static_cast<size_t>(B);
   if (w->fpart_n < need_part || w->fws_bytes < need_ws || w->fcand_n < n_regions * cap || w->fzero_n < need_zero) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(stream, &cs);
@@ -519,7 +562,8 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
     tail.nch = plan.nch;
     tail.min_score = min_score;
     tail.overflow = foverflow;
-    tail.part = w->fpart;
+    tail.fin_keys = w->fpart;
+    tail.fin_count = w->fzero + off_fin;
     tail.ticket = ftickets;
     tail.tile_ctr = w->fzero + off_ctr;
     if (xseq != 0u) {
@@ -617,6 +661,211 @@ int check_search_args(wdbx_b200_engine* e, int B, int k, int metric) {
   if (k > WDBX_B200_MAX_K) return fail(WDBX_B200_ERR_LIMIT, "k=%d exceeds WDBX_B200_MAX_K=%d", k, WDBX_B200_MAX_K);
   if (B > 65535) return fail(WDBX_B200_ERR_LIMIT, "B=%d exceeds 65535 queries per call", B);
   if (metric < 0 || metric > 2) return fail(WDBX_B200_ERR_ARG, "unknown metric %d", metric);
+  return WDBX_B200_OK;
+}
+
+
+// Collective search of all segments + on-device key exchange with the peer ranks.  Caller holds e->mu.
+// Every rank takes the same decisions here (they depend on B, k, dim only -- never on the rank's own rows), and
+// the routes a rank may take for one search (fused filter kernel, K1 scan, stand-alone exchange kernel) all
+// speak the same exchange protocol under the same sequence number.
+int exchange_search_locked(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B, int k, int metric,
+                           uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream,
+                           float min_score = -INFINITY, bool use_allow = false) {
+  if (e->xworld < 2) return fail(WDBX_B200_ERR_ARG, "exchange not attached (call wdbx_b200_exchange_init/attach first)");
+  if (B > kXchgMaxB || k > kXchgMaxK)
+    return fail(WDBX_B200_ERR_LIMIT, "fused exchange supports B <= %d queries and k <= %d", kXchgMaxB, kXchgMaxK);
+  // the K1 scan (and the flag-gated re-run behind the filter) exchanges from ONE query block: batches larger
+  // than the block the plan allows for this shape (e.g. 1 query for dim 64) run as consecutive collective passes
+  ScanPlan plan;
+  const int prc = scan_plan(e->dim, e->dpad, e->elem_bytes, k, B, e->sm_count, e->tune, &plan);
+  if (prc != 0) return fail(prc == -4 ? WDBX_B200_ERR_LIMIT : WDBX_B200_ERR_ARG, "invalid scan shape (dim=%d k=%d)", e->dim, k);
+  if (B > plan.queries_per_block) {
+    const int qb = plan.queries_per_block;
+    for (int b0 = 0; b0 < B; b0 += qb) {
+      const int nb = std::min(qb, B - b0);
+      const size_t o = static_cast<size_t>(b0) * k;
+      const int rc = exchange_search_locked(e, s0, s1, q_dev + static_cast<size_t>(b0) * e->dim, nb, k, metric,
+                                            keys_out ? keys_out + o : nullptr, scores_out ? scores_out + o : nullptr,
+                                            gids_out ? gids_out + o : nullptr, counts_out ? counts_out + b0 : nullptr, stream,
+                                            min_score, use_allow);
+      if (rc != WDBX_B200_OK) return rc;
+    }
+    return WDBX_B200_OK;
+  }
+  e->xseq += 1;
+  if (e->xseq == 0u) e->xseq = 1u;   // 0 means "no exchange"
+  const unsigned int seq = e->xseq;
+  int rc;
+  // (the regime choice must not depend on this rank's own row count: use_gemm looks at the segments' bytes, which
+  // row striping keeps within one row of every other rank's -- and every route speaks the same protocol anyway)
+  const bool filtered = use_allow || min_score > -INFINITY;
+  if (e->gemm_mode != 1 && use_gemm(e, s0, s1, B, k) && (filter_fused_tail(B) || !filtered)) {
+    if (filter_fused_tail(B)) {
+      // bf16-filter path, ONE launch: filter + in-kernel refine; its last CTA pushes / awaits / merges the keys
+      rc = filter_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream, seq,
+                           min_score, use_allow);
+    } else {
+      // 128-query filter kernel (WDBX_B200_FILTER_SMALL=0): local exact top-k, then the stand-alone exchange kernel
+      if (!e->xkeys) CU_TRY(cudaMalloc(&e->xkeys, static_cast<size_t>(kXchgMaxB) * kXchgMaxK * 8));
+      rc = filter_segments(e, s0, s1, q_dev, B, k, metric, e->xkeys, nullptr, nullptr, nullptr, stream);
+      if (rc == WDBX_B200_OK) {
+        CU_TRY(launch_exchange_merge(e->xpeer, e->xworld, e->xrank, seq, e->xkeys, B, k, keys_out, scores_out, gids_out,
+                                     counts_out, stream));
+        e->launches.fetch_add(1, std::memory_order_relaxed);
+      }
+    }
+    if (rc != WDBX_B200_ERR_OOM) return rc;
+    cudaGetLastError();
+    e->shadow_min_bytes = -1;
+    if (!e->shadow_warned) {
+      e->shadow_warned = true;
+      fprintf(stderr, "[wdbx_b200] device %d: no memory for the bf16 shadow; small batches are served by the fp32 scan "
+                      "(about half the queries/s)\n", e->device);
+    }
+  }
+  return scan_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream, seq, nullptr,
+                       min_score, use_allow);
+}
+
+
+// ---- host-buffer searches ------------------------------------------------------------------------------
+// result block layout (device and pinned host): keys[nres] u64 | gids[nres] i64 | scores[nres] f32 | counts[lists*B] i32
+struct ResLayout {
+  size_t nres, off_keys, off_gids, off_scores, off_counts, bytes;
+  ResLayout(int lists, int B, int k) {
+    nres = static_cast<size_t>(lists) * B * k;
+    off_keys = 0;
+    off_gids = nres * 8;
+    off_scores = nres * 16;
+    off_counts = nres * 20;
+    bytes = off_counts + static_cast<size_t>(lists) * B * 4;
+  }
+};
+
+// device-side staging of the host path (queries, packed results); pinned mirrors when `pinned`
+int ensure_host_buffers(wdbx_b200_engine* e, size_t nq, size_t bytes, bool pinned) {
+  if (e->q_floats < nq || (pinned && !e->hq_pinned)) {
+    cudaFreeHost(e->hq_pinned); e->hq_pinned = nullptr;
+    cudaFree(e->dq); e->dq = nullptr;
+    e->q_floats = 0;
+    if (pinned) CU_TRY(cudaMallocHost(&e->hq_pinned, nq * 4));
+    CU_TRY(cudaMalloc(&e->dq, nq * 4));
+    e->q_floats = nq;
+  }
+  if (e->res_bytes < bytes || (pinned && !e->hres_pinned)) {
+    cudaFreeHost(e->hres_pinned); e->hres_pinned = nullptr;
+    cudaFree(e->dres); e->dres = nullptr;
+    e->res_bytes = 0;
+    if (pinned) CU_TRY(cudaMallocHost(&e->hres_pinned, bytes));
+    CU_TRY(cudaMalloc(&e->dres, bytes));
+    e->res_bytes = bytes;
+  }
+  return WDBX_B200_OK;
+}
+
+// copy the per-segment "allowed rows" bitmaps of one filtered search to the device.  Caller holds e->mu.
+int upload_allow(wdbx_b200_engine* e, const uint32_t* const* allow_bitmaps, cudaStream_t st) {
+  for (int s = 0; s < e->nseg; ++s) {
+    Segment& sg = e->seg[s];
+    const size_t words = static_cast<size_t>((sg.n_rows + 31) / 32);
+    if (words == 0) continue;
+    if (sg.allow_words < words) {
+      CU_TRY(cudaStreamSynchronize(st));
+      cudaFree(sg.allow);
+      sg.allow = nullptr;
+      sg.allow_words = 0;
+      const size_t cap_words = static_cast<size_t>(sg.cap_rows / 32 + 1);
+      CU_TRY(cudaMalloc(&sg.allow, cap_words * 4));
+      sg.allow_words = cap_words;
+    }
+    if (allow_bitmaps[s]) CU_TRY(cudaMemcpyAsync(sg.allow, allow_bitmaps[s], words * 4, cudaMemcpyHostToDevice, st));
+    else CU_TRY(cudaMemsetAsync(sg.allow, 0xFF, words * 4, st));  // NULL entry = every row allowed
+  }
+  return WDBX_B200_OK;
+}
+
+// Launch the searches of one host call on `st` (queries already in e->dq): `lists` result lists into e->dres.
+// exchange: collective search with the peer engines / ranks.  Takes e->mu.
+int launch_host_lists(wdbx_b200_engine* e, int segment, bool exchange, const float* q_dev, int B, int k, int metric,
+                      float min_score, const uint32_t* const* allow_bitmaps, const ResLayout& R, cudaStream_t st,
+                      uint64_t* keys0 = nullptr, float* scores0 = nullptr, long long* gids0 = nullptr, int* counts0 = nullptr) {
+  std::lock_guard<std::mutex> lk(e->mu);
+  const bool per_segment = segment == WDBX_B200_EACH_SEGMENT;
+  const int lists = per_segment ? e->nseg : 1;
+  const bool use_allow = allow_bitmaps != nullptr;
+  const bool filtered = use_allow || min_score > -INFINITY;
+  if (use_allow) {
+    const int rc = upload_allow(e, allow_bitmaps, st);
+    if (rc != WDBX_B200_OK) return rc;
+  }
+  // outputs: the engine's packed result block, unless the caller wants them somewhere else on this device
+  uint64_t* keys = keys0 ? keys0 : reinterpret_cast<uint64_t*>(e->dres + R.off_keys);
+  float* scores = scores0 ? scores0 : reinterpret_cast<float*>(e->dres + R.off_scores);
+  long long* gids = gids0 ? gids0 : reinterpret_cast<long long*>(e->dres + R.off_gids);
+  int* counts = counts0 ? counts0 : reinterpret_cast<int*>(e->dres + R.off_counts);
+  for (int l = 0; l < lists; ++l) {
+    const size_t o = static_cast<size_t>(l) * B * k;
+    const int s0 = per_segment ? l : (segment >= 0 ? segment : 0);
+    const int s1 = per_segment ? l + 1 : (segment >= 0 ? segment + 1 : e->nseg);
+    int* cnt = counts + static_cast<size_t>(l) * B;
+    int rc;
+    if (exchange) {
+      rc = exchange_search_locked(e, s0, s1, q_dev, B, k, metric, keys + o, scores + o, gids + o, cnt, st, min_score, use_allow);
+    } else if (filtered) {
+      // small batches on the filter path consult the bitmap / floor in the fused filter kernel (candidates only);
+      // everything else takes the streaming kernel
+      rc = WDBX_B200_ERR_OOM;
+      if (e->gemm_mode != 1 && use_gemm(e, s0, s1, B, k) && filter_fused_tail(B)) {
+        rc = filter_segments(e, s0, s1, q_dev, B, k, metric, keys + o, scores + o, gids + o, cnt, st, 0u, min_score, use_allow);
+        if (rc == WDBX_B200_ERR_OOM) {
+          cudaGetLastError();
+          e->shadow_min_bytes = -1;
+        }
+      }
+      if (rc == WDBX_B200_ERR_OOM)
+        rc = scan_segments(e, s0, s1, q_dev, B, k, metric, keys + o, scores + o, gids + o, cnt, st, 0u, nullptr, min_score,
+                           use_allow);
+    } else {
+      rc = search_segments(e, s0, s1, q_dev, B, k, metric, keys + o, scores + o, gids + o, cnt, st);
+    }
+    if (rc != WDBX_B200_OK) return rc;
+  }
+  return WDBX_B200_OK;
+}
+
+// One engine, host buffers in and out: pinned H2D -> launches -> ONE D2H of the packed result -> synchronise.
+int host_search(wdbx_b200_engine* e, int segment, bool exchange, const float* q_host, int B, int k, int metric,
+                float min_score, const uint32_t* const* allow_bitmaps, float* scores_host, int64_t* gids_host,
+                uint64_t* keys_host, int32_t* counts_host) {
+  int rc = check_search_args(e, B, k, metric);
+  if (rc != WDBX_B200_OK) return rc;
+  if (!q_host) return fail(WDBX_B200_ERR_ARG, "q_host is NULL");
+  if (segment < WDBX_B200_EACH_SEGMENT || segment >= e->nseg)
+    return fail(WDBX_B200_ERR_ARG, "segment %d outside [-2, %d)", segment, e->nseg);
+  DeviceGuard guard(e->device);
+  std::lock_guard<std::mutex> hlk(e->host_mu);
+  const int lists = segment == WDBX_B200_EACH_SEGMENT ? e->nseg : 1;
+  const size_t nq = static_cast<size_t>(B) * e->dim;
+  const ResLayout R(lists, B, k);
+  rc = ensure_host_buffers(e, nq, R.bytes, true);
+  if (rc != WDBX_B200_OK) return rc;
+  memcpy(e->hq_pinned, q_host, nq * 4);
+  cudaStream_t st = e->hstream;
+  CU_TRY(cudaMemcpyAsync(e->dq, e->hq_pinned, nq * 4, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaEventRecord(e->ev0, st));
+  rc = launch_host_lists(e, segment, exchange, e->dq, B, k, metric, min_score, allow_bitmaps, R, st);
+  if (rc != WDBX_B200_OK) return rc;
+  CU_TRY(cudaEventRecord(e->ev1, st));
+  CU_TRY(cudaMemcpyAsync(e->hres_pinned, e->dres, R.bytes, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  float ms = 0.0f;
+  if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_search_ms = ms;
+  if (keys_host) memcpy(keys_host, e->hres_pinned + R.off_keys, R.nres * 8);
+  if (gids_host) memcpy(gids_host, e->hres_pinned + R.off_gids, R.nres * 8);
+  if (scores_host) memcpy(scores_host, e->hres_pinned + R.off_scores, R.nres * 4);
+  if (counts_host) memcpy(counts_host, e->hres_pinned + R.off_counts, static_cast<size_t>(lists) * B * 4);
+  e->searches.fetch_add(1, std::memory_order_relaxed);
   return WDBX_B200_OK;
 }
 
@@ -953,145 +1202,14 @@ int wdbx_b200_search(wdbx_b200_engine* e, int segment, const float* q_dev, int B
 
 int wdbx_b200_search_host(wdbx_b200_engine* e, int segment, const float* q_host, int B, int k, int metric,
                           float* scores_host, int64_t* gids_host, uint64_t* keys_host, int32_t* counts_host) {
-  int rc = check_search_args(e, B, k, metric);
-  if (rc != WDBX_B200_OK) return rc;
-  if (!q_host) return fail(WDBX_B200_ERR_ARG, "q_host is NULL");
-  if (segment < WDBX_B200_EACH_SEGMENT || segment >= e->nseg)
-    return fail(WDBX_B200_ERR_ARG, "segment %d outside [-2, %d)", segment, e->nseg);
-  DeviceGuard guard(e->device);
-  std::lock_guard<std::mutex> hlk(e->host_mu);
-  const bool per_segment = segment == WDBX_B200_EACH_SEGMENT;
-  const int lists = per_segment ? e->nseg : 1;
-  const size_t nq = static_cast<size_t>(B) * e->dim;
-  const size_t nres = static_cast<size_t>(lists) * B * k;
-  // result block layout: keys[nres] u64 | gids[nres] i64 | scores[nres] f32 | counts[lists*B] i32
-  const size_t off_keys = 0, off_gids = nres * 8, off_scores = nres * 16, off_counts = nres * 20;
-  const size_t bytes = off_counts + static_cast<size_t>(lists) * B * 4;
-  if (e->q_floats < nq) {
-    cudaFreeHost(e->hq_pinned); e->hq_pinned = nullptr;
-    cudaFree(e->dq); e->dq = nullptr;
-    e->q_floats = 0;
-    CU_TRY(cudaMallocHost(&e->hq_pinned, nq * 4));
-    CU_TRY(cudaMalloc(&e->dq, nq * 4));
-    e->q_floats = nq;
-  }
-  if (e->res_bytes < bytes) {
-    cudaFreeHost(e->hres_pinned); e->hres_pinned = nullptr;
-    cudaFree(e->dres); e->dres = nullptr;
-    e->res_bytes = 0;
-    CU_TRY(cudaMallocHost(&e->hres_pinned, bytes));
-    CU_TRY(cudaMalloc(&e->dres, bytes));
-    e->res_bytes = bytes;
-  }
-  memcpy(e->hq_pinned, q_host, nq * 4);
-  cudaStream_t st = e->hstream;
-  CU_TRY(cudaMemcpyAsync(e->dq, e->hq_pinned, nq * 4, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaEventRecord(e->ev0, st));
-  {
-    std::lock_guard<std::mutex> lk(e->mu);
-    for (int l = 0; l < lists; ++l) {
-      const size_t o = static_cast<size_t>(l) * B * k;
-      const int s0 = per_segment ? l : (segment >= 0 ? segment : 0);
-      const int s1 = per_segment ? l + 1 : (segment >= 0 ? segment + 1 : e->nseg);
-      rc = search_segments(e, s0, s1, e->dq, B, k, metric,
-                         reinterpret_cast<uint64_t*>(e->dres + off_keys) + o,
-                         reinterpret_cast<float*>(e->dres + off_scores) + o,
-                         reinterpret_cast<long long*>(e->dres + off_gids) + o,
-                         reinterpret_cast<int*>(e->dres + off_counts) + static_cast<size_t>(l) * B, st);
-      if (rc != WDBX_B200_OK) return rc;
-    }
-  }
-  CU_TRY(cudaEventRecord(e->ev1, st));
-  CU_TRY(cudaMemcpyAsync(e->hres_pinned, e->dres, bytes, cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaStreamSynchronize(st));
-  float ms = 0.0f;
-  if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_search_ms = ms;
-  if (keys_host) memcpy(keys_host, e->hres_pinned + off_keys, nres * 8);
-  if (gids_host) memcpy(gids_host, e->hres_pinned + off_gids, nres * 8);
-  if (scores_host) memcpy(scores_host, e->hres_pinned + off_scores, nres * 4);
-  if (counts_host) memcpy(counts_host, e->hres_pinned + off_counts, static_cast<size_t>(lists) * B * 4);
-  e->searches.fetch_add(1, std::memory_order_relaxed);
-  return WDBX_B200_OK;
+  return host_search(e, segment, false, q_host, B, k, metric, -INFINITY, nullptr, scores_host, gids_host, keys_host, counts_host);
 }
 
 int wdbx_b200_search_filtered_host(wdbx_b200_engine* e, const float* q_host, int B, int k, int metric, float min_score,
                                    const uint32_t* const* allow_bitmaps, float* scores_host, int64_t* gids_host,
                                    int32_t* counts_host) {
-  int rc = check_search_args(e, B, k, metric);
-  if (rc != WDBX_B200_OK) return rc;
-  if (!q_host) return fail(WDBX_B200_ERR_ARG, "q_host is NULL");
-  DeviceGuard guard(e->device);
-  std::lock_guard<std::mutex> hlk(e->host_mu);
-  const size_t nq = static_cast<size_t>(B) * e->dim;
-  const size_t nres = static_cast<size_t>(B) * k;
-  const size_t off_gids = nres * 8, off_scores = nres * 16, off_counts = nres * 20;
-  const size_t bytes = off_counts + static_cast<size_t>(B) * 4;
-  if (e->q_floats < nq) {
-    cudaFreeHost(e->hq_pinned); e->hq_pinned = nullptr;
-    cudaFree(e->dq); e->dq = nullptr;
-    e->q_floats = 0;
-    CU_TRY(cudaMallocHost(&e->hq_pinned, nq * 4));
-    CU_TRY(cudaMalloc(&e->dq, nq * 4));
-    e->q_floats = nq;
-  }
-  if (e->res_bytes < bytes) {
-    cudaFreeHost(e->hres_pinned); e->hres_pinned = nullptr;
-    cudaFree(e->dres); e->dres = nullptr;
-    e->res_bytes = 0;
-    CU_TRY(cudaMallocHost(&e->hres_pinned, bytes));
-    CU_TRY(cudaMalloc(&e->dres, bytes));
-    e->res_bytes = bytes;
-  }
-  memcpy(e->hq_pinned, q_host, nq * 4);
-  cudaStream_t st = e->hstream;
-  CU_TRY(cudaMemcpyAsync(e->dq, e->hq_pinned, nq * 4, cudaMemcpyHostToDevice, st));
-  {
-    std::lock_guard<std::mutex> lk(e->mu);
-    bool use_allow = false;
-    if (allow_bitmaps) {
-      use_allow = true;
-      for (int s = 0; s < e->nseg; ++s) {
-        Segment& sg = e->seg[s];
-        const size_t words = static_cast<size_t>((sg.n_rows + 31) / 32);
-        if (words == 0) continue;
-        if (sg.allow_words < words) {
-          CU_TRY(cudaStreamSynchronize(st));
-          cudaFree(sg.allow);
-          sg.allow = nullptr;
-          sg.allow_words = 0;
-          const size_t cap_words = static_cast<size_t>(sg.cap_rows / 32 + 1);
-          CU_TRY(cudaMalloc(&sg.allow, cap_words * 4));
-          sg.allow_words = cap_words;
-        }
-        if (allow_bitmaps[s]) CU_TRY(cudaMemcpyAsync(sg.allow, allow_bitmaps[s], words * 4, cudaMemcpyHostToDevice, st));
-        else CU_TRY(cudaMemsetAsync(sg.allow, 0xFF, words * 4, st));  // NULL entry = every row allowed
-      }
-    }
-    // small batches on the filter path consult the bitmap / floor in the fused filter kernel (candidates only);
-    // everything else takes the streaming kernel
-    rc = WDBX_B200_ERR_OOM;
-    if (e->gemm_mode != 1 && use_gemm(e, 0, e->nseg, B, k) && filter_fused_tail(B)) {
-      rc = filter_segments(e, 0, e->nseg, e->dq, B, k, metric, nullptr, reinterpret_cast<float*>(e->dres + off_scores),
-                           reinterpret_cast<long long*>(e->dres + off_gids), reinterpret_cast<int*>(e->dres + off_counts), st,
-                           0u, min_score, use_allow);
-      if (rc == WDBX_B200_ERR_OOM) {
-        cudaGetLastError();
-        e->shadow_min_bytes = -1;
-      }
-    }
-    if (rc == WDBX_B200_ERR_OOM)
-      rc = scan_segments(e, 0, e->nseg, e->dq, B, k, metric, nullptr, reinterpret_cast<float*>(e->dres + off_scores),
-                         reinterpret_cast<long long*>(e->dres + off_gids), reinterpret_cast<int*>(e->dres + off_counts), st,
-                         0u, nullptr, min_score, use_allow);
-    if (rc != WDBX_B200_OK) return rc;
-  }
-  CU_TRY(cudaMemcpyAsync(e->hres_pinned, e->dres, bytes, cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaStreamSynchronize(st));
-  if (gids_host) memcpy(gids_host, e->hres_pinned + off_gids, nres * 8);
-  if (scores_host) memcpy(scores_host, e->hres_pinned + off_scores, nres * 4);
-  if (counts_host) memcpy(counts_host, e->hres_pinned + off_counts, static_cast<size_t>(B) * 4);
-  e->searches.fetch_add(1, std::memory_order_relaxed);
-  return WDBX_B200_OK;
+  return host_search(e, WDBX_B200_ALL_SEGMENTS, false, q_host, B, k, metric, min_score, allow_bitmaps, scores_host, gids_host,
+                     nullptr, counts_host);
 }
 
 int wdbx_b200_merge(wdbx_b200_engine* e, const uint64_t* keys_dev, int G, int B, int k, uint64_t* keys_out,
@@ -1151,69 +1269,6 @@ int wdbx_b200_exchange_attach(wdbx_b200_engine* e, int world, const void* ipc_ha
   return WDBX_B200_OK;
 }
 
-}  // extern "C"
-
-namespace {
-
-// Collective search of all segments + on-device key exchange with the peer ranks.  Caller holds e->mu.
-// Every rank takes the same decisions here (they depend on B, k, dim only -- never on the rank's own rows), and
-// the routes a rank may take for one search (fused filter kernel, K1 scan, stand-alone exchange kernel) all
-// speak the same exchange protocol under the same sequence number.
-int exchange_search_locked(wdbx_b200_engine* e, const float* q_dev, int B, int k, int metric, uint64_t* keys_out,
-                           float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream) {
-  if (e->xworld < 2) return fail(WDBX_B200_ERR_ARG, "exchange not attached (call wdbx_b200_exchange_init/attach first)");
-  if (B > kXchgMaxB || k > kXchgMaxK)
-    return fail(WDBX_B200_ERR_LIMIT, "fused exchange supports B <= %d queries and k <= %d", kXchgMaxB, kXchgMaxK);
-  // the K1 scan (and the flag-gated re-run behind the filter) exchanges from ONE query block: batches larger
-  // than the block the plan allows for this shape (e.g. 1 query for dim 64) run as consecutive collective passes
-  ScanPlan plan;
-  const int prc = scan_plan(e->dim, e->dpad, e->elem_bytes, k, B, e->sm_count, e->tune, &plan);
-  if (prc != 0) return fail(prc == -4 ? WDBX_B200_ERR_LIMIT : WDBX_B200_ERR_ARG, "invalid scan shape (dim=%d k=%d)", e->dim, k);
-  if (B > plan.queries_per_block) {
-    const int qb = plan.queries_per_block;
-    for (int b0 = 0; b0 < B; b0 += qb) {
-      const int nb = std::min(qb, B - b0);
-      const size_t o = static_cast<size_t>(b0) * k;
-      const int rc = exchange_search_locked(e, q_dev + static_cast<size_t>(b0) * e->dim, nb, k, metric,
-                                            keys_out ? keys_out + o : nullptr, scores_out ? scores_out + o : nullptr,
-                                            gids_out ? gids_out + o : nullptr, counts_out ? counts_out + b0 : nullptr, stream);
-      if (rc != WDBX_B200_OK) return rc;
-    }
-    return WDBX_B200_OK;
-  }
-  e->xseq += 1;
-  if (e->xseq == 0u) e->xseq = 1u;   // 0 means "no exchange"
-  const unsigned int seq = e->xseq;
-  int rc;
-  if (e->gemm_mode != 1 && use_gemm(e, 0, e->nseg, B, k)) {
-    if (filter_fused_tail(B)) {
-      // bf16-filter path, ONE launch: filter + in-kernel refine; its last CTA pushes / awaits / merges the keys
-      rc = filter_segments(e, 0, e->nseg, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream, seq);
-    } else {
-      // 128-query filter kernel (WDBX_B200_FILTER_SMALL=0): local exact top-k, then the stand-alone exchange kernel
-      if (!e->xkeys) CU_TRY(cudaMalloc(&e->xkeys, static_cast<size_t>(kXchgMaxB) * kXchgMaxK * 8));
-      rc = filter_segments(e, 0, e->nseg, q_dev, B, k, metric, e->xkeys, nullptr, nullptr, nullptr, stream);
-      if (rc == WDBX_B200_OK) {
-        CU_TRY(launch_exchange_merge(e->xpeer, e->xworld, e->xrank, seq, e->xkeys, B, k, keys_out, scores_out, gids_out,
-                                     counts_out, stream));
-        e->launches.fetch_add(1, std::memory_order_relaxed);
-      }
-    }
-    if (rc != WDBX_B200_ERR_OOM) return rc;
-    cudaGetLastError();
-    e->shadow_min_bytes = -1;
-    if (!e->shadow_warned) {
-      e->shadow_warned = true;
-      fprintf(stderr, "[wdbx_b200] device %d: no memory for the bf16 shadow; small batches are served by the fp32 scan "
-                      "(about half the queries/s)\n", e->device);
-    }
-  }
-  return scan_segments(e, 0, e->nseg, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream, seq);
-}
-
-}  // namespace
-
-extern "C" {
 
 int wdbx_b200_search_exchange(wdbx_b200_engine* e, const float* q_dev, int B, int k, int metric, uint64_t* keys_out,
                               float* scores_out, int64_t* gids_out, int32_t* counts_out, void* cuda_stream) {
@@ -1222,62 +1277,35 @@ int wdbx_b200_search_exchange(wdbx_b200_engine* e, const float* q_dev, int B, in
   if (!q_dev) return fail(WDBX_B200_ERR_ARG, "q_dev is NULL");
   DeviceGuard guard(e->device);
   std::lock_guard<std::mutex> lk(e->mu);
-  rc = exchange_search_locked(e, q_dev, B, k, metric, keys_out, scores_out, reinterpret_cast<long long*>(gids_out),
-                              counts_out, static_cast<cudaStream_t>(cuda_stream));
+  rc = exchange_search_locked(e, 0, e->nseg, q_dev, B, k, metric, keys_out, scores_out,
+                              reinterpret_cast<long long*>(gids_out), counts_out, static_cast<cudaStream_t>(cuda_stream));
   if (rc == WDBX_B200_OK) e->searches.fetch_add(1, std::memory_order_relaxed);
   return rc;
 }
 
 int wdbx_b200_search_exchange_host(wdbx_b200_engine* e, const float* q_host, int B, int k, int metric,
                                    float* scores_host, int64_t* gids_host, uint64_t* keys_host, int32_t* counts_host) {
-  int rc = check_search_args(e, B, k, metric);
-  if (rc != WDBX_B200_OK) return rc;
-  if (!q_host) return fail(WDBX_B200_ERR_ARG, "q_host is NULL");
-  DeviceGuard guard(e->device);
-  std::lock_guard<std::mutex> hlk(e->host_mu);
-  const size_t nq = static_cast<size_t>(B) * e->dim;
-  const size_t nres = static_cast<size_t>(B) * k;
-  // result block layout: keys[nres] u64 | gids[nres] i64 | scores[nres] f32 | counts[B] i32
-  const size_t off_keys = 0, off_gids = nres * 8, off_scores = nres * 16, off_counts = nres * 20;
-  const size_t bytes = off_counts + static_cast<size_t>(B) * 4;
-  if (e->q_floats < nq) {
-    cudaFreeHost(e->hq_pinned); e->hq_pinned = nullptr;
-    cudaFree(e->dq); e->dq = nullptr;
-    e->q_floats = 0;
-    CU_TRY(cudaMallocHost(&e->hq_pinned, nq * 4));
-    CU_TRY(cudaMalloc(&e->dq, nq * 4));
-    e->q_floats = nq;
-  }
-  if (e->res_bytes < bytes) {
-    cudaFreeHost(e->hres_pinned); e->hres_pinned = nullptr;
-    cudaFree(e->dres); e->dres = nullptr;
-    e->res_bytes = 0;
-    CU_TRY(cudaMallocHost(&e->hres_pinned, bytes));
-    CU_TRY(cudaMalloc(&e->dres, bytes));
-    e->res_bytes = bytes;
-  }
-  memcpy(e->hq_pinned, q_host, nq * 4);
-  cudaStream_t st = e->hstream;
-  CU_TRY(cudaMemcpyAsync(e->dq, e->hq_pinned, nq * 4, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaEventRecord(e->ev0, st));
-  {
-    std::lock_guard<std::mutex> lk(e->mu);
-    rc = exchange_search_locked(e, e->dq, B, k, metric, reinterpret_cast<uint64_t*>(e->dres + off_keys),
-                                reinterpret_cast<float*>(e->dres + off_scores),
-                                reinterpret_cast<long long*>(e->dres + off_gids),
-                                reinterpret_cast<int*>(e->dres + off_counts), st);
-    if (rc != WDBX_B200_OK) return rc;
-  }
-  CU_TRY(cudaEventRecord(e->ev1, st));
-  CU_TRY(cudaMemcpyAsync(e->hres_pinned, e->dres, bytes, cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaStreamSynchronize(st));
-  float ms = 0.0f;
-  if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_search_ms = ms;
-  if (keys_host) memcpy(keys_host, e->hres_pinned + off_keys, nres * 8);
-  if (gids_host) memcpy(gids_host, e->hres_pinned + off_gids, nres * 8);
-  if (scores_host) memcpy(scores_host, e->hres_pinned + off_scores, nres * 4);
-  if (counts_host) memcpy(counts_host, e->hres_pinned + off_counts, static_cast<size_t>(B) * 4);
-  e->searches.fetch_add(1, std::memory_order_relaxed);
+  return host_search(e, WDBX_B200_ALL_SEGMENTS, true, q_host, B, k, metric, -INFINITY, nullptr, scores_host, gids_host,
+                     keys_host, counts_host);
+}
+
+int wdbx_b200_search_exchange_filtered_host(wdbx_b200_engine* e, const float* q_host, int B, int k, int metric,
+                                            float min_score, const uint32_t* const* allow_bitmaps, float* scores_host,
+                                            int64_t* gids_host, int32_t* counts_host) {
+  return host_search(e, WDBX_B200_ALL_SEGMENTS, true, q_host, B, k, metric, min_score, allow_bitmaps, scores_host, gids_host,
+                     nullptr, counts_host);
+}
+
+int wdbx_b200_set_option(wdbx_b200_engine* e, const char* name, long long value) {
+  if (!e || !name) return fail(WDBX_B200_ERR_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  const std::string n(name);
+  if (n == "shadow_min_mb") e->shadow_min_bytes = value < 0 ? -1 : value << 20;
+  else if (n == "gemm_min_batch") e->gemm_min_batch = static_cast<int>(value);
+  else if (n == "gemm_mode") e->gemm_mode = static_cast<int>(value);
+  else if (n == "pdl") e->pdl = value != 0;
+  else if (n == "queries_per_pass") e->tune.queries_per_pass = static_cast<int>(value);
+  else return fail(WDBX_B200_ERR_ARG, "unknown option '%s'", name);
   return WDBX_B200_OK;
 }
 
@@ -1340,6 +1368,334 @@ int wdbx_b200_get_stats(wdbx_b200_engine* e, wdbx_b200_stats* out) {
   out->kernel_launches = e->launches.load();
   out->searches = e->searches.load();
   out->last_search_ms = e->last_search_ms;
+  return WDBX_B200_OK;
+}
+
+// ---- single process, several GPUs ------------------------------------------------------------------------
+// north_star: "the shard manager maps num_shards onto the 8 GPUs of one box" with the REST server / CLI
+// (wdbx/api/server.py:141-152, wdbx/cli.py:541) untouched, i.e. from ONE ordinary Python process.  A group ties
+// G engines (one per device, rows of every segment striped over them by the host layer) together: peer access is
+// enabled directly (no CUDA IPC), every search is launched on all G devices from the calling thread, and the
+// devices merge their top-k among themselves with the same NVLink exchange the one-process-per-GPU layout uses
+// (small batches) or by peer copies of the packed keys to device 0 + merge kernel K3 (any B, k).
+
+int wdbx_b200_group_create(wdbx_b200_engine* const* engines, int n, wdbx_b200_group** out) {
+  if (!out) return fail(WDBX_B200_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (!engines || n < 2 || n > kMaxPeers) return fail(WDBX_B200_ERR_ARG, "a group needs 2..%d engines", kMaxPeers);
+  for (int i = 0; i < n; ++i) {
+    wdbx_b200_engine* e = engines[i];
+    if (!e) return fail(WDBX_B200_ERR_ARG, "engine %d is NULL", i);
+    if (e->dim != engines[0]->dim || e->dtype != engines[0]->dtype || e->nseg != engines[0]->nseg)
+      return fail(WDBX_B200_ERR_ARG, "engines of a group must share dim, dtype and num_segments");
+    if (e->xworld != 0 || e->xbuf) return fail(WDBX_B200_ERR_ARG, "engine %d already takes part in an exchange", i);
+    for (int j = 0; j < i; ++j)
+      if (engines[j]->device == e->device) return fail(WDBX_B200_ERR_ARG, "engines %d and %d share device %d", j, i, e->device);
+  }
+  for (int i = 0; i < n; ++i) {
+    DeviceGuard guard(engines[i]->device);
+    for (int j = 0; j < n; ++j) {
+      if (i == j) continue;
+      int can = 0;
+      CU_TRY(cudaDeviceCanAccessPeer(&can, engines[i]->device, engines[j]->device));
+      if (!can) return fail(WDBX_B200_ERR_CUDA, "device %d cannot access device %d (no NVLink / P2P)", engines[i]->device,
+                            engines[j]->device);
+      const cudaError_t pe = cudaDeviceEnablePeerAccess(engines[j]->device, 0);
+      if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return fail(WDBX_B200_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", engines[i]->device, engines[j]->device,
+                    cudaGetErrorString(pe));
+      }
+      cudaGetLastError();
+    }
+    CU_TRY(cudaMalloc(&engines[i]->xbuf, kXchgBytes));
+    CU_TRY(cudaMemset(engines[i]->xbuf, 0, kXchgBytes));
+  }
+  wdbx_b200_group* g = new (std::nothrow) wdbx_b200_group();
+  if (!g) return fail(WDBX_B200_ERR_OOM, "host allocation failed");
+  g->eng.assign(engines, engines + n);
+  g->ev.resize(n, nullptr);
+  for (int i = 0; i < n; ++i) {
+    wdbx_b200_engine* e = engines[i];
+    std::lock_guard<std::mutex> lk(e->mu);
+    for (int r = 0; r < n; ++r) e->xpeer[r] = engines[r]->xbuf;   // peer access: plain device pointers
+    e->xrank = i;
+    e->xworld = n;
+    e->xseq = 0;
+    DeviceGuard guard(e->device);
+    if (cudaEventCreateWithFlags(&g->ev[i], cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      wdbx_b200_group_destroy(g);
+      return fail(WDBX_B200_ERR_CUDA, "event creation failed");
+    }
+  }
+  g->rcs.assign(n, WDBX_B200_OK);
+  g->errs.assign(n, std::string());
+  if (env_int("WDBX_B200_GROUP_THREADS", 1) != 0)
+    for (int i = 1; i < n; ++i) g->workers.emplace_back(group_worker, g, i);
+  *out = g;
+  return WDBX_B200_OK;
+}
+
+void wdbx_b200_group_destroy(wdbx_b200_group* g) {
+  if (!g) return;
+  g->stop.store(true, std::memory_order_release);
+  {
+    std::lock_guard<std::mutex> lk(g->wmu);
+    g->wcv.notify_all();
+  }
+  for (auto& t : g->workers) t.join();
+  for (size_t i = 0; i < g->eng.size(); ++i) {
+    wdbx_b200_engine* e = g->eng[i];
+    DeviceGuard guard(e->device);
+    cudaDeviceSynchronize();
+    {
+      std::lock_guard<std::mutex> lk(e->mu);
+      e->xworld = 0;   // the engines live on (their owner destroys them); they just stop exchanging
+    }
+    if (g->ev[i]) cudaEventDestroy(g->ev[i]);
+    if (i == 0) {
+      cudaFree(g->gkeys);
+      if (g->ev_in) cudaEventDestroy(g->ev_in);
+      if (g->ev_out) cudaEventDestroy(g->ev_out);
+    }
+  }
+  cudaFreeHost(g->hq);
+  cudaFreeHost(g->hres);
+  cudaGetLastError();
+  delete g;
+}
+
+}  // extern "C"
+
+namespace {
+
+// One engine's share of a group search: queries in (from the group's pinned buffer, or from device 0 after
+// `ev_in`), launches, and -- batches beyond the exchange's limits -- its keys to device 0.
+int group_launch_one(wdbx_b200_group* g, int i, const GroupJob& j) {
+  const int G = static_cast<int>(g->eng.size());
+  wdbx_b200_engine* e = g->eng[i];
+  wdbx_b200_engine* e0 = g->eng[0];
+  const int nseg = e0->nseg;
+  const int lists = j.segment == WDBX_B200_EACH_SEGMENT ? nseg : 1;
+  const size_t nq = static_cast<size_t>(j.B) * e0->dim;
+  const ResLayout R(lists, j.B, j.k);
+  DeviceGuard guard(e->device);
+  int rc = ensure_host_buffers(e, nq, R.bytes, false);
+  if (rc != WDBX_B200_OK) return rc;
+  cudaStream_t st = e->hstream;
+  if (j.q_dev0 == nullptr) {
+    CU_TRY(cudaMemcpyAsync(e->dq, g->hq, nq * 4, cudaMemcpyHostToDevice, st));
+  } else {
+    CU_TRY(cudaStreamWaitEvent(st, j.ev_in, 0));
+    CU_TRY(cudaMemcpyPeerAsync(e->dq, e->device, j.q_dev0, e0->device, nq * 4, st));
+  }
+  if (i == 0) CU_TRY(cudaEventRecord(e->ev0, st));
+  const uint32_t* const* al = j.allow ? j.allow + static_cast<size_t>(i) * nseg : nullptr;
+  const bool direct = j.exchange && i == 0;   // engine 0's exchange kernel may write the caller's buffers itself
+  rc = launch_host_lists(e, j.segment, j.exchange, e->dq, j.B, j.k, j.metric, j.min_score, al, R, st,
+                         direct ? j.out0_keys : nullptr, direct ? j.out0_scores : nullptr, direct ? j.out0_gids : nullptr,
+                         direct ? j.out0_counts : nullptr);
+  if (rc != WDBX_B200_OK) return rc;
+  if (!j.exchange) {
+    // this device's [lists][B][k] keys -> device 0, laid out [lists][G][B][k] for the merge kernel
+    const size_t per = static_cast<size_t>(j.B) * j.k;
+    for (int l = 0; l < lists; ++l)
+      CU_TRY(cudaMemcpyPeerAsync(g->gkeys + (static_cast<size_t>(l) * G + i) * per, e0->device,
+                                 reinterpret_cast<uint64_t*>(e->dres + R.off_keys) + static_cast<size_t>(l) * per, e->device,
+                                 per * 8, st));
+    CU_TRY(cudaEventRecord(g->ev[i], st));
+  }
+  return WDBX_B200_OK;
+}
+
+// Launcher threads: engine i > 0 is driven by its own thread so that the G devices start within a few
+// microseconds of each other (from one thread the last of 8 devices started ~140 us after the first, and the
+// on-device exchange makes everybody wait for it).  Workers spin briefly after a job, then sleep.
+void group_worker(wdbx_b200_group* g, int i) {
+  cudaSetDevice(g->eng[i]->device);
+  uint64_t seen = 0;
+  for (;;) {
+    int spins = 0;
+    while (g->gen.load(std::memory_order_acquire) == seen && !g->stop.load(std::memory_order_acquire)) {
+      if (++spins < 4000) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        continue;
+      }
+      std::unique_lock<std::mutex> lk(g->wmu);
+      g->sleepers.fetch_add(1);
+      g->wcv.wait(lk, [&] { return g->gen.load(std::memory_order_acquire) != seen || g->stop.load(); });
+      g->sleepers.fetch_sub(1);
+    }
+    if (g->stop.load(std::memory_order_acquire)) return;
+    seen = g->gen.load(std::memory_order_acquire);
+    g_err[0] = 0;
+    const int rc = group_launch_one(g, i, g->job);
+    g->rcs[i] = rc;
+    if (rc != WDBX_B200_OK) g->errs[i] = g_err;
+    g->done.fetch_add(1, std::memory_order_release);
+  }
+}
+
+// Launch one search on every engine of the group.  The queries are either in the group's pinned host buffer
+// (q_dev0 == NULL) or on device 0 (q_dev0, ordered after `ev_in`).  The merged result ends up on device 0: in
+// engine 0's packed result block, or in the caller's device pointers (out0_*).  Caller holds g->mu.
+int group_launch(wdbx_b200_group* g, int segment, const float* q_dev0, cudaEvent_t ev_in, int B, int k, int metric,
+                 float min_score, const uint32_t* const* allow, const ResLayout& R, uint64_t* out0_keys, float* out0_scores,
+                 long long* out0_gids, int* out0_counts) {
+  const int G = static_cast<int>(g->eng.size());
+  wdbx_b200_engine* e0 = g->eng[0];
+  const int lists = segment == WDBX_B200_EACH_SEGMENT ? e0->nseg : 1;
+  const bool exchange = B <= kXchgMaxB && k <= kXchgMaxK;
+  if (!exchange) {
+    const size_t need = static_cast<size_t>(lists) * G * B * k;
+    if (g->gkeys_n < need) {
+      DeviceGuard guard(e0->device);
+      CU_TRY(cudaStreamSynchronize(e0->hstream));
+      cudaFree(g->gkeys);
+      g->gkeys = nullptr;
+      g->gkeys_n = 0;
+      CU_TRY(cudaMalloc(&g->gkeys, need * 8));
+      g->gkeys_n = need;
+    }
+  }
+  GroupJob& j = g->job;
+  j.segment = segment; j.q_dev0 = q_dev0; j.ev_in = ev_in; j.B = B; j.k = k; j.metric = metric;
+  j.min_score = min_score; j.allow = allow; j.exchange = exchange;
+  j.out0_keys = out0_keys; j.out0_scores = out0_scores; j.out0_gids = out0_gids; j.out0_counts = out0_counts;
+  int rc = WDBX_B200_OK;
+  if (g->workers.empty()) {
+    for (int i = 0; i < G && rc == WDBX_B200_OK; ++i) rc = group_launch_one(g, i, j);
+  } else {
+    g->done.store(0, std::memory_order_relaxed);
+    g->gen.fetch_add(1, std::memory_order_release);
+    if (g->sleepers.load() > 0) {
+      std::lock_guard<std::mutex> lk(g->wmu);
+      g->wcv.notify_all();
+    }
+    rc = group_launch_one(g, 0, j);
+    for (int spins = 0; g->done.load(std::memory_order_acquire) < G - 1; ++spins)
+      if (spins > 20000) std::this_thread::yield();
+    for (int i = 1; i < G; ++i)
+      if (rc == WDBX_B200_OK && g->rcs[i] != WDBX_B200_OK) rc = fail(g->rcs[i], "device %d: %s", g->eng[i]->device, g->errs[i].c_str());
+  }
+  if (rc != WDBX_B200_OK) return rc;
+  if (!exchange) {
+    DeviceGuard guard(e0->device);
+    cudaStream_t st = e0->hstream;
+    for (int i = 1; i < G; ++i) CU_TRY(cudaStreamWaitEvent(st, g->ev[i], 0));
+    const size_t per = static_cast<size_t>(B) * k;
+    uint64_t* keys = out0_keys ? out0_keys : reinterpret_cast<uint64_t*>(e0->dres + R.off_keys);
+    float* scores = out0_scores ? out0_scores : reinterpret_cast<float*>(e0->dres + R.off_scores);
+    long long* gids = out0_gids ? out0_gids : reinterpret_cast<long long*>(e0->dres + R.off_gids);
+    int* counts = out0_counts ? out0_counts : reinterpret_cast<int*>(e0->dres + R.off_counts);
+    for (int l = 0; l < lists; ++l) {
+      CU_TRY(launch_merge_topk(g->gkeys + static_cast<size_t>(l) * G * per, G, B, k, keys + l * per, scores + l * per,
+                               gids + l * per, counts + static_cast<size_t>(l) * B, st));
+      e0->launches.fetch_add(1, std::memory_order_relaxed);
+    }
+  }
+  return WDBX_B200_OK;
+}
+
+int check_group_args(wdbx_b200_group* g, int segment, int B, int k, int metric) {
+  if (!g) return fail(WDBX_B200_ERR_ARG, "group is NULL");
+  const int rc = check_search_args(g->eng[0], B, k, metric);
+  if (rc != WDBX_B200_OK) return rc;
+  if (segment < WDBX_B200_EACH_SEGMENT || segment >= g->eng[0]->nseg)
+    return fail(WDBX_B200_ERR_ARG, "segment %d outside [-2, %d)", segment, g->eng[0]->nseg);
+  return WDBX_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wdbx_b200_group_search_host(wdbx_b200_group* g, int segment, const float* q_host, int B, int k, int metric,
+                                float min_score, const uint32_t* const* allow_bitmaps, float* scores_host,
+                                int64_t* gids_host, uint64_t* keys_host, int32_t* counts_host) {
+  int rc = check_group_args(g, segment, B, k, metric);
+  if (rc != WDBX_B200_OK) return rc;
+  if (!q_host) return fail(WDBX_B200_ERR_ARG, "q_host is NULL");
+  std::lock_guard<std::mutex> glk(g->mu);
+  wdbx_b200_engine* e0 = g->eng[0];
+  const int lists = segment == WDBX_B200_EACH_SEGMENT ? e0->nseg : 1;
+  const size_t nq = static_cast<size_t>(B) * e0->dim;
+  const ResLayout R(lists, B, k);
+  {
+    DeviceGuard guard(e0->device);
+    if (g->hq_floats < nq) {
+      cudaFreeHost(g->hq); g->hq = nullptr; g->hq_floats = 0;
+      CU_TRY(cudaHostAlloc(&g->hq, nq * 4, cudaHostAllocPortable));
+      g->hq_floats = nq;
+    }
+    if (g->hres_bytes < R.bytes) {
+      cudaFreeHost(g->hres); g->hres = nullptr; g->hres_bytes = 0;
+      CU_TRY(cudaHostAlloc(&g->hres, R.bytes, cudaHostAllocPortable));
+      g->hres_bytes = R.bytes;
+    }
+  }
+  memcpy(g->hq, q_host, nq * 4);
+  rc = group_launch(g, segment, nullptr, nullptr, B, k, metric, min_score, allow_bitmaps, R, nullptr, nullptr, nullptr, nullptr);
+  // every launched kernel must finish before the buffers are reused, error or not (peers wait for each other)
+  int first_err = rc;
+  {
+    DeviceGuard guard(e0->device);
+    if (rc == WDBX_B200_OK) {
+      cudaError_t ce = cudaEventRecord(e0->ev1, e0->hstream);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(g->hres, e0->dres, R.bytes, cudaMemcpyDeviceToHost, e0->hstream);
+      if (ce != cudaSuccess) first_err = fail(WDBX_B200_ERR_CUDA, "result copy: %s", cudaGetErrorString(ce));
+    }
+  }
+  for (wdbx_b200_engine* e : g->eng) {
+    DeviceGuard guard(e->device);
+    const cudaError_t ce = cudaStreamSynchronize(e->hstream);
+    if (ce != cudaSuccess && first_err == WDBX_B200_OK)
+      first_err = fail(WDBX_B200_ERR_CUDA, "device %d: %s", e->device, cudaGetErrorString(ce));
+  }
+  if (first_err != WDBX_B200_OK) return first_err;
+  float ms = 0.0f;
+  {
+    DeviceGuard guard(e0->device);
+    if (cudaEventElapsedTime(&ms, e0->ev0, e0->ev1) == cudaSuccess) e0->last_search_ms = ms;
+    else cudaGetLastError();
+  }
+  if (keys_host) memcpy(keys_host, g->hres + R.off_keys, R.nres * 8);
+  if (gids_host) memcpy(gids_host, g->hres + R.off_gids, R.nres * 8);
+  if (scores_host) memcpy(scores_host, g->hres + R.off_scores, R.nres * 4);
+  if (counts_host) memcpy(counts_host, g->hres + R.off_counts, static_cast<size_t>(lists) * B * 4);
+  for (wdbx_b200_engine* e : g->eng) e->searches.fetch_add(1, std::memory_order_relaxed);
+  return WDBX_B200_OK;
+}
+
+int wdbx_b200_group_search(wdbx_b200_group* g, const float* q_dev0, int B, int k, int metric, uint64_t* keys_out,
+                           float* scores_out, int64_t* gids_out, int32_t* counts_out, void* cuda_stream) {
+  int rc = check_group_args(g, WDBX_B200_ALL_SEGMENTS, B, k, metric);
+  if (rc != WDBX_B200_OK) return rc;
+  if (!q_dev0) return fail(WDBX_B200_ERR_ARG, "q_dev0 is NULL");
+  std::lock_guard<std::mutex> glk(g->mu);
+  wdbx_b200_engine* e0 = g->eng[0];
+  cudaStream_t user = static_cast<cudaStream_t>(cuda_stream);
+  const ResLayout R(1, B, k);
+  {
+    DeviceGuard guard(e0->device);
+    if (!g->ev_in) {
+      CU_TRY(cudaEventCreateWithFlags(&g->ev_in, cudaEventDisableTiming));
+      CU_TRY(cudaEventCreateWithFlags(&g->ev_out, cudaEventDisableTiming));
+    }
+    CU_TRY(cudaEventRecord(g->ev_in, user));   // the queries are ready once the caller's stream gets here
+  }
+  rc = group_launch(g, WDBX_B200_ALL_SEGMENTS, q_dev0, g->ev_in, B, k, metric, -INFINITY, nullptr, R, keys_out, scores_out,
+                    reinterpret_cast<long long*>(gids_out), counts_out);
+  if (rc != WDBX_B200_OK) return rc;
+  {
+    DeviceGuard guard(e0->device);
+    CU_TRY(cudaEventRecord(g->ev_out, e0->hstream));
+    CU_TRY(cudaStreamWaitEvent(user, g->ev_out, 0));   // the caller's stream continues after device 0's merge
+  }
+  for (wdbx_b200_engine* e : g->eng) e->searches.fetch_add(1, std::memory_order_relaxed);
   return WDBX_B200_OK;
 }
 

@@ -49,7 +49,7 @@ constexpr int BK = 64;        // bf16 elements per K block = 128 bytes
 constexpr int STAGES_SINGLE = 4; // single-CTA ring (48 KB / stage)
 constexpr int STAGES_PAIR = 6;   // CTA-pair ring (32 KB / stage per CTA)
 constexpr int kThreads = 384;   // 4 control warps + 8 epilogue warps
-constexpr int kMaxKFilter = 32;   // shared lower-bound list = one 128-byte line per query; refine lists = one key per lane
+constexpr int kMaxKFilter = 128;  // shared lower-bound list = up to four 128-byte lines per query; lists = 1 or 4 keys per lane
 constexpr uint32_t Q_TILE_BYTES = BM * BK * 2;  // 16 KB
 constexpr uint32_t TMEM_COLS = 2 * BN;
 
@@ -227,15 +227,24 @@ __device__ __forceinline__ float lower_insert(unsigned int* slots, unsigned int*
   for (int attempt = 0; attempt < 8; ++attempt) {
     unsigned int vmin = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
     int imin = 0;
-    for (int i4 = 0; i4 < k; i4 += 4) {
-      const uint4 v4 = __ldcg(reinterpret_cast<const uint4*>(slots + i4));
-      const unsigned int vv[4] = {v4.x, v4.y, v4.z, v4.w};
+    // 32 slots (eight 16-byte loads) in flight per round: one L2 round trip for k <= 32, four for k = 128
+    for (int i0 = 0; i0 < k; i0 += 32) {
+      uint4 v4[8];
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        if (i4 + jj < k) {
-          const unsigned int v = vv[jj];
-          if (v < vmin) { second = vmin; vmin = v; imin = i4 + jj; }
-          else if (v < second) second = v;
+      for (int j = 0; j < 8; ++j)
+        v4[j] = (i0 + 4 * j < k) ? __ldcg(reinterpret_cast<const uint4*>(slots + i0 + 4 * j))
+                                 : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const unsigned int vv[4] = {v4[j].x, v4[j].y, v4[j].z, v4[j].w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int i = i0 + 4 * j + jj;
+          if (i < k) {
+            const unsigned int v = vv[jj];
+            if (v < vmin) { second = vmin; vmin = v; imin = i; }
+            else if (v < second) second = v;
+          }
         }
       }
     }
@@ -587,7 +596,8 @@ struct SmallTail {
   int dim, dpad, row_bytes, cpr, lpr_log2, nch, bf16;
   float min_score;
   int* overflow;
-  uint64_t* part;
+  uint64_t* fin_keys;          // [B][kFinalCap] exact keys that reached the query's bound
+  unsigned int* fin_count;     // [B] zero at launch
   unsigned int* ticket;
   XchgCtx xchg;
   uint64_t* keys_out;
@@ -596,13 +606,19 @@ struct SmallTail {
   int* counts_out;
 };
 
+constexpr int kFinalCap = 2048;   // exact keys per query that may reach the last CTA (normally a few dozen)
+
 // Re-score CU x G candidates of one query exactly as K1 does: lanes-per-row lpr, chunk c = lig + j*lpr
 // accumulated in j order with the x,y,z,w fmaf chain, xor-butterfly over the lpr lanes, K1's score formula.
-// The exact ranking key replaces the candidate entry in place.
+// A key whose exact score reaches the query's bound L (a lower bound of the exact k-th best score, so no
+// top-k row is below it) is appended to the query's FINAL list in global memory; everything else -- almost
+// every candidate -- ends here.  All chunks of a row are requested before the first is consumed (NB = 8
+// chunks per lane cover rows up to 4096 bytes x lanes-per-row / 32 in one round trip).
 template <bool BF16, bool L2>
 __device__ __forceinline__ void rescore_unit(const SmallTail& tp, const float* q_s, float qinv, bool cosine,
-                                             unsigned long long* cand, int cnt, int base, const float* inv_norm, int lane) {
-  constexpr int CU = 2;
+                                             const unsigned long long* cand, int cnt, int base, const float* inv_norm,
+                                             float L, unsigned int* fin_count, uint64_t* fin_keys, int lane) {
+  constexpr int CU = 2, NB = 8;
   const int lpr_log2 = tp.lpr_log2, lpr = 1 << lpr_log2, G = 32 >> lpr_log2;
   const int g = lane >> lpr_log2, lig = lane & (lpr - 1);
   bool have[CU];
@@ -612,7 +628,6 @@ __device__ __forceinline__ void rescore_unit(const SmallTail& tp, const float* q
   for (int u = 0; u < CU; ++u) {
     const int ci = base + u * G + g;
     have[u] = ci < cnt;
-    // (entries outside the unit may already hold another warp's re-scored key: never read them)
     row[u] = have[u] ? static_cast<long long>(__ldcg(cand + ci) & 0xFFFFFFFFull) : 0ll;
     rp[u] = tp.rows + static_cast<size_t>(row[u]) * tp.row_bytes;
   }
@@ -626,12 +641,12 @@ __device__ __forceinline__ void rescore_unit(const SmallTail& tp, const float* q
   float dot[CU];
 #pragma unroll
   for (int u = 0; u < CU; ++u) dot[u] = 0.0f;
-  for (int j0 = 0; j0 < tp.nch; j0 += 4) {
-    uint4 raw[CU][4];
+  for (int j0 = 0; j0 < tp.nch; j0 += NB) {
+    uint4 raw[CU][NB];
 #pragma unroll
     for (int u = 0; u < CU; ++u) {
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
+      for (int v = 0; v < NB; ++v) {
         const int c = lig + ((j0 + v) << lpr_log2);
         raw[u][v] = (j0 + v < tp.nch && c < tp.cpr) ? __ldg(reinterpret_cast<const uint4*>(rp[u] + c * 16))
                                                     : make_uint4(0u, 0u, 0u, 0u);
@@ -641,7 +656,7 @@ __device__ __forceinline__ void rescore_unit(const SmallTail& tp, const float* q
     for (int u = 0; u < CU; ++u) {
       float acc1 = dot[u];
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
+      for (int v = 0; v < NB; ++v) {
         const int c = lig + ((j0 + v) << lpr_log2);
         if (j0 + v < tp.nch && c < tp.cpr) {
           if (!BF16) {
@@ -683,50 +698,55 @@ __device__ __forceinline__ void rescore_unit(const SmallTail& tp, const float* q
     if (L2) sc = -sc;
     else if (cosine) sc = sc * inx[u] * qinv;
     sc = (sc != sc) ? __int_as_float(0xff800000) : sc;
-    // score floor exactly as K1 applies it (a row passes when s >= min_score)
-    const uint64_t key = (sc >= tp.min_score) ? pack_key(sc, gid[u]) : 0ull;
-    if (have[u] && lig == 0) cand[base + u * G + g] = key;
+    // L already includes the caller's score floor, applied exactly as K1 does (a row passes when s >= floor)
+    if (have[u] && lig == 0 && sc >= L) {
+      const unsigned int pos = atomicAdd(fin_count, 1u);
+      if (pos < static_cast<unsigned int>(kFinalCap)) fin_keys[pos] = pack_key(sc, gid[u]);
+    }
   }
 }
 
-// Last-CTA fold of all per-CTA lists of one query: the [n_lists][k] keys are read as ONE flat array, 32 keys per
-// warp step and four steps in flight (a single L2 round trip for 148 lists of 10), each chunk sorted in registers
-// and merged into the warp's list, then a tree over the warps.  (Merging list by list -- grid_merge_fast -- paid
-// one dependent round trip per 48 lists: 12 us of a 300 us launch.)
+// Sorted top-k list of n keys in global memory (one query's FINAL list): 32 keys per warp step, four steps in
+// flight, each chunk sorted in registers and merged into the warp's list; a tree over the warps only when more
+// than one warp had work.  All threads of the CTA call it; the result lands in final_list (shared memory).
 template <int S>
-__device__ __forceinline__ void grid_merge_flat(const uint64_t* keys, int n_keys, uint64_t* scratch, uint64_t* final_list,
-                                                int k, int warp, int lane, int nwarps) {
+__device__ __forceinline__ void final_topk(const uint64_t* keys, int n_keys, uint64_t* scratch, uint64_t* final_list,
+                                           int k, int warp, int lane, int nwarps) {
   uint64_t acc[S];
 #pragma unroll
   for (int s = 0; s < S; ++s) acc[s] = 0ull;
   const int nchunks = (n_keys + 31) >> 5;
-  for (int c0 = warp; c0 < nchunks; c0 += 4 * nwarps) {
-    uint64_t v[4];
+  const bool solo = nchunks <= 4;   // CTA-uniform: warp 0 alone, no barrier
+  const int wstride = solo ? 1 : nwarps;
+  if (!solo || warp == 0) {
+    for (int c0 = solo ? 0 : warp; c0 < nchunks; c0 += 4 * wstride) {
+      uint64_t v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int idx = (c0 + j * nwarps) * 32 + lane;
-      v[j] = idx < n_keys ? __ldcg(reinterpret_cast<const unsigned long long*>(keys + idx)) : 0ull;
-    }
+      for (int j = 0; j < 4; ++j) {
+        const int idx = (c0 + j * wstride) * 32 + lane;
+        v[j] = idx < n_keys ? __ldcg(reinterpret_cast<const unsigned long long*>(keys + idx)) : 0ull;
+      }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (c0 + j * nwarps < nchunks) {   // warp-uniform
-        uint64_t b4[S];
+      for (int j = 0; j < 4; ++j) {
+        if (c0 + j * wstride < nchunks) {   // warp-uniform
+          uint64_t b4[S];
 #pragma unroll
-        for (int s = 0; s < S; ++s) b4[s] = 0ull;
-        b4[0] = scan::warp_sort32_desc(v[j], lane);
-        scan::warp_merge<S>(acc, b4, lane);
+          for (int s = 0; s < S; ++s) b4[s] = 0ull;
+          b4[0] = scan::warp_sort32_desc(v[j], lane);
+          scan::warp_merge<S>(acc, b4, lane);
+        }
       }
     }
   }
-  scan::block_tree_merge<S>(acc, scratch, warp, lane, nwarps);
+  if (!solo) scan::block_tree_merge<S>(acc, scratch, warp, lane, nwarps);
   if (warp == 0) scan::store_list<S>(final_list, acc, k, lane);
 }
 
 // Everything after the CTA's last tile (all kThreads threads call it; `ring` = the idle TMA stage ring).
 template <int METRIC, int S>
 __device__ __forceinline__ void small_tail(const FilterParams& p, const SmallTail& tp, unsigned char* ring,
-                                           const unsigned int* wcount, int slice, unsigned long long t_entry,
-                                           unsigned long long t_loop) {
+                                           const unsigned int* wcount, const unsigned int* Lq, int slice,
+                                           unsigned long long t_entry, unsigned long long t_loop) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned long long ts[10];
 #pragma unroll
@@ -737,9 +757,10 @@ __device__ __forceinline__ void small_tail(const FilterParams& p, const SmallTai
   uint64_t* scratch = reinterpret_cast<uint64_t*>(ring);                 // [kTailWarps][32 * S] merge scratch
   uint64_t* final_list = scratch + kTailWarps * 32 * S;                  // [32 * S]
   float* qinv_s = reinterpret_cast<float*>(final_list + 32 * S);         // [SQ] 1/|q| as K1 computes it
-  int* cnt_s = reinterpret_cast<int*>(qinv_s + SQ);                      // [SQ] candidates of this CTA per query
-  int* flag_s = cnt_s + SQ;                                              // [SQ + 2] last-CTA flag | any overflow | per query
-  const size_t q_off = scan::align128(static_cast<size_t>(kTailWarps + 1) * 32 * S * 8 + (3 * SQ + 2) * 4);
+  float* L_s = qinv_s + SQ;                                              // [SQ] lower bound of the exact k-th best score
+  int* cnt_s = reinterpret_cast<int*>(L_s + SQ);                         // [SQ] candidates of this CTA per query
+  int* flag_s = cnt_s + SQ;                                              // [2 SQ + 2] last CTA | any overflow | overflow, count per query
+  const size_t q_off = scan::align128(static_cast<size_t>(kTailWarps + 1) * 32 * S * 8 + (5 * SQ + 2) * 4);
   float* q_s = reinterpret_cast<float*>(ring + q_off);                   // [QG][dpad] fp32 queries, zero padded
   int QG = static_cast<int>((static_cast<size_t>(S_STAGES) * S_STAGE_BYTES - q_off) / (static_cast<size_t>(dpad) * 4));
   QG = QG < B ? QG : B;                                                  // >= 1: the host routes larger rows to K1
@@ -751,7 +772,12 @@ __device__ __forceinline__ void small_tail(const FilterParams& p, const SmallTai
       c = 0;
     }
     cnt_s[tid] = c;
-    if (tid < B) p.cand_count[static_cast<size_t>(tid) * p.s_total + my_slice] = wcount[tid];   // statistics only
+    if (tid < B) {
+      p.cand_count[static_cast<size_t>(tid) * p.s_total + my_slice] = wcount[tid];   // statistics only
+      // the settled shared bound (the k-th largest lower bound any CTA has seen) or the CTA's own / the floor
+      const unsigned int g = __ldcg(p.lower_glob + tid);
+      L_s[tid] = unmono_f32(max(max(g, Lq[tid]), 0x007FFFFFu));
+    }
   }
   __syncthreads();
   const bool cosine = METRIC == kCosine;
@@ -786,30 +812,15 @@ __device__ __forceinline__ void small_tail(const FilterParams& p, const SmallTai
       const int jl = __ffs(__ballot_sync(FULL_MASK, incl > u)) - 1;
       const int c = u - __shfl_sync(FULL_MASK, incl - myu, jl);
       const int j = j0 + jl;
-      unsigned long long* cand = p.cand + (static_cast<size_t>(j) * p.s_total + my_slice) * p.cap;
-      if (tp.bf16) rescore_unit<true, METRIC == kL2>(tp, q_s + jl * dpad, qinv_s[j], cosine, cand, cnt_s[j], c * upc, p.inv_norm, lane);
-      else rescore_unit<false, METRIC == kL2>(tp, q_s + jl * dpad, qinv_s[j], cosine, cand, cnt_s[j], c * upc, p.inv_norm, lane);
+      const unsigned long long* cand = p.cand + (static_cast<size_t>(j) * p.s_total + my_slice) * p.cap;
+      if (tp.bf16) rescore_unit<true, METRIC == kL2>(tp, q_s + jl * dpad, qinv_s[j], cosine, cand, cnt_s[j], c * upc, p.inv_norm,
+                                                     L_s[j], tp.fin_count + j, tp.fin_keys + static_cast<size_t>(j) * kFinalCap, lane);
+      else rescore_unit<false, METRIC == kL2>(tp, q_s + jl * dpad, qinv_s[j], cosine, cand, cnt_s[j], c * upc, p.inv_norm,
+                                              L_s[j], tp.fin_count + j, tp.fin_keys + static_cast<size_t>(j) * kFinalCap, lane);
     }
-    __syncthreads();
+    if (j0 + QG < B) __syncthreads();   // q_s is rewritten by the next group
   }
   stamp(2);
-  // per query: the CTA's exact keys -> one sorted k-list (register bitonic sort + merge), published for the last CTA
-  for (int j = warp; j < B; j += kTailWarps) {
-    const unsigned long long* cand = p.cand + (static_cast<size_t>(j) * p.s_total + my_slice) * p.cap;
-    const int cnt = cnt_s[j];
-    uint64_t acc[S];
-#pragma unroll
-    for (int s = 0; s < S; ++s) acc[s] = 0ull;
-    for (int base = 0; base < cnt; base += 32) {
-      uint64_t b4[S];
-#pragma unroll
-      for (int s = 0; s < S; ++s) b4[s] = 0ull;
-      b4[0] = scan::warp_sort32_desc(base + lane < cnt ? __ldcg(cand + base + lane) : 0ull, lane);
-      scan::warp_merge<S>(acc, b4, lane);
-    }
-    scan::store_list<S>(tp.part + (static_cast<size_t>(j) * p.s_total + my_slice) * k, acc, k, lane);
-  }
-  stamp(3);
   __threadfence();
   __syncthreads();
   stamp(4);
@@ -817,18 +828,25 @@ __device__ __forceinline__ void small_tail(const FilterParams& p, const SmallTai
   __syncthreads();
   stamp(5);
   if (p.trace && tid == 128 && flag_s[0] == 0)
-    printf("TRACE cta %d cand %d entry %llu loop_end %llu tail_in %llu q_ready %llu rescored %llu listed %llu fenced %llu ticket %llu\n",
-           slice, cnt_s[0], t_entry, t_loop - t_entry, ts[0], ts[1], ts[2], ts[3], ts[4], ts[5]);
+    printf("TRACE cta %d cand %d entry %llu loop_end %llu tail_in %llu q_ready %llu rescored %llu fenced %llu ticket %llu\n",
+           slice, cnt_s[0], t_entry, t_loop - t_entry, ts[0], ts[1], ts[2], ts[4], ts[5]);
   if (flag_s[0] == 0) return;
-  // ---- last CTA of the search: fold the s_total lists of every query, exchange across GPUs, emit
+  // ---- last CTA of the search: per query the few exact keys that reached the bound -> top-k, exchange, emit
   __threadfence();
+  if (tid < B) {
+    const int n = static_cast<int>(__ldcg(tp.fin_count + tid));
+    int o = *reinterpret_cast<volatile int*>(tp.overflow + tid);
+    if (n > kFinalCap) {   // only without any bound (fewer than k live rows offered) on a huge candidate set
+      tp.overflow[tid] = 1;
+      o = 1;
+    }
+    flag_s[2 + tid] = o;
+    flag_s[2 + SQ + tid] = n;
+  }
+  __syncthreads();
   if (tid == 0) {
     int any = 0;
-    for (int j = 0; j < B; ++j) {
-      const int o = *reinterpret_cast<volatile int*>(tp.overflow + j);
-      flag_s[2 + j] = o;
-      any |= o;
-    }
+    for (int j = 0; j < B; ++j) any |= flag_s[2 + j];
     flag_s[1] = any;
   }
   __syncthreads();
@@ -837,8 +855,8 @@ __device__ __forceinline__ void small_tail(const FilterParams& p, const SmallTai
   if (xchg && flag_s[1]) return;   // a query overflowed: the flag-gated K1 launch redoes the whole collective search
   for (int j = 0; j < B; ++j) {
     const bool over = flag_s[2 + j] != 0;   // CTA-uniform
-    if (!over) grid_merge_flat<S>(tp.part + static_cast<size_t>(j) * p.s_total * k, p.s_total * k, scratch, final_list, k,
-                                  warp, lane, kTailWarps);
+    if (!over) final_topk<S>(tp.fin_keys + static_cast<size_t>(j) * kFinalCap, flag_s[2 + SQ + j], scratch, final_list, k,
+                             warp, lane, kTailWarps);
     stamp(7);
     if (warp == 0) {
       __syncwarp();
@@ -852,7 +870,7 @@ __device__ __forceinline__ void small_tail(const FilterParams& p, const SmallTai
                         tp.gids_out ? tp.gids_out + static_cast<size_t>(j) * k : nullptr, tp.counts_out ? tp.counts_out + j : nullptr);
       }
     }
-    __syncthreads();
+    if (j + 1 < B) __syncthreads();
   }
   if (xchg && warp == 0) {
     const bool ok = scan::xchg_publish_wait(tp.xchg, lane);
@@ -862,9 +880,9 @@ __device__ __forceinline__ void small_tail(const FilterParams& p, const SmallTai
                             tp.gids_out ? tp.gids_out + static_cast<size_t>(j) * k : nullptr, tp.counts_out ? tp.counts_out + j : nullptr);
   }
   stamp(8);
-  if (p.trace && tid == 128)
-    printf("TRACE LAST cta %d cand %d entry %llu loop_end %llu tail_in %llu q_ready %llu rescored %llu listed %llu fenced %llu ticket %llu flags %llu merged %llu done %llu\n",
-           slice, cnt_s[0], t_entry, t_loop - t_entry, ts[0], ts[1], ts[2], ts[3], ts[4], ts[5], ts[6], ts[7], ts[8]);
+  if (p.trace && tid == 0)
+    printf("TRACE LAST cta %d cand %d entry %llu loop_end %llu tail_in %llu q_ready %llu rescored %llu fenced %llu ticket %llu flags %llu merged %llu done %llu keys %d\n",
+           slice, cnt_s[0], t_entry, t_loop - t_entry, ts[0], ts[1], ts[2], ts[4], ts[5], ts[6], ts[7], ts[8], flag_s[2 + SQ]);
 }
 
 template <int METRIC>
@@ -1117,6 +1135,8 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
       uint32_t r[SQ];
       if (!parked) {
         mbar_wait(smem_u32(tmem_full + a), (static_cast<uint32_t>(it) >> 1) & 1u);
+        if (p.trace && threadIdx.x == 128 && (it == 0 || it == 1 || it == 2 || it == 4 || it == 8 || it == 16 || it == 24))
+          printf("TILE cta %d it %d at %llu tile %d\n", slice, it, gtime_ns() - t_entry, t);
         tc_fence_after();
         __syncwarp();
         tmem_ld16(taddr0 + static_cast<uint32_t>(a * 2 * SQ), r);
@@ -1221,8 +1241,8 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
     tmem_dealloc(tmem_base, S_TMEM_COLS);
   }
   // the TMA ring is idle (every load was consumed by an MMA that an epilogue warp has waited for): reuse it
-  if (k <= 32) small_tail<METRIC, 1>(p, tp, stage_base, wcount, slice, t_entry, t_loop);
-  else small_tail<METRIC, 4>(p, tp, stage_base, wcount, slice, t_entry, t_loop);
+  if (k <= 32) small_tail<METRIC, 1>(p, tp, stage_base, wcount, Lq, slice, t_entry, t_loop);
+  else small_tail<METRIC, 4>(p, tp, stage_base, wcount, Lq, slice, t_entry, t_loop);
 }
 
 constexpr size_t kFilterSmallSmem = 1024 + static_cast<size_t>(S_STAGES) * S_STAGE_BYTES + (8 * SQ + SQ) * 4 +
@@ -1256,7 +1276,7 @@ struct RefineParams {
   int* counts_out;
 };
 
-template <bool BF16, bool L2>
+template <bool BF16, bool L2, int S>
 __global__ void __launch_bounds__(256, 2) refine_topk_kernel(const __grid_constant__ RefineParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
@@ -1264,8 +1284,8 @@ __global__ void __launch_bounds__(256, 2) refine_topk_kernel(const __grid_consta
   const int k = p.k, dpad = p.dpad;
   float* q_s = reinterpret_cast<float*>(smem);                                   // [dpad]
   float* misc = reinterpret_cast<float*>(smem + scan::align128(static_cast<size_t>(dpad) * 4));
-  uint64_t* scratch = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(misc) + 128);  // [nwarps][32]
-  uint64_t* final_list = scratch + static_cast<size_t>(nwarps) * 32;                                // [32]
+  uint64_t* scratch = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(misc) + 128);  // [nwarps][32 * S]
+  uint64_t* final_list = scratch + static_cast<size_t>(nwarps) * 32 * S;                            // [32 * S]
 
   // any (query, slice) region that overflowed => adversarial data: let K1 redo this query exactly
   {
@@ -1294,13 +1314,19 @@ __global__ void __launch_bounds__(256, 2) refine_topk_kernel(const __grid_consta
   const bool cosine = p.metric == kCosine;
   const int lpr_log2 = p.lpr_log2, lpr = 1 << lpr_log2, G = 32 >> lpr_log2;
   const int g = lane >> lpr_log2, lig = lane & (lpr - 1);
-  // k <= 32: a best-first list is one key per lane.  Scored keys are parked one per lane (`batch`); a
+  // k <= 32 * S: a best-first list is S keys per lane.  Scored keys are parked one per lane (`batch`); a
   // full batch is sorted (bitonic network over the lanes) and merged into `acc` in registers.
-  uint64_t acc = 0ull, batch = 0ull;
+  uint64_t acc[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) acc[s] = 0ull;
+  uint64_t batch = 0ull;
   int nb = 0;
   auto flush = [&]() {
-    batch = scan::warp_sort32_desc(batch, lane);
-    acc = scan::warp_merge32(acc, batch, lane);
+    uint64_t b4[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) b4[s] = 0ull;
+    b4[0] = scan::warp_sort32_desc(batch, lane);
+    scan::warp_merge<S>(acc, b4, lane);
     batch = 0ull;
     nb = 0;
   };
@@ -1412,11 +1438,10 @@ __global__ void __launch_bounds__(256, 2) refine_topk_kernel(const __grid_consta
   if (nb > 0) flush();
   // CTA list: binary tree over the warps (registers + shared memory), then -- several CTAs per query --
   // partial list -> global and the last CTA of this query (atomic ticket) folds all of them the same way
-  uint64_t mine[1] = {acc};
-  scan::block_tree_merge<1>(mine, scratch, warp, lane, nwarps);
+  scan::block_tree_merge<S>(acc, scratch, warp, lane, nwarps);
   if (gridDim.y > 1) {
     if (warp == 0) {
-      scan::store_list<1>(p.part + (static_cast<size_t>(q) * gridDim.y + blockIdx.y) * k, mine, k, lane);
+      scan::store_list<S>(p.part + (static_cast<size_t>(q) * gridDim.y + blockIdx.y) * k, acc, k, lane);
       __threadfence();
       __syncwarp();
       if (lane == 0) misc[1] = __uint_as_float(atomicAdd(p.tickets + q, 1u));
@@ -1424,10 +1449,10 @@ __global__ void __launch_bounds__(256, 2) refine_topk_kernel(const __grid_consta
     __syncthreads();
     if (__float_as_uint(misc[1]) != gridDim.y - 1) return;
     __threadfence();
-    scan::grid_merge_fast<1>(p.part + static_cast<size_t>(q) * gridDim.y * k, static_cast<int>(gridDim.y), scratch,
+    scan::grid_merge_fast<S>(p.part + static_cast<size_t>(q) * gridDim.y * k, static_cast<int>(gridDim.y), scratch,
                              final_list, k, warp, lane, nwarps);
   } else if (warp == 0) {
-    scan::store_list<1>(final_list, mine, k, lane);
+    scan::store_list<S>(final_list, acc, k, lane);
   }
   if (warp == 0) {
     __syncwarp();
@@ -1492,6 +1517,8 @@ bool small_batch_mode(int B) {
 int filter_regions_per_slice(int B) { return small_batch_mode(B) ? kSmallWarpRegions : 2; }
 
 int filter_max_k() { return kMaxKFilter; }
+
+int filter_final_cap() { return kFinalCap; }
 
 int filter_ld16(int dim) { return (dim + 7) / 8 * 8; }
 
@@ -1648,7 +1675,8 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, cons
     tp.bf16 = tail->elem_bytes == 2 ? 1 : 0;
     tp.min_score = tail->min_score;
     tp.overflow = tail->overflow;
-    tp.part = tail->part;
+    tp.fin_keys = tail->fin_keys;
+    tp.fin_count = tail->fin_count;
     tp.ticket = tail->ticket;
     tp.xchg = tail->xchg;
     tp.keys_out = tail->keys_out;
@@ -1717,15 +1745,22 @@ cudaError_t launch_refine_topk(const SegDesc* segs, int n_seg, const float* q, i
   p.gids_out = gids_out;
   p.counts_out = counts_out;
   const int warps = warps_per_cta_refine();
+  const int S = k <= 32 ? 1 : 4;
   const size_t smem = ((static_cast<size_t>(dpad) * 4 + 127) & ~static_cast<size_t>(127)) + 128 +
-                      (static_cast<size_t>(warps) * 32 + 32) * 8;
+                      (static_cast<size_t>(warps) * 32 + 32) * S * 8;
   const bool bf16 = elem_bytes == 2, l2 = metric == kL2;
   auto go = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     kern<<<dim3(B, ctas_per_query > 1 ? ctas_per_query : 1, 1), warps * 32, smem, stream>>>(p);
   };
-  if (bf16) { if (l2) go(refine_topk_kernel<true, true>); else go(refine_topk_kernel<true, false>); }
-  else { if (l2) go(refine_topk_kernel<false, true>); else go(refine_topk_kernel<false, false>); }
+#define WDBX_REFINE(SS)                                                                                   \
+  do {                                                                                                    \
+    if (bf16) { if (l2) go(refine_topk_kernel<true, true, SS>); else go(refine_topk_kernel<true, false, SS>); }   \
+    else { if (l2) go(refine_topk_kernel<false, true, SS>); else go(refine_topk_kernel<false, false, SS>); }      \
+  } while (0)
+  if (S == 1) WDBX_REFINE(1);
+  else WDBX_REFINE(4);
+#undef WDBX_REFINE
   return cudaGetLastError();
 }
 

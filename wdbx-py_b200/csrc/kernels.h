@@ -106,6 +106,7 @@ cudaError_t launch_gemm_topk(const SegDesc& seg, int dim, int dpad, const float*
 
 // K2b: bf16 tensor-core filter + exact fp32 refine (results bit-identical to K1).  See gemm_filter.cu.
 int filter_max_k();
+int filter_final_cap();
 int filter_ld16(int dim);
 size_t filter_query_workspace_bytes(int B, int dim);
 int filter_slices_for(long long n_rows, int B, int sm_count);
@@ -124,7 +125,8 @@ struct FilterTail {
   int lpr_log2, nch;         // K1's lane mapping (scan_plan): the re-scored keys are bit-identical to K1's
   float min_score;           // score floor (-inf = none)
   int* overflow;             // [B] set when a candidate region overflowed (the flag-gated K1 launch re-runs the query)
-  uint64_t* part;            // [B][s_total][k] per-CTA partial lists
+  uint64_t* fin_keys;        // [B][filter_final_cap()] exact keys that reached the query's bound (final lists)
+  unsigned int* fin_count;   // [B] zero at launch
   unsigned int* ticket;      // zero at launch; the CTA that draws s_total - 1 finishes the search
   unsigned int* tile_ctr;    // [kMaxSeg] zero at launch: dynamic tile counter of every segment's launch
   XchgCtx xchg;

@@ -58,8 +58,14 @@ SIGNATURES = {
     "wdbx_b200_search_exchange": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "wdbx_b200_set_tuning": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "wdbx_b200_set_kernel_timing": (C.c_int, [_P, C.c_int]),
+    "wdbx_b200_set_option": (C.c_int, [_P, C.c_char_p, C.c_longlong]),
     "wdbx_b200_search_exchange_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "wdbx_b200_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "wdbx_b200_search_exchange_filtered_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P]),
+    "wdbx_b200_group_create": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
+    "wdbx_b200_group_destroy": (None, [_P]),
+    "wdbx_b200_group_search_host": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, _P]),
+    "wdbx_b200_group_search": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

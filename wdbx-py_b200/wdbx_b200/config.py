@@ -14,6 +14,7 @@ from typing import Any, Dict, Optional
 DEFAULTS: Dict[str, Any] = {
     "VECTOR_STORE_SAVE_IMMEDIATELY": False,
     "GPU_DEVICE": None,         # default: LOCAL_RANK or 0
+    "GPU_DEVICES": None,        # single process, several GPUs: "all", "0-7", "0,1,2,3" or a list (multi_engine.py)
     "GPU_DTYPE": "fp32",        # fp32 | bf16 (storage)
     "GPU_METRIC": "cosine",     # cosine | ip | l2
     "GPU_CAPACITY_ROWS": 0,     # rows to reserve per shard up front

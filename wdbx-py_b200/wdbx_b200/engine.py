@@ -195,10 +195,12 @@ class Engine:
                                                        _np_ptr(scores), _np_ptr(gids), None, _np_ptr(counts)))
         return scores, gids, counts
 
-    def search_filtered_host(self, queries, k: int, metric="cosine", min_score: float = float("-inf"), allow=None):
+    def search_filtered_host(self, queries, k: int, metric="cosine", min_score: float = float("-inf"), allow=None,
+                             exchange: bool = False):
         """Opt-in pre-filtered search: ``allow`` is a list (one entry per segment) of uint32 bitmaps over the
         segment's rows (bit 1 = row may be returned; None = all rows), ``min_score`` a score floor.
-        Returns (scores, gids, counts) of the exact top-k among the allowed rows, merged over segments."""
+        Returns (scores, gids, counts) of the exact top-k among the allowed rows, merged over segments.
+        ``exchange``: COLLECTIVE form (every rank passes the bitmaps of its own rows; on-device NVLink merge)."""
         q = np.ascontiguousarray(queries, dtype=np.float32)
         if q.ndim == 1:
             q = q[None, :]
@@ -222,9 +224,9 @@ class Engine:
                     keep.append(b)
                     arr[s] = b.ctypes.data
             ptrs = C.cast(arr, C.c_void_p)
-        check(self._lib.wdbx_b200_search_filtered_host(self._handle(), _np_ptr(q), B, k, _metric_code(metric),
-                                                       C.c_float(min_score), ptrs, _np_ptr(scores), _np_ptr(gids),
-                                                       _np_ptr(counts)))
+        fn = self._lib.wdbx_b200_search_exchange_filtered_host if exchange else self._lib.wdbx_b200_search_filtered_host
+        check(fn(self._handle(), _np_ptr(q), B, k, _metric_code(metric), C.c_float(min_score), ptrs, _np_ptr(scores),
+                 _np_ptr(gids), _np_ptr(counts)))
         return scores, gids, counts
 
     def search(self, q_dev, k: int, metric="cosine", segment: int = ALL_SEGMENTS, out: Optional[Dict] = None,
@@ -304,6 +306,11 @@ class Engine:
     # ------------------------------------------------------------------ misc
     def set_tuning(self, warps: int = 0, stages: int = 0, rows_unroll: int = 0, grid: int = 0, evict_first: int = -1):
         check(self._lib.wdbx_b200_set_tuning(self._handle(), warps, stages, rows_unroll, grid, evict_first))
+
+    def set_option(self, name: str, value: int):
+        """Routing knob of a live engine ("shadow_min_mb", "gemm_min_batch", "gemm_mode", "pdl", "queries_per_pass");
+        results are identical for every setting.  Benchmark hook."""
+        check(self._lib.wdbx_b200_set_option(self._handle(), name.encode(), int(value)))
 
     def set_kernel_timing(self, enable: bool = True):
         """Bracket the dominant kernel of every search with CUDA events; `stats()` then carries

@@ -163,12 +163,21 @@ class VectorStore:
             max_workers=int(self.config.get("VECTOR_STORE_THREADS", min(8, os.cpu_count() or 4))))
 
         self._create_dirs()
-        if _engine_factory is not None:
-            self.engine = _engine_factory(self.dist.device, self.vector_dim, self.dtype, self.num_shards)
+        # GPU_DEVICES: one ordinary process drives several GPUs (multi_engine.py); under torchrun every rank has one
+        from .multi_engine import MultiEngine, parse_devices
+
+        devices = parse_devices(self.config.get("GPU_DEVICES", None)) if self.dist.world == 1 else None
+        self.devices = devices if devices and len(devices) > 1 else [self.dist.device if not devices else devices[0]]
+        if len(self.devices) > 1:
+            self.engine = MultiEngine(self.devices, self.vector_dim, self.dtype, self.num_shards,
+                                      _engine_factory=_engine_factory,
+                                      _group_factory=getattr(_engine_factory, "group_factory", None))
+        elif _engine_factory is not None:
+            self.engine = _engine_factory(self.devices[0], self.vector_dim, self.dtype, self.num_shards)
         else:
             from .engine import Engine  # raises ImportError / B200Error loudly when the GPU path is unusable
 
-            self.engine = Engine(self.dist.device, self.vector_dim, self.dtype, self.num_shards)
+            self.engine = Engine(self.devices[0], self.vector_dim, self.dtype, self.num_shards)
         cap = int(self.config.get("GPU_CAPACITY_ROWS", 0) or 0)
         if cap > 0:
             for s in range(self.num_shards):
@@ -193,7 +202,7 @@ class VectorStore:
         self._init_indices()
         self._load_data()
         logger.info("VectorStore initialized: %d shards on %d GPU(s), dim=%d, metric=%s, dtype=%s",
-                    self.num_shards, self.dist.world, self.vector_dim, self.metric, self.dtype)
+                    self.num_shards, max(self.dist.world, len(self.devices)), self.vector_dim, self.metric, self.dtype)
 
     # ------------------------------------------------------------------ setup
     def _create_dirs(self):
@@ -763,7 +772,7 @@ class VectorStore:
                filter_metadata: Optional[Dict[str, Any]] = None) -> List[Tuple[str, float, Dict[str, Any]]]:
         """Reference: vector_store.py:301-353 (same result list, same filter / threshold order)."""
         query_np = self._query_array(query_vector)
-        if filter_metadata and self.prefilter and self.dist.world == 1:
+        if filter_metadata and self.prefilter and (self.dist.world == 1 or self._fused):
             # opt-in (GPU_PREFILTER): exact top-`limit` AMONG the matching rows + threshold push-down
             lists = self._guard([], self._search_prefiltered, query_np, limit, threshold, filter_metadata)
             return [(vid, score, self.metadata.get(vid, {})) for vid, score in (lists[0] if lists else [])]
@@ -794,6 +803,8 @@ class VectorStore:
         maps = []
         for s in range(self.num_shards):
             order = np.concatenate(self._row_gids[s]) if self._row_gids[s] else np.empty(0, np.uint32)
+            if self.dist.world > 1:
+                order = order[self.dist.rank::self.dist.world]   # this rank's stripe, in local row order
             ok = np.fromiter((self._matches_filter(self._id_of(int(g)), filter_metadata) for g in order),
                              dtype=bool, count=order.shape[0])
             pad = (-ok.shape[0]) % 32
@@ -813,7 +824,12 @@ class VectorStore:
         with self._lock:
             maps = self._allow_bitmaps(filter_metadata)
         floor = float(threshold) if threshold > 0 else float("-inf")
-        scores, gids, counts = self.engine.search_filtered_host(q[None, :], k, self.metric, floor, maps)
+        if self.dist.world == 1:
+            scores, gids, counts = self.engine.search_filtered_host(q[None, :], k, self.metric, floor, maps)
+        else:   # SPMD: every rank passes the bitmaps of ITS rows; the ranks merge on the device (NVLink exchange)
+            scores, gids, counts = self.engine.search_filtered_host(q[None, :], k, self.metric, floor, maps, exchange=True)
+            if (counts < 0).any():
+                raise RuntimeError("fused exchange timed out: a peer rank did not join the collective search")
         c = int(counts[0])
         return [[(self._id_of(int(g)), float(s)) for g, s in zip(gids[0, :c], scores[0, :c])]]
 
@@ -904,7 +920,8 @@ class VectorStore:
             "gpu": {
                 "world_size": self.dist.world,
                 "rank": self.dist.rank,
-                "device": self.dist.device,
+                "device": self.devices[0],
+                "devices": list(self.devices),
                 "metric": self.metric,
                 "dtype": self.dtype,
                 "engine": est,
