@@ -37,14 +37,17 @@ for line in txt.splitlines():
         d = dict(zip(re.findall(r"([a-z_]+) \d+", line), map(int, re.findall(r"[a-z_]+ (\d+)", line))))
         d["last"] = "LAST" in line
         rows.append(d)
-tiles = {}
+per_cta = {}
 for line in txt.splitlines():
-    if line.startswith("TILE"):
-        _, _, c, _, it, _, at, _, tl = line.split()
-        tiles.setdefault(int(it), []).append(int(at))
-for it in sorted(tiles):
-    v = sorted(tiles[it])
-    print(f"accumulator of the CTA's tile #{it:2d} ready: min {v[0]/1e3:7.1f}  median {v[len(v)//2]/1e3:7.1f}  max {v[-1]/1e3:7.1f} us after the CTA's entry")
+    if line.startswith("TILES"):
+        parts = line.split()
+        cta, i0 = int(parts[2]), int(parts[4])
+        per_cta.setdefault(cta, {}).update({i0 + j: int(v) for j, v in enumerate(parts[6:14])})
+if per_cta:
+    print("time at which the accumulator of the CTA's n-th tile was ready (us after the CTA's entry), and the step between tiles:")
+    for cta in sorted(per_cta)[:4]:
+        ts = [per_cta[cta][i] for i in sorted(per_cta[cta]) if per_cta[cta][i] > 0]
+        print(f"  cta {cta:3d}: first {ts[0]/1e3:.1f}  " + " ".join(f"{(b - a)/1e3:.1f}" for a, b in zip(ts, ts[1:])))
 if not rows:
     print(txt[-2000:])
     sys.exit(1)

@@ -7,6 +7,24 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include <cstdio>
+
+// -DWDBX_DEBUG_BOUNDS (python __graft_entry__.py debug -> libwdbx_b200_dbg.so): device-side asserts on every
+// candidate / list / ring / TMEM / tile index the kernels compute.  compute-sanitizer is not available on the
+// GPU pool, so the ragged-shape parity suites are run once per round against this build (profiles/).
+#ifdef WDBX_DEBUG_BOUNDS
+#define WDBX_ASSERT(cond)                                                                                   \
+  do {                                                                                                      \
+    if (!(cond)) {                                                                                          \
+      printf("WDBX_ASSERT failed: %s  at %s:%d  block (%d,%d) thread %d\n", #cond, __FILE__, __LINE__,      \
+             static_cast<int>(blockIdx.x), static_cast<int>(blockIdx.y), static_cast<int>(threadIdx.x));    \
+      __trap();                                                                                             \
+    }                                                                                                       \
+  } while (0)
+#else
+#define WDBX_ASSERT(cond) do { } while (0)
+#endif
+
 namespace wdbx {
 
 constexpr unsigned FULL_MASK = 0xFFFFFFFFu;

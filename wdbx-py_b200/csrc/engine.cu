@@ -4,6 +4,8 @@
 // host path, and the launch plumbing for kernels K1/K3/K4.
 #include "../../include/wdbx_b200.h"
 
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -46,7 +48,149 @@ int fail(int code, const char* fmt, ...) {
     }                                                                                                  \
   } while (0)
 
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+// ---- growable device arrays ----------------------------------------------------------------------------
+// A segment's arrays grow IN PLACE: a virtual address range is reserved once (CUDA virtual memory management,
+// cuMemAddressReserve) and physical memory is mapped behind it as rows arrive (cuMemCreate + cuMemMap).  The base
+// pointer never changes, so growth needs no copy, no transient second buffer and no synchronisation with searches
+// in flight (they only read rows that existed when they were launched) -- the reference's analogue is
+// IndexFlatIP.add appending in place (wdbx/core/indexing.py:890).  The earlier realloc-and-copy growth held up to
+// 2.5x the store for a moment and threw the bf16 shadow away.  If the driver entry points are unavailable the
+// buffer falls back to realloc + copy.
+struct VmmApi {
+  PFN_cuMemAddressReserve_v10020 reserve = nullptr;
+  PFN_cuMemAddressFree_v10020 afree = nullptr;
+  PFN_cuMemCreate_v10020 create = nullptr;
+  PFN_cuMemRelease_v10020 release = nullptr;
+  PFN_cuMemMap_v10020 map = nullptr;
+  PFN_cuMemUnmap_v10020 unmap = nullptr;
+  PFN_cuMemSetAccess_v10020 set_access = nullptr;
+  PFN_cuMemGetAllocationGranularity_v10020 granularity = nullptr;
+  bool ok = false;
+};
+
+const VmmApi& vmm() {
+  static VmmApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    if (env_int("WDBX_B200_VMM", 1) == 0) return;
+    auto get = [](const char* name, void** fn) {
+      cudaDriverEntryPointQueryResult q;
+      return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess &&
+             *fn != nullptr;
+    };
+    api.ok = get("cuMemAddressReserve", reinterpret_cast<void**>(&api.reserve)) &&
+             get("cuMemAddressFree", reinterpret_cast<void**>(&api.afree)) &&
+             get("cuMemCreate", reinterpret_cast<void**>(&api.create)) &&
+             get("cuMemRelease", reinterpret_cast<void**>(&api.release)) &&
+             get("cuMemMap", reinterpret_cast<void**>(&api.map)) && get("cuMemUnmap", reinterpret_cast<void**>(&api.unmap)) &&
+             get("cuMemSetAccess", reinterpret_cast<void**>(&api.set_access)) &&
+             get("cuMemGetAllocationGranularity", reinterpret_cast<void**>(&api.granularity));
+    cudaGetLastError();
+  });
+  return api;
+}
+
+struct GrowBuf {
+  unsigned char* ptr = nullptr;   // base (stable once reserved)
+  size_t bytes = 0;               // usable bytes (mapped, or allocated in fallback mode)
+  // virtual-memory mode
+  CUdeviceptr va = 0;
+  size_t va_bytes = 0, gran = 0;
+  std::vector<CUmemGenericAllocationHandle> handles;
+  std::vector<size_t> sizes;
+  bool vm = false;
+};
+
+void growbuf_free(GrowBuf& b) {
+  if (b.vm) {
+    const VmmApi& v = vmm();
+    size_t off = 0;
+    for (size_t i = 0; i < b.handles.size(); ++i) {
+      v.unmap(b.va + off, b.sizes[i]);
+      v.release(b.handles[i]);
+      off += b.sizes[i];
+    }
+    if (b.va) v.afree(b.va, b.va_bytes);
+  } else {
+    cudaFree(b.ptr);
+  }
+  b = GrowBuf();
+}
+
+// Make at least `need` bytes usable, preserving the first `keep` bytes.  `max_bytes`: upper bound the array can ever
+// reach (sizes the address reservation).  Returns cudaSuccess / cudaErrorMemoryAllocation / another error; on
+// failure the buffer is unchanged.  *moved is set when the base pointer changed (fallback mode only: the caller
+// must then wait for in-flight readers before freeing the old copy -- done here with a device synchronise).
+cudaError_t growbuf_grow(GrowBuf& b, int device, size_t need, size_t keep, size_t max_bytes, cudaStream_t stream) {
+  if (need <= b.bytes) return cudaSuccess;
+  const VmmApi& v = vmm();
+  if (v.ok && (b.vm || b.ptr == nullptr)) {
+    CUmemAllocationProp prop;
+    memset(&prop, 0, sizeof(prop));
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    if (b.va == 0) {
+      size_t gran = 0;
+      if (v.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0) gran = 2u << 20;
+      const size_t want = (std::max(max_bytes, need) + gran - 1) / gran * gran;
+      CUdeviceptr va = 0;
+      if (v.reserve(&va, want, 0, 0, 0) == CUDA_SUCCESS) {
+        b.va = va;
+        b.va_bytes = want;
+        b.gran = gran;
+        b.vm = true;
+        b.ptr = reinterpret_cast<unsigned char*>(va);
+      }
+    }
+    if (b.vm) {
+      if (need > b.va_bytes) return cudaErrorMemoryAllocation;   // beyond the reservation (cannot happen: max_bytes)
+      const size_t add = (need - b.bytes + b.gran - 1) / b.gran * b.gran;
+      CUmemGenericAllocationHandle h;
+      if (v.create(&h, add, &prop, 0) != CUDA_SUCCESS) return cudaErrorMemoryAllocation;
+      if (v.map(b.va + b.bytes, add, 0, h, 0) != CUDA_SUCCESS) {
+        v.release(h);
+        return cudaErrorMemoryAllocation;
+      }
+      CUmemAccessDesc acc;
+      memset(&acc, 0, sizeof(acc));
+      acc.location = prop.location;
+      acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+      if (v.set_access(b.va + b.bytes, add, &acc, 1) != CUDA_SUCCESS) {
+        v.unmap(b.va + b.bytes, add);
+        v.release(h);
+        return cudaErrorUnknown;
+      }
+      b.handles.push_back(h);
+      b.sizes.push_back(add);
+      b.bytes += add;
+      return cudaSuccess;
+    }
+  }
+  // fallback: realloc + copy; readers of the old buffer (any stream) must finish before it is freed
+  unsigned char* n = nullptr;
+  cudaError_t err = cudaMalloc(&n, need);
+  if (err != cudaSuccess) { cudaGetLastError(); return err; }
+  if (keep > 0 && b.ptr) {
+    err = cudaMemcpyAsync(n, b.ptr, keep, cudaMemcpyDeviceToDevice, stream);
+    if (err != cudaSuccess) { cudaFree(n); return err; }
+  }
+  err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) { cudaFree(n); return err; }
+  cudaFree(b.ptr);
+  b.ptr = n;
+  b.bytes = need;
+  return cudaSuccess;
+}
+
 struct Segment {
+  GrowBuf b_rows, b_inv, b_sq, b_gids, b_tomb, b_shadow, b_rres;   // backing stores of the pointers below
   unsigned char* rows = nullptr;
   float* inv_norm = nullptr;
   float* sqnorm = nullptr;
@@ -78,12 +222,13 @@ struct Workspace {
   size_t fzero_n = 0;
   uint64_t* fpart = nullptr;  // refine partial lists [ctas_per_query][B][k]
   size_t fpart_n = 0;
+  // large-k select path: every row's key [chunk][rows] | selected keys [chunk][1024] | select state
+  uint64_t* sel_all = nullptr;
+  size_t sel_all_n = 0;
+  uint64_t* sel_keys = nullptr;
+  unsigned int* sel_ws = nullptr;
+  int sel_chunk = 0;
 };
-
-int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return (v && *v) ? atoi(v) : dflt;
-}
 
 }  // namespace
 
@@ -101,6 +246,9 @@ struct wdbx_b200_engine {
   int gemm_mode = 0;        // 0 = bf16 filter + exact refine (K2b), 1 = 3xTF32 with fused top-k (K2)
   int pdl = 1;              // programmatic dependent launch between the launches of a search (WDBX_B200_PDL=0 disables)
   bool shadow_warned = false;
+  std::vector<void*> retired;   // workspaces outgrown during a stream capture (freed with the engine)
+  bool shadow_failed = false;   // the bf16 shadow could not be allocated: fp32 stores are served by K1 only
+  size_t total_mem = 0;         // device memory (sizes the address reservations of the growable arrays)
   cudaStream_t mstream = nullptr;  // mutations
   // staging for host-sourced appends
   float* stage_rows = nullptr;
@@ -176,6 +324,24 @@ namespace {
 
 void group_worker(wdbx_b200_group* g, int i);
 
+// While the caller's stream is being captured into a CUDA graph, host-side calls such as cudaMalloc (workspace
+// growth) or a kernel's first-use set-up are legal only in the thread's RELAXED capture mode: switch for the
+// duration of one search call, restore afterwards.
+struct CaptureRelax {
+  bool active = false;
+  cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+  explicit CaptureRelax(cudaStream_t stream) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)
+      active = cudaThreadExchangeStreamCaptureMode(&mode) == cudaSuccess;
+    else
+      cudaGetLastError();
+  }
+  ~CaptureRelax() {
+    if (active) cudaThreadExchangeStreamCaptureMode(&mode);
+  }
+};
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = false;
@@ -194,65 +360,97 @@ int64_t round_cap(int64_t rows) { return (rows + 127) / 128 * 128; }
 
 void free_segment(Segment& s) {
   cudaFree(s.allow);
-  cudaFree(s.shadow);
-  cudaFree(s.rres);
-  cudaFree(s.rows);
-  cudaFree(s.inv_norm);
-  cudaFree(s.sqnorm);
-  cudaFree(s.gids);
-  cudaFree(s.tomb);
+  growbuf_free(s.b_shadow);
+  growbuf_free(s.b_rres);
+  growbuf_free(s.b_rows);
+  growbuf_free(s.b_inv);
+  growbuf_free(s.b_sq);
+  growbuf_free(s.b_gids);
+  growbuf_free(s.b_tomb);
   s = Segment();
 }
 
-// grow segment to hold at least `rows` rows.  Caller holds e->mu.
+// rows the segment could ever hold on this device (sizes the address reservations)
+int64_t segment_max_rows(const wdbx_b200_engine* e) {
+  const size_t per_row = static_cast<size_t>(e->dpad) * e->elem_bytes;
+  int64_t by_mem = static_cast<int64_t>(e->total_mem / (per_row ? per_row : 1)) + 1024;
+  return std::min<int64_t>(by_mem, 0xFFFFFFF0ll);
+}
+
+bool shadow_wanted(const wdbx_b200_engine* e) {
+  return e->dtype == WDBX_B200_F32 && e->gemm_mode != 1 && e->gemm_min_batch > 0 && !e->shadow_failed;
+}
+
+void refresh_pointers(Segment& s) {
+  s.rows = s.b_rows.ptr;
+  s.inv_norm = reinterpret_cast<float*>(s.b_inv.ptr);
+  s.sqnorm = reinterpret_cast<float*>(s.b_sq.ptr);
+  s.gids = reinterpret_cast<uint32_t*>(s.b_gids.ptr);
+  s.tomb = reinterpret_cast<uint32_t*>(s.b_tomb.ptr);
+  s.shadow = s.b_shadow.ptr;
+  s.rres = reinterpret_cast<float*>(s.b_rres.ptr);
+}
+
+// bf16 shadow + per-row residual bound for `cap` rows (fp32 stores: the operand of the tensor-core filter).
+// Failure is not an error: the engine then serves every search from the stored rows and says so once.
+void grow_shadow(wdbx_b200_engine* e, Segment& s, int64_t cap) {
+  const int ld16 = filter_ld16(e->dim);
+  const int64_t maxr = segment_max_rows(e);
+  const cudaError_t e1 = growbuf_grow(s.b_shadow, e->device, static_cast<size_t>(cap) * ld16 * 2,
+                                      static_cast<size_t>(s.shadow_rows) * ld16 * 2, static_cast<size_t>(maxr) * ld16 * 2, e->mstream);
+  const cudaError_t e2 = e1 == cudaSuccess ? growbuf_grow(s.b_rres, e->device, static_cast<size_t>(cap) * 4,
+                                                          static_cast<size_t>(s.shadow_rows) * 4, static_cast<size_t>(maxr) * 4,
+                                                          e->mstream)
+                                           : e1;
+  refresh_pointers(s);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    cudaGetLastError();
+    e->shadow_failed = true;
+    if (!e->shadow_warned) {
+      e->shadow_warned = true;
+      fprintf(stderr, "[wdbx_b200] device %d: no memory for the bf16 shadow of the stored rows; every search is served by "
+                      "the fp32 scan (about half the queries/s on large stores)\n", e->device);
+    }
+    return;
+  }
+  s.shadow_cap = std::min<int64_t>(static_cast<int64_t>(s.b_shadow.bytes / (static_cast<size_t>(ld16) * 2)),
+                                   static_cast<int64_t>(s.b_rres.bytes / 4));
+}
+
+// Grow the segment IN PLACE to hold at least `rows` rows (see GrowBuf).  Caller holds e->mu, device is set.
 int ensure_capacity(wdbx_b200_engine* e, Segment& s, int64_t rows) {
   if (rows <= s.cap_rows) return WDBX_B200_OK;
   int64_t cap = std::max<int64_t>(round_cap(rows), 1024);
-  if (s.cap_rows > 0) cap = std::max<int64_t>(cap, round_cap(s.cap_rows + s.cap_rows / 2));
+  // mapping more memory is cheap but not free: grow by at least 1/8 of the current size
+  if (s.cap_rows > 0) cap = std::max<int64_t>(cap, round_cap(s.cap_rows + s.cap_rows / 8));
+  const int64_t maxr = segment_max_rows(e);
+  cap = std::max<int64_t>(round_cap(rows), std::min<int64_t>(cap, maxr));   // over-allocation never exceeds the device
   const size_t rb = row_bytes(e);
-  unsigned char* nrows = nullptr;
-  float *ninv = nullptr, *nsq = nullptr;
-  uint32_t *ngid = nullptr, *ntomb = nullptr;
-  auto cleanup = [&] {
-    cudaFree(nrows); cudaFree(ninv); cudaFree(nsq); cudaFree(ngid); cudaFree(ntomb);
-  };
-  cudaError_t err;
-  if ((err = cudaMalloc(&nrows, static_cast<size_t>(cap) * rb)) != cudaSuccess ||
-      (err = cudaMalloc(&ninv, static_cast<size_t>(cap) * 4)) != cudaSuccess ||
-      (err = cudaMalloc(&nsq, static_cast<size_t>(cap) * 4)) != cudaSuccess ||
-      (err = cudaMalloc(&ngid, static_cast<size_t>(cap) * 4)) != cudaSuccess) {
-    cleanup();
-    cudaGetLastError();
-    return fail(WDBX_B200_ERR_OOM, "cudaMalloc for %lld rows of %zu bytes failed: %s", (long long)cap, rb,
-                cudaGetErrorString(err));
+  const size_t n = static_cast<size_t>(s.n_rows), c = static_cast<size_t>(cap), m = static_cast<size_t>(std::max(maxr, cap));
+  struct Part { GrowBuf* b; size_t per; } parts[4] = {{&s.b_rows, rb}, {&s.b_inv, 4}, {&s.b_sq, 4}, {&s.b_gids, 4}};
+  for (const Part& p : parts) {
+    const cudaError_t err = growbuf_grow(*p.b, e->device, c * p.per, n * p.per, m * p.per, e->mstream);
+    refresh_pointers(s);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      return fail(err == cudaErrorMemoryAllocation ? WDBX_B200_ERR_OOM : WDBX_B200_ERR_CUDA,
+                  "cannot grow segment to %lld rows of %zu bytes: %s", (long long)cap, rb, cudaGetErrorString(err));
+    }
   }
   if (s.tomb) {
-    if ((err = cudaMalloc(&ntomb, static_cast<size_t>(cap / 32) * 4)) != cudaSuccess) {
-      cleanup();
+    const size_t old_words = s.tomb_host.size(), words = c / 32;
+    const cudaError_t err = growbuf_grow(s.b_tomb, e->device, words * 4, old_words * 4, (m / 32 + 1) * 4, e->mstream);
+    refresh_pointers(s);
+    if (err != cudaSuccess) {
       cudaGetLastError();
-      return fail(WDBX_B200_ERR_OOM, "cudaMalloc tombstones failed: %s", cudaGetErrorString(err));
+      return fail(WDBX_B200_ERR_OOM, "cannot grow the tombstone bitmap: %s", cudaGetErrorString(err));
     }
-    s.tomb_host.resize(static_cast<size_t>(cap / 32), 0u);
+    s.tomb_host.resize(words, 0u);
+    if (words > old_words)
+      CU_TRY(cudaMemsetAsync(s.tomb + old_words, 0, (words - old_words) * 4, e->mstream));
   }
-  if (s.n_rows > 0) {
-    CU_TRY(cudaMemcpyAsync(nrows, s.rows, static_cast<size_t>(s.n_rows) * rb, cudaMemcpyDeviceToDevice, e->mstream));
-    CU_TRY(cudaMemcpyAsync(ninv, s.inv_norm, static_cast<size_t>(s.n_rows) * 4, cudaMemcpyDeviceToDevice, e->mstream));
-    CU_TRY(cudaMemcpyAsync(nsq, s.sqnorm, static_cast<size_t>(s.n_rows) * 4, cudaMemcpyDeviceToDevice, e->mstream));
-    CU_TRY(cudaMemcpyAsync(ngid, s.gids, static_cast<size_t>(s.n_rows) * 4, cudaMemcpyDeviceToDevice, e->mstream));
-  }
-  if (ntomb) {
-    CU_TRY(cudaMemcpyAsync(ntomb, s.tomb_host.data(), s.tomb_host.size() * 4, cudaMemcpyHostToDevice, e->mstream));
-  }
-  // in-flight searches (any stream) may still read the old buffers
-  CU_TRY(cudaDeviceSynchronize());
-  cudaFree(s.rows); cudaFree(s.inv_norm); cudaFree(s.sqnorm); cudaFree(s.gids); cudaFree(s.tomb);
-  cudaFree(s.shadow);  // rebuilt lazily by the next batched search
-  cudaFree(s.rres);
-  s.shadow = nullptr;
-  s.rres = nullptr;
-  s.shadow_rows = s.shadow_cap = 0;
-  s.rows = nrows; s.inv_norm = ninv; s.sqnorm = nsq; s.gids = ngid; s.tomb = ntomb;
   s.cap_rows = cap;
+  if (shadow_wanted(e)) grow_shadow(e, s, cap);
   return WDBX_B200_OK;
 }
 
@@ -268,11 +466,17 @@ int get_workspace(wdbx_b200_engine* e, cudaStream_t stream, size_t cand_keys, in
     w->stream = stream;
   }
   if (w->cand_keys < cand_keys || w->n_counters < n_counters || w->qsplit_floats < qsplit_floats) {
+    // Growing while `stream` is being captured into a CUDA graph is fine: nothing is enqueued here, the old buffers
+    // (earlier captured nodes may reference them) are retired instead of freed, and the stream is not synchronised.
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(stream, &cs);
-    if (cs != cudaStreamCaptureStatusNone)
-      return fail(WDBX_B200_ERR_ARG, "workspace must grow during stream capture: run one warm-up search of this shape first");
-    CU_TRY(cudaStreamSynchronize(stream));
+    const bool capturing = cs != cudaStreamCaptureStatusNone;
+    if (!capturing) CU_TRY(cudaStreamSynchronize(stream));
+    auto cudaFree = [&](void* ptr) {   // shadows ::cudaFree inside this block
+      if (ptr == nullptr) return;
+      if (capturing) e->retired.push_back(ptr);
+      else ::cudaFree(ptr);
+    };
     if (w->cand_keys < cand_keys) {
       cudaFree(w->cand);
       w->cand = nullptr;
@@ -305,9 +509,11 @@ int get_workspace(wdbx_b200_engine* e, cudaStream_t stream, size_t cand_keys, in
 int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B, int k, int metric,
                   uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream,
                   unsigned int xseq = 0u, const int* only_flag = nullptr, float min_score = -INFINITY,
-                  bool use_allow = false) {
+                  bool use_allow = false, uint64_t* all_keys = nullptr) {
   // xseq != 0: collective search, the last CTA exchanges its lists with the peer ranks under this sequence number
   const bool exchange = xseq != 0u;
+  // all_keys != NULL: large-k mode, the kernel writes every row's ranking key instead of keeping lists (plan as for k = 1)
+  if (all_keys != nullptr) k = 1;
   ScanPlan plan;
   const int rc = scan_plan(e->dim, e->dpad, e->elem_bytes, k, B, e->sm_count, e->tune, &plan);
   if (rc == -4) return fail(WDBX_B200_ERR_LIMIT, "dimension %d too large for the scan kernel's shared-memory stage", e->dim);
@@ -325,6 +531,7 @@ int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B
     p.seg[n].tomb = sg.n_dead > 0 ? sg.tomb : nullptr;
     p.seg[n].allow = use_allow ? sg.allow : nullptr;
     p.seg[n].n_rows = sg.n_rows;
+    p.seg_row_base[n] = n == 0 ? 0 : p.seg_row_base[n - 1] + e->seg[s - 1].n_rows;
     tiles += (sg.n_rows + plan.tile_rows - 1) / plan.tile_rows;
     bytes += sg.n_rows * static_cast<long long>(row_bytes(e));
     p.tile_end[n] = tiles;
@@ -362,6 +569,8 @@ int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B
   p.counts_out = counts_out;
   p.only_flag = only_flag;
   p.min_score = min_score;
+  p.all_keys = all_keys;
+  p.all_rows = n > 0 ? p.seg_row_base[n - 1] + e->seg[s1 - 1].n_rows : 0;
   if (exchange) {
     if (e->xworld < 2) return fail(WDBX_B200_ERR_ARG, "exchange not attached (call wdbx_b200_exchange_init/attach first)");
     if (B > plan.queries_per_block || B > kXchgMaxB || k > kXchgMaxK)
@@ -450,20 +659,17 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
     Segment& sg = e->seg[s];
     if (!f32 || sg.n_rows == 0) continue;
     if (!sg.shadow || sg.shadow_cap < sg.n_rows) {
+      // normally built by append (eager); here only when the shadow was switched on after the rows arrived
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(stream, &cs);
+      if (cs != cudaStreamCaptureStatusNone)
+        return fail(WDBX_B200_ERR_ARG, "the bf16 shadow must be built during stream capture: run one warm-up search first");
       CU_TRY(cudaStreamSynchronize(stream));
-      cudaFree(sg.shadow);
-      cudaFree(sg.rres);
-      sg.shadow = nullptr;
-      sg.rres = nullptr;
-      sg.shadow_rows = sg.shadow_cap = 0;
-      if (cudaMalloc(&sg.shadow, static_cast<size_t>(sg.cap_rows) * ld16 * 2) != cudaSuccess ||
-          cudaMalloc(&sg.rres, static_cast<size_t>(sg.cap_rows) * 4) != cudaSuccess) {
-        cudaGetLastError();
-        cudaFree(sg.shadow);
-        sg.shadow = nullptr;
+      e->shadow_failed = false;
+      grow_shadow(e, sg, sg.cap_rows);
+      if (e->shadow_failed || sg.shadow_cap < sg.n_rows)
         return fail(WDBX_B200_ERR_OOM, "no device memory for the bf16 shadow of segment %d", s);
-      }
-      sg.shadow_cap = sg.cap_rows;
+      CU_TRY(cudaStreamSynchronize(e->mstream));
     }
     if (sg.shadow_rows < sg.n_rows) {
       CU_TRY(launch_shadow_rows(reinterpret_cast<const float*>(sg.rows + static_cast<size_t>(sg.shadow_rows) * row_bytes(e)),
@@ -509,11 +715,17 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   const size_t off_fin = off_ctr + static_cast<size_t>(kMaxSeg);   // [B] final-list counts (fused small-batch kernel)
   const size_t need_zero = off_fin + static_cast<size_t>(B);
   if (w->fpart_n < need_part || w->fws_bytes < need_ws || w->fcand_n < n_regions * cap || w->fzero_n < need_zero) {
+    // Growing while `stream` is being captured into a CUDA graph is fine: nothing is enqueued here, the old buffers
+    // (earlier captured nodes may reference them) are retired instead of freed, and the stream is not synchronised.
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(stream, &cs);
-    if (cs != cudaStreamCaptureStatusNone)
-      return fail(WDBX_B200_ERR_ARG, "workspace must grow during stream capture: run one warm-up search of this shape first");
-    CU_TRY(cudaStreamSynchronize(stream));
+    const bool capturing = cs != cudaStreamCaptureStatusNone;
+    if (!capturing) CU_TRY(cudaStreamSynchronize(stream));
+    auto cudaFree = [&](void* ptr) {   // shadows ::cudaFree inside this block
+      if (ptr == nullptr) return;
+      if (capturing) e->retired.push_back(ptr);
+      else ::cudaFree(ptr);
+    };
     if (w->fws_bytes < need_ws) {
       cudaFree(w->fws); w->fws = nullptr; w->fws_bytes = 0;
       CU_TRY(cudaMalloc(&w->fws, need_ws));
@@ -619,6 +831,83 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   return rrc;
 }
 
+// Large k (128 < k <= 1024): the scan writes every row's ranking key, a radix select picks the k best
+// (select_topk.cu).  Queries go through in chunks of up to 8 (one streamed pass of the rows each).
+// Caller holds e->mu, device is set.
+constexpr int kSelectMinK = 128;
+
+int select_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B, int k, int metric, uint64_t* keys_out,
+                    float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream, float min_score = -INFINITY,
+                    bool use_allow = false) {
+  long long rows = 0;
+  for (int s = s0; s < s1; ++s) rows += e->seg[s].n_rows;
+  if (rows == 0)
+    return scan_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream, 0u, nullptr,
+                         min_score, use_allow);
+  ScanPlan plan;
+  if (scan_plan(e->dim, e->dpad, e->elem_bytes, 1, B, e->sm_count, e->tune, &plan) != 0)
+    return fail(WDBX_B200_ERR_ARG, "invalid scan shape (dim=%d)", e->dim);
+  // keys of one chunk of queries: at most 2 GiB of workspace
+  int chunk = std::min(B, plan.queries_per_block);
+  while (chunk > 1 && static_cast<size_t>(chunk) * rows * 8 > (2ull << 30)) chunk >>= 1;
+  Workspace* w = nullptr;
+  int rc = get_workspace(e, stream, 0, 0, &w);
+  if (rc != WDBX_B200_OK) return rc;
+  const size_t need_all = static_cast<size_t>(chunk) * rows;
+  if (w->sel_all_n < need_all || w->sel_chunk < chunk) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cs);
+    const bool capturing = cs != cudaStreamCaptureStatusNone;
+    if (!capturing) CU_TRY(cudaStreamSynchronize(stream));
+    auto drop = [&](void* ptr) {
+      if (ptr == nullptr) return;
+      if (capturing) e->retired.push_back(ptr);
+      else cudaFree(ptr);
+    };
+    if (w->sel_all_n < need_all) {
+      drop(w->sel_all); w->sel_all = nullptr; w->sel_all_n = 0;
+      CU_TRY(cudaMalloc(&w->sel_all, need_all * 8));
+      w->sel_all_n = need_all;
+    }
+    if (w->sel_chunk < chunk) {
+      drop(w->sel_keys); drop(w->sel_ws);
+      w->sel_keys = nullptr; w->sel_ws = nullptr; w->sel_chunk = 0;
+      CU_TRY(cudaMalloc(&w->sel_keys, static_cast<size_t>(chunk) * 1024 * 8));
+      CU_TRY(cudaMalloc(&w->sel_ws, select_workspace_words(chunk) * 4));
+      w->sel_chunk = chunk;
+    }
+  }
+  ScanTuning saved = e->tune;
+  if (chunk < plan.queries_per_block) e->tune.queries_per_pass = chunk;   // one block of `chunk` queries per launch
+  for (int b0 = 0; b0 < B && rc == WDBX_B200_OK; b0 += chunk) {
+    const int nb = std::min(chunk, B - b0);
+    const size_t o = static_cast<size_t>(b0) * k;
+    rc = scan_segments(e, s0, s1, q_dev + static_cast<size_t>(b0) * e->dim, nb, k, metric, nullptr, nullptr, nullptr, nullptr,
+                       stream, 0u, nullptr, min_score, use_allow, w->sel_all);
+    if (rc != WDBX_B200_OK) break;
+    const cudaError_t ce = launch_select_topk(w->sel_all, rows, nb, k, w->sel_ws, w->sel_keys, e->sm_count,
+                                              keys_out ? keys_out + o : nullptr, scores_out ? scores_out + o : nullptr,
+                                              gids_out ? gids_out + o : nullptr, counts_out ? counts_out + b0 : nullptr, stream);
+    if (ce != cudaSuccess) {
+      cudaGetLastError();
+      rc = fail(WDBX_B200_ERR_CUDA, "select launch: %s", cudaGetErrorString(ce));
+    }
+    e->launches.fetch_add(11, std::memory_order_relaxed);
+  }
+  e->tune = saved;
+  return rc;
+}
+
+// the exact streaming path for any k: running lists (k <= 128) or key dump + radix select (larger k)
+int scan_any_k(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B, int k, int metric, uint64_t* keys_out,
+               float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream, float min_score = -INFINITY,
+               bool use_allow = false) {
+  if (k > kSelectMinK)
+    return select_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream, min_score, use_allow);
+  return scan_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream, 0u, nullptr, min_score,
+                       use_allow);
+}
+
 // Regime choice.  Tensor path (K2b filter + exact refine) for batches of gemm_min_batch queries or more;
 // for SMALLER batches on fp32 storage too once the segments are large (shadow_min_bytes): the filter
 // streams the 2-byte shadow rows instead of the 4-byte stored rows, i.e. half the HBM bytes per query, and
@@ -627,6 +916,9 @@ bool use_gemm(const wdbx_b200_engine* e, int s0, int s1, int B, int k) {
   if (e->gemm_min_batch <= 0) return false;
   if (e->gemm_mode == 1) return B >= e->gemm_min_batch && e->dtype == WDBX_B200_F32 && k <= gemm_max_k();
   if (k > filter_max_k()) return false;
+  // 32 < k <= 128: only the small-batch kernel, whose bound server inserts into the wide shared list cooperatively
+  if (k > 32 && !filter_fused_tail(B)) return false;
+  if (e->dtype == WDBX_B200_F32 && e->shadow_failed) return false;   // no room for the bf16 shadow (said so once)
   if (static_cast<size_t>(e->dpad) * 4 > 160 * 1024) return false;   // the fused tail stages fp32 queries in shared memory
   if (B >= e->gemm_min_batch) return true;
   if (e->dtype != WDBX_B200_F32 || e->shadow_min_bytes < 0) return false;
@@ -651,7 +943,7 @@ int search_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
                       "(about half the queries/s)\n", e->device);
     }
   }
-  return scan_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream);
+  return scan_any_k(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream);
 }
 
 int check_search_args(wdbx_b200_engine* e, int B, int k, int metric) {
@@ -824,8 +1116,7 @@ int launch_host_lists(wdbx_b200_engine* e, int segment, bool exchange, const flo
         }
       }
       if (rc == WDBX_B200_ERR_OOM)
-        rc = scan_segments(e, s0, s1, q_dev, B, k, metric, keys + o, scores + o, gids + o, cnt, st, 0u, nullptr, min_score,
-                           use_allow);
+        rc = scan_any_k(e, s0, s1, q_dev, B, k, metric, keys + o, scores + o, gids + o, cnt, st, min_score, use_allow);
     } else {
       rc = search_segments(e, s0, s1, q_dev, B, k, metric, keys + o, scores + o, gids + o, cnt, st);
     }
@@ -919,6 +1210,7 @@ int wdbx_b200_create(int device, int dim, int dtype, int num_segments, wdbx_b200
   e->dpad = (dim + epc - 1) / epc * epc;
   e->nseg = num_segments;
   e->sm_count = prop.multiProcessorCount;
+  e->total_mem = prop.totalGlobalMem;
   e->tune.warps = env_int("WDBX_B200_WARPS", 0);
   e->tune.stages = env_int("WDBX_B200_STAGES", 0);
   e->tune.rows_unroll = env_int("WDBX_B200_UNROLL", 0);
@@ -962,7 +1254,11 @@ void wdbx_b200_destroy(wdbx_b200_engine* e) {
     cudaFree(w.fcand);
     cudaFree(w.fzero);
     cudaFree(w.fpart);
+    cudaFree(w.sel_all);
+    cudaFree(w.sel_keys);
+    cudaFree(w.sel_ws);
   }
+  for (void* ptr : e->retired) cudaFree(ptr);
   for (int r = 0; r < kMaxPeers; ++r)
     if (e->xopened[r]) cudaIpcCloseMemHandle(e->xpeer[r]);
   cudaFree(e->xbuf);
@@ -1053,6 +1349,15 @@ int wdbx_b200_append(wdbx_b200_engine* e, int segment, const float* rows, int64_
     CU_TRY(launch_append_rows(src, m, e->dim, e->dpad, bf16, s.rows + static_cast<size_t>(r0) * rb, s.inv_norm + r0,
                               s.sqnorm + r0, s.gids + r0, gsrc, e->next_gid + static_cast<uint32_t>(done), e->mstream));
     e->launches.fetch_add(1, std::memory_order_relaxed);
+    if (s.shadow && s.shadow_rows == r0 && s.shadow_cap >= r0 + m) {
+      // eager bf16 shadow (fp32 stores): built right behind the rows, so no search ever allocates or builds it
+      const int ld16 = filter_ld16(e->dim);
+      CU_TRY(launch_shadow_rows(reinterpret_cast<const float*>(s.rows + static_cast<size_t>(r0) * rb), m, e->dpad, ld16,
+                                static_cast<unsigned char*>(s.shadow) + static_cast<size_t>(r0) * ld16 * 2, s.rres + r0,
+                                e->mstream));
+      e->launches.fetch_add(1, std::memory_order_relaxed);
+      s.shadow_rows = r0 + m;
+    }
     // the staging buffers are reused by the next chunk
     CU_TRY(cudaStreamSynchronize(e->mstream));
   }
@@ -1113,7 +1418,13 @@ int wdbx_b200_tombstone(wdbx_b200_engine* e, int segment, int64_t row, int dead)
   if (!s.tomb) {
     if (!dead) return WDBX_B200_OK;
     const size_t words = static_cast<size_t>(s.cap_rows / 32);
-    CU_TRY(cudaMalloc(&s.tomb, words * 4));
+    const size_t max_words = static_cast<size_t>(std::max<int64_t>(segment_max_rows(e), s.cap_rows) / 32 + 1);
+    const cudaError_t ge = growbuf_grow(s.b_tomb, e->device, words * 4, 0, max_words * 4, e->mstream);
+    refresh_pointers(s);
+    if (ge != cudaSuccess) {
+      cudaGetLastError();
+      return fail(WDBX_B200_ERR_OOM, "cannot allocate the tombstone bitmap: %s", cudaGetErrorString(ge));
+    }
     CU_TRY(cudaMemsetAsync(s.tomb, 0, words * 4, e->mstream));
     s.tomb_host.assign(words, 0u);
   }
@@ -1191,6 +1502,7 @@ int wdbx_b200_search(wdbx_b200_engine* e, int segment, const float* q_dev, int B
   if (segment != WDBX_B200_ALL_SEGMENTS && (segment < 0 || segment >= e->nseg))
     return fail(WDBX_B200_ERR_ARG, "segment %d outside [0, %d)", segment, e->nseg);
   DeviceGuard guard(e->device);
+  CaptureRelax relax(static_cast<cudaStream_t>(cuda_stream));
   std::lock_guard<std::mutex> lk(e->mu);
   const int s0 = segment == WDBX_B200_ALL_SEGMENTS ? 0 : segment;
   const int s1 = segment == WDBX_B200_ALL_SEGMENTS ? e->nseg : segment + 1;
@@ -1276,6 +1588,7 @@ int wdbx_b200_search_exchange(wdbx_b200_engine* e, const float* q_dev, int B, in
   if (rc != WDBX_B200_OK) return rc;
   if (!q_dev) return fail(WDBX_B200_ERR_ARG, "q_dev is NULL");
   DeviceGuard guard(e->device);
+  CaptureRelax relax(static_cast<cudaStream_t>(cuda_stream));
   std::lock_guard<std::mutex> lk(e->mu);
   rc = exchange_search_locked(e, 0, e->nseg, q_dev, B, k, metric, keys_out, scores_out,
                               reinterpret_cast<long long*>(gids_out), counts_out, static_cast<cudaStream_t>(cuda_stream));
@@ -1360,8 +1673,8 @@ int wdbx_b200_get_stats(wdbx_b200_engine* e, wdbx_b200_stats* out) {
     out->rows_total += sg.n_rows;
     out->rows_live += sg.n_rows - sg.n_dead;
     out->capacity_rows += sg.cap_rows;
-    out->bytes_resident += sg.cap_rows * per_row + (sg.tomb ? sg.cap_rows / 8 : 0) +
-                           (sg.shadow ? sg.shadow_cap * (static_cast<int64_t>(filter_ld16(e->dim)) * 2 + 4) : 0);
+    out->bytes_resident += static_cast<int64_t>(sg.b_rows.bytes + sg.b_inv.bytes + sg.b_sq.bytes + sg.b_gids.bytes +
+                                                sg.b_tomb.bytes + sg.b_shadow.bytes + sg.b_rres.bytes);
     out->seg_rows[s] = sg.n_rows;
     out->seg_live[s] = sg.n_rows - sg.n_dead;
   }

@@ -33,6 +33,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 
 #include "scan_topk_kernel.cuh"
 #include "tc05.cuh"
@@ -258,6 +259,84 @@ __device__ __forceinline__ float lower_insert(unsigned int* slots, unsigned int*
   }
   const float g = unmono_f32(max(result, 0x007FFFFFu));
   return g > L ? g : L;
+}
+
+// Cooperative form for the small-batch kernel's BOUND SERVER (warp 3): up to 8 offers (lower bounds of 8 distinct
+// rows, one per lane 0..7 of a lane GROUP, 0 = none) enter one query's shared list in one go.  A group is GL
+// lanes: 8 for k <= 32 (4 slots per lane; four queries are served side by side by one warp), 32 for k <= 128.
+// One L2 round trip snapshots all slots, the i-th largest offer is paired with the i-th smallest slot and
+// compare-and-swapped in parallel; offers that lost a race retry against a fresh snapshot.  Ties between equal
+// slots (the empty list at the first tile!) are broken by a per-CTA rotation `rot`, so that the 148 servers do not
+// all aim at the same slots.  Returns the minimum of the (stale) snapshot with this group's successful writes
+// applied -- a valid lower bound of the exact k-th best score once every slot is filled (0 otherwise) -- and
+// publishes it through `glob`.  `slots` / `glob` / `k_valid` are per group (k_valid = 0: the group idles); offers
+// still unplaced after `max_rounds` stay in `o` (the bound server retries them on its next sweep).
+template <int GL>
+__device__ __forceinline__ unsigned int list_multi_insert(unsigned int* slots, unsigned int* glob, int k_valid, unsigned int& o,
+                                                          int lane, unsigned int rot, int max_rounds) {
+  const int gl = lane & (GL - 1);                       // lane inside the group
+  const unsigned gmask = GL == 32 ? FULL_MASK : (0xFFu << (lane & ~7));
+  const int gbase = lane & ~(GL - 1);
+  const int k = k_valid;
+  unsigned int result = 0u;
+  for (int round = 0; round < max_rounds; ++round) {
+    const unsigned offering = __ballot_sync(FULL_MASK, gl < 8 && o != 0u && k > 0);
+    if (offering == 0u) break;                           // warp-uniform: every group is done
+    const int n_off = __popc(offering & gmask);
+    uint4 v4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    if (4 * gl < k && n_off > 0) v4 = __ldcg(reinterpret_cast<const uint4*>(slots + 4 * gl));
+    unsigned int v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+      if (4 * gl + jj >= k) v[jj] = 0xFFFFFFFFu;
+    // rank of this lane's offer among the group's offers, largest first (ties by lane)
+    int rank = 0;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      const unsigned int ol = __shfl_sync(FULL_MASK, o, gbase + l);
+      if (ol > o || (ol == o && l < gl)) ++rank;
+    }
+    // the smallest slots, smallest first; the lane whose offer has rank r takes the r-th
+    unsigned int w[4] = {v[0], v[1], v[2], v[3]};
+    unsigned int tv = 0xFFFFFFFFu;
+    int ti = -1;
+    for (int r = 0; r < 8; ++r) {                        // (groups with fewer offers just compute a few unused targets)
+      const unsigned int lm = min(min(w[0], w[1]), min(w[2], w[3]));
+      const unsigned int gm = __reduce_min_sync(gmask, lm);
+      // owner among the lanes that hold the minimum: first one at or after the rotation point
+      const unsigned eq = (__ballot_sync(FULL_MASK, lm == gm) & gmask) >> gbase;          // GL-bit field
+      const unsigned r0 = rot & (GL - 1);
+      const unsigned hi = eq >> r0;
+      const int owner = hi ? static_cast<int>(r0) + __ffs(hi) - 1 : __ffs(eq) - 1;
+      int idx = -1;
+      if (gl == owner) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          if (idx < 0 && w[jj] == gm) { idx = 4 * gl + jj; w[jj] = 0xFFFFFFFFu; }
+      }
+      idx = __shfl_sync(FULL_MASK, idx, gbase + owner);
+      if (gl < 8 && o != 0u && rank == r) { tv = gm; ti = idx; }
+    }
+    bool placed = false;
+    if (gl < 8 && o != 0u && k > 0) {
+      if (ti < 0 || tv == 0xFFFFFFFFu || o <= tv) o = 0u;            // not among the k best bounds of list + offers
+      else placed = atomicCAS(slots + ti, tv, o) == tv;               // lost a race: retry on the next snapshot
+    }
+    // apply this group's successful writes to the snapshot
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      const bool pl = __shfl_sync(FULL_MASK, placed ? 1 : 0, gbase + l) != 0;
+      const int pi = __shfl_sync(FULL_MASK, ti, gbase + l);
+      const unsigned int pv = __shfl_sync(FULL_MASK, o, gbase + l);
+      if (pl && (pi >> 2) == gl) v[pi & 3] = pv;
+    }
+    if (placed) o = 0u;
+    const unsigned int lm = min(min(v[0], v[1]), min(v[2], v[3]));
+    const unsigned int gm = __reduce_min_sync(gmask, lm);
+    if (k > 0 && gm > 0x007FFFFFu && gm != 0xFFFFFFFFu && gm > result) result = gm;
+  }
+  if (result > 0x007FFFFFu && gl == 0) atomicMax(glob, result);
+  return result;
 }
 
 // NCTA = 1: one CTA per 128-query block.  NCTA = 2: a CTA PAIR (cluster of two SMs of one TPC, cta_group::2)
@@ -531,6 +610,8 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 bool dead = false;
                 if (p.tomb != nullptr) dead = (__ldg(p.tomb + (row >> 5)) >> (row & 31)) & 1u;
                 if (!dead) {
+                  WDBX_ASSERT(row >= 0 && row < p.n_rows && region < static_cast<size_t>(p.B) * p.s_total);
+                  WDBX_ASSERT(static_cast<uint32_t>(a * BN + c0 + 32) <= TMEM_COLS);
                   if (n_cand < static_cast<unsigned int>(p.cap))
                     my_cand[n_cand] = (static_cast<unsigned long long>(p.seg) << 32) | static_cast<unsigned long long>(row);
                   ++n_cand;
@@ -617,7 +698,8 @@ constexpr int kFinalCap = 2048;   // exact keys per query that may reach the las
 template <bool BF16, bool L2>
 __device__ __forceinline__ void rescore_unit(const SmallTail& tp, const float* q_s, float qinv, bool cosine,
                                              const unsigned long long* cand, int cnt, int base, const float* inv_norm,
-                                             float L, unsigned int* fin_count, uint64_t* fin_keys, int lane) {
+                                             long long n_rows, float L, unsigned int* fin_count, uint64_t* fin_keys, int lane) {
+  (void)n_rows;
   constexpr int CU = 2, NB = 8;
   const int lpr_log2 = tp.lpr_log2, lpr = 1 << lpr_log2, G = 32 >> lpr_log2;
   const int g = lane >> lpr_log2, lig = lane & (lpr - 1);
@@ -629,6 +711,7 @@ __device__ __forceinline__ void rescore_unit(const SmallTail& tp, const float* q
     const int ci = base + u * G + g;
     have[u] = ci < cnt;
     row[u] = have[u] ? static_cast<long long>(__ldcg(cand + ci) & 0xFFFFFFFFull) : 0ll;
+    WDBX_ASSERT(row[u] >= 0 && row[u] < n_rows);
     rp[u] = tp.rows + static_cast<size_t>(row[u]) * tp.row_bytes;
   }
   float inx[CU];
@@ -814,9 +897,9 @@ __device__ __forceinline__ void small_tail(const FilterParams& p, const SmallTai
       const int j = j0 + jl;
       const unsigned long long* cand = p.cand + (static_cast<size_t>(j) * p.s_total + my_slice) * p.cap;
       if (tp.bf16) rescore_unit<true, METRIC == kL2>(tp, q_s + jl * dpad, qinv_s[j], cosine, cand, cnt_s[j], c * upc, p.inv_norm,
-                                                     L_s[j], tp.fin_count + j, tp.fin_keys + static_cast<size_t>(j) * kFinalCap, lane);
+                                                     p.n_rows, L_s[j], tp.fin_count + j, tp.fin_keys + static_cast<size_t>(j) * kFinalCap, lane);
       else rescore_unit<false, METRIC == kL2>(tp, q_s + jl * dpad, qinv_s[j], cosine, cand, cnt_s[j], c * upc, p.inv_norm,
-                                              L_s[j], tp.fin_count + j, tp.fin_keys + static_cast<size_t>(j) * kFinalCap, lane);
+                                              p.n_rows, L_s[j], tp.fin_count + j, tp.fin_keys + static_cast<size_t>(j) * kFinalCap, lane);
     }
     if (j0 + QG < B) __syncthreads();   // q_s is rewritten by the next group
   }
@@ -910,6 +993,9 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
   uint64_t* sched_empty = sched_full + 4;    // [4]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sched_empty + 4);
   int* tile_ring = reinterpret_cast<int*>(tmem_ptr + 4);   // [4] tile index per ring slot, -1 = no more tiles
+  unsigned int* tile_ts = reinterpret_cast<unsigned int*>(tile_ring + 4);   // [48] trace: ns at which tile #it was ready
+  unsigned int* offer = tile_ts + 48;        // [8][SQ] mailbox: best lower bound each epilogue warp has seen per query
+  unsigned int* epi_done = offer + 8 * SQ;   // epilogue warps that have finished their tiles
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.y;
@@ -968,6 +1054,8 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
       Tq[j] = t0;
     }
     for (int i = lane; i < SQ; i += 32) wcount[i] = 0u;
+    for (int i = lane; i < 48; i += 32) tile_ts[i] = 0u;
+    for (int i = lane; i < 8 * SQ + 1; i += 32) offer[i] = 0u;   // (+ epi_done)
   }
   tc_fence_before();
   __syncthreads();
@@ -986,6 +1074,20 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(sched_empty + slot));
     return t;
+  };
+
+  const float c_l2 = p.c_l2;
+  auto fast_thr = [&](float l, int j) -> float {
+    if (METRIC == kCosine) {
+      const float t = (l - q_C_s[j]) * q_nrm_s[j];
+      return t - 1e-6f * (fabsf(t) + q_nrm_s[j]);
+    }
+    if (METRIC == kL2) return (l + q_sq_s[j] * (1.0f - c_l2)) - 1e-6f * (fabsf(l) + 2.0f * q_sq_s[j]);
+    return l - 1e-6f * fabsf(l);
+  };
+  auto raise_bound = [&](int j, float nl) {   // any thread: publish a better bound of query j to the CTA
+    const unsigned int m = mono_u32(nl);
+    if (atomicMax(Lq + j, m) < m) Tq[j] = fast_thr(nl, j);
   };
 
   if (warp == 0) {
@@ -1013,6 +1115,7 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
     publish(0, t_cur);
     for (int sq = 0; t_cur >= 0; ++sq) {
       const int raw_nxt = draw();
+      WDBX_ASSERT(t_cur >= 0 && t_cur < p.n_tiles && stage >= 0 && stage < S_STAGES);
       const int row0 = t_cur * BN;
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
         mbar_wait(smem_u32(empty_bar + stage), phase ^ 1u);
@@ -1062,6 +1165,53 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
       if (elect_one()) umma_commit(smem_u32(tmem_full + a));
       __syncwarp();
     }
+  } else if (warp == 3) {
+    // ===== BOUND SERVER.  The epilogue warps never touch the shared lower-bound list in global memory themselves
+    // (1184 warps compare-and-swapping one cache line at the first tile stalled every epilogue -- and with it the
+    // accumulators, the MMAs and the TMA ring -- for ~35 us of a 300 us launch): they drop their best lower bound per
+    // query into a shared-memory mailbox and move on; this otherwise idle warp carries the offers into the list
+    // (list_multi_insert: all of a query's offers in one or two L2 round trips), picks up the bounds other CTAs
+    // have published, and raises the CTA's thresholds.
+    const unsigned int rot = static_cast<unsigned int>(blockIdx.y) * 5u + 1u;   // spreads the CTAs over equal slots
+    // one sweep = ONE insert round for every query (four queries side by side while k <= 32), results published after
+    // every round: a first -- weak -- bound reaches the epilogue after a few microseconds and tightens from there
+    auto serve = [&](auto gl_tag) {
+      constexpr int GL = decltype(gl_tag)::value;
+      constexpr int QPR = 32 / GL;              // queries per round
+      constexpr int NS = SQ / QPR;              // rounds per sweep at most
+      unsigned int pend[NS];                    // this lane's pending offer per round slot
+#pragma unroll
+      for (int sidx = 0; sidx < NS; ++sidx) pend[sidx] = 0u;
+      for (;;) {
+        if (*reinterpret_cast<volatile unsigned int*>(epi_done) >= 8u) break;   // late offers would only polish the bound
+        bool work = false;
+#pragma unroll
+        for (int sidx = 0; sidx < NS; ++sidx) {
+          if (sidx * QPR < p.B) {               // warp-uniform
+            const int grp = lane / GL, gl = lane & (GL - 1);
+            const int j = sidx * QPR + grp;
+            const bool qv = j < p.B;
+            if (qv && gl < 8) pend[sidx] = max(pend[sidx], atomicExch(offer + gl * SQ + j, 0u));
+            const unsigned int cur = qv ? *reinterpret_cast<volatile unsigned int*>(Lq + j) : 0u;
+            if (pend[sidx] <= cur) pend[sidx] = 0u;   // cannot beat the list's minimum any more
+            if (__any_sync(FULL_MASK, pend[sidx] != 0u)) {
+              work = true;
+              const unsigned int nl = list_multi_insert<GL>(p.lower_list + static_cast<size_t>(qv ? j : 0) * kMaxKFilter,
+                                                            p.lower_glob + (qv ? j : 0), qv ? k : 0, pend[sidx], lane, rot, 1);
+              if (qv && gl == 0 && nl > cur) raise_bound(j, unmono_f32(nl));
+            }
+          }
+        }
+        if (lane < p.B) {
+          const unsigned int g = __ldcg(p.lower_glob + lane);
+          if (g > *reinterpret_cast<volatile unsigned int*>(Lq + lane)) raise_bound(lane, unmono_f32(g));
+        }
+        __syncwarp();
+        if (!work) __nanosleep(300);
+      }
+    };
+    if (k <= 32) serve(std::integral_constant<int, 8>{});
+    else serve(std::integral_constant<int, 32>{});
   } else if (warp >= 4) {
     // ===== epilogue: 8 warps, one X row of the tile per thread (TMEM lane = row inside the 128-row sub-tile)
     const int ew = warp - 4;
@@ -1071,23 +1221,10 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
     // fast test per (row, query), see gemm_filter_kernel (same inequalities, thresholds with 1e-6 slack); admitted
     // pairs are decided by the reference form (bound_eval) below.  L / T live in shared memory per query and are
     // shared by the whole CTA.
-    const float c_l2 = p.c_l2;
     auto qbound = [&](int j) -> QueryBound {
       QueryBound b;
       b.A = q_A_s[j]; b.C = q_C_s[j]; b.qinv = q_inv_s[j]; b.qnrm = q_nrm_s[j]; b.qsq = q_sq_s[j];
       return b;
-    };
-    auto fast_thr = [&](float l, int j) -> float {
-      if (METRIC == kCosine) {
-        const float t = (l - q_C_s[j]) * q_nrm_s[j];
-        return t - 1e-6f * (fabsf(t) + q_nrm_s[j]);
-      }
-      if (METRIC == kL2) return (l + q_sq_s[j] * (1.0f - c_l2)) - 1e-6f * (fabsf(l) + 2.0f * q_sq_s[j]);
-      return l - 1e-6f * fabsf(l);
-    };
-    auto raise_bound = [&](int j, float nl) {   // any thread: publish a better bound of query j to the CTA
-      const unsigned int m = mono_u32(nl);
-      if (atomicMax(Lq + j, m) < m) Tq[j] = fast_thr(nl, j);
     };
     auto load_row = [&](int t, float& inx, float& sq, float& rr) {
       const long long row = static_cast<long long>(t) * BN + row_in_tile;
@@ -1104,7 +1241,6 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
     const int t_first = t_nxt;   // the CTA's first tile is parked (decided last)
     float inx_next, sq_next, rr_next;
     load_row(t_nxt, inx_next, sq_next, rr_next);
-    unsigned int glob_next = 0u;
     uint32_t r0[SQ];   // the parked accumulators of this thread's row of the first tile
 #pragma unroll
     for (int j = 0; j < SQ; ++j) r0[j] = 0u;
@@ -1113,6 +1249,8 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
       const bool parked = t_nxt < 0;
       const int t = parked ? t_first : t_nxt;
       const int a = it & 1;
+      WDBX_ASSERT(t >= 0 && t < p.n_tiles);
+      WDBX_ASSERT(static_cast<uint32_t>(a * 2 * SQ + sub * SQ + SQ) <= S_TMEM_COLS);
       const long long row = static_cast<long long>(t) * BN + row_in_tile;
       const bool row_valid = row < p.n_rows;
       const float inx = inx_next, sq = sq_next, rr = rr_next;
@@ -1121,12 +1259,14 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
       const float fe = (METRIC == kL2) ? 2.0f * xn : xn;
       const float fr = (METRIC == kCosine) ? rr * inx : ((METRIC == kL2) ? 2.0f * rr : rr);
       const float sqs = sq * ((1.0f - c_l2) * (1.0f - 1e-6f));
-      if (ew == 0 && lane < p.B) {
-        // bounds published by other CTAs: prefetched one tile ahead, except right after the parked tile, whose
-        // offers (every CTA's, all at the same moment) are exactly what tile 1 needs to see
-        const unsigned int gl = (it <= 1) ? __ldcg(p.lower_glob + lane) : glob_next;
-        if (gl > 0x007FFFFFu) raise_bound(lane, unmono_f32(gl));
-        glob_next = __ldcg(p.lower_glob + lane);
+      if (it == 1) {
+        // the offers of the parked tile are on their way through the bound server: give the first bound a moment
+        // (shared-memory polling, bounded) rather than appending this whole tile against "no bound yet"
+        for (int spin = 0; spin < 400; ++spin) {
+          const bool have = lane >= p.B || *reinterpret_cast<volatile unsigned int*>(Lq + lane) > 0x007FFFFFu;
+          if (__all_sync(FULL_MASK, have)) break;
+          __nanosleep(100);
+        }
       }
       if (!parked) {
         t_nxt = fetch_tile(it + 1);
@@ -1135,8 +1275,7 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
       uint32_t r[SQ];
       if (!parked) {
         mbar_wait(smem_u32(tmem_full + a), (static_cast<uint32_t>(it) >> 1) & 1u);
-        if (p.trace && threadIdx.x == 128 && (it == 0 || it == 1 || it == 2 || it == 4 || it == 8 || it == 16 || it == 24))
-          printf("TILE cta %d it %d at %llu tile %d\n", slice, it, gtime_ns() - t_entry, t);
+        if (p.trace && threadIdx.x == 128 && it < 48) tile_ts[it] = static_cast<unsigned int>(gtime_ns() - t_entry);
         tc_fence_after();
         __syncwarp();
         tmem_ld16(taddr0 + static_cast<uint32_t>(a * 2 * SQ), r);
@@ -1191,12 +1330,9 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
             if (lane == j) my_best = unmono_f32(max(wbest, 0x007FFFFFu));
           }
           if (lane < p.B && ((any >> lane) & 1u)) {
-            const float L = unmono_f32(max(*reinterpret_cast<volatile unsigned int*>(Lq + lane), 0x007FFFFFu));
-            if (my_best > L) {
-              const float nl = lower_insert(p.lower_list + static_cast<size_t>(lane) * kMaxKFilter, p.lower_glob + lane, k,
-                                            my_best, L);
-              if (nl > L) raise_bound(lane, nl);
-            }
+            // hand the warp's best row of this tile to the bound server (never block on global memory here)
+            const unsigned int m = mono_u32(my_best);
+            if (m > max(*reinterpret_cast<volatile unsigned int*>(Lq + lane), 0x007FFFFFu)) atomicMax(offer + ew * SQ + lane, m);
           }
           __syncwarp();
         }
@@ -1222,6 +1358,7 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
                 const unsigned int idx = base + __popc(tm & ((1u << lane) - 1u));
                 if (idx < static_cast<unsigned int>(p.cap)) {
                   const size_t region = static_cast<size_t>(j) * p.s_total + static_cast<size_t>(p.slice_base + slice);
+                  WDBX_ASSERT(j < p.B && region < static_cast<size_t>(p.B) * p.s_total && row >= 0 && row < p.n_rows);
                   p.cand[region * p.cap + idx] = (static_cast<unsigned long long>(p.seg) << 32) | static_cast<unsigned long long>(row);
                 }
               }
@@ -1231,11 +1368,20 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
       }
       if (parked) break;
     }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      atomicAdd(epi_done, 1u);
+    }
   }
 
   const unsigned long long t_loop = p.trace ? gtime_ns() : 0ull;
   tc_fence_before();
   __syncthreads();
+  if (p.trace && threadIdx.x == 128 && (slice % 16) == 0)   // a sample of CTAs, after the loop: does not disturb it
+    for (int i = 0; i + 8 <= 48; i += 8)
+      printf("TILES cta %d from %d : %u %u %u %u %u %u %u %u\n", slice, i, tile_ts[i], tile_ts[i + 1], tile_ts[i + 2],
+             tile_ts[i + 3], tile_ts[i + 4], tile_ts[i + 5], tile_ts[i + 6], tile_ts[i + 7]);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, S_TMEM_COLS);
@@ -1246,7 +1392,7 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
 }
 
 constexpr size_t kFilterSmallSmem = 1024 + static_cast<size_t>(S_STAGES) * S_STAGE_BYTES + (8 * SQ + SQ) * 4 +
-                                    (2 * S_STAGES + 12) * 8 + 16 + 16;
+                                    (2 * S_STAGES + 12) * 8 + 16 + 16 + 48 * 4 + (8 * SQ + 4) * 4;
 
 constexpr size_t filter_smem(int ncta) {
   const size_t stages = ncta == 2 ? STAGES_PAIR : STAGES_SINGLE;
@@ -1352,6 +1498,7 @@ __global__ void __launch_bounds__(256, 2) refine_topk_kernel(const __grid_consta
       const unsigned long long ent = have[u] ? cand[ci] : cand[0];
       sg[u] = static_cast<int>(ent >> 32);
       row[u] = static_cast<long long>(ent & 0xFFFFFFFFull);
+      WDBX_ASSERT(!have[u] || (sg[u] >= 0 && sg[u] < kMaxSeg && row[u] < p.seg[sg[u]].n_rows));
       rp[u] = p.seg[sg[u]].rows + static_cast<size_t>(row[u]) * p.row_bytes;
     }
     float inx[CU];

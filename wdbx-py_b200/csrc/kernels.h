@@ -74,6 +74,9 @@ struct ScanParams {
   int xchg_rank;
   int xchg_slot;                   // seq & 1
   unsigned int xchg_seq;           // collective sequence number (same on all ranks)
+  uint64_t* all_keys;      // large-k mode: [B][all_rows] ranking key of every row (NULL = normal top-k mode)
+  long long all_rows;      // rows over all scanned segments
+  long long seg_row_base[kMaxSeg];  // first index of segment n inside a query's all_keys row
   float min_score;         // score floor (threshold push-down); -inf = none
   const int* only_flag;    // optional [B]: a query block runs only if one of its queries is flagged
                            // (K2b re-runs queries whose candidate list overflowed); NULL = run all
@@ -146,6 +149,12 @@ cudaError_t launch_refine_topk(const SegDesc* segs, int n_seg, const float* q, i
                                const unsigned int* cand_count, int cap, int s_total, int* overflow, int ctas_per_query,
                                uint64_t* part, unsigned int* tickets, uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out,
                                cudaStream_t stream);
+
+// Large k (128 < k <= 1024): exact top-k of n_keys ranking keys per query by radix select (select_topk.cu).
+size_t select_workspace_words(int B);
+cudaError_t launch_select_topk(const uint64_t* all_keys, long long n_keys, int B, int k, unsigned int* workspace,
+                               uint64_t* sel_keys, int sm_count, uint64_t* keys_out, float* scores_out, long long* gids_out,
+                               int* counts_out, cudaStream_t stream);
 
 // K3: merge G best-first lists per query.
 cudaError_t launch_merge_topk(const uint64_t* keys, int G, int B, int k, uint64_t* keys_out, float* scores_out,

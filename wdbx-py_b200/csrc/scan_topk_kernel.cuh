@@ -444,6 +444,7 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
     const float inr = inr_n;
     if (t + GW < total) prefetch(t + GW);
 
+    WDBX_ASSERT(stage >= 0 && stage < p.stages && T.nrows > 0 && T.nrows <= p.tile_rows && T.row0 + T.nrows <= p.seg[T.seg].n_rows);
     mbar_wait(my_bar + stage * 8, parity);
     const unsigned char* sb = my_stage + static_cast<size_t>(stage) * p.stage_bytes;
 
@@ -541,6 +542,29 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
     if (L2) s = -s;
     else if (cosine) s = s * inr * my_qinv;
     s = (s != s) ? __int_as_float(0xff800000) : s;
+    if (p.all_keys != nullptr) {
+      // LARGE-k mode (k > 128, select_topk.cu): no running lists -- the ranking key of EVERY (query, row) goes to
+      // HBM (8 bytes per row and query next to the row's hundreds of bytes; 0 = dead / filtered / below the floor) and
+      // a radix select finds the k best afterwards
+      if (leader && my_r < T.nrows && my_b < nq) {
+        const long long row = T.row0 + my_r;
+        bool ok = s >= p.min_score;
+        const uint32_t* tomb = p.seg[T.seg].tomb;
+        if (tomb != nullptr && ((__ldg(tomb + (row >> 5)) >> (row & 31)) & 1u)) ok = false;
+        const uint32_t* allow = p.seg[T.seg].allow;
+        if (allow != nullptr && !((__ldg(allow + (row >> 5)) >> (row & 31)) & 1u)) ok = false;
+        const uint32_t gid = __ldg(p.seg[T.seg].gids + row);
+        WDBX_ASSERT(p.seg_row_base[T.seg] + row < p.all_rows && qbase + my_b < p.B);
+        p.all_keys[static_cast<size_t>(qbase + my_b) * p.all_rows + p.seg_row_base[T.seg] + row] = ok ? pack_key(s, gid) : 0ull;
+      }
+      __syncwarp();
+      if (t_issue < total) issue(stage);
+      if (++stage == p.stages) {
+        stage = 0;
+        parity ^= 1u;
+      }
+      continue;
+    }
     const bool pass = leader && (my_r < T.nrows) && (my_b < nq) && (s >= my_thr_f);
     unsigned m = __ballot_sync(FULL_MASK, pass);
     while (m) {
@@ -555,6 +579,7 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
       if (allow != nullptr && !((__ldg(allow + (row >> 5)) >> (row & 31)) & 1u)) continue;
       const uint32_t gid = __ldg(p.seg[T.seg].gids + row);
       const uint64_t key = pack_key(sv, gid);
+      WDBX_ASSERT(sb_ >= 0 && sb_ < QB && row >= 0 && row < p.seg[T.seg].n_rows && T.seg < p.n_seg);
       uint64_t* list = my_lists + sb_ * k;
       if (key > list[k - 1]) {
         const uint64_t nthr = list_insert(list, k, key, lane);
@@ -574,6 +599,7 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
   // overlap the merge tail of the previous search on this stream; from here on we touch the
   // workspace / outputs / exchange buffers that the previous grid may still be using.
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (p.all_keys != nullptr) return;   // large-k mode: the select kernels behind us do the rest
 
   // ---- CTA merge: fold the nwarps lists of every query and publish k keys per query
   __syncthreads();

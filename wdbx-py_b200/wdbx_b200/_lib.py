@@ -9,7 +9,10 @@ import ctypes as C
 import threading
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libwdbx_b200.so"
+import os
+
+# WDBX_B200_LIB: load another build of the same ABI (the -DWDBX_DEBUG_BOUNDS library, `python __graft_entry__.py debug`)
+LIB_PATH = Path(os.environ.get("WDBX_B200_LIB") or Path(__file__).resolve().parent / "libwdbx_b200.so")
 
 MAX_SEGMENTS = 64
 MAX_K = 1024
