@@ -25,7 +25,22 @@
 #define WDBX_ASSERT(cond) do { } while (0)
 #endif
 
+#include <atomic>
+
 namespace wdbx {
+
+// Kernel attributes (cudaFuncSetAttribute: opt-in shared memory) belong to a DEVICE: a process that drives several
+// GPUs (engine groups) must set them once on each.  `mask` = one bit per device already done.
+template <typename F>
+inline cudaError_t once_per_device(std::atomic<unsigned long long>& mask, F&& fn) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return cudaGetLastError();
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  const cudaError_t e = fn();   // two threads may race here for one device: the calls are idempotent
+  if (e == cudaSuccess) mask.fetch_or(bit, std::memory_order_release);
+  return e;
+}
 
 constexpr unsigned FULL_MASK = 0xFFFFFFFFu;
 

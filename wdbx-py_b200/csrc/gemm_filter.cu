@@ -1738,20 +1738,19 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, cons
                                int slice_base, int s_total, const FilterTail* tail, bool pdl, cudaStream_t stream) {
   if (seg.n_rows <= 0 || n_slices <= 0) return cudaSuccess;
   if (tail != nullptr && tail->tile_ctr == nullptr) return cudaErrorInvalidValue;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    auto set = [&](auto kern, int ncta) {
-      if (attr_err == cudaSuccess)
-        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(filter_smem(ncta)));
+  static std::atomic<unsigned long long> attr_done{0ull};
+  const cudaError_t attr_err = once_per_device(attr_done, [&] {
+    cudaError_t err = cudaSuccess;
+    auto set = [&](auto kern, size_t bytes) {
+      if (err == cudaSuccess) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
     };
-    set(gemm_filter_kernel<kCosine, 1>, 1); set(gemm_filter_kernel<kIP, 1>, 1); set(gemm_filter_kernel<kL2, 1>, 1);
-    set(gemm_filter_kernel<kCosine, 2>, 2); set(gemm_filter_kernel<kIP, 2>, 2); set(gemm_filter_kernel<kL2, 2>, 2);
-    auto set_small = [&](auto kern) {
-      if (attr_err == cudaSuccess)
-        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFilterSmallSmem));
-    };
-    set_small(gemm_filter_small_kernel<kCosine>); set_small(gemm_filter_small_kernel<kIP>); set_small(gemm_filter_small_kernel<kL2>);
+    set(gemm_filter_kernel<kCosine, 1>, filter_smem(1)); set(gemm_filter_kernel<kIP, 1>, filter_smem(1));
+    set(gemm_filter_kernel<kL2, 1>, filter_smem(1));
+    set(gemm_filter_kernel<kCosine, 2>, filter_smem(2)); set(gemm_filter_kernel<kIP, 2>, filter_smem(2));
+    set(gemm_filter_kernel<kL2, 2>, filter_smem(2));
+    set(gemm_filter_small_kernel<kCosine>, kFilterSmallSmem); set(gemm_filter_small_kernel<kIP>, kFilterSmallSmem);
+    set(gemm_filter_small_kernel<kL2>, kFilterSmallSmem);
+    return err;
   });
   if (attr_err != cudaSuccess) return attr_err;
   const int ld = filter_ld16(dim);

@@ -403,14 +403,14 @@ cudaError_t launch_split_queries(const float* q, int B, int dim, float* workspac
 cudaError_t launch_gemm_topk(const SegDesc& seg, int dim, int dpad, const float* workspace, int B, int k, int metric,
                              int n_slices, int slice_base, uint64_t* out_lists, cudaStream_t stream) {
   if (seg.n_rows <= 0 || n_slices <= 0) return cudaSuccess;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(gemm_topk_kernel<kCosine>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(gemm_topk_kernel<kIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(gemm_topk_kernel<kL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
+  static std::atomic<unsigned long long> attr_done{0ull};
+  const cudaError_t attr_err = once_per_device(attr_done, [&] {
+    cudaError_t err = cudaFuncSetAttribute(gemm_topk_kernel<kCosine>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(gemm_topk_kernel<kIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(gemm_topk_kernel<kL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
+    return err;
   });
   if (attr_err != cudaSuccess) return attr_err;
   const int ld = (dim + 3) / 4 * 4;

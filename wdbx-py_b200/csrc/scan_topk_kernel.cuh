@@ -724,10 +724,9 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
 template <int QB, int U, bool BF16, bool L2>
 cudaError_t launch_one(const ScanParams& p, const ScanPlan& plan, cudaStream_t stream) {
   auto kern = scan_topk_kernel<QB, U, BF16, L2>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  static std::atomic<unsigned long long> attr_done{0ull};
+  const cudaError_t attr_err = once_per_device(attr_done, [&] {
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) return attr_err;
   dim3 grid(plan.grid, (p.B + QB - 1) / QB, 1), block(plan.warps * 32, 1, 1);
