@@ -140,8 +140,10 @@ int wdbx_b200_read_rows(wdbx_b200_engine* e, int segment, int64_t row0, int64_t 
  * (a cudaStream_t; NULL = legacy default stream).  q_dev: [B, dim] fp32 on the device.
  * Outputs (device pointers, any may be NULL): keys_out [B,k] packed ranking keys best-first
  * (0 = empty slot), scores_out [B,k] fp32, gids_out [B,k] int64 (-1 = empty), counts_out [B].
- * Scores never go to HBM: kernel K1 streams the rows once and keeps the running top-k in
- * registers.  No allocation, no synchronisation => CUDA-graph capturable.
+ * Scores never go to HBM (k <= 128): the filter path (K2b) streams a 2-byte shadow of the rows through the
+ * tensor cores and re-scores the few surviving rows exactly; the streaming scan (K1) keeps running top-k lists
+ * in shared memory; both answers are bit-identical.  k > 128 dumps 8-byte keys and radix-selects.  No
+ * synchronisation in steady state => CUDA-graph capturable, the first call after ingest included.
  * Replaces: FaissIndex.search (indexing.py:983-1030) -- normalise the query (:1002),
  * IndexFlatIP.search (:1013) -- and, for ALL_SEGMENTS, the per-shard loop + sort of
  * VectorStore.search (vector_store.py:323-330, :345). */
