@@ -251,7 +251,10 @@ int wdbx_b200_set_tuning(wdbx_b200_engine* e, int warps, int stages, int rows_un
 
 /* Change a routing knob of a live engine (the WDBX_B200_* environment variables read at creation):
  * "shadow_min_mb" (-1 = never use the bf16-shadow filter for small batches, else the store size in MiB from which
- * it is used), "gemm_min_batch" (0 = never use the tensor-core path), "gemm_mode", "pdl", "queries_per_pass".
+ * it is used), "gemm_min_batch" (0 = never use the tensor-core path), "gemm_mode", "pdl", "queries_per_pass",
+ * "overlap" (1 = consecutive device-resident small-batch searches on one stream overlap on the device: the next
+ * search streams its first tiles while the previous one finishes its tail; results stay in launch order.  Contract:
+ * the query buffer of such a search must not be produced by work enqueued on that stream after the previous search).
  * Results are identical for every setting; benchmark hook (bench.py times the fp32 streaming scan and the
  * filter path on the same resident matrix).  No reference counterpart. */
 int wdbx_b200_set_option(wdbx_b200_engine* e, const char* name, long long value);

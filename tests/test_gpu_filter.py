@@ -325,3 +325,54 @@ def test_l2_bound_covers_norm_rounding_for_large_rows(built_lib):
     np.testing.assert_array_equal(g2, g1)
     np.testing.assert_array_equal(s2.view(np.uint32), s1.view(np.uint32))
     e2.close(); e1.close()
+
+
+@pytest.mark.parametrize("B,k", [(1, 10), (5, 10), (2, 100)])
+def test_overlapping_searches_keep_results_and_order(built_lib, B, k):
+    """Opt-in `overlap`: consecutive device-resident searches on one stream overlap on the device (double-buffered
+    per-search state, search-number ordering).  Every one of 300 back-to-back searches -- distinct queries, own output
+    buffers, a streaming-scan search (k = 200) thrown in every 50 -- must equal the fully ordered run bit for bit."""
+    import torch
+    from wdbx_b200.engine import new_out
+
+    n, dim = 400_000, 256
+    dev = torch.device("cuda", 0)
+    os.environ["WDBX_B200_SHADOW_MIN_MB"] = "0"
+    try:
+        eng = _engine(dim)
+    finally:
+        os.environ.pop("WDBX_B200_SHADOW_MIN_MB", None)
+    g = torch.Generator(device=dev).manual_seed(3)
+    X = torch.randn((n, dim), generator=g, device=dev)
+    X[1000:1040] = X[7]                      # a clump of duplicates: ties by gid
+    eng.append(0, X)
+    Q = torch.randn((300, B, dim), generator=g, device=dev)
+    Q[17, 0] = X[7]
+
+    def run(overlap):
+        eng.set_option("overlap", 1 if overlap else 0)
+        outs = [new_out(B, k, dev) for _ in range(300)]
+        big = []
+        torch.cuda.synchronize()
+        for i in range(300):
+            eng.search(Q[i], k, "cosine", out=outs[i])
+            if i % 50 == 49:
+                big.append(eng.search(Q[i][:1], 200, "cosine"))      # K1 key dump + select between fused searches
+        torch.cuda.synchronize()
+        return [o["keys"].clone() for o in outs], [b["keys"].clone() for b in big], [o["counts"].clone() for o in outs]
+
+    ref_keys, ref_big, ref_cnt = run(False)
+    for _ in range(2):
+        got_keys, got_big, got_cnt = run(True)
+        for i in range(300):
+            assert torch.equal(got_keys[i], ref_keys[i]), i
+            assert torch.equal(got_cnt[i], ref_cnt[i]), i
+        for a, b in zip(got_big, ref_big):
+            assert torch.equal(a, b)
+    # the fully ordered run itself is right
+    s = (X @ Q[17, 0]) / (X.norm(dim=1) * Q[17, 0].norm())
+    want = torch.topk(s, k).indices
+    gids = (~(ref_keys[17][0] & 0xFFFFFFFF)) & 0xFFFFFFFF
+    assert set(gids.tolist()) == set(want.tolist()) or k > 40
+    eng.set_option("overlap", 0)
+    eng.close()

@@ -228,6 +228,11 @@ struct Workspace {
   uint64_t* sel_keys = nullptr;
   unsigned int* sel_ws = nullptr;
   int sel_chunk = 0;
+  // overlapping consecutive searches of the fused small-batch path (see filter_segments)
+  unsigned int* done = nullptr;    // device: number of the last such search that has completely finished
+  unsigned int fseq = 0;           // host: number of the last such search launched on this stream
+  unsigned int prep_target = 0;    // host: prep CTAs launched so far in overlap mode (device count: done[1])
+  bool last_fused = false;         // the launch before this one on the stream was such a search
 };
 
 }  // namespace
@@ -245,6 +250,8 @@ struct wdbx_b200_engine {
   int gemm_min_batch = 16;  // B >= this => tcgen05 path (0 = never); measured crossover vs K1 (8 queries/pass) ~ 12-16
   int gemm_mode = 0;        // 0 = bf16 filter + exact refine (K2b), 1 = 3xTF32 with fused top-k (K2)
   int pdl = 1;              // programmatic dependent launch between the launches of a search (WDBX_B200_PDL=0 disables)
+  int overlap = 0;          // consecutive device-resident small-batch searches on one stream may overlap (opt-in, see
+                            // filter_segments; WDBX_B200_OVERLAP / wdbx_b200_set_option "overlap")
   bool shadow_warned = false;
   std::vector<void*> retired;   // workspaces outgrown during a stream capture (freed with the engine)
   bool shadow_failed = false;   // the bf16 shadow could not be allocated: fp32 stores are served by K1 only
@@ -465,6 +472,7 @@ int get_workspace(wdbx_b200_engine* e, cudaStream_t stream, size_t cand_keys, in
     w = &e->ws.back();
     w->stream = stream;
   }
+  w->last_fused = false;   // (filter_segments re-arms it when a fused small-batch search has been launched completely)
   if (w->cand_keys < cand_keys || w->n_counters < n_counters || w->qsplit_floats < qsplit_floats) {
     // Growing while `stream` is being captured into a CUDA graph is fine: nothing is enqueued here, the old buffers
     // (earlier captured nodes may reference them) are retired instead of freed, and the stream is not synchronised.
@@ -509,13 +517,27 @@ int get_workspace(wdbx_b200_engine* e, cudaStream_t stream, size_t cand_keys, in
 int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B, int k, int metric,
                   uint64_t* keys_out, float* scores_out, long long* gids_out, int* counts_out, cudaStream_t stream,
                   unsigned int xseq = 0u, const int* only_flag = nullptr, float min_score = -INFINITY,
-                  bool use_allow = false, uint64_t* all_keys = nullptr) {
+                  bool use_allow = false, uint64_t* all_keys = nullptr, unsigned int* done_ctr = nullptr,
+                  unsigned int* done_blocks = nullptr, unsigned int done_sn = 0u) {
   // xseq != 0: collective search, the last CTA exchanges its lists with the peer ranks under this sequence number
   const bool exchange = xseq != 0u;
   // all_keys != NULL: large-k mode, the kernel writes every row's ranking key instead of keeping lists (plan as for k = 1)
   if (all_keys != nullptr) k = 1;
   ScanPlan plan;
-  const int rc = scan_plan(e->dim, e->dpad, e->elem_bytes, k, B, e->sm_count, e->tune, &plan);
+  ScanTuning tune = e->tune;
+  if (only_flag != nullptr && done_ctr != nullptr) {
+    // flag-gated re-run behind the fused filter kernel: normally every CTA exits at once.  Launched with the smallest
+    // footprint the kernel runs with (ONE warp, one stage, one row per lane group; one query per block unless the
+    // exchange needs them together) so that its CTAs fit NEXT TO a resident filter CTA -- 384 x 152 registers and 212 KB
+    // of shared memory leave room for 3k registers and ~14 KB -- and still leave room for the next search's prep CTAs
+    // (32 threads x 32 registers): only then can the launches of the next search begin while this search finishes its
+    // tail.  A real re-run is slow in this shape; it only happens on data that defeats the filter.
+    tune.warps = 1;
+    tune.stages = 1;
+    tune.rows_unroll = 1;
+    if (!exchange) tune.queries_per_pass = 1;
+  }
+  const int rc = scan_plan(e->dim, e->dpad, e->elem_bytes, k, B, e->sm_count, tune, &plan);
   if (rc == -4) return fail(WDBX_B200_ERR_LIMIT, "dimension %d too large for the scan kernel's shared-memory stage", e->dim);
   if (rc != 0) return fail(WDBX_B200_ERR_ARG, "invalid scan shape (dim=%d k=%d)", e->dim, k);
   ScanParams p;
@@ -569,6 +591,9 @@ int scan_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int B
   p.counts_out = counts_out;
   p.only_flag = only_flag;
   p.min_score = min_score;
+  p.done_ctr = done_ctr;
+  p.done_blocks = done_blocks;
+  p.done_sn = done_sn;
   p.all_keys = all_keys;
   p.all_rows = n > 0 ? p.seg_row_base[n - 1] + e->seg[s1 - 1].n_rows : 0;
   if (exchange) {
@@ -682,6 +707,9 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
     }
   }
   if (built) CU_TRY(cudaStreamSynchronize(stream));  // later searches on other streams must see the shadow
+  bool prev_fused = false;   // was the previous launch on this stream's workspace a fused small-batch search?
+  for (auto& x : e->ws)
+    if (x.stream == stream) prev_fused = x.last_fused;
   Workspace* w = nullptr;
   int wrc = get_workspace(e, stream, 0, 0, &w);
   if (wrc != WDBX_B200_OK) return wrc;
@@ -713,8 +741,23 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   const size_t off_glob = off_list + static_cast<size_t>(B) * lk;
   const size_t off_ctr = off_glob + static_cast<size_t>(B);   // [kMaxSeg] dynamic tile counters (fused small-batch kernel)
   const size_t off_fin = off_ctr + static_cast<size_t>(kMaxSeg);   // [B] final-list counts (fused small-batch kernel)
-  const size_t need_zero = off_fin + static_cast<size_t>(B);
-  if (w->fpart_n < need_part || w->fws_bytes < need_ws || w->fcand_n < n_regions * cap || w->fzero_n < need_zero) {
+  const size_t off_doneb = off_fin + static_cast<size_t>(B);        // [1] query blocks of the closing launch that are finished
+  const size_t need_zero = off_doneb + 1;
+  // OVERLAPPING CONSECUTIVE SEARCHES (fused small-batch path).  Every piece of per-search state is double-buffered
+  // (parity of the search's number on this stream), the query prep orders itself behind search n-2 -- the previous user
+  // of its buffers -- by NUMBER instead of waiting for the launch before it, the flag-gated K1 launch that closes a search
+  // is small enough to sit next to a filter CTA, and the filter's last CTA waits for search n-1 before it exchanges /
+  // emits.  So prep(n+1) and the first tiles of filter(n+1) run on the SMs that search n has already left while its last
+  // CTAs still re-score, merge and exchange: back-to-back searches cost the streaming time plus a few microseconds, not
+  // plus the ~25 us tail and two launch gaps.  Results and exchanges stay in launch order.
+  // OPT-IN (`overlap`): the prep of search n+1 then no longer waits for the launch before it, so the caller must not
+  // produce the QUERY buffer of a device-resident search with work enqueued on the same stream after the previous search
+  // (queries staged up front, CUDA-graph loops, bench.py's throughput loop).  Off: same launches, fully ordered.
+  const size_t par_mult = fused ? 2 : 1;
+  const size_t ws_stride = (need_ws + 255) / 256 * 256;
+  const size_t zero_stride = (need_zero + 63) / 64 * 64;
+  if (w->fpart_n < need_part * par_mult || w->fws_bytes < ws_stride * par_mult || w->fcand_n < n_regions * cap * par_mult ||
+      w->fzero_n < zero_stride * par_mult || (fused && !w->done)) {
     // Growing while `stream` is being captured into a CUDA graph is fine: nothing is enqueued here, the old buffers
     // (earlier captured nodes may reference them) are retired instead of freed, and the stream is not synchronised.
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -726,34 +769,60 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
       if (capturing) e->retired.push_back(ptr);
       else ::cudaFree(ptr);
     };
-    if (w->fws_bytes < need_ws) {
+    if (w->fws_bytes < ws_stride * par_mult) {
       cudaFree(w->fws); w->fws = nullptr; w->fws_bytes = 0;
-      CU_TRY(cudaMalloc(&w->fws, need_ws));
-      w->fws_bytes = need_ws;
+      CU_TRY(cudaMalloc(&w->fws, ws_stride * 2));
+      w->fws_bytes = ws_stride * 2;
     }
-    if (w->fcand_n < n_regions * cap) {
+    if (w->fcand_n < n_regions * cap * par_mult) {
       cudaFree(w->fcand); w->fcand = nullptr; w->fcand_n = 0;
-      CU_TRY(cudaMalloc(&w->fcand, n_regions * cap * 8));
-      w->fcand_n = n_regions * cap;
+      CU_TRY(cudaMalloc(&w->fcand, n_regions * cap * 2 * 8));
+      w->fcand_n = n_regions * cap * 2;
     }
-    if (w->fpart_n < need_part) {
+    if (w->fpart_n < need_part * par_mult) {
       cudaFree(w->fpart); w->fpart = nullptr; w->fpart_n = 0;
-      CU_TRY(cudaMalloc(&w->fpart, need_part * 8));
-      w->fpart_n = need_part;
+      CU_TRY(cudaMalloc(&w->fpart, std::max<size_t>(need_part * 2, 1) * 8));
+      w->fpart_n = need_part * 2;
     }
-    if (w->fzero_n < need_zero) {
+    if (w->fzero_n < zero_stride * par_mult) {
       cudaFree(w->fzero); w->fzero = nullptr; w->fzero_n = 0;
-      CU_TRY(cudaMalloc(&w->fzero, need_zero * 4));
-      w->fzero_n = need_zero;
+      CU_TRY(cudaMalloc(&w->fzero, zero_stride * 2 * 4));
+      w->fzero_n = zero_stride * 2;
     }
+    if (!w->done) {
+      CU_TRY(cudaMalloc(&w->done, 64));
+      CU_TRY(cudaMemset(w->done, 0, 64));
+    }
+    prev_fused = false;   // whatever ran before has been waited for (or is ordered by the capture)
   }
-  unsigned int* fcount = w->fzero;
-  int* foverflow = reinterpret_cast<int*>(w->fzero + off_over);
-  unsigned int* ftickets = w->fzero + off_ticket;
-  unsigned int* lower_list = w->fzero + off_list;
-  unsigned int* lower_glob = w->fzero + off_glob;
+  // this search's number and buffers
+  unsigned int sn = 0u;
+  size_t par = 0;
+  if (fused) {
+    sn = ++w->fseq;
+    if (sn == 0u) sn = w->fseq = 1u;
+    par = sn & 1u;
+  }
+  unsigned int* zbase = w->fzero + par * zero_stride;
+  unsigned char* wsbase = static_cast<unsigned char*>(w->fws) + par * ws_stride;
+  unsigned long long* candbase = w->fcand + par * n_regions * cap;
+  uint64_t* partbase = w->fpart + par * need_part;
+  unsigned int* fcount = zbase;
+  int* foverflow = reinterpret_cast<int*>(zbase + off_over);
+  unsigned int* ftickets = zbase + off_ticket;
+  unsigned int* lower_list = zbase + off_list;
+  unsigned int* lower_glob = zbase + off_glob;
   const bool pdl = e->pdl != 0;
-  CU_TRY(launch_prep_queries(q_dev, B, e->dim, w->fws, w->fzero, need_zero, pdl, stream));  // also zeroes w->fzero
+  // (also zeroes this search's state block).  Fused path: ordered by search number; programmatic launch only behind
+  // another fused search -- behind anything else the launch waits for the stream as usual
+  // (never while the stream is being captured: a replayed graph would find its counts already reached)
+  cudaStreamCaptureStatus ocs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(stream, &ocs);
+  const bool overlap = fused && pdl && e->overlap != 0 && prev_fused && ocs == cudaStreamCaptureStatusNone;
+  unsigned int prep_ctas = 0;
+  CU_TRY(launch_prep_queries(q_dev, B, e->dim, wsbase, zbase, need_zero, fused, fused ? w->done : nullptr,
+                             sn >= 2u ? sn - 2u : 0u, overlap, pdl, overlap ? w->done + 1 : nullptr, &prep_ctas, stream));
+  if (overlap) w->prep_target += prep_ctas;
   e->launches.fetch_add(1, std::memory_order_relaxed);
   // the operand-rounding part of the filter's error bound is derived from the data (per-row |x - bf16(x)|,
   // per-query |q - bf16(q)|); these are the accumulation terms on top (gemm_filter.cu, "error bound")
@@ -774,10 +843,14 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
     tail.nch = plan.nch;
     tail.min_score = min_score;
     tail.overflow = foverflow;
-    tail.fin_keys = w->fpart;
-    tail.fin_count = w->fzero + off_fin;
+    tail.fin_keys = partbase;
+    tail.fin_count = zbase + off_fin;
     tail.ticket = ftickets;
-    tail.tile_ctr = w->fzero + off_ctr;
+    tail.tile_ctr = zbase + off_ctr;
+    tail.done_ctr = w->done;
+    tail.done_sn = sn;
+    tail.prep_count = overlap ? w->done + 1 : nullptr;
+    tail.prep_target = w->prep_target;
     if (xseq != 0u) {
       for (int r = 0; r < e->xworld; ++r) tail.xchg.peer[r] = e->xpeer[r];
       tail.xchg.world = e->xworld;
@@ -806,7 +879,7 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
     d.n_rows = sg.n_rows;
     if (sg.n_rows == 0) continue;
     CU_TRY(launch_gemm_filter(f32 ? sg.shadow : static_cast<const void*>(sg.rows), f32 ? ld16 : e->dpad,
-                              f32 ? sg.rres : nullptr, d, s, e->dim, w->fws, B, k, metric, acc_rel, c_l2, slices[s], w->fcand,
+                              f32 ? sg.rres : nullptr, d, s, e->dim, wsbase, B, k, metric, acc_rel, c_l2, slices[s], candbase,
                               fcount, lower_glob, lower_list, cap, slice_base, s_total, fused ? &tail : nullptr, pdl, stream));
     e->launches.fetch_add(1, std::memory_order_relaxed);
     slice_base += slices[s];
@@ -814,14 +887,16 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   if (e->ktiming) CU_TRY(cudaEventRecord(e->kev1, stream));
   if (!fused) {
     CU_TRY(launch_refine_topk(descs, kMaxSeg, q_dev, B, e->dim, e->dpad, e->elem_bytes, plan.lpr_log2, plan.nch, k, metric,
-                              w->fcand, fcount, cap, s_total, foverflow, refine_ctas, w->fpart, ftickets, keys_out, scores_out,
+                              candbase, fcount, cap, s_total, foverflow, refine_ctas, partbase, ftickets, keys_out, scores_out,
                               gids_out, counts_out, stream));
     e->launches.fetch_add(1, std::memory_order_relaxed);
   }
   // exact re-run (K1) of the queries whose candidate list overflowed; exits immediately otherwise.  Collective
   // searches: a flagged query makes the filter's last CTA skip the exchange and K1 redo all B queries with it.
   const int rrc = scan_segments(e, s0, s1, q_dev, B, k, metric, keys_out, scores_out, gids_out, counts_out, stream,
-                                xseq, foverflow, min_score, use_allow);
+                                xseq, foverflow, min_score, use_allow, nullptr, fused ? w->done : nullptr,
+                                fused ? zbase + off_doneb : nullptr, sn);
+  w->last_fused = fused && rrc == WDBX_B200_OK;
   if (e->ktiming) {
     e->last_kernel = 2;
     e->kpending = true;
@@ -1224,6 +1299,7 @@ int wdbx_b200_create(int device, int dim, int dtype, int num_segments, wdbx_b200
   }
   e->gemm_mode = env_int("WDBX_B200_GEMM_MODE", 0);
   e->pdl = env_int("WDBX_B200_PDL", 1);
+  e->overlap = env_int("WDBX_B200_OVERLAP", 0);
   ScanPlan plan;
   if (scan_plan(dim, e->dpad, e->elem_bytes, 10, 1, e->sm_count, e->tune, &plan) != 0) {
     delete e;
@@ -1257,6 +1333,7 @@ void wdbx_b200_destroy(wdbx_b200_engine* e) {
     cudaFree(w.sel_all);
     cudaFree(w.sel_keys);
     cudaFree(w.sel_ws);
+    cudaFree(w.done);
   }
   for (void* ptr : e->retired) cudaFree(ptr);
   for (int r = 0; r < kMaxPeers; ++r)
@@ -1617,6 +1694,7 @@ int wdbx_b200_set_option(wdbx_b200_engine* e, const char* name, long long value)
   else if (n == "gemm_min_batch") e->gemm_min_batch = static_cast<int>(value);
   else if (n == "gemm_mode") e->gemm_mode = static_cast<int>(value);
   else if (n == "pdl") e->pdl = value != 0;
+  else if (n == "overlap") e->overlap = value != 0;
   else if (n == "queries_per_pass") e->tune.queries_per_pass = static_cast<int>(value);
   else return fail(WDBX_B200_ERR_ARG, "unknown option '%s'", name);
   return WDBX_B200_OK;

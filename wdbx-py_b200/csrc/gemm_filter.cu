@@ -78,6 +78,8 @@ struct FilterParams {
   int cap;                    // entries per (query, slice) region
   int slice_base, s_total;    // this launch fills slices [slice_base, slice_base + n_slices) of s_total
   unsigned int* tile_ctr;     // small-batch kernel: the launch's dynamic tile counter (zero at launch)
+  const unsigned int* prep_count;   // overlap mode: CTAs of prep kernels finished on this workspace (monotone) ...
+  unsigned int prep_target;         // ... and the count at which THIS search's prep is complete; NULL = griddepcontrol.wait
   int trace;                  // WDBX_B200_FILTER_TRACE=1: every CTA prints its phase timestamps (small-batch kernel)
 };
 
@@ -151,44 +153,73 @@ __device__ __forceinline__ void bound_eval(float d, float inx, float sq, float r
 // ---------------------------------------------------------------- prep: queries -> bf16 + norms
 // (rows B .. Bpad-1 are zero padding up to a whole 128-query block, so that the TMA box of the query
 // tile never leaves the tensor: a mostly out-of-bounds box measurably slows the load pipeline)
+// Bounded wait (~3 s) until search number `sn` of this workspace has completed (see engine.cu, "overlapping
+// consecutive searches"); sn == 0: nothing to wait for.
+__device__ __forceinline__ void wait_search_done(const unsigned int* done_ctr, unsigned int sn) {
+  if (done_ctr == nullptr || sn == 0u) return;
+  const long long t0 = clock64();
+  unsigned int v;
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(done_ctr) : "memory");
+    if (v >= sn) break;
+    if (clock64() - t0 > 6000000000ll) break;
+    __nanosleep(200);
+  } while (true);
+}
+
 __global__ void prep_queries_kernel(const float* __restrict__ q, int B, int Bpad, int dim, int ld,
                                     __nv_bfloat16* __restrict__ qb, float* __restrict__ q_inv, float* __restrict__ q_nrm,
                                     float* __restrict__ q_sq, float* __restrict__ q_bn, float* __restrict__ q_tn,
-                                    unsigned int* __restrict__ zero, size_t n_zero) {
-  // programmatic dependent launch: the filter kernel behind us may start its set-up now; we wait for the previous
-  // search on this stream (it still reads the state and the query workspace that we rewrite below)
+                                    unsigned int* __restrict__ zero, size_t n_zero, const unsigned int* done_ctr,
+                                    unsigned int wait_sn, int pdl_wait, unsigned int* prep_count) {
+  // programmatic dependent launch: the filter kernel behind us may start its set-up now.  The buffers rewritten
+  // below are the ones search `wait_sn` used (per-search state is double-buffered on the fused small-batch path): wait for
+  // that search by NUMBER rather than for the whole launch before us, so that this kernel -- and the filter behind it
+  // -- can run while the previous search still finishes its tail.  Other paths (pdl_wait) wait for the stream.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x == 0) wait_search_done(done_ctr, wait_sn);
+  __syncthreads();
   // per-search state of the filter (candidate counts, flags, tickets, lower-bound lists) starts at zero
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_zero;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
     zero[i] = 0u;
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= Bpad) return;
-  float ss = 0.0f, sb = 0.0f, st = 0.0f;
-  for (int c = lane; c < ld; c += 32) {
-    const float v = (c < dim && b < B) ? q[static_cast<size_t>(b) * dim + c] : 0.0f;
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    qb[static_cast<size_t>(b) * ld + c] = h;
-    const float hb = __bfloat162float(h);
-    const float t = v - hb;              // exact
-    ss = fmaf(v, v, ss);
-    sb = fmaf(hb, hb, sb);
-    st = fmaf(t, t, st);
-  }
+  if (b < Bpad) {
+    float ss = 0.0f, sb = 0.0f, st = 0.0f;
+    for (int c = lane; c < ld; c += 32) {
+      const float v = (c < dim && b < B) ? q[static_cast<size_t>(b) * dim + c] : 0.0f;
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      qb[static_cast<size_t>(b) * ld + c] = h;
+      const float hb = __bfloat162float(h);
+      const float t = v - hb;              // exact
+      ss = fmaf(v, v, ss);
+      sb = fmaf(hb, hb, sb);
+      st = fmaf(t, t, st);
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    ss += __shfl_xor_sync(FULL_MASK, ss, o);
-    sb += __shfl_xor_sync(FULL_MASK, sb, o);
-    st += __shfl_xor_sync(FULL_MASK, st, o);
+    for (int o = 16; o > 0; o >>= 1) {
+      ss += __shfl_xor_sync(FULL_MASK, ss, o);
+      sb += __shfl_xor_sync(FULL_MASK, sb, o);
+      st += __shfl_xor_sync(FULL_MASK, st, o);
+    }
+    if (lane == 0) {
+      q_sq[b] = ss;
+      q_nrm[b] = sqrtf(ss);
+      q_inv[b] = ss > 0.0f ? 1.0f / sqrtf(ss) : 0.0f;
+      q_bn[b] = sqrtf(sb) * 1.0001f;
+      q_tn[b] = sqrtf(st) * 1.0001f;
+    }
   }
-  if (lane == 0) {
-    q_sq[b] = ss;
-    q_nrm[b] = sqrtf(ss);
-    q_inv[b] = ss > 0.0f ? 1.0f / sqrtf(ss) : 0.0f;
-    q_bn[b] = sqrtf(sb) * 1.0001f;
-    q_tn[b] = sqrtf(st) * 1.0001f;
+  // overlap mode: the filter kernel behind us does not wait for this LAUNCH (griddepcontrol.wait would also wait for
+  // everything before it on the stream) but for this count: every CTA reports once its writes are visible
+  if (prep_count != nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(prep_count, 1u);
+    }
   }
 }
 
@@ -681,6 +712,8 @@ struct SmallTail {
   unsigned int* fin_count;     // [B] zero at launch
   unsigned int* ticket;
   XchgCtx xchg;
+  const unsigned int* done_ctr;   // searches completed on this workspace
+  unsigned int done_sn;           // this search's number
   uint64_t* keys_out;
   float* scores_out;
   long long* gids_out;
@@ -915,6 +948,9 @@ __device__ __forceinline__ void small_tail(const FilterParams& p, const SmallTai
            slice, cnt_s[0], t_entry, t_loop - t_entry, ts[0], ts[1], ts[2], ts[4], ts[5]);
   if (flag_s[0] == 0) return;
   // ---- last CTA of the search: per query the few exact keys that reached the bound -> top-k, exchange, emit
+  // (consecutive searches overlap on the device; their exchanges and results stay in order)
+  if (tid == 0) wait_search_done(tp.done_ctr, tp.done_sn - 1u);
+  __syncthreads();
   __threadfence();
   if (tid < B) {
     const int n = static_cast<int>(__ldcg(tp.fin_count + tid));
@@ -1024,7 +1060,24 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_ptr), S_TMEM_COLS);
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (p.prep_count != nullptr) {
+    // overlap mode: wait for OUR prep by count (it ran early, next to the previous search's last CTAs), not for the
+    // launches before it -- this is what lets the first tiles stream while the previous search finishes its tail
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      unsigned int v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.prep_count) : "memory");
+        if (static_cast<int>(v - p.prep_target) >= 0) break;
+        if (clock64() - t0 > 6000000000ll) break;
+        __nanosleep(100);
+      } while (true);
+      asm volatile("fence.proxy.async;" ::: "memory");   // the query tile is read through TMA (async proxy)
+    }
+    __syncthreads();
+  } else {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
   if (warp == 3) {
     for (int j = lane; j < SQ; j += 32) {
       const bool v = j < p.B;
@@ -1708,15 +1761,19 @@ cudaError_t launch_shadow_rows(const float* rows, long long n, int dpad, int ld1
 }
 
 cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace, unsigned int* zero, size_t n_zero,
-                                bool pdl, cudaStream_t stream) {
+                                bool small, const unsigned int* done_ctr, unsigned int wait_sn, bool overlap, bool pdl,
+                                unsigned int* prep_count, unsigned int* prep_ctas, cudaStream_t stream) {
   const int ld = filter_ld16(dim);
-  const int bp = filter_bpad(B);
+  const int bp = filter_bpad(B);           // layout of the workspace (norm arrays are [bp])
+  const int rows = small ? SQ : bp;        // rows the filter's TMA box can touch: 16 for the small-batch kernel
   __nv_bfloat16* qb = static_cast<__nv_bfloat16*>(workspace);
   float* f = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + (static_cast<size_t>(bp) * ld * 2 + 15) / 16 * 16);
-  const int wpb = 8;
+  // small-batch path: one-warp CTAs (32 registers x 32 threads) find room on an SM that a filter CTA and a gated K1
+  // CTA already share, so the prep of the next search can run while the previous search finishes (engine.cu)
+  const int wpb = small ? 1 : 8;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((bp + wpb - 1) / wpb, 1, 1);
+  cfg.gridDim = dim3((rows + wpb - 1) / wpb, 1, 1);
   cfg.blockDim = dim3(wpb * 32, 1, 1);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -1724,8 +1781,11 @@ cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace,
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, prep_queries_kernel, q, B, bp, dim, ld, qb, f, f + bp, f + 2 * bp, f + 3 * bp, f + 4 * bp,
-                            zero, n_zero);
+  // overlap: the search orders itself behind search wait_sn through done_ctr only; otherwise it waits for the stream
+  const int pdl_wait = overlap ? 0 : 1;
+  if (prep_ctas) *prep_ctas = cfg.gridDim.x;
+  return cudaLaunchKernelEx(&cfg, prep_queries_kernel, q, B, rows, dim, ld, qb, f, f + bp, f + 2 * bp, f + 3 * bp, f + 4 * bp,
+                            zero, n_zero, done_ctr, wait_sn, pdl_wait, prep_count);
 }
 
 bool filter_fused_tail(int B) { return small_batch_mode(B); }
@@ -1793,6 +1853,8 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, cons
   p.slice_base = slice_base;
   p.s_total = s_total;
   p.tile_ctr = tail != nullptr ? tail->tile_ctr + seg_index : nullptr;
+  p.prep_count = tail != nullptr ? tail->prep_count : nullptr;
+  p.prep_target = tail != nullptr ? tail->prep_target : 0u;
   {
     const char* tv = getenv("WDBX_B200_FILTER_TRACE");
     p.trace = (tv && tv[0] == '1') ? 1 : 0;
@@ -1825,6 +1887,8 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, cons
     tp.fin_count = tail->fin_count;
     tp.ticket = tail->ticket;
     tp.xchg = tail->xchg;
+    tp.done_ctr = tail->done_ctr;
+    tp.done_sn = tail->done_sn;
     tp.keys_out = tail->keys_out;
     tp.scores_out = tail->scores_out;
     tp.gids_out = tail->gids_out;

@@ -80,6 +80,11 @@ struct ScanParams {
   float min_score;         // score floor (threshold push-down); -inf = none
   const int* only_flag;    // optional [B]: a query block runs only if one of its queries is flagged
                            // (K2b re-runs queries whose candidate list overflowed); NULL = run all
+  // flag-gated launches close a numbered search of the fused filter path: once every query block has finished (or
+  // found nothing to do) the search number is published, see "overlapping consecutive searches" in engine.cu
+  unsigned int* done_ctr;     // NULL = nothing to publish
+  unsigned int* done_blocks;  // zero at launch: query blocks finished so far
+  unsigned int done_sn;
   uint64_t* keys_out;      // [B][k] or NULL
   float* scores_out;       // [B][k] or NULL
   long long* gids_out;     // [B][k] or NULL
@@ -119,7 +124,8 @@ float filter_c_l2(int dpad);
 // bf16 shadow rows + per-row upper bound of |x - bf16(x)| (rres)
 cudaError_t launch_shadow_rows(const float* rows, long long n, int dpad, int ld16, void* dst, float* rres, cudaStream_t stream);
 cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace, unsigned int* zero, size_t n_zero,
-                                bool pdl, cudaStream_t stream);
+                                bool small, const unsigned int* done_ctr, unsigned int wait_sn, bool overlap, bool pdl,
+                                unsigned int* prep_count, unsigned int* prep_ctas, cudaStream_t stream);
 // Small batches (filter_fused_tail(B)): the filter kernel itself re-scores its candidates, and the last CTA of
 // the search merges all CTA lists, runs the cross-GPU exchange and emits -- no refine / exchange launch.
 struct FilterTail {
@@ -133,6 +139,10 @@ struct FilterTail {
   unsigned int* ticket;      // zero at launch; the CTA that draws s_total - 1 finishes the search
   unsigned int* tile_ctr;    // [kMaxSeg] zero at launch: dynamic tile counter of every segment's launch
   XchgCtx xchg;
+  const unsigned int* prep_count;   // overlap mode: the filter waits for its prep by CTA count (NULL: by launch order)
+  unsigned int prep_target;
+  unsigned int* done_ctr;    // search numbers completed on this workspace (the last CTA waits for done_sn - 1 before it
+  unsigned int done_sn;      // exchanges / emits: searches overlap on the device, their results stay ordered)
   uint64_t* keys_out;
   float* scores_out;
   long long* gids_out;

@@ -342,7 +342,14 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
     asm volatile("griddepcontrol.wait;" ::: "memory");   // the flags are written by the launch before us
     bool any = false;
     for (int b = 0; b < nq; ++b) any = any || (p.only_flag[qbase + b] != 0);
-    if (!any) return;
+    if (!any) {
+      // nothing to redo for this query block: its first CTA reports the block as finished
+      if (p.done_ctr != nullptr && blockIdx.x == 0 && tid == 0) {
+        __threadfence();
+        if (atomicAdd(p.done_blocks, 1u) == gridDim.y - 1) atomicMax(p.done_ctr, p.done_sn);
+      }
+      return;
+    }
   }
 
   // ---- shared memory carve-up (mirrors scan_plan)
@@ -719,6 +726,10 @@ __global__ void __launch_bounds__(max_threads(QB, U), 1) scan_topk_kernel(const 
     }
   }
   if (tid == 0) p.counters[blockIdx.y] = 0u;  // re-arm for the next launch
+  if (p.done_ctr != nullptr && tid == 0) {    // (only the last CTA of the query block gets here)
+    __threadfence();
+    if (atomicAdd(p.done_blocks, 1u) == gridDim.y - 1) atomicMax(p.done_ctr, p.done_sn);
+  }
 }
 
 template <int QB, int U, bool BF16, bool L2>

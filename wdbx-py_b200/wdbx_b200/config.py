@@ -20,6 +20,7 @@ DEFAULTS: Dict[str, Any] = {
     "GPU_CAPACITY_ROWS": 0,     # rows to reserve per shard up front
     "GPU_STRICT": False,        # raise instead of "log + []" on engine errors
     "GPU_PREFILTER": False,     # opt-in: filter_metadata becomes a device-side PRE-filter (full k among matches)
+    "GPU_OVERLAP": False,        # device-resident searches (search_device) may overlap on the device; see wdbx_b200.h "overlap"
     "GPU_FUSED_EXCHANGE": True,  # multi-GPU: fuse the cross-GPU merge into the scan kernel (NVLink P2P)
     "GPU_BATCH_WINDOW_US": 200,  # micro-batching window of vector_search_async
     "GPU_BATCH_MAX": 64,         # queries coalesced into one pass by the async front-end (10M x 768: 64 queries

@@ -178,6 +178,8 @@ class VectorStore:
             from .engine import Engine  # raises ImportError / B200Error loudly when the GPU path is unusable
 
             self.engine = Engine(self.devices[0], self.vector_dim, self.dtype, self.num_shards)
+        if bool(self.config.get("GPU_OVERLAP", False)) and hasattr(self.engine, "set_option"):
+            self.engine.set_option("overlap", 1)
         cap = int(self.config.get("GPU_CAPACITY_ROWS", 0) or 0)
         if cap > 0:
             for s in range(self.num_shards):
