@@ -458,6 +458,10 @@ def run_gpu(args):
                          # the same launch expressed in SURVEY.md 8d's K1 bytes (fp32 rows): what a scan of the
                          # stored rows would have had to stream in this time
                          "fp32_scan_equivalent_gbs": k1_bytes / (kernel_ms * 1e-3) / 1e9,
+                         "step_vs_kernel": ("kernel_ms is one launch timed ALONE (events around it serialise the stream); in the "
+                                            "timed region consecutive searches overlap on the device -- search n+1 streams its "
+                                            "first tiles while search n re-scores / merges / exchanges -- so ms_per_step can be "
+                                            "smaller than kernel_ms"),
                          "note": ("achieved/frac use the bytes this kernel must read; with SURVEY.md 8d's K1 bytes "
                                   "(fp32 rows, which this path no longer streams) the same launch would read as "
                                   f"frac {k1_bytes / (kernel_ms * 1e-3) / 1e9 / peak:.2f}") if kernel_id == 2 else None},

@@ -166,3 +166,34 @@ def test_single_process_group_matches_one_gpu(built_lib, route, monkeypatch):
     assert a == b_ and 0 < len(a) <= 9 and all(m.get("even") for _, _, m in a)
     for st in (one, multi, pre_m, pre_1):
         st.close()
+
+
+@pytest.mark.timeout(300)
+def test_exchange_batches_larger_than_the_scan_block(built_lib):
+    """at small dimensions the streaming scan scores fewer queries per block than the fused exchange
+    admits (dim 64 fp32: one), so a batch of 2..8 queries must run as consecutive collective passes instead of
+    failing with ERR_LIMIT.  Single-process group over 2 GPUs, scan route and filter route."""
+    import torch
+    import wdbx_b200
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = np.random.default_rng(12)
+    for dim in (64, 128):
+        X = rng.standard_normal((30000, dim), dtype=np.float32)
+        Q = rng.standard_normal((7, dim), dtype=np.float32)
+        for shadow in ("-1", "0"):
+            os.environ["WDBX_B200_SHADOW_MIN_MB"] = shadow
+            try:
+                one = wdbx_b200.VectorStore(dim, tempfile.mkdtemp(), dist=wdbx_b200.DistContext(0, 1, 0),
+                                            config=wdbx_b200.WDBXConfig({"GPU_STRICT": True}))
+                two = wdbx_b200.VectorStore(dim, tempfile.mkdtemp(), dist=wdbx_b200.DistContext(0, 1, 0),
+                                            config=wdbx_b200.WDBXConfig({"GPU_STRICT": True, "GPU_DEVICES": "0,1"}))
+            finally:
+                os.environ.pop("WDBX_B200_SHADOW_MIN_MB", None)
+            for st in (one, two):
+                st.bulk_load(X)
+            a, b = one.search_batch(Q, 10), two.search_batch(Q, 10)          # B = 7 <= 8: the on-device exchange
+            np.testing.assert_array_equal(a.gids, b.gids)
+            np.testing.assert_array_equal(a.scores.view(np.uint32), b.scores.view(np.uint32))
+            one.close(); two.close()
