@@ -250,6 +250,7 @@ struct wdbx_b200_engine {
   int gemm_min_batch = 16;  // B >= this => tcgen05 path (0 = never); measured crossover vs K1 (8 queries/pass) ~ 12-16
   int gemm_mode = 0;        // 0 = bf16 filter + exact refine (K2b), 1 = 3xTF32 with fused top-k (K2)
   int pdl = 1;              // programmatic dependent launch between the launches of a search (WDBX_B200_PDL=0 disables)
+  bool host_call = false;   // the search being launched came through a host-buffer entry point (copies around it)
   int overlap = 0;          // consecutive device-resident small-batch searches on one stream may overlap (opt-in, see
                             // filter_segments; WDBX_B200_OVERLAP / wdbx_b200_set_option "overlap")
   bool shadow_warned = false;
@@ -818,7 +819,7 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   // (never while the stream is being captured: a replayed graph would find its counts already reached)
   cudaStreamCaptureStatus ocs = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(stream, &ocs);
-  const bool overlap = fused && pdl && e->overlap != 0 && prev_fused && ocs == cudaStreamCaptureStatusNone;
+  const bool overlap = fused && pdl && e->overlap != 0 && !e->host_call && prev_fused && ocs == cudaStreamCaptureStatusNone;
   unsigned int prep_ctas = 0;
   CU_TRY(launch_prep_queries(q_dev, B, e->dim, wsbase, zbase, need_zero, fused, fused ? w->done : nullptr,
                              sn >= 2u ? sn - 2u : 0u, overlap, pdl, overlap ? w->done + 1 : nullptr, &prep_ctas, stream));
@@ -1158,6 +1159,11 @@ int launch_host_lists(wdbx_b200_engine* e, int segment, bool exchange, const flo
                       float min_score, const uint32_t* const* allow_bitmaps, const ResLayout& R, cudaStream_t st,
                       uint64_t* keys0 = nullptr, float* scores0 = nullptr, long long* gids0 = nullptr, int* counts0 = nullptr) {
   std::lock_guard<std::mutex> lk(e->mu);
+  struct HostCall {   // host-buffer searches are synchronous: never overlapped with their predecessor
+    wdbx_b200_engine* e;
+    explicit HostCall(wdbx_b200_engine* e_) : e(e_) { e->host_call = true; }
+    ~HostCall() { e->host_call = false; }
+  } host_call(e);
   const bool per_segment = segment == WDBX_B200_EACH_SEGMENT;
   const int lists = per_segment ? e->nseg : 1;
   const bool use_allow = allow_bitmaps != nullptr;
@@ -2040,7 +2046,12 @@ int wdbx_b200_group_search_host(wdbx_b200_group* g, int segment, const float* q_
       if (ce != cudaSuccess) first_err = fail(WDBX_B200_ERR_CUDA, "result copy: %s", cudaGetErrorString(ce));
     }
   }
-  for (wdbx_b200_engine* e : g->eng) {
+  // device 0's stream ends after the merge, i.e. after every peer's keys arrived (exchange) or were copied over
+  // (gather) -- hence after every device's H2D of the shared pinned query buffer.  The peers' streams need no host
+  // synchronisation of their own on the good path (their buffers are reused in stream order).
+  for (size_t i = 0; i < g->eng.size(); ++i) {
+    if (i > 0 && first_err == WDBX_B200_OK) break;
+    wdbx_b200_engine* e = g->eng[i];
     DeviceGuard guard(e->device);
     const cudaError_t ce = cudaStreamSynchronize(e->hstream);
     if (ce != cudaSuccess && first_err == WDBX_B200_OK)
