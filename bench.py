@@ -53,7 +53,8 @@ def _peaks():
 
 def _traffic_from_profile(kernel_id: int):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
-    names = (["r02_gemm_filter_small_c3_ncu_summary.json", "gemm_filter_b1_ncu_summary.json"] if kernel_id == 2
+    names = (["r02_gemm_filter_small_i8_c3_ncu_summary.json"] if kernel_id == 3
+             else ["r02_gemm_filter_small_c3_ncu_summary.json", "gemm_filter_b1_ncu_summary.json"] if kernel_id == 2
              else ["scan_topk_c3_ncu_summary.json"])
     for name in names:
         try:
@@ -364,7 +365,13 @@ def run_gpu(args):
     store.engine.set_kernel_timing(False)
     kernel_ms = reduce_max(sum(k_ms) / len(k_ms))
     ld16 = (DIM + 7) // 8 * 8
-    if kernel_id == 2:
+    ld8 = (DIM + 15) // 16 * 16
+    if kernel_id == 3:
+        kernel_name = ("gemm_filter_small_kernel<int8> (K2b, B<=16: kind::i8 tcgen05 filter over the 1-byte shadow rows + in-kernel "
+                       "exact re-score, last-CTA merge and cross-GPU exchange -- the whole search is this one launch)")
+        algo_bytes = local_rows * ld8 + local_rows * 12         # 1-byte shadow rows + 1/|x|, row scale, residual norm
+        algo_note = "rows x dim x 1 (int8 shadow) + rows x 12 (1/|x|, scale, |r|): the bytes THIS kernel must read"
+    elif kernel_id == 2:
         kernel_name = ("gemm_filter_small_kernel (K2b, B<=16: bf16 tcgen05 filter over the 2-byte shadow rows + in-kernel exact "
                        "re-score, last-CTA merge and cross-GPU exchange -- the whole search is this one launch)")
         algo_bytes = local_rows * ld16 * 2 + local_rows * 4     # 2-byte shadow rows + 1/|x| per row
@@ -464,7 +471,7 @@ def run_gpu(args):
                                             "smaller than kernel_ms"),
                          "note": ("achieved/frac use the bytes this kernel must read; with SURVEY.md 8d's K1 bytes "
                                   "(fp32 rows, which this path no longer streams) the same launch would read as "
-                                  f"frac {k1_bytes / (kernel_ms * 1e-3) / 1e9 / peak:.2f}") if kernel_id == 2 else None},
+                                  f"frac {k1_bytes / (kernel_ms * 1e-3) / 1e9 / peak:.2f}") if kernel_id >= 2 else None},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": DIM * 4,
                     "d2h_bytes_per_step": K * 20 + 4, "api": "VectorStore.search (host list in, tuples out)",

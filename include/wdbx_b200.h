@@ -63,7 +63,8 @@ typedef struct wdbx_b200_stats {
   int32_t dtype;
   int32_t num_segments;
   int32_t sm_count;
-  int32_t last_kernel;  /* dominant kernel of the last timed search: 0 none, 1 K1 streaming scan, 2 K2b bf16 filter */
+  int32_t last_kernel;  /* dominant kernel of the last timed search: 0 none, 1 K1 streaming scan, 2 K2b filter over the
+                           bf16 shadow, 3 K2b small-batch filter over the int8 shadow */
   int64_t rows_total;     /* rows appended over all segments (tombstoned rows included) */
   int64_t rows_live;      /* rows_total minus tombstones */
   int64_t capacity_rows;  /* rows that fit without growing */

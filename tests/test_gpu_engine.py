@@ -239,11 +239,11 @@ def test_segments_grow_in_place_without_a_transient_copy(built_lib):
             eng.set_kernel_timing(True)
             out = eng.search(Q, 10, "cosine")
             torch.cuda.synchronize()
-            assert eng.stats()["last_kernel"] == 2                     # the filter path, shadow already there
+            assert eng.stats()["last_kernel"] in (2, 3)                # the filter path, shadows already there
             eng.set_kernel_timing(False)
     st = eng.stats()
     assert st["rows_total"] == step * steps
-    steady = st["rows_total"] * (dim * 4 + dim * 2 + 16)               # rows + shadow + per-row arrays
+    steady = st["rows_total"] * (dim * 4 + dim * 2 + dim + 28)         # rows + bf16 and int8 shadows + per-row arrays
     assert st["bytes_resident"] <= 1.25 * steady
     assert peak_used <= 1.10 * used + (256 << 20), (peak_used, used)    # no transient second copy while growing
     # rows appended in 12 steps answer exactly like the streaming scan over the same rows

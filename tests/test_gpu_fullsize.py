@@ -106,7 +106,8 @@ def test_full_size_config(built_lib, name, n, dim, dtype, metric, k, B, route, k
         out = eng.search(Q, k, metric)
     torch.cuda.synchronize()
     if kernel:
-        assert eng.stats()["last_kernel"] == kernel, (name, eng.stats()["last_kernel"])
+        got_kernel = eng.stats()["last_kernel"]   # 2 = filter over the bf16 shadow, 3 = small-batch filter over the int8 shadow
+        assert got_kernel == kernel or (kernel == 2 and got_kernel == 3 and B <= 16), (name, got_kernel)
     eng.set_kernel_timing(False)
     got_s, got_g, cnt = out["scores"].cpu().numpy(), out["gids"].cpu().numpy(), out["counts"].cpu().numpy()
     assert np.all(cnt == k)

@@ -191,6 +191,11 @@ cudaError_t growbuf_grow(GrowBuf& b, int device, size_t need, size_t keep, size_
 
 struct Segment {
   GrowBuf b_rows, b_inv, b_sq, b_gids, b_tomb, b_shadow, b_rres;   // backing stores of the pointers below
+  GrowBuf b_shadow8, b_sc8, b_rres8;
+  void* shadow8 = nullptr;   // int8 copy of the fp32 rows (x ~ sc8 * xi) for the small-batch filter kernel
+  float* sc8 = nullptr;      // per-row scale
+  float* rres8 = nullptr;    // per-row bound of |x - sc8 * xi|
+  int64_t shadow8_rows = 0, shadow8_cap = 0;
   unsigned char* rows = nullptr;
   float* inv_norm = nullptr;
   float* sqnorm = nullptr;
@@ -256,6 +261,8 @@ struct wdbx_b200_engine {
   bool shadow_warned = false;
   std::vector<void*> retired;   // workspaces outgrown during a stream capture (freed with the engine)
   bool shadow_failed = false;   // the bf16 shadow could not be allocated: fp32 stores are served by K1 only
+  int filter_i8 = 1;            // small batches stream a 1-byte (int8) shadow instead of the bf16 one (WDBX_B200_FILTER_I8)
+  bool shadow8_failed = false;
   size_t total_mem = 0;         // device memory (sizes the address reservations of the growable arrays)
   cudaStream_t mstream = nullptr;  // mutations
   // staging for host-sourced appends
@@ -370,6 +377,9 @@ void free_segment(Segment& s) {
   cudaFree(s.allow);
   growbuf_free(s.b_shadow);
   growbuf_free(s.b_rres);
+  growbuf_free(s.b_shadow8);
+  growbuf_free(s.b_sc8);
+  growbuf_free(s.b_rres8);
   growbuf_free(s.b_rows);
   growbuf_free(s.b_inv);
   growbuf_free(s.b_sq);
@@ -397,6 +407,9 @@ void refresh_pointers(Segment& s) {
   s.tomb = reinterpret_cast<uint32_t*>(s.b_tomb.ptr);
   s.shadow = s.b_shadow.ptr;
   s.rres = reinterpret_cast<float*>(s.b_rres.ptr);
+  s.shadow8 = s.b_shadow8.ptr;
+  s.sc8 = reinterpret_cast<float*>(s.b_sc8.ptr);
+  s.rres8 = reinterpret_cast<float*>(s.b_rres8.ptr);
 }
 
 // bf16 shadow + per-row residual bound for `cap` rows (fp32 stores: the operand of the tensor-core filter).
@@ -423,6 +436,33 @@ void grow_shadow(wdbx_b200_engine* e, Segment& s, int64_t cap) {
   }
   s.shadow_cap = std::min<int64_t>(static_cast<int64_t>(s.b_shadow.bytes / (static_cast<size_t>(ld16) * 2)),
                                    static_cast<int64_t>(s.b_rres.bytes / 4));
+  if (e->filter_i8 && !e->shadow8_failed) {
+    // the 1-byte shadow of the small-batch kernel; failing to get it only means that kernel streams the bf16 shadow
+    const int ld8 = filter_ld8(e->dim);
+    const size_t c = static_cast<size_t>(cap), n8 = static_cast<size_t>(s.shadow8_rows), m = static_cast<size_t>(maxr);
+    cudaError_t e8 = growbuf_grow(s.b_shadow8, e->device, c * ld8, n8 * ld8, m * ld8, e->mstream);
+    if (e8 == cudaSuccess) e8 = growbuf_grow(s.b_sc8, e->device, c * 4, n8 * 4, m * 4, e->mstream);
+    if (e8 == cudaSuccess) e8 = growbuf_grow(s.b_rres8, e->device, c * 4, n8 * 4, m * 4, e->mstream);
+    refresh_pointers(s);
+    if (e8 != cudaSuccess) {
+      cudaGetLastError();
+      e->shadow8_failed = true;
+    } else {
+      s.shadow8_cap = std::min<int64_t>(static_cast<int64_t>(s.b_shadow8.bytes / static_cast<size_t>(ld8)),
+                                        std::min<int64_t>(static_cast<int64_t>(s.b_sc8.bytes / 4),
+                                                          static_cast<int64_t>(s.b_rres8.bytes / 4)));
+    }
+  }
+}
+
+// build the int8 shadow of rows [r0, r0 + m) of a segment on `stream` (rows must already be stored)
+int build_shadow8(wdbx_b200_engine* e, Segment& s, int64_t r0, int64_t m, cudaStream_t stream) {
+  const int ld8 = filter_ld8(e->dim);
+  CU_TRY(launch_shadow8_rows(reinterpret_cast<const float*>(s.rows + static_cast<size_t>(r0) * static_cast<size_t>(e->dpad) * 4), m,
+                             e->dpad, ld8, static_cast<unsigned char*>(s.shadow8) + static_cast<size_t>(r0) * ld8, s.sc8 + r0,
+                             s.rres8 + r0, stream));
+  e->launches.fetch_add(1, std::memory_order_relaxed);
+  return WDBX_B200_OK;
 }
 
 // Grow the segment IN PLACE to hold at least `rows` rows (see GrowBuf).  Caller holds e->mu, device is set.
@@ -707,6 +747,27 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
       built = true;
     }
   }
+  // small batches stream the 1-byte shadow when every segment has one (normally built by append)
+  bool use_i8 = fused && f32 && e->filter_i8 != 0 && !e->shadow8_failed;
+  for (int s = s0; s < s1 && use_i8; ++s) {
+    Segment& sg = e->seg[s];
+    if (sg.n_rows == 0) continue;
+    if (!sg.shadow8 || sg.shadow8_cap < sg.n_rows) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(stream, &cs);
+      if (cs != cudaStreamCaptureStatusNone) { use_i8 = false; break; }
+      CU_TRY(cudaStreamSynchronize(stream));
+      grow_shadow(e, sg, sg.cap_rows);
+      CU_TRY(cudaStreamSynchronize(e->mstream));
+      if (e->shadow8_failed || !sg.shadow8 || sg.shadow8_cap < sg.n_rows) { use_i8 = false; break; }
+    }
+    if (sg.shadow8_rows < sg.n_rows) {
+      const int brc = build_shadow8(e, sg, sg.shadow8_rows, sg.n_rows - sg.shadow8_rows, stream);
+      if (brc != WDBX_B200_OK) return brc;
+      sg.shadow8_rows = sg.n_rows;
+      built = true;
+    }
+  }
   if (built) CU_TRY(cudaStreamSynchronize(stream));  // later searches on other streams must see the shadow
   bool prev_fused = false;   // was the previous launch on this stream's workspace a fused small-batch search?
   for (auto& x : e->ws)
@@ -822,7 +883,7 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   const bool overlap = fused && pdl && e->overlap != 0 && !e->host_call && prev_fused && ocs == cudaStreamCaptureStatusNone;
   unsigned int prep_ctas = 0;
   CU_TRY(launch_prep_queries(q_dev, B, e->dim, wsbase, zbase, need_zero, fused, fused ? w->done : nullptr,
-                             sn >= 2u ? sn - 2u : 0u, overlap, pdl, overlap ? w->done + 1 : nullptr, &prep_ctas, stream));
+                             sn >= 2u ? sn - 2u : 0u, overlap, pdl, overlap ? w->done + 1 : nullptr, &prep_ctas, use_i8, stream));
   if (overlap) w->prep_target += prep_ctas;
   e->launches.fetch_add(1, std::memory_order_relaxed);
   // the operand-rounding part of the filter's error bound is derived from the data (per-row |x - bf16(x)|,
@@ -879,8 +940,10 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
     d.allow = use_allow ? sg.allow : nullptr;
     d.n_rows = sg.n_rows;
     if (sg.n_rows == 0) continue;
-    CU_TRY(launch_gemm_filter(f32 ? sg.shadow : static_cast<const void*>(sg.rows), f32 ? ld16 : e->dpad,
-                              f32 ? sg.rres : nullptr, d, s, e->dim, wsbase, B, k, metric, acc_rel, c_l2, slices[s], candbase,
+    tail.rowscale = use_i8 ? sg.sc8 : nullptr;
+    CU_TRY(launch_gemm_filter(use_i8 ? sg.shadow8 : (f32 ? sg.shadow : static_cast<const void*>(sg.rows)),
+                              use_i8 ? filter_ld8(e->dim) : (f32 ? ld16 : e->dpad),
+                              use_i8 ? sg.rres8 : (f32 ? sg.rres : nullptr), d, s, e->dim, wsbase, B, k, metric, acc_rel, c_l2, slices[s], candbase,
                               fcount, lower_glob, lower_list, cap, slice_base, s_total, fused ? &tail : nullptr, pdl, stream));
     e->launches.fetch_add(1, std::memory_order_relaxed);
     slice_base += slices[s];
@@ -899,7 +962,7 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
                                 fused ? zbase + off_doneb : nullptr, sn);
   w->last_fused = fused && rrc == WDBX_B200_OK;
   if (e->ktiming) {
-    e->last_kernel = 2;
+    e->last_kernel = use_i8 ? 3 : 2;
     e->kpending = true;
     e->last_fcount = fcount;
     e->last_fregions = n_regions;
@@ -1306,6 +1369,7 @@ int wdbx_b200_create(int device, int dim, int dtype, int num_segments, wdbx_b200
   e->gemm_mode = env_int("WDBX_B200_GEMM_MODE", 0);
   e->pdl = env_int("WDBX_B200_PDL", 1);
   e->overlap = env_int("WDBX_B200_OVERLAP", 0);
+  e->filter_i8 = env_int("WDBX_B200_FILTER_I8", 1);
   ScanPlan plan;
   if (scan_plan(dim, e->dpad, e->elem_bytes, 10, 1, e->sm_count, e->tune, &plan) != 0) {
     delete e;
@@ -1441,6 +1505,11 @@ int wdbx_b200_append(wdbx_b200_engine* e, int segment, const float* rows, int64_
       e->launches.fetch_add(1, std::memory_order_relaxed);
       s.shadow_rows = r0 + m;
     }
+    if (s.shadow8 && s.shadow8_rows == r0 && s.shadow8_cap >= r0 + m) {
+      const int brc = build_shadow8(e, s, r0, m, e->mstream);
+      if (brc != WDBX_B200_OK) return brc;
+      s.shadow8_rows = r0 + m;
+    }
     // the staging buffers are reused by the next chunk
     CU_TRY(cudaStreamSynchronize(e->mstream));
   }
@@ -1481,6 +1550,10 @@ int wdbx_b200_overwrite(wdbx_b200_engine* e, int segment, int64_t row, const flo
                               ld16, static_cast<unsigned char*>(s.shadow) + static_cast<size_t>(row) * ld16 * 2, s.rres + row,
                               e->mstream));
     e->launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  if (s.shadow8 && row < s.shadow8_rows) {
+    const int brc = build_shadow8(e, s, row, 1, e->mstream);
+    if (brc != WDBX_B200_OK) return brc;
   }
   if (s.tomb && ((s.tomb_host[row >> 5] >> (row & 31)) & 1u)) {
     s.tomb_host[row >> 5] &= ~(1u << (row & 31));
@@ -1536,6 +1609,7 @@ int wdbx_b200_clear(wdbx_b200_engine* e, int segment) {
     s.n_rows = 0;
     s.n_dead = 0;
     s.shadow_rows = 0;
+    s.shadow8_rows = 0;
     if (s.tomb) {
       std::fill(s.tomb_host.begin(), s.tomb_host.end(), 0u);
       CU_TRY(cudaMemset(s.tomb, 0, s.tomb_host.size() * 4));
@@ -1701,6 +1775,7 @@ int wdbx_b200_set_option(wdbx_b200_engine* e, const char* name, long long value)
   else if (n == "gemm_mode") e->gemm_mode = static_cast<int>(value);
   else if (n == "pdl") e->pdl = value != 0;
   else if (n == "overlap") e->overlap = value != 0;
+  else if (n == "filter_i8") e->filter_i8 = value != 0;
   else if (n == "queries_per_pass") e->tune.queries_per_pass = static_cast<int>(value);
   else return fail(WDBX_B200_ERR_ARG, "unknown option '%s'", name);
   return WDBX_B200_OK;
@@ -1729,7 +1804,7 @@ int wdbx_b200_get_stats(wdbx_b200_engine* e, wdbx_b200_stats* out) {
     if (cudaEventSynchronize(e->kev1) == cudaSuccess && cudaEventElapsedTime(&ms, e->kev0, e->kev1) == cudaSuccess) {
       out->last_kernel = e->last_kernel;
       out->last_kernel_ms = ms;
-      if (e->last_kernel == 2 && e->last_fcount && e->last_fregions > 0) {
+      if (e->last_kernel >= 2 && e->last_fcount && e->last_fregions > 0) {
         // measurement hook only: rows the filter passed on to the exact refine (summed over queries)
         std::vector<unsigned int> h(e->last_fregions);
         if (cudaMemcpy(h.data(), e->last_fcount, h.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess) {
@@ -1758,7 +1833,8 @@ int wdbx_b200_get_stats(wdbx_b200_engine* e, wdbx_b200_stats* out) {
     out->rows_live += sg.n_rows - sg.n_dead;
     out->capacity_rows += sg.cap_rows;
     out->bytes_resident += static_cast<int64_t>(sg.b_rows.bytes + sg.b_inv.bytes + sg.b_sq.bytes + sg.b_gids.bytes +
-                                                sg.b_tomb.bytes + sg.b_shadow.bytes + sg.b_rres.bytes);
+                                                sg.b_tomb.bytes + sg.b_shadow.bytes + sg.b_rres.bytes + sg.b_shadow8.bytes +
+                                                sg.b_sc8.bytes + sg.b_rres8.bytes);
     out->seg_rows[s] = sg.n_rows;
     out->seg_live[s] = sg.n_rows - sg.n_dead;
   }

@@ -50,6 +50,7 @@ constexpr int BK = 64;        // bf16 elements per K block = 128 bytes
 constexpr int STAGES_SINGLE = 4; // single-CTA ring (48 KB / stage)
 constexpr int STAGES_PAIR = 6;   // CTA-pair ring (32 KB / stage per CTA)
 constexpr int kThreads = 384;   // 4 control warps + 8 epilogue warps
+constexpr int SQ_I8 = 16;         // queries of the int8 small-batch operand (two digit rows each)
 constexpr int kMaxKFilter = 128;  // shared lower-bound list = up to four 128-byte lines per query; lists = 1 or 4 keys per lane
 constexpr uint32_t Q_TILE_BYTES = BM * BK * 2;  // 16 KB
 constexpr uint32_t TMEM_COLS = 2 * BN;
@@ -78,6 +79,9 @@ struct FilterParams {
   int cap;                    // entries per (query, slice) region
   int slice_base, s_total;    // this launch fills slices [slice_base, slice_base + n_slices) of s_total
   unsigned int* tile_ctr;     // small-batch kernel: the launch's dynamic tile counter (zero at launch)
+  const float* rowscale;      // int8 shadow (small-batch kernel): x ~ rowscale[row] * xi  (NULL: bf16 operand)
+  const float* q_s1;          // int8 queries: q ~ q_s1[j] * q1 + q_s2[j] * q2  (two int8 digits per element)
+  const float* q_s2;
   const unsigned int* prep_count;   // overlap mode: CTAs of prep kernels finished on this workspace (monotone) ...
   unsigned int prep_target;         // ... and the count at which THIS search's prep is complete; NULL = griddepcontrol.wait
   int trace;                  // WDBX_B200_FILTER_TRACE=1: every CTA prints its phase timestamps (small-batch kernel)
@@ -243,6 +247,117 @@ __global__ void shadow_rows_kernel(const float* __restrict__ rows, long long n, 
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sr += __shfl_xor_sync(FULL_MASK, sr, o);
   if (lane == 0) rres[r] = sqrtf(sr) * 1.0001f;
+}
+
+// ---------------------------------------------------------------- int8 operands (small-batch kernel)
+// A 1-byte shadow halves the bytes a small-batch search streams once more (10M x 768: 7.7 GB instead of 15.4).
+// Row: x ~ sx * xi, xi = rint(x / sx) in [-127, 127], sx = max|x| / 127 -- symmetric per-row scaling, whose
+// residual on Gaussian-like rows is ~0.8 % of |x| (e4m3 would be 3.6 %).  Query: TWO int8 digits per element,
+// q ~ s1 * q1 + s2 * q2 with s2 = s1 / 254 (residual ~3e-5 |q|); the digits are two rows of the N = 32 operand, so
+// one kind::i8 MMA (exact int32 accumulation, SASS UTCIMMA) produces both partial dot products.  The bound is the
+// same data-derived one as for bf16 operands: x.q = x~.q~ + r.q~ + x.t with the ACTUAL residual norms |r| (stored
+// per row, rres8) and |t| -- heavy-tailed rows (one huge element eats the scale) simply carry a larger |r|.
+__global__ void shadow8_rows_kernel(const float* __restrict__ rows, long long n, int dpad, int ld8,
+                                    signed char* __restrict__ dst, float* __restrict__ sx_out, float* __restrict__ rres) {
+  const int lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n) return;
+  const float* s = rows + r * dpad;
+  signed char* d = dst + r * ld8;
+  float mx = 0.0f;
+  bool bad = false;
+  for (int c = lane; c < dpad; c += 32) {
+    const float v = s[c];
+    bad = bad || !(fabsf(v) <= 3.0e38f);     // NaN / inf
+    mx = fmaxf(mx, fabsf(v));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, o));
+  bad = __any_sync(FULL_MASK, bad);
+  const float sx = mx > 0.0f ? mx / 127.0f : 0.0f;
+  const float rinv = mx > 0.0f ? 127.0f / mx : 0.0f;
+  float sr = 0.0f;
+  for (int c = lane; c < ld8; c += 32) {
+    const float v = c < dpad ? s[c] : 0.0f;
+    float xi = rintf(v * rinv);
+    xi = fminf(fmaxf(xi, -127.0f), 127.0f);
+    if (bad) xi = 0.0f;
+    d[c] = static_cast<signed char>(static_cast<int>(xi));
+    const float t = v - sx * xi;
+    sr = fmaf(t, t, sr);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sr += __shfl_xor_sync(FULL_MASK, sr, o);
+  if (lane == 0) {
+    sx_out[r] = bad ? 0.0f : sx;
+    // 1.001: fp32 rounding of sx * xi and of the sum; NaN / inf rows get NaN: such a row is always a candidate
+    rres[r] = bad ? __int_as_float(0x7fc00000) : sqrtf(sr) * 1.001f;
+  }
+}
+
+// queries -> two int8 digits per element (rows j and 16 + j of a [32][ld8] operand) + norms and scales
+__global__ void prep_queries_i8_kernel(const float* __restrict__ q, int B, int dim, int ld8, signed char* __restrict__ qi,
+                                       float* __restrict__ q_inv, float* __restrict__ q_nrm, float* __restrict__ q_sq,
+                                       float* __restrict__ q_bn, float* __restrict__ q_tn, float* __restrict__ q_s1,
+                                       float* __restrict__ q_s2, unsigned int* __restrict__ zero, size_t n_zero,
+                                       const unsigned int* done_ctr, unsigned int wait_sn, int pdl_wait,
+                                       unsigned int* prep_count) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x == 0) wait_search_done(done_ctr, wait_sn);
+  __syncthreads();
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_zero;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    zero[i] = 0u;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b < SQ_I8) {
+    const bool live = b < B;
+    float mx = 0.0f;
+    for (int c = lane; c < dim; c += 32) mx = fmaxf(mx, live ? fabsf(q[static_cast<size_t>(b) * dim + c]) : 0.0f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, o));
+    const bool ok = mx > 0.0f && mx <= 3.0e38f;    // zero / NaN / inf queries: all digits 0, t = q (an honest, huge bound)
+    const float s1 = ok ? mx / 127.0f : 0.0f, r1 = ok ? 127.0f / mx : 0.0f;
+    const float s2 = s1 / 254.0f, r2 = ok ? 254.0f * r1 : 0.0f;
+    float ss = 0.0f, sb = 0.0f, st = 0.0f;
+    for (int c = lane; c < ld8; c += 32) {
+      const float v = (c < dim && live) ? q[static_cast<size_t>(b) * dim + c] : 0.0f;
+      float d1 = fminf(fmaxf(rintf(v * r1), -127.0f), 127.0f);
+      const float e1 = v - s1 * d1;
+      float d2 = fminf(fmaxf(rintf(e1 * r2), -127.0f), 127.0f);
+      if (!ok) { d1 = 0.0f; d2 = 0.0f; }
+      qi[static_cast<size_t>(b) * ld8 + c] = static_cast<signed char>(static_cast<int>(d1));
+      qi[static_cast<size_t>(SQ_I8 + b) * ld8 + c] = static_cast<signed char>(static_cast<int>(d2));
+      const float qt = fmaf(s2, d2, s1 * d1);      // q~ (fp32 rounding of it is covered by the 1.01 below)
+      const float t = v - qt;
+      ss = fmaf(v, v, ss);
+      sb = fmaf(qt, qt, sb);
+      st = fmaf(t, t, st);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ss += __shfl_xor_sync(FULL_MASK, ss, o);
+      sb += __shfl_xor_sync(FULL_MASK, sb, o);
+      st += __shfl_xor_sync(FULL_MASK, st, o);
+    }
+    if (lane == 0) {
+      q_sq[b] = ss;
+      q_nrm[b] = sqrtf(ss);
+      q_inv[b] = ss > 0.0f ? 1.0f / sqrtf(ss) : 0.0f;
+      q_bn[b] = sqrtf(sb) * 1.0001f;
+      q_tn[b] = sqrtf(st) * 1.01f + 2e-7f * sqrtf(ss);
+      q_s1[b] = s1;
+      q_s2[b] = s2;
+    }
+  }
+  if (prep_count != nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(prep_count, 1u);
+    }
+  }
 }
 
 // ---------------------------------------------------------------- filter kernel
@@ -697,6 +812,11 @@ constexpr uint32_t SX_BYTES = BN * BK * 2;             // 32 KB: 256 rows x 64 d
 constexpr uint32_t SQ_BYTES = SQ * BK * 2;             // 2 KB
 constexpr uint32_t S_STAGE_BYTES = SX_BYTES + SQ_BYTES;
 constexpr uint32_t S_TMEM_COLS = 64;                   // 2 buffers x 2 sub-tiles x 16 columns
+// int8 operands: a stage is 256 rows x 128 one-byte dims (the same 32 KB) + the 32-row query operand (4 KB)
+constexpr uint32_t SQ8_BYTES = 2 * SQ * 128;           // 4 KB: 16 queries x 2 digits x 128 dims
+constexpr uint32_t S8_STAGE_BYTES = SX_BYTES + SQ8_BYTES;
+constexpr uint32_t S8_TMEM_COLS = 128;                 // 2 buffers x 2 sub-tiles x 32 columns
+constexpr int S8_STAGES = 5;                           // 5 x 36 KB: leaves room for the co-resident gate / prep CTAs
 constexpr int kSmallWarpRegions = 1;                   // candidate regions per (query, slice): one, shared by the CTA
 constexpr int kTailWarps = kThreads / 32;
 
@@ -860,7 +980,7 @@ __device__ __forceinline__ void final_topk(const uint64_t* keys, int n_keys, uin
 
 // Everything after the CTA's last tile (all kThreads threads call it; `ring` = the idle TMA stage ring).
 template <int METRIC, int S>
-__device__ __forceinline__ void small_tail(const FilterParams& p, const SmallTail& tp, unsigned char* ring,
+__device__ __forceinline__ void small_tail(const FilterParams& p, const SmallTail& tp, unsigned char* ring, size_t ring_bytes,
                                            const unsigned int* wcount, const unsigned int* Lq, int slice,
                                            unsigned long long t_entry, unsigned long long t_loop) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -878,7 +998,7 @@ __device__ __forceinline__ void small_tail(const FilterParams& p, const SmallTai
   int* flag_s = cnt_s + SQ;                                              // [2 SQ + 2] last CTA | any overflow | overflow, count per query
   const size_t q_off = scan::align128(static_cast<size_t>(kTailWarps + 1) * 32 * S * 8 + (5 * SQ + 2) * 4);
   float* q_s = reinterpret_cast<float*>(ring + q_off);                   // [QG][dpad] fp32 queries, zero padded
-  int QG = static_cast<int>((static_cast<size_t>(S_STAGES) * S_STAGE_BYTES - q_off) / (static_cast<size_t>(dpad) * 4));
+  int QG = static_cast<int>((ring_bytes - q_off) / (static_cast<size_t>(dpad) * 4));
   QG = QG < B ? QG : B;                                                  // >= 1: the host routes larger rows to K1
   const size_t my_slice = static_cast<size_t>(p.slice_base + slice);
   if (tid < SQ) {
@@ -1004,14 +1124,19 @@ __device__ __forceinline__ void small_tail(const FilterParams& p, const SmallTai
            slice, cnt_s[0], t_entry, t_loop - t_entry, ts[0], ts[1], ts[2], ts[4], ts[5], ts[6], ts[7], ts[8], flag_s[2 + SQ]);
 }
 
-template <int METRIC>
+template <int METRIC, bool I8>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_q,
                          const __grid_constant__ FilterParams p, const __grid_constant__ SmallTail tp) {
+  constexpr uint32_t STAGE_BYTES = I8 ? S8_STAGE_BYTES : S_STAGE_BYTES;   // X tile + query operand
+  constexpr uint32_t TMEM_COLS_S = I8 ? S8_TMEM_COLS : S_TMEM_COLS;
+  constexpr int NQ = I8 ? 2 * SQ : SQ;                                     // accumulator columns per sub-tile
+  constexpr int KB_ELEMS = I8 ? 128 : BK;                                  // dims per 128-byte K block
+  constexpr int NST = I8 ? S8_STAGES : S_STAGES;                           // ring depth
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* stage_base = smem;
-  unsigned int* Lq = reinterpret_cast<unsigned int*>(smem + S_STAGES * S_STAGE_BYTES);  // [SQ] mono(best known bound)
+  unsigned int* Lq = reinterpret_cast<unsigned int*>(smem + NST * STAGE_BYTES);  // [SQ] mono(best known bound)
   float* Tq = reinterpret_cast<float*>(Lq + SQ);                                        // [SQ] fast-test threshold
   float* q_inv_s = Tq + SQ;
   float* q_nrm_s = q_inv_s + SQ;
@@ -1032,6 +1157,8 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
   unsigned int* tile_ts = reinterpret_cast<unsigned int*>(tile_ring + 4);   // [48] trace: ns at which tile #it was ready
   unsigned int* offer = tile_ts + 48;        // [8][SQ] mailbox: best lower bound each epilogue warp has seen per query
   unsigned int* epi_done = offer + 8 * SQ;   // epilogue warps that have finished their tiles
+  float* q_s1_s = reinterpret_cast<float*>(epi_done + 4);   // [SQ] int8 queries: scale of the first digit ...
+  float* q_s2_s = q_s1_s + SQ;                               // [SQ] ... and of the second
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.y;
@@ -1045,7 +1172,7 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_x);
     prefetch_tmap(&tm_q);
-    for (int s = 0; s < S_STAGES; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(smem_u32(full_bar + s), 1);
       mbar_init(smem_u32(empty_bar + s), 1);
     }
@@ -1059,7 +1186,7 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_ptr), S_TMEM_COLS);
+  if (warp == 2) tmem_alloc(smem_u32(tmem_ptr), TMEM_COLS_S);
   if (p.prep_count != nullptr) {
     // overlap mode: wait for OUR prep by count (it ran early, next to the previous search's last CTAs), not for the
     // launches before it -- this is what lets the first tiles stream while the previous search finishes its tail
@@ -1089,6 +1216,8 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
       q_A_s[j] = b.A;
       q_C_s[j] = b.C;
       q_fA_s[j] = (METRIC == kCosine) ? b.A * b.qnrm : b.A;
+      q_s1_s[j] = (I8 && v) ? p.q_s1[j] : 0.0f;
+      q_s2_s[j] = (I8 && v) ? p.q_s2[j] : 0.0f;
       // the caller's score floor is a valid lower bound of every RETURNED score from the start
       float t0 = NEG_INF;
       unsigned int l0 = 0u;
@@ -1168,25 +1297,26 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
     publish(0, t_cur);
     for (int sq = 0; t_cur >= 0; ++sq) {
       const int raw_nxt = draw();
-      WDBX_ASSERT(t_cur >= 0 && t_cur < p.n_tiles && stage >= 0 && stage < S_STAGES);
+      WDBX_ASSERT(t_cur >= 0 && t_cur < p.n_tiles && stage >= 0 && stage < NST);
       const int row0 = t_cur * BN;
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
         mbar_wait(smem_u32(empty_bar + stage), phase ^ 1u);
-        const uint32_t sb = smem_u32(stage_base) + static_cast<uint32_t>(stage) * S_STAGE_BYTES;
+        const uint32_t sb = smem_u32(stage_base) + static_cast<uint32_t>(stage) * STAGE_BYTES;
         const uint32_t bar = smem_u32(full_bar) + static_cast<uint32_t>(stage) * 8u;
         if (elect_one()) {
-          mbar_expect_tx(bar, S_STAGE_BYTES);
-          tma_load_2d(sb, &tm_x, kb * BK, row0, bar);
-          tma_load_2d(sb + SX_BYTES, &tm_q, kb * BK, 0, bar);
+          mbar_expect_tx(bar, STAGE_BYTES);
+          tma_load_2d(sb, &tm_x, kb * KB_ELEMS, row0, bar);
+          tma_load_2d(sb + SX_BYTES, &tm_q, kb * KB_ELEMS, 0, bar);
         }
         __syncwarp();
-        if (++stage == S_STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == NST) { stage = 0; phase ^= 1u; }
       }
       t_cur = settle(raw_nxt);
       publish(sq + 1, t_cur);
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc(128, SQ, 1u);  // M = 128 X rows, N = 16 queries, BF16 x BF16 -> F32
+    // M = 128 X rows; N = 16 queries (BF16 x BF16 -> F32) or 16 queries x 2 int8 digits (S8 x S8 -> S32)
+    const uint32_t idesc = I8 ? make_idesc_i8(128, NQ) : make_idesc(128, SQ, 1u);
     int stage = 0;
     uint32_t phase = 0;
     for (int sq = 0;; ++sq) {
@@ -1194,11 +1324,11 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
       const int a = sq & 1;
       mbar_wait(smem_u32(tmem_empty + a), ((static_cast<uint32_t>(sq) >> 1) & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(a * 2 * SQ);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(a * 2 * NQ);
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
         mbar_wait(smem_u32(full_bar + stage), phase);
         tc_fence_after();
-        const uint32_t sb = smem_u32(stage_base) + static_cast<uint32_t>(stage) * S_STAGE_BYTES;
+        const uint32_t sb = smem_u32(stage_base) + static_cast<uint32_t>(stage) * STAGE_BYTES;
         const uint64_t d_x0 = make_desc_kmajor(sb, 128, 2);
         const uint64_t d_x1 = make_desc_kmajor(sb + SX_BYTES / 2, 128, 2);
         const uint64_t d_q = make_desc_kmajor(sb + SX_BYTES, 128, 2);
@@ -1207,13 +1337,18 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
             const uint64_t adv = static_cast<uint64_t>((kk * 16 * 2) >> 4);
-            umma_f16(d_tmem, d_x0 + adv, d_q + adv, idesc, (kb | kk) ? 1u : 0u);
-            umma_f16(d_tmem + SQ, d_x1 + adv, d_q + adv, idesc, (kb | kk) ? 1u : 0u);
+            if (I8) {   // 32 bytes = 32 int8 dims per instruction: the same descriptor walk as 16 bf16 dims
+              umma_i8(d_tmem, d_x0 + adv, d_q + adv, idesc, (kb | kk) ? 1u : 0u);
+              umma_i8(d_tmem + NQ, d_x1 + adv, d_q + adv, idesc, (kb | kk) ? 1u : 0u);
+            } else {
+              umma_f16(d_tmem, d_x0 + adv, d_q + adv, idesc, (kb | kk) ? 1u : 0u);
+              umma_f16(d_tmem + NQ, d_x1 + adv, d_q + adv, idesc, (kb | kk) ? 1u : 0u);
+            }
           }
           umma_commit(ebar);
         }
         __syncwarp();
-        if (++stage == S_STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == NST) { stage = 0; phase ^= 1u; }
       }
       if (elect_one()) umma_commit(smem_u32(tmem_full + a));
       __syncwarp();
@@ -1270,7 +1405,7 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
     const int ew = warp - 4;
     const int quarter = warp & 3, sub = ew >> 2;
     const int row_in_tile = sub * 128 + quarter * 32 + lane;
-    const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(sub * SQ);
+    const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(sub * NQ);
     // fast test per (row, query), see gemm_filter_kernel (same inequalities, thresholds with 1e-6 slack); admitted
     // pairs are decided by the reference form (bound_eval) below.  L / T live in shared memory per query and are
     // shared by the whole CTA.
@@ -1279,21 +1414,23 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
       b.A = q_A_s[j]; b.C = q_C_s[j]; b.qinv = q_inv_s[j]; b.qnrm = q_nrm_s[j]; b.qsq = q_sq_s[j];
       return b;
     };
-    auto load_row = [&](int t, float& inx, float& sq, float& rr) {
+    auto load_row = [&](int t, float& inx, float& sq, float& rr, float& sx) {
       const long long row = static_cast<long long>(t) * BN + row_in_tile;
       inx = 0.0f;
       sq = 0.0f;
       rr = 0.0f;
+      sx = 0.0f;
       if (t >= 0 && row < p.n_rows) {
         if (METRIC == kCosine) inx = __ldg(p.inv_norm + row);
         else sq = __ldg(p.sqnorm + row);
         if (p.rres != nullptr) rr = __ldg(p.rres + row);
+        if (I8) sx = __ldg(p.rowscale + row);
       }
     };
     int t_nxt = fetch_tile(0);
     const int t_first = t_nxt;   // the CTA's first tile is parked (decided last)
-    float inx_next, sq_next, rr_next;
-    load_row(t_nxt, inx_next, sq_next, rr_next);
+    float inx_next, sq_next, rr_next, sx_next;
+    load_row(t_nxt, inx_next, sq_next, rr_next, sx_next);
     uint32_t r0[SQ];   // the parked accumulators of this thread's row of the first tile
 #pragma unroll
     for (int j = 0; j < SQ; ++j) r0[j] = 0u;
@@ -1303,10 +1440,10 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
       const int t = parked ? t_first : t_nxt;
       const int a = it & 1;
       WDBX_ASSERT(t >= 0 && t < p.n_tiles);
-      WDBX_ASSERT(static_cast<uint32_t>(a * 2 * SQ + sub * SQ + SQ) <= S_TMEM_COLS);
+      WDBX_ASSERT(static_cast<uint32_t>(a * 2 * NQ + sub * NQ + NQ) <= TMEM_COLS_S);
       const long long row = static_cast<long long>(t) * BN + row_in_tile;
       const bool row_valid = row < p.n_rows;
-      const float inx = inx_next, sq = sq_next, rr = rr_next;
+      const float inx = inx_next, sq = sq_next, rr = rr_next, sx = sx_next;
       // per-row terms of the fast test: cosine fr = rho_x; ip fe = |x|, fr = |r|; l2 fe = 2|x|, fr = 2|r|, sqs = shrunk |x|^2
       const float xn = sqrtf(sq) * 1.00001f;
       const float fe = (METRIC == kL2) ? 2.0f * xn : xn;
@@ -1323,7 +1460,7 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
       }
       if (!parked) {
         t_nxt = fetch_tile(it + 1);
-        load_row(t_nxt >= 0 ? t_nxt : t_first, inx_next, sq_next, rr_next);
+        load_row(t_nxt >= 0 ? t_nxt : t_first, inx_next, sq_next, rr_next, sx_next);
       }
       uint32_t r[SQ];
       if (!parked) {
@@ -1331,8 +1468,21 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
         if (p.trace && threadIdx.x == 128 && it < 48) tile_ts[it] = static_cast<unsigned int>(gtime_ns() - t_entry);
         tc_fence_after();
         __syncwarp();
-        tmem_ld16(taddr0 + static_cast<uint32_t>(a * 2 * SQ), r);
-        tmem_ld_wait();
+        if (I8) {
+          // exact integer partial dots of the two query digits -> the dot-product estimate in the row's real units:
+          // d = sx * (s1 * A1 + s2 * A2); from here on the epilogue is the same as for bf16 operands
+          uint32_t ri[32];
+          tmem_ld32(taddr0 + static_cast<uint32_t>(a * 2 * NQ), ri);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < SQ; ++j) {
+            const float a1 = static_cast<float>(static_cast<int>(ri[j])), a2 = static_cast<float>(static_cast<int>(ri[SQ + j]));
+            r[j] = __float_as_uint(sx * fmaf(a2, q_s2_s[j], a1 * q_s1_s[j]));
+          }
+        } else {
+          tmem_ld16(taddr0 + static_cast<uint32_t>(a * 2 * NQ), r);
+          tmem_ld_wait();
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(tmem_empty + a));   // the accumulator is in registers: free it now
@@ -1437,15 +1587,18 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
              tile_ts[i + 3], tile_ts[i + 4], tile_ts[i + 5], tile_ts[i + 6], tile_ts[i + 7]);
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, S_TMEM_COLS);
+    tmem_dealloc(tmem_base, TMEM_COLS_S);
   }
   // the TMA ring is idle (every load was consumed by an MMA that an epilogue warp has waited for): reuse it
-  if (k <= 32) small_tail<METRIC, 1>(p, tp, stage_base, wcount, Lq, slice, t_entry, t_loop);
-  else small_tail<METRIC, 4>(p, tp, stage_base, wcount, Lq, slice, t_entry, t_loop);
+  constexpr size_t kRing = static_cast<size_t>(NST) * STAGE_BYTES;
+  if (k <= 32) small_tail<METRIC, 1>(p, tp, stage_base, kRing, wcount, Lq, slice, t_entry, t_loop);
+  else small_tail<METRIC, 4>(p, tp, stage_base, kRing, wcount, Lq, slice, t_entry, t_loop);
 }
 
 constexpr size_t kFilterSmallSmem = 1024 + static_cast<size_t>(S_STAGES) * S_STAGE_BYTES + (8 * SQ + SQ) * 4 +
-                                    (2 * S_STAGES + 12) * 8 + 16 + 16 + 48 * 4 + (8 * SQ + 4) * 4;
+                                    (2 * S_STAGES + 12) * 8 + 16 + 16 + 48 * 4 + (8 * SQ + 4) * 4 + 2 * SQ * 4;
+constexpr size_t kFilterSmallSmemI8 = kFilterSmallSmem - static_cast<size_t>(S_STAGES) * S_STAGE_BYTES +
+                                      static_cast<size_t>(S8_STAGES) * S8_STAGE_BYTES;
 
 constexpr size_t filter_smem(int ncta) {
   const size_t stages = ncta == 2 ? STAGES_PAIR : STAGES_SINGLE;
@@ -1688,6 +1841,19 @@ bool encode_map_bf16(CUtensorMap* map, const void* base, long long rows, int col
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// [rows, ld] int8 row-major, logical width `cols`; box = 128 bytes x box_rows, 128B swizzle, OOB -> 0
+bool encode_map_i8(CUtensorMap* map, const void* base, long long rows, int cols, int ld, int box_rows) {
+  auto fn = get_encode_bf16();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows > 0 ? rows : 1)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld)};
+  cuuint32_t box[2] = {128, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // CTA pairs (cta_group::2) halve the L2 -> shared-memory traffic of the X operand but couple the two
 // epilogues; measured on B200 (10M x 768): faster for 2-4 query blocks (B 129..512: 72k vs 64k QPS at
 // B=256), equal at 8 blocks, slower beyond (power-capped either way).  WDBX_B200_FILTER_PAIR=0 / 1
@@ -1721,6 +1887,9 @@ int filter_max_k() { return kMaxKFilter; }
 int filter_final_cap() { return kFinalCap; }
 
 int filter_ld16(int dim) { return (dim + 7) / 8 * 8; }
+
+// int8 shadow / query operand: row pitch in bytes (a multiple of 16 for TMA)
+int filter_ld8(int dim) { return (dim + 15) / 16 * 16; }
 
 // workspace layout (bytes): qb16 [Bpad][ld16] bf16 | q_inv, q_nrm, q_sq, q_bn, q_tn [Bpad] f32 each; Bpad = B rounded up to 128
 static int filter_bpad(int B) { return (B + BM - 1) / BM * BM; }
@@ -1760,9 +1929,38 @@ cudaError_t launch_shadow_rows(const float* rows, long long n, int dpad, int ld1
   return cudaGetLastError();
 }
 
+cudaError_t launch_shadow8_rows(const float* rows, long long n, int dpad, int ld8, void* dst, float* sx, float* rres,
+                                cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const int wpb = 8;
+  shadow8_rows_kernel<<<static_cast<unsigned>((n + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+      rows, n, dpad, ld8, static_cast<signed char*>(dst), sx, rres);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace, unsigned int* zero, size_t n_zero,
                                 bool small, const unsigned int* done_ctr, unsigned int wait_sn, bool overlap, bool pdl,
-                                unsigned int* prep_count, unsigned int* prep_ctas, cudaStream_t stream) {
+                                unsigned int* prep_count, unsigned int* prep_ctas, bool i8, cudaStream_t stream) {
+  if (i8) {
+    // int8 small-batch operand: [32][ld8] digits | q_inv, q_nrm, q_sq, q_bn, q_tn, s1, s2 [16 each]
+    const int ld8 = filter_ld8(dim);
+    signed char* qi = static_cast<signed char*>(workspace);
+    float* f = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + static_cast<size_t>(2 * SQ_I8) * ld8);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(SQ_I8, 1, 1);      // one-warp CTAs (see below)
+    cfg.blockDim = dim3(32, 1, 1);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const int pdl_wait = overlap ? 0 : 1;
+    if (prep_ctas) *prep_ctas = cfg.gridDim.x;
+    return cudaLaunchKernelEx(&cfg, prep_queries_i8_kernel, q, B, dim, ld8, qi, f, f + SQ_I8, f + 2 * SQ_I8, f + 3 * SQ_I8,
+                              f + 4 * SQ_I8, f + 5 * SQ_I8, f + 6 * SQ_I8, zero, n_zero, done_ctr, wait_sn, pdl_wait, prep_count);
+  }
   const int ld = filter_ld16(dim);
   const int bp = filter_bpad(B);           // layout of the workspace (norm arrays are [bp])
   const int rows = small ? SQ : bp;        // rows the filter's TMA box can touch: 16 for the small-batch kernel
@@ -1798,6 +1996,7 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, cons
                                int slice_base, int s_total, const FilterTail* tail, bool pdl, cudaStream_t stream) {
   if (seg.n_rows <= 0 || n_slices <= 0) return cudaSuccess;
   if (tail != nullptr && tail->tile_ctr == nullptr) return cudaErrorInvalidValue;
+  const bool i8 = tail != nullptr && tail->rowscale != nullptr;
   static std::atomic<unsigned long long> attr_done{0ull};
   const cudaError_t attr_err = once_per_device(attr_done, [&] {
     cudaError_t err = cudaSuccess;
@@ -1808,8 +2007,10 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, cons
     set(gemm_filter_kernel<kL2, 1>, filter_smem(1));
     set(gemm_filter_kernel<kCosine, 2>, filter_smem(2)); set(gemm_filter_kernel<kIP, 2>, filter_smem(2));
     set(gemm_filter_kernel<kL2, 2>, filter_smem(2));
-    set(gemm_filter_small_kernel<kCosine>, kFilterSmallSmem); set(gemm_filter_small_kernel<kIP>, kFilterSmallSmem);
-    set(gemm_filter_small_kernel<kL2>, kFilterSmallSmem);
+    set(gemm_filter_small_kernel<kCosine, false>, kFilterSmallSmem); set(gemm_filter_small_kernel<kIP, false>, kFilterSmallSmem);
+    set(gemm_filter_small_kernel<kL2, false>, kFilterSmallSmem);
+    set(gemm_filter_small_kernel<kCosine, true>, kFilterSmallSmemI8); set(gemm_filter_small_kernel<kIP, true>, kFilterSmallSmemI8);
+    set(gemm_filter_small_kernel<kL2, true>, kFilterSmallSmemI8);
     return err;
   });
   if (attr_err != cudaSuccess) return attr_err;
@@ -1823,9 +2024,13 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, cons
   if (small && tail == nullptr) return cudaErrorInvalidValue;
   const int ncta = (!small && pair_mode(n_qblocks)) ? 2 : 1;
   CUtensorMap tm_x, tm_q;
-  if (!encode_map_bf16(&tm_x, xb, seg.n_rows, dim, ld_x, BN / ncta) ||
-      !encode_map_bf16(&tm_q, ws, bp, dim, ld, small ? SQ : BM))
+  if (i8) {
+    if (!encode_map_i8(&tm_x, xb, seg.n_rows, dim, ld_x, BN) || !encode_map_i8(&tm_q, ws, 2 * SQ_I8, dim, filter_ld8(dim), 2 * SQ_I8))
+      return cudaErrorInvalidValue;
+  } else if (!encode_map_bf16(&tm_x, xb, seg.n_rows, dim, ld_x, BN / ncta) ||
+             !encode_map_bf16(&tm_q, ws, bp, dim, ld, small ? SQ : BM)) {
     return cudaErrorInvalidValue;
+  }
   FilterParams p;
   p.inv_norm = seg.inv_norm;
   p.sqnorm = seg.sqnorm;
@@ -1839,7 +2044,20 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, cons
   p.n_rows = seg.n_rows;
   p.B = B;
   p.k = k;
-  p.n_kblocks = (dim + BK - 1) / BK;
+  p.n_kblocks = i8 ? (dim + 127) / 128 : (dim + BK - 1) / BK;
+  p.rowscale = i8 ? tail->rowscale : nullptr;
+  p.q_s1 = nullptr;
+  p.q_s2 = nullptr;
+  if (i8) {   // the int8 prep's workspace layout (launch_prep_queries)
+    const float* fi = reinterpret_cast<const float*>(ws + static_cast<size_t>(2 * SQ_I8) * filter_ld8(dim));
+    p.q_inv = fi;
+    p.q_nrm = fi + SQ_I8;
+    p.q_sq = fi + 2 * SQ_I8;
+    p.q_bn = fi + 3 * SQ_I8;
+    p.q_tn = fi + 4 * SQ_I8;
+    p.q_s1 = fi + 5 * SQ_I8;
+    p.q_s2 = fi + 6 * SQ_I8;
+  }
   p.n_tiles = static_cast<int>((seg.n_rows + BN - 1) / BN);
   p.n_slices = n_slices;
   p.seg = seg_index;
@@ -1863,7 +2081,7 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, cons
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(n_qblocks, n_slices, 1);
   cfg.blockDim = dim3(kThreads, 1, 1);
-  cfg.dynamicSmemBytes = small ? kFilterSmallSmem : filter_smem(ncta);
+  cfg.dynamicSmemBytes = small ? (i8 ? kFilterSmallSmemI8 : kFilterSmallSmem) : filter_smem(ncta);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   cfg.attrs = attr;
@@ -1897,9 +2115,14 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, cons
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = pdl ? 1 : 0;
     auto go = [&](auto kern) { return cudaLaunchKernelEx(&cfg, kern, tm_x, tm_q, p, tp); };
-    if (metric == kCosine) return go(gemm_filter_small_kernel<kCosine>);
-    if (metric == kL2) return go(gemm_filter_small_kernel<kL2>);
-    return go(gemm_filter_small_kernel<kIP>);
+    if (i8) {
+      if (metric == kCosine) return go(gemm_filter_small_kernel<kCosine, true>);
+      if (metric == kL2) return go(gemm_filter_small_kernel<kL2, true>);
+      return go(gemm_filter_small_kernel<kIP, true>);
+    }
+    if (metric == kCosine) return go(gemm_filter_small_kernel<kCosine, false>);
+    if (metric == kL2) return go(gemm_filter_small_kernel<kL2, false>);
+    return go(gemm_filter_small_kernel<kIP, false>);
   }
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;

@@ -125,7 +125,11 @@ float filter_c_l2(int dpad);
 cudaError_t launch_shadow_rows(const float* rows, long long n, int dpad, int ld16, void* dst, float* rres, cudaStream_t stream);
 cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace, unsigned int* zero, size_t n_zero,
                                 bool small, const unsigned int* done_ctr, unsigned int wait_sn, bool overlap, bool pdl,
-                                unsigned int* prep_count, unsigned int* prep_ctas, cudaStream_t stream);
+                                unsigned int* prep_count, unsigned int* prep_ctas, bool i8, cudaStream_t stream);
+int filter_ld8(int dim);
+// int8 shadow rows (x ~ sx * xi, xi in [-127, 127]) + per-row scale + upper bound of |x - sx * xi|
+cudaError_t launch_shadow8_rows(const float* rows, long long n, int dpad, int ld8, void* dst, float* sx, float* rres,
+                                cudaStream_t stream);
 // Small batches (filter_fused_tail(B)): the filter kernel itself re-scores its candidates, and the last CTA of
 // the search merges all CTA lists, runs the cross-GPU exchange and emits -- no refine / exchange launch.
 struct FilterTail {
@@ -139,6 +143,7 @@ struct FilterTail {
   unsigned int* ticket;      // zero at launch; the CTA that draws s_total - 1 finishes the search
   unsigned int* tile_ctr;    // [kMaxSeg] zero at launch: dynamic tile counter of every segment's launch
   XchgCtx xchg;
+  const float* rowscale;     // int8 shadow: per-row scale (x ~ rowscale * xi); NULL = bf16 operand
   const unsigned int* prep_count;   // overlap mode: the filter waits for its prep by CTA count (NULL: by launch order)
   unsigned int prep_target;
   unsigned int* done_ctr;    // search numbers completed on this workspace (the last CTA waits for done_sn - 1 before it

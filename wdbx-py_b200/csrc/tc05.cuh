@@ -101,6 +101,29 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       : "memory");
 }
 
+// kind::i8: signed 8-bit operands, exact int32 accumulation in TMEM (SASS UTCIMMA); K = 32 per instruction
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// cute::UMMA::InstrDescriptor for kind::i8: c_format = S32 (2), a / b format = signed 8 bit (1), K-major
+__device__ __forceinline__ uint32_t make_idesc_i8(int M, int N) {
+  uint32_t d = 0;
+  d |= 2u << 4;
+  d |= 1u << 7;
+  d |= 1u << 10;
+  d |= static_cast<uint32_t>(N >> 3) << 17;
+  d |= static_cast<uint32_t>(M >> 4) << 24;
+  return d;
+}
+
 // ---- CTA-pair (cta_group::2) variants: two SMs of one TPC run one M=256 MMA; each CTA stages its own
 // 128 rows of A and HALF of B, the leader (cluster rank 0) issues the MMA, completion is multicast.
 __device__ __forceinline__ uint32_t cluster_ctarank() {
