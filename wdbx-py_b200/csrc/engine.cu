@@ -804,7 +804,8 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
   const size_t off_ctr = off_glob + static_cast<size_t>(B);   // [kMaxSeg] dynamic tile counters (fused small-batch kernel)
   const size_t off_fin = off_ctr + static_cast<size_t>(kMaxSeg);   // [B] final-list counts (fused small-batch kernel)
   const size_t off_doneb = off_fin + static_cast<size_t>(B);        // [1] query blocks of the closing launch that are finished
-  const size_t need_zero = off_doneb + 1;
+  const size_t off_pm = (off_doneb + 1 + 15) / 16 * 16;             // [B][filter_max_k] partition maxima (fused small-batch kernel)
+  const size_t need_zero = off_pm + (fused ? static_cast<size_t>(B) * lk : 0);
   // OVERLAPPING CONSECUTIVE SEARCHES (fused small-batch path).  Every piece of per-search state is double-buffered
   // (parity of the search's number on this stream), the query prep orders itself behind search n-2 -- the previous user
   // of its buffers -- by NUMBER instead of waiting for the launch before it, the flag-gated K1 launch that closes a search
@@ -909,6 +910,7 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
     tail.fin_count = zbase + off_fin;
     tail.ticket = ftickets;
     tail.tile_ctr = zbase + off_ctr;
+    tail.part_max = zbase + off_pm;
     tail.done_ctr = w->done;
     tail.done_sn = sn;
     tail.prep_count = overlap ? w->done + 1 : nullptr;

@@ -79,6 +79,7 @@ struct FilterParams {
   int cap;                    // entries per (query, slice) region
   int slice_base, s_total;    // this launch fills slices [slice_base, slice_base + n_slices) of s_total
   unsigned int* tile_ctr;     // small-batch kernel: the launch's dynamic tile counter (zero at launch)
+  unsigned int* part_max;     // small-batch kernel: [B][kMaxKFilter] best lower bound per warp PARTITION (see bound server)
   const float* rowscale;      // int8 shadow (small-batch kernel): x ~ rowscale[row] * xi  (NULL: bf16 operand)
   const float* q_s1;          // int8 queries: q ~ q_s1[j] * q1 + q_s2[j] * q2  (two int8 digits per element)
   const float* q_s2;
@@ -1394,6 +1395,31 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
           const unsigned int g = __ldcg(p.lower_glob + lane);
           if (g > *reinterpret_cast<volatile unsigned int*>(Lq + lane)) raise_bound(lane, unmono_f32(g));
         }
+        // PARTITION MAXIMA: slot s holds the best lower bound among the rows of the warps with number = s (mod k) --
+        // k disjoint row sets, so the smallest slot is a lower bound of the exact k-th best score too.  Looser than the
+        // list (it sits near rank k ln k) but every update is ONE fire-and-forget atomicMax from the epilogue: it is
+        // there one round trip after the first tile, while the exact list takes ~10 compare-and-swap rounds to settle.
+        for (int j0 = 0; j0 < p.B; j0 += 4) {
+          uint4 v4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            v4[u] = (j0 + u < p.B && 4 * lane < k)
+                        ? __ldcg(reinterpret_cast<const uint4*>(p.part_max + static_cast<size_t>(j0 + u) * kMaxKFilter + 4 * lane))
+                        : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (j0 + u < p.B) {   // warp-uniform
+              unsigned int vv[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                if (4 * lane + jj >= k) vv[jj] = 0xFFFFFFFFu;
+              const unsigned int gm = __reduce_min_sync(FULL_MASK, min(min(vv[0], vv[1]), min(vv[2], vv[3])));
+              if (lane == 0 && gm > 0x007FFFFFu && gm != 0xFFFFFFFFu &&
+                  gm > *reinterpret_cast<volatile unsigned int*>(Lq + j0 + u))
+                raise_bound(j0 + u, unmono_f32(gm));
+            }
+          }
+        }
         __syncwarp();
         if (!work) __nanosleep(300);
       }
@@ -1427,6 +1453,9 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
         if (I8) sx = __ldg(p.rowscale + row);
       }
     };
+    // the rows this warp ever sees form one of k partitions of the store (warp number modulo k)
+    const int pm_slot = static_cast<int>((static_cast<unsigned int>(p.slice_base + slice) * 8u + static_cast<unsigned int>(ew)) %
+                                         static_cast<unsigned int>(k));
     int t_nxt = fetch_tile(0);
     const int t_first = t_nxt;   // the CTA's first tile is parked (decided last)
     float inx_next, sq_next, rr_next, sx_next;
@@ -1535,7 +1564,11 @@ gemm_filter_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
           if (lane < p.B && ((any >> lane) & 1u)) {
             // hand the warp's best row of this tile to the bound server (never block on global memory here)
             const unsigned int m = mono_u32(my_best);
-            if (m > max(*reinterpret_cast<volatile unsigned int*>(Lq + lane), 0x007FFFFFu)) atomicMax(offer + ew * SQ + lane, m);
+            if (m > max(*reinterpret_cast<volatile unsigned int*>(Lq + lane), 0x007FFFFFu)) {
+              atomicMax(offer + ew * SQ + lane, m);
+              // ... and, fire-and-forget, into this warp's slot of the PARTITION MAXIMA (one reduction, no retry)
+              atomicMax(p.part_max + static_cast<size_t>(lane) * kMaxKFilter + pm_slot, m);
+            }
           }
           __syncwarp();
         }
@@ -2067,6 +2100,7 @@ cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, cons
   p.cand_count = cand_count;
   p.lower_glob = lower_glob;
   p.lower_list = lower_list;
+  p.part_max = tail != nullptr ? tail->part_max : nullptr;
   p.cap = cap;
   p.slice_base = slice_base;
   p.s_total = s_total;

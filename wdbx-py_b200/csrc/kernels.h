@@ -143,6 +143,7 @@ struct FilterTail {
   unsigned int* ticket;      // zero at launch; the CTA that draws s_total - 1 finishes the search
   unsigned int* tile_ctr;    // [kMaxSeg] zero at launch: dynamic tile counter of every segment's launch
   XchgCtx xchg;
+  unsigned int* part_max;    // [B][filter_max_k()] zero at launch: partition maxima of the lower bounds
   const float* rowscale;     // int8 shadow: per-row scale (x ~ rowscale * xi); NULL = bf16 operand
   const unsigned int* prep_count;   // overlap mode: the filter waits for its prep by CTA count (NULL: by launch order)
   unsigned int prep_target;
