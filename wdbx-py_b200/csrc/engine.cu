@@ -396,7 +396,10 @@ int64_t segment_max_rows(const wdbx_b200_engine* e) {
 }
 
 bool shadow_wanted(const wdbx_b200_engine* e) {
-  return e->dtype == WDBX_B200_F32 && e->gemm_mode != 1 && e->gemm_min_batch > 0 && !e->shadow_failed;
+  if (e->gemm_mode == 1 || e->gemm_min_batch <= 0) return false;
+  if (e->dtype == WDBX_B200_F32) return !e->shadow_failed;
+  // bf16 stores are their own bf16 operand; what they can still gain is the 1-byte shadow of the small-batch kernel
+  return e->filter_i8 != 0 && !e->shadow8_failed && e->shadow_min_bytes >= 0;
 }
 
 void refresh_pointers(Segment& s) {
@@ -417,25 +420,27 @@ void refresh_pointers(Segment& s) {
 void grow_shadow(wdbx_b200_engine* e, Segment& s, int64_t cap) {
   const int ld16 = filter_ld16(e->dim);
   const int64_t maxr = segment_max_rows(e);
-  const cudaError_t e1 = growbuf_grow(s.b_shadow, e->device, static_cast<size_t>(cap) * ld16 * 2,
-                                      static_cast<size_t>(s.shadow_rows) * ld16 * 2, static_cast<size_t>(maxr) * ld16 * 2, e->mstream);
-  const cudaError_t e2 = e1 == cudaSuccess ? growbuf_grow(s.b_rres, e->device, static_cast<size_t>(cap) * 4,
-                                                          static_cast<size_t>(s.shadow_rows) * 4, static_cast<size_t>(maxr) * 4,
-                                                          e->mstream)
-                                           : e1;
-  refresh_pointers(s);
-  if (e1 != cudaSuccess || e2 != cudaSuccess) {
-    cudaGetLastError();
-    e->shadow_failed = true;
-    if (!e->shadow_warned) {
-      e->shadow_warned = true;
-      fprintf(stderr, "[wdbx_b200] device %d: no memory for the bf16 shadow of the stored rows; every search is served by "
-                      "the fp32 scan (about half the queries/s on large stores)\n", e->device);
+  if (e->dtype == WDBX_B200_F32) {
+    const cudaError_t e1 = growbuf_grow(s.b_shadow, e->device, static_cast<size_t>(cap) * ld16 * 2,
+                                        static_cast<size_t>(s.shadow_rows) * ld16 * 2, static_cast<size_t>(maxr) * ld16 * 2, e->mstream);
+    const cudaError_t e2 = e1 == cudaSuccess ? growbuf_grow(s.b_rres, e->device, static_cast<size_t>(cap) * 4,
+                                                            static_cast<size_t>(s.shadow_rows) * 4, static_cast<size_t>(maxr) * 4,
+                                                            e->mstream)
+                                             : e1;
+    refresh_pointers(s);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      cudaGetLastError();
+      e->shadow_failed = true;
+      if (!e->shadow_warned) {
+        e->shadow_warned = true;
+        fprintf(stderr, "[wdbx_b200] device %d: no memory for the bf16 shadow of the stored rows; every search is served by "
+                        "the fp32 scan (about half the queries/s on large stores)\n", e->device);
+      }
+      return;
     }
-    return;
+    s.shadow_cap = std::min<int64_t>(static_cast<int64_t>(s.b_shadow.bytes / (static_cast<size_t>(ld16) * 2)),
+                                     static_cast<int64_t>(s.b_rres.bytes / 4));
   }
-  s.shadow_cap = std::min<int64_t>(static_cast<int64_t>(s.b_shadow.bytes / (static_cast<size_t>(ld16) * 2)),
-                                   static_cast<int64_t>(s.b_rres.bytes / 4));
   if (e->filter_i8 && !e->shadow8_failed) {
     // the 1-byte shadow of the small-batch kernel; failing to get it only means that kernel streams the bf16 shadow
     const int ld8 = filter_ld8(e->dim);
@@ -458,8 +463,7 @@ void grow_shadow(wdbx_b200_engine* e, Segment& s, int64_t cap) {
 // build the int8 shadow of rows [r0, r0 + m) of a segment on `stream` (rows must already be stored)
 int build_shadow8(wdbx_b200_engine* e, Segment& s, int64_t r0, int64_t m, cudaStream_t stream) {
   const int ld8 = filter_ld8(e->dim);
-  CU_TRY(launch_shadow8_rows(reinterpret_cast<const float*>(s.rows + static_cast<size_t>(r0) * static_cast<size_t>(e->dpad) * 4), m,
-                             e->dpad, ld8, static_cast<unsigned char*>(s.shadow8) + static_cast<size_t>(r0) * ld8, s.sc8 + r0,
+  CU_TRY(launch_shadow8_rows(s.rows + static_cast<size_t>(r0) * row_bytes(e), e->dtype == WDBX_B200_BF16, m, e->dpad, ld8, static_cast<unsigned char*>(s.shadow8) + static_cast<size_t>(r0) * ld8, s.sc8 + r0,
                              s.rres8 + r0, stream));
   e->launches.fetch_add(1, std::memory_order_relaxed);
   return WDBX_B200_OK;
@@ -748,7 +752,7 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
     }
   }
   // small batches stream the 1-byte shadow when every segment has one (normally built by append)
-  bool use_i8 = fused && f32 && e->filter_i8 != 0 && !e->shadow8_failed;
+  bool use_i8 = fused && e->filter_i8 != 0 && !e->shadow8_failed;
   for (int s = s0; s < s1 && use_i8; ++s) {
     Segment& sg = e->seg[s];
     if (sg.n_rows == 0) continue;
@@ -1062,7 +1066,10 @@ bool use_gemm(const wdbx_b200_engine* e, int s0, int s1, int B, int k) {
   if (e->dtype == WDBX_B200_F32 && e->shadow_failed) return false;   // no room for the bf16 shadow (said so once)
   if (static_cast<size_t>(e->dpad) * 4 > 160 * 1024) return false;   // the fused tail stages fp32 queries in shared memory
   if (B >= e->gemm_min_batch) return true;
-  if (e->dtype != WDBX_B200_F32 || e->shadow_min_bytes < 0) return false;
+  if (e->shadow_min_bytes < 0) return false;
+  // small batches: worth it only where the filter streams fewer bytes than the scan would -- fp32 stores (bf16 or int8
+  // shadow) and bf16 stores that carry the int8 shadow
+  if (e->dtype != WDBX_B200_F32 && (e->filter_i8 == 0 || e->shadow8_failed)) return false;
   long long bytes = 0;
   for (int s = s0; s < s1; ++s) bytes += e->seg[s].n_rows * static_cast<long long>(row_bytes(e));
   return bytes >= e->shadow_min_bytes;

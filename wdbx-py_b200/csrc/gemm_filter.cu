@@ -258,12 +258,21 @@ __global__ void shadow_rows_kernel(const float* __restrict__ rows, long long n, 
 // one kind::i8 MMA (exact int32 accumulation, SASS UTCIMMA) produces both partial dot products.  The bound is the
 // same data-derived one as for bf16 operands: x.q = x~.q~ + r.q~ + x.t with the ACTUAL residual norms |r| (stored
 // per row, rres8) and |t| -- heavy-tailed rows (one huge element eats the scale) simply carry a larger |r|.
-__global__ void shadow8_rows_kernel(const float* __restrict__ rows, long long n, int dpad, int ld8,
+template <bool SRC_BF16>
+__global__ void shadow8_rows_kernel(const void* __restrict__ rows_raw, long long n, int dpad, int ld8,
                                     signed char* __restrict__ dst, float* __restrict__ sx_out, float* __restrict__ rres) {
   const int lane = threadIdx.x & 31;
   const long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n) return;
-  const float* s = rows + r * dpad;
+  // the STORED row (fp32, or bf16 for bf16 stores: the residual is measured against what the exact path scores)
+  struct Row {
+    const void* p;
+    __device__ float operator[](int c) const {
+      if (SRC_BF16) return __bfloat162float(static_cast<const __nv_bfloat16*>(p)[c]);
+      return static_cast<const float*>(p)[c];
+    }
+  };
+  const Row s{static_cast<const unsigned char*>(rows_raw) + static_cast<size_t>(r) * dpad * (SRC_BF16 ? 2 : 4)};
   signed char* d = dst + r * ld8;
   float mx = 0.0f;
   bool bad = false;
@@ -1962,12 +1971,15 @@ cudaError_t launch_shadow_rows(const float* rows, long long n, int dpad, int ld1
   return cudaGetLastError();
 }
 
-cudaError_t launch_shadow8_rows(const float* rows, long long n, int dpad, int ld8, void* dst, float* sx, float* rres,
-                                cudaStream_t stream) {
+cudaError_t launch_shadow8_rows(const void* rows, bool src_bf16, long long n, int dpad, int ld8, void* dst, float* sx,
+                                float* rres, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   const int wpb = 8;
-  shadow8_rows_kernel<<<static_cast<unsigned>((n + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
-      rows, n, dpad, ld8, static_cast<signed char*>(dst), sx, rres);
+  const unsigned grid = static_cast<unsigned>((n + wpb - 1) / wpb);
+  if (src_bf16)
+    shadow8_rows_kernel<true><<<grid, wpb * 32, 0, stream>>>(rows, n, dpad, ld8, static_cast<signed char*>(dst), sx, rres);
+  else
+    shadow8_rows_kernel<false><<<grid, wpb * 32, 0, stream>>>(rows, n, dpad, ld8, static_cast<signed char*>(dst), sx, rres);
   return cudaGetLastError();
 }
 

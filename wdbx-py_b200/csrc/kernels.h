@@ -128,8 +128,8 @@ cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace,
                                 unsigned int* prep_count, unsigned int* prep_ctas, bool i8, cudaStream_t stream);
 int filter_ld8(int dim);
 // int8 shadow rows (x ~ sx * xi, xi in [-127, 127]) + per-row scale + upper bound of |x - sx * xi|
-cudaError_t launch_shadow8_rows(const float* rows, long long n, int dpad, int ld8, void* dst, float* sx, float* rres,
-                                cudaStream_t stream);
+cudaError_t launch_shadow8_rows(const void* rows, bool src_bf16, long long n, int dpad, int ld8, void* dst, float* sx,
+                                float* rres, cudaStream_t stream);
 // Small batches (filter_fused_tail(B)): the filter kernel itself re-scores its candidates, and the last CTA of
 // the search merges all CTA lists, runs the cross-GPU exchange and emits -- no refine / exchange launch.
 struct FilterTail {
