@@ -870,6 +870,19 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
     if (sn == 0u) sn = w->fseq = 1u;
     par = sn & 1u;
   }
+  // from here on the search has a number: if anything below fails, publish it as finished anyway
+  struct DoneGuard {
+    unsigned int* done;
+    unsigned int sn;
+    cudaStream_t stream;
+    bool armed;
+    ~DoneGuard() {
+      if (armed && done != nullptr && sn != 0u) {
+        launch_publish_done(done, sn, stream);
+        cudaGetLastError();
+      }
+    }
+  } done_guard{fused ? w->done : nullptr, sn, stream, true};
   unsigned int* zbase = w->fzero + par * zero_stride;
   unsigned char* wsbase = static_cast<unsigned char*>(w->fws) + par * ws_stride;
   unsigned long long* candbase = w->fcand + par * n_regions * cap;
@@ -967,6 +980,7 @@ int filter_segments(wdbx_b200_engine* e, int s0, int s1, const float* q_dev, int
                                 xseq, foverflow, min_score, use_allow, nullptr, fused ? w->done : nullptr,
                                 fused ? zbase + off_doneb : nullptr, sn);
   w->last_fused = fused && rrc == WDBX_B200_OK;
+  done_guard.armed = rrc != WDBX_B200_OK;   // the closing launch publishes the number itself
   if (e->ktiming) {
     e->last_kernel = use_i8 ? 3 : 2;
     e->kpending = true;

@@ -2033,6 +2033,17 @@ cudaError_t launch_prep_queries(const float* q, int B, int dim, void* workspace,
 
 bool filter_fused_tail(int B) { return small_batch_mode(B); }
 
+namespace {
+__global__ void publish_done_kernel(unsigned int* done_ctr, unsigned int sn) { atomicMax(done_ctr, sn); }
+}  // namespace
+
+// A numbered search that could not be launched completely must still be marked finished, or the searches behind it
+// would each wait (bounded, but seconds) for a number that never comes.
+cudaError_t launch_publish_done(unsigned int* done_ctr, unsigned int sn, cudaStream_t stream) {
+  publish_done_kernel<<<1, 1, 0, stream>>>(done_ctr, sn);
+  return cudaGetLastError();
+}
+
 // One launch per segment.  xb = bf16 matrix [n_rows][ld_x] (shadow, or the stored rows of a bf16 engine).
 cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, const SegDesc& seg, int seg_index, int dim,
                                const void* workspace, int B, int k, int metric, float acc_rel, float c_l2, int n_slices,

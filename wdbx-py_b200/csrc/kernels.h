@@ -155,6 +155,7 @@ struct FilterTail {
   int* counts_out;
 };
 bool filter_fused_tail(int B);
+cudaError_t launch_publish_done(unsigned int* done_ctr, unsigned int sn, cudaStream_t stream);
 cudaError_t launch_gemm_filter(const void* xb, int ld_x, const float* rres, const SegDesc& seg, int seg_index, int dim,
                                const void* workspace, int B, int k, int metric, float acc_rel, float c_l2, int n_slices,
                                unsigned long long* cand,
