@@ -293,7 +293,7 @@ __global__ void shadow8_rows_kernel(const void* __restrict__ rows_raw, long long
     xi = fminf(fmaxf(xi, -127.0f), 127.0f);
     if (bad) xi = 0.0f;
     d[c] = static_cast<signed char>(static_cast<int>(xi));
-    const float t = v - sx * xi;
+    const float t = fmaf(-sx, xi, v);   // ONE rounding of the exact residual (an unfused sx * xi could round it to 0)
     sr = fmaf(t, t, sr);
   }
 #pragma unroll
