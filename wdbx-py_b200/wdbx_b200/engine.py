@@ -308,13 +308,15 @@ class Engine:
         check(self._lib.wdbx_b200_set_tuning(self._handle(), warps, stages, rows_unroll, grid, evict_first))
 
     def set_option(self, name: str, value: int):
-        """Routing knob of a live engine ("shadow_min_mb", "gemm_min_batch", "gemm_mode", "pdl", "queries_per_pass");
+        """Routing knob of a live engine ("shadow_min_mb", "gemm_min_batch", "gemm_mode", "pdl", "overlap", "filter_i8",
+        "queries_per_pass");
         results are identical for every setting.  Benchmark hook."""
         check(self._lib.wdbx_b200_set_option(self._handle(), name.encode(), int(value)))
 
     def set_kernel_timing(self, enable: bool = True):
         """Bracket the dominant kernel of every search with CUDA events; `stats()` then carries
-        `last_kernel` (1 = K1 scan, 2 = K2b filter) and `last_kernel_ms`.  Measurement hook."""
+        `last_kernel` (1 = K1 scan, 2 = K2b filter over the bf16 shadow, 3 = small-batch filter over the int8 shadow) and
+        `last_kernel_ms`.  Measurement hook."""
         check(self._lib.wdbx_b200_set_kernel_timing(self._handle(), 1 if enable else 0))
 
     def stats(self) -> Dict:
