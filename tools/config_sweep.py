@@ -55,9 +55,14 @@ def run(name, n, dim, dtype, metric, k, B, iters, gemm=16, shadow_mb=None):
         r.update(kernel="K1 scan_topk (stored rows)", kernel_hbm_gbs=stored * passes / kernel_ms / 1e6,
                  frac_of_measured_hbm_peak=stored * passes / kernel_ms / 1e6 / PEAK)
     else:
-        shadow = n * ((dim + 7) // 8 * 8) * 2 + 4 * n
+        if kid == 3:   # small-batch kernel over the 1-byte shadow (+ 1/|x|, scale, |r| per row)
+            shadow = n * ((dim + 15) // 16 * 16) + 12 * n
+            kname = "K2b gemm_filter_small (kind::i8 tcgen05 over the 1-byte shadow, in-kernel exact re-score, one launch)"
+        else:
+            shadow = n * ((dim + 7) // 8 * 8) * 2 + 4 * n
+            kname = "K2b gemm_filter (bf16 tcgen05 over the 2-byte shadow) + exact fp32 refine"
         fl = 2.0 * n * dim * B
-        r.update(kernel="K2b gemm_filter (bf16 tcgen05 over the 2-byte shadow) + exact fp32 refine",
+        r.update(kernel=kname,
                  kernel_hbm_gbs=shadow / kernel_ms / 1e6, frac_of_measured_hbm_peak=shadow / kernel_ms / 1e6 / PEAK,
                  useful_tflops=fl / ms / 1e9, frac_of_measured_bf16_peak=fl / ms / 1e9 / BF16_PEAK,
                  fp32_scan_equivalent_gbs=stored / ms / 1e6)
