@@ -8,7 +8,7 @@ import pytest
 
 import wdbx_b200
 from tests import golden_checks as gc
-from tests.fake_engine import FakeEngine, pack_keys, unpack_keys
+from tests.fake_engine import FakeEngine, FakeGroup, pack_keys, unpack_keys
 
 
 def make_store(dim, shards, **cfg):
@@ -352,6 +352,35 @@ def test_single_process_multi_device_store_matches_one_device(tmp_path):
         back = build(tmp_path / "multi", **cfg)
         assert _multi_probe(back, X, Q) == want
         back.close()
+
+
+def test_multi_device_append_is_all_or_nothing():
+    """A device that cannot make room fails the append BEFORE any stripe is written: the segment's positions stay
+    aligned over the devices and the next append works (multi_engine.py, pre-flight reserve)."""
+    from wdbx_b200.multi_engine import MultiEngine
+
+    class Tight(FakeEngine):
+        limit = None
+
+        def reserve(self, segment, rows):
+            self.reserved = max(getattr(self, "reserved", 0), rows)
+            if self.limit is not None and rows > self.limit:
+                raise MemoryError(f"device {self.device}: cannot hold {rows} rows")
+
+    me = MultiEngine([0, 1, 2], 4, "fp32", 1, _engine_factory=Tight, _group_factory=FakeGroup)
+    X = np.arange(40, dtype=np.float32).reshape(10, 4)
+    assert me.append(0, X[:5]) == 0
+    assert [e.rows[0].shape[0] for e in me.engines] == [2, 2, 1]
+    assert [e.reserved for e in me.engines] == [2, 2, 1]
+    me.engines[2].limit = 1                     # device 2 is full
+    with pytest.raises(MemoryError):
+        me.append(0, X[5:])                     # would put rows 5 and 8 on device 2
+    assert [e.rows[0].shape[0] for e in me.engines] == [2, 2, 1] and me._seg_rows == [5]
+    me.engines[2].limit = None
+    assert me.append(0, X[5:]) == 5
+    assert [e.rows[0].shape[0] for e in me.engines] == [4, 3, 3]
+    np.testing.assert_array_equal(me.read_rows(0, 0, 10), X)
+    me.close()
 
 
 def test_gpu_devices_spec_parsing():

@@ -165,8 +165,14 @@ class MultiEngine:
         if gids.shape[0] != m:
             raise ValueError("gids length mismatch")
         G = self.G
+        # all-or-nothing: make room on EVERY device first (reserve is where a device runs out of memory), so a failure
+        # cannot leave some stripes appended and others not -- that would shift every later position of the segment
         for d, e in enumerate(self.engines):
             off = (d - n0) % G           # first appended row that lands on device d
+            if off < m:
+                e.reserve(segment, (n0 + off) // G + (m - off + G - 1) // G)
+        for d, e in enumerate(self.engines):
+            off = (d - n0) % G
             if off >= m:
                 continue
             part = rows[off::G]
