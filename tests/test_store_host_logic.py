@@ -391,3 +391,56 @@ def test_gpu_devices_spec_parsing():
     assert parse_devices([1, 0]) == [1, 0] and parse_devices(2) == [0, 1] and parse_devices("1-2,4") == [1, 2, 4]
     with pytest.raises(ValueError):
         parse_devices("0,0")
+
+
+def test_searches_inside_an_append_resolve_ids_and_metadata(tmp_path):
+    """Searches do not take the store lock (the reference runs them on a thread pool next to `add`,
+    indexing.py:692).  A search that lands right after the device append -- before the host bookkeeping of that
+    append is complete -- must already see the new rows under their ids, with their metadata (the reference sets
+    metadata before index.add, vector_store.py:241-246), never under the str(gid) fallback."""
+    seen = []
+
+    class Hooked(FakeEngine):
+        hook = None
+
+        def append(self, segment, rows, gids=None):
+            first = super().append(segment, rows, gids=gids)
+            if Hooked.hook is not None:
+                Hooked.hook()
+            return first
+
+    st = wdbx_b200.VectorStore(4, tmp_path, num_shards=2, config=wdbx_b200.WDBXConfig({"GPU_STRICT": True}),
+                               dist=wdbx_b200.DistContext(0, 1, 0), _engine_factory=Hooked)
+    q = [1.0, 0.0, 0.0, 0.0]
+
+    def probe():
+        located = set(st._loc)
+        seen.append((st.search(q, limit=50), located))
+        seen.append((st.search(q, limit=50, filter_metadata={"tag": "new"}), located))
+
+    # later rows score higher, so a search inside their append returns THEM (k is clipped to the old live count)
+    Hooked.hook = probe
+    assert st.store("a", [1.0, 0.6, 0.0, 0.0], {"tag": "new"})
+    assert st.batch_store({"b": [1.0, 0.5, 0.0, 0.0], "c": [1.0, 0.4, 0.0, 0.0]}, {"b": {"tag": "new"}, "c": {"tag": "new"}}) == 2
+    assert st.bulk_load(np.asarray([[1.0, 0.3, 0.0, 0.0], [1.0, 0.2, 0.0, 0.0], [1.0, 0.1, 0.0, 0.0]], np.float32), id_prefix="k") == 3
+    Hooked.hook = None
+    known = {"a", "b", "c", "k0", "k1", "k2"}
+    early = 0
+    for res, located in seen:
+        for vid, score, meta in res:
+            assert vid in known, f"a search inside an append saw the fallback id {vid!r}"
+            if vid in ("a", "b", "c"):
+                assert meta == {"tag": "new"}
+                early += vid not in located
+            else:
+                early += 1        # bulk rows are only ever probed inside their own bulk_load here
+    assert early > 0, "no probe hit the window this test is about"
+    # a failing append leaves nothing behind: no id, no metadata, and the next store works
+    def boom():
+        raise RuntimeError("device append failed")
+    Hooked.hook = boom
+    st.strict = False
+    assert st.store("z", [0.0, 1.0, 0.0, 0.0], {"tag": "z"}) is False
+    Hooked.hook = None
+    assert "z" not in st.metadata and st._locate("z") is None
+    st.close()

@@ -457,16 +457,25 @@ class VectorStore:
             ns = np.arange(n0, n0 + m)
             gids = np.arange(g0, g0 + m, dtype=np.uint32)
             mine = (ns % world) == rank
-            if mine.any():
-                sel = np.asarray(fresh)[mine]
-                rows = mat if len(sel) == mat.shape[0] else mat[sel]
-                first = self.engine.append(shard, rows, gids=gids[mine])
-                expect = self.shard_map.owner(int(ns[mine][0]))[1]
-                if first != expect:
-                    raise RuntimeError(f"shard {shard}: device row {first} != expected {expect} (store out of sync)")
+            # gid -> id FIRST: searches do not take the store lock (the reference's thread pool runs them next to
+            # `add`, indexing.py:692), and one that lands between the device append and the bookkeeping below must
+            # already resolve the new rows' ids instead of the str(gid) fallback
+            for i in fresh:
+                self._gid_to_id.append(ids[i])
+            try:
+                if mine.any():
+                    sel = np.asarray(fresh)[mine]
+                    rows = mat if len(sel) == mat.shape[0] else mat[sel]
+                    first = self.engine.append(shard, rows, gids=gids[mine])
+                    expect = self.shard_map.owner(int(ns[mine][0]))[1]
+                    if first != expect:
+                        raise RuntimeError(f"shard {shard}: device row {first} != expected {expect} (store out of sync)")
+            except BaseException:
+                for g in range(g0, g0 + m):     # the gids stay consumed (they only have to be unique)
+                    self._gid_to_id[g] = None
+                raise
             for j, i in enumerate(fresh):
                 self._loc[ids[i]] = (shard, n0 + j, g0 + j)
-                self._gid_to_id.append(ids[i])
             self._row_gids[shard].append(gids)
             self._shard_count[shard] += m
             self._shard_live[shard] += m
@@ -516,10 +525,20 @@ class VectorStore:
             shard = self._get_shard_for_id(vector_id)
             with self._lock:
                 loc = self._locate(vector_id)
-                ok = self.indices[loc[0] if loc else shard].add(vector_id, vec)
-                if ok:
-                    self.metadata[vector_id] = metadata or {}
-                    self._version += 1
+                # metadata BEFORE the row becomes searchable, as the reference does (vector_store.py:241-246): a
+                # concurrent search that finds the new row must see (and post-filter on) its metadata
+                had, prev = vector_id in self.metadata, self.metadata.get(vector_id)
+                self.metadata[vector_id] = metadata or {}
+                ok = False
+                try:
+                    ok = self.indices[loc[0] if loc else shard].add(vector_id, vec)
+                finally:
+                    if ok:
+                        self._version += 1
+                    elif had:
+                        self.metadata[vector_id] = prev
+                    else:
+                        self.metadata.pop(vector_id, None)
             if ok and self.config.get("VECTOR_STORE_SAVE_IMMEDIATELY", False):
                 self._save_metadata()
             return bool(ok)
@@ -545,11 +564,22 @@ class VectorStore:
                 shard_vectors.setdefault(shard, {})[vector_id] = vec
             stored = 0
             for shard, vecs in shard_vectors.items():
-                if self.indices[shard].batch_add(vecs):
-                    stored += len(vecs)
-                    for vid in vecs:
-                        self.metadata[vid] = metadata.get(vid, {})
-                    self._version += 1
+                prev = {vid: self.metadata[vid] for vid in vecs if vid in self.metadata}
+                for vid in vecs:                      # metadata first (see store)
+                    self.metadata[vid] = metadata.get(vid, {})
+                ok = False
+                try:
+                    ok = self.indices[shard].batch_add(vecs)
+                finally:
+                    if ok:
+                        stored += len(vecs)
+                        self._version += 1
+                    else:
+                        for vid in vecs:
+                            if vid in prev:
+                                self.metadata[vid] = prev[vid]
+                            else:
+                                self.metadata.pop(vid, None)
         if self.config.get("VECTOR_STORE_SAVE_IMMEDIATELY", False):
             self._save_metadata()
         return stored
@@ -583,30 +613,38 @@ class VectorStore:
                         raise ValueError(f"id_prefix {id_prefix!r} collides with the existing id {vid!r}")
             g0 = len(self._gid_to_id)
             base = list(self._shard_count)
-            for s in range(S):
-                cnt = (n - s + S - 1) // S if n > s else 0
-                if cnt == 0:
-                    continue
-                n0 = base[s]
-                ns = np.arange(n0, n0 + cnt)
-                mine = (ns % world) == rank
-                src_idx = s + S * np.arange(cnt)
-                gids = (g0 + src_idx).astype(np.uint32)
-                if local is not None:
-                    if int(mine.sum()) != int(local.shape[0]):
-                        raise ValueError("local tensor does not match this rank's stripe")
-                    self.engine.append(s, local, gids=gids[mine])
-                elif mine.any():
-                    sel = src_idx[mine]
-                    part = rows[sel] if not (S == 1 and world == 1) else rows
-                    self.engine.append(s, part, gids=gids[mine])
-                self._row_gids[s].append(gids)
-                self._shard_count[s] += cnt
-                self._shard_live[s] += cnt
+            # the synthetic id range FIRST (see _add_rows: concurrent searches must resolve the new rows' ids)
             self._gid_to_id.skip(n)
             self._bulk.append((g0, g0 + n, id_prefix))
             self._bulk_starts.append(g0)
             self._bulk_rows[g0] = tuple(base)
+            s = 0
+            try:
+                for s in range(S):
+                    cnt = (n - s + S - 1) // S if n > s else 0
+                    if cnt == 0:
+                        continue
+                    n0 = base[s]
+                    ns = np.arange(n0, n0 + cnt)
+                    mine = (ns % world) == rank
+                    src_idx = s + S * np.arange(cnt)
+                    gids = (g0 + src_idx).astype(np.uint32)
+                    if local is not None:
+                        if int(mine.sum()) != int(local.shape[0]):
+                            raise ValueError("local tensor does not match this rank's stripe")
+                        self.engine.append(s, local, gids=gids[mine])
+                    elif mine.any():
+                        sel = src_idx[mine]
+                        part = rows[sel] if not (S == 1 and world == 1) else rows
+                        self.engine.append(s, part, gids=gids[mine])
+                    self._row_gids[s].append(gids)
+                    self._shard_count[s] += cnt
+                    self._shard_live[s] += cnt
+            except BaseException:
+                # shards s .. S-1 never received their rows: their ids of this bulk must not resolve to positions
+                self._bulk_cleared.setdefault(g0, set()).update(range(s, S))
+                self._version += 1
+                raise
             self._version += 1
         return n
 
