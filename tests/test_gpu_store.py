@@ -169,3 +169,74 @@ def test_opt_in_prefilter_on_device(built_lib):
         hi = pre.search(q.tolist(), limit=10, threshold=float(sc[4] + sc[5]) / 2, filter_metadata={"tag": "a"})
         assert [g[0] for g in hi] == [f"r{r}" for r in rows[:5]]       # threshold pushed into the kernel
     pre.close(); ref.close()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("route", ["filter", "scan"])
+def test_concurrent_searches_appends_and_deletes(built_lib, route, monkeypatch):
+    """The reference runs index searches on a 4-thread pool next to `add` with no locks of its own (indexing.py:692,
+    :1045-1048; SURVEY.md 8b "the engine must serialise append-vs-search itself").  Reader threads search while a
+    writer stores and deletes: every answer must be a well-formed top-10 of SOME state in between (sorted, distinct,
+    known ids, right metadata), the segments grow in place under the searches (the shadows with them on the filter
+    route), and once the writer is done every reader's query returns exactly the oracle's list for the final store."""
+    import threading
+
+    monkeypatch.setenv("WDBX_B200_GEMM_MIN_BATCH", "1" if route == "filter" else "0")
+    rng = np.random.default_rng(99)
+    dim, n0, n_new = 128, 40000, 240
+    X = rng.standard_normal((n0 + n_new, dim), dtype=np.float32)
+    Q = rng.standard_normal((3, dim), dtype=np.float32)
+    X[n0 + 5] = Q[0] * 2.0                  # a new row that takes over first place for reader 0
+    st = make_store(dim, 2)
+    st.bulk_load(X[:n0], id_prefix="v")
+    errors, done = [], threading.Event()
+
+    def reader(t):
+        try:
+            ql, last = Q[t].tolist(), None
+            first = st.search(ql, limit=10)
+            while True:
+                fin = done.is_set()
+                res = st.search(ql, limit=10)
+                ids = [r[0] for r in res]
+                assert len(res) == 10 and len(set(ids)) == 10, ids
+                assert all(a[1] >= b[1] for a, b in zip(res, res[1:])), res
+                for vid, _, meta in res:
+                    assert vid[0] in "vw" and vid[1:].isdigit(), vid
+                    assert meta == ({"i": int(vid[1:])} if vid[0] == "w" else {}), (vid, meta)
+                last = res
+                if fin:
+                    break
+            out[t] = (first, last)
+        except BaseException as e:   # noqa: BLE001
+            errors.append(repr(e))
+
+    def writer():
+        try:
+            for i in range(n_new):
+                assert st.store(f"w{i}", X[n0 + i].tolist(), {"i": i})
+                if i % 6 == 0:
+                    assert st.delete(f"v{i}")
+        except BaseException as e:   # noqa: BLE001
+            errors.append(repr(e))
+        finally:
+            done.set()
+
+    out = {}
+    threads = [threading.Thread(target=reader, args=(t,)) for t in range(3)] + [threading.Thread(target=writer)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(150)
+    assert not errors, errors[:3]
+    assert not any(th.is_alive() for th in threads)
+    dead = np.zeros(n0 + n_new, bool)
+    dead[np.arange(0, n_new, 6)] = True
+    names = [f"v{i}" for i in range(n0)] + [f"w{i}" for i in range(n_new)]
+    for t in range(3):
+        rows, _ = oracle.topk_desc(oracle.scores_fp64(X, Q[t], "cosine"), 10, dead=dead)
+        assert [r[0] for r in out[t][1]] == [names[r] for r in rows], t
+        assert st.search(Q[t].tolist(), limit=10) == out[t][1]
+    assert out[0][1][0][0] == "w5"
+    assert st.count() == n0 + n_new - len(np.arange(0, n_new, 6))
+    st.close()
