@@ -344,3 +344,52 @@ def test_large_k_radix_select(built_lib, n, dim, k, B, metric, dtype, nseg):
     got = gf[0, : cf[0]]
     assert np.all(ok[got]) and np.all(sf[0, : cf[0]] >= floor) and np.all(np.diff(sf[0, : cf[0]]) <= 0)
     eng.close()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("route", ["filter", "scan", "select"])
+def test_searches_on_several_streams_at_once(built_lib, route, monkeypatch):
+    """"`search` is re-entrant per (engine, stream)".  Three host threads drive device-resident searches
+    on three CUDA streams of one engine at the same time (the kernels of different streams share the SMs); every
+    result must equal the one-stream answer bit for bit -- per-stream workspaces, nothing engine-global on the path."""
+    import threading
+
+    import torch
+
+    monkeypatch.setenv("WDBX_B200_GEMM_MIN_BATCH", "0" if route == "scan" else "1")
+    rng = np.random.default_rng(31)
+    n, dim = 120000, 256
+    k = 200 if route == "select" else 10
+    eng = _engine(dim)
+    eng.append(0, torch.from_numpy(rng.standard_normal((n, dim), dtype=np.float32)).cuda())
+    nq = 24
+    Qd = torch.from_numpy(rng.standard_normal((nq, 1, dim), dtype=np.float32)).cuda()
+    want = []
+    for i in range(nq):
+        o = eng.search(Qd[i], k, "cosine")
+        torch.cuda.synchronize()
+        want.append((o["gids"].cpu().numpy().copy(), o["scores"].cpu().numpy().copy()))
+    errors = []
+
+    def worker(t):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for rep in range(4):
+                    outs = [eng.search(Qd[(i + 5 * t) % nq], k, "cosine", stream=st) for i in range(nq)]   # own buffers each
+                    st.synchronize()
+                    for i, o in enumerate(outs):
+                        g, s = want[(i + 5 * t) % nq]
+                        np.testing.assert_array_equal(o["gids"].cpu().numpy(), g)
+                        np.testing.assert_array_equal(o["scores"].cpu().numpy().view(np.uint32), s.view(np.uint32))
+        except BaseException as e:   # noqa: BLE001
+            errors.append(f"stream {t}: {e!r}"[:400])
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(3)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(150)
+    assert not any(th.is_alive() for th in threads)
+    assert not errors, errors
+    eng.close()
