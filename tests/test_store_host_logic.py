@@ -444,3 +444,34 @@ def test_searches_inside_an_append_resolve_ids_and_metadata(tmp_path):
     Hooked.hook = None
     assert "z" not in st.metadata and st._locate("z") is None
     st.close()
+
+
+def test_filter_operator_ladder_matches_the_reference_grid(tmp_path):
+    """tests/golden/filter_ops_golden.json holds what the reference's unmodified `VectorStore._matches_filter`
+    (wdbx/core/vector_store.py:414-463) answers -- or raises -- on 660 (metadata, filter) pairs; ours must agree on
+    every one, exceptions (by type) included."""
+    import json
+    from pathlib import Path
+
+    g = json.loads((Path(__file__).resolve().parent / "golden" / "filter_ops_golden.json").read_text())
+    st = wdbx_b200.VectorStore(4, tmp_path, num_shards=1, dist=wdbx_b200.DistContext(0, 1, 0), _engine_factory=FakeEngine)
+
+    def ours(f):
+        try:
+            return bool(st._matches_filter("id", f))
+        except Exception as e:   # noqa: BLE001
+            return "raises:" + type(e).__name__
+
+    it = iter(g["outcomes"])
+    n = 0
+    for md in g["metadata"]:
+        st.metadata = {"id": md}
+        for f in g["filters"]:
+            want = next(it)
+            assert ours(f) == want, (md, f, want)
+            n += 1
+    st.metadata = {}
+    for f, want in zip(g["filters"], g["no_entry"]):
+        assert ours(f) == want, ("no metadata entry", f, want)
+    assert n == len(g["outcomes"]) == 660
+    st.close()
