@@ -216,9 +216,10 @@ def test_data_feeders_csv_jsonl(tmp_path):
 
     assert du.parse_vector("[1, 2.5, -3]") == [1.0, 2.5, -3.0]
     assert du.parse_vector("1, 2,3") == [1.0, 2.0, 3.0] and du.parse_vector("1 2 3") == [1.0, 2.0, 3.0]
-    assert du.parse_vector("array([1., 2.])") == [1.0, 2.0] and du.parse_vector({"embedding": [1, 2]}) == [1.0, 2.0]
-    with pytest.raises(ValueError):
-        du.parse_vector("not a vector")
+    assert du.parse_vector("[1. 2.]") == [1.0, 2.0] and du.parse_vector({"embedding": [1, 2]}) == [1.0, 2.0]
+    for bad in ("not a vector", "array([1., 2.])"):     # numpy's repr (with commas) is rejected by the reference too
+        with pytest.raises(ValueError):
+            du.parse_vector(bad)
     csv_path = tmp_path / "v.csv"
     csv_path.write_text('id,vec,lang\na,"[1,0,0,0]",en\nb,"0 1 0 0",de\nbad,"oops",xx\nc,"0,0,1,0",en\n')
     vecs, meta = du.load_vectors_from_csv(str(csv_path), "vec", id_column="id", metadata_columns=["lang"])
@@ -475,3 +476,51 @@ def test_filter_operator_ladder_matches_the_reference_grid(tmp_path):
         assert ours(f) == want, ("no metadata entry", f, want)
     assert n == len(g["outcomes"]) == 660
     st.close()
+
+
+def test_feeders_match_the_reference_on_the_loader_grid(tmp_path):
+    """tests/golden/loader_golden.json: the reference's unmodified parse_vector / load_vectors_from_csv /
+    load_vectors_from_jsonl (wdbx/utils/data_utils.py) on 51 vector notations and 27 loader calls over small files
+    (quoted multi-line cells, bad rows, duplicate ids, index vs name addressing, missing columns / fields / files);
+    ours must return the same dictionaries and raise the same exception types."""
+    import json
+    import logging
+    from pathlib import Path
+
+    from wdbx_b200 import data_utils as du
+
+    g = json.loads((Path(__file__).resolve().parent / "golden" / "loader_golden.json").read_text())
+
+    def jsonable(x):
+        if isinstance(x, dict):
+            return {(k if isinstance(k, str) else f"<{k!r}>"): jsonable(v) for k, v in x.items()}
+        if isinstance(x, (list, tuple)):
+            return [jsonable(v) for v in x]
+        if isinstance(x, float) and (x != x or x in (float("inf"), float("-inf"))):
+            return f"<{x!r}>"
+        return x
+
+    def outcome(fn, *a, **kw):
+        try:
+            return jsonable({"ok": fn(*a, **kw)})
+        except Exception as e:   # noqa: BLE001
+            return {"raises": type(e).__name__}
+
+    # the parse inputs as they were before JSON flattened them (a tuple among them): the literal grid of the generator
+    logging.disable(logging.CRITICAL)
+    try:
+        src = (Path(__file__).resolve().parent / "golden" / "make_loader_golden.py").read_text()
+        ns = {}
+        exec(src[src.index("PARSE = ["):src.index("CSV_FILES = {")], ns)   # the literal grid only, nothing from /root/reference
+        assert jsonable(ns["PARSE"]) == g["parse_inputs"]
+        for x, want in zip(ns["PARSE"], g["parse"]):
+            assert outcome(du.parse_vector, x) == want, (x, want)
+        for name, text in list(g["csv_files"].items()) + list(g["jsonl_files"].items()):
+            with open(tmp_path / name, "w", encoding="utf-8", newline="") as f:
+                f.write(text)
+        for (name, kw), want in zip(g["csv_calls"], g["csv"]):
+            assert outcome(du.load_vectors_from_csv, str(tmp_path / name), **kw) == want, (name, kw)
+        for (name, kw), want in zip(g["jsonl_calls"], g["jsonl"]):
+            assert outcome(du.load_vectors_from_jsonl, str(tmp_path / name), **kw) == want, (name, kw)
+    finally:
+        logging.disable(logging.NOTSET)

@@ -17,8 +17,11 @@ Metadata = Dict[str, Dict[str, Any]]
 
 
 def parse_vector(vector_data: Union[str, List, Dict]) -> List[float]:
-    """list | '[1, 2]' | '1,2' | '1 2' | 'array([1., 2.])' | {'vector'|'embedding'|'values'|'data': ...}
-    -> list of floats (reference: data_utils.py:174-231)."""
+    """list | '[1, 2]' | '1,2' | '1 2' | '[1. 2.]' (numpy str) | {'vector'|'embedding'|'values'|'data': ...}
+    -> list of floats.  Same acceptance set and the same exception types as the reference (data_utils.py:174-231;
+    tests/golden/loader_golden.json): a JSON array whose elements are not numbers raises what ``float`` raises
+    (only a JSON syntax error falls through to the other notations), and ``'array([1., 2.])'`` -- numpy's repr, with
+    commas -- is NOT accepted, exactly as there."""
     if isinstance(vector_data, list):
         return [float(x) for x in vector_data]
     if isinstance(vector_data, dict):
@@ -31,19 +34,18 @@ def parse_vector(vector_data: Union[str, List, Dict]) -> List[float]:
     text = vector_data.strip()
     if text.startswith("[") and text.endswith("]"):
         try:
-            return [float(x) for x in json.loads(text)]
-        except (json.JSONDecodeError, TypeError, ValueError):
-            pass
-    for splitter in (lambda t: t.split(","), lambda t: t.split()):
+            parsed = json.loads(text)
+        except json.JSONDecodeError:
+            parsed = None
+        else:
+            return [float(x) for x in parsed]
+    stripped = text.replace("array(", "").replace(")", "").replace("[", "").replace("]", "")
+    for pieces in (lambda: text.split(","), lambda: text.split(), lambda: stripped.split()):
         try:
-            return [float(x.strip()) for x in splitter(text)]
+            return [float(x.strip()) for x in pieces()]
         except ValueError:
             pass
-    cleaned = text.replace("array(", "").replace(")", "").replace("[", "").replace("]", "").replace(",", " ")
-    try:
-        return [float(x) for x in cleaned.split()]
-    except ValueError:
-        raise ValueError(f"Could not parse vector from string: {vector_data}") from None
+    raise ValueError(f"Could not parse vector from string: {vector_data}")
 
 
 def load_vectors_from_csv(file_path: str, vector_column: Union[str, int], id_column: Optional[Union[str, int]] = None,
@@ -55,7 +57,7 @@ def load_vectors_from_csv(file_path: str, vector_column: Union[str, int], id_col
     metadata: Metadata = {}
     by_name = isinstance(vector_column, str) or bool(metadata_columns and any(isinstance(c, str) for c in metadata_columns))
     try:
-        with open(file_path, "r", encoding="utf-8", newline="") as f:
+        with open(file_path, "r", encoding="utf-8") as f:   # universal newlines, as the reference opens it
             if by_name:
                 rows = csv.DictReader(f, delimiter=delimiter)
             else:
