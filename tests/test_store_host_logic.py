@@ -146,6 +146,10 @@ def test_async_micro_batching_matches_sync():
     # filtered requests bypass the batcher and keep the reference semantics
     f = asyncio.run(st.search_async(Q[0].tolist(), limit=5, filter_metadata={"i": {"$lt": 100}}))
     assert f == st.search(Q[0].tolist(), limit=5, filter_metadata={"i": {"$lt": 100}})
+    # a query of the wrong dimension: logged and [] like the reference's index-level convention (indexing.py:1028-1030);
+    # GPU_STRICT raises (the WDBX facade validates dimensions itself and always raises, wdbx.py:323-326)
+    assert asyncio.run(st.search_async([0.0] * 3)) == [] and st.search([0.0] * 3) == []
+    st.strict = True
     with pytest.raises(ValueError, match="dimension mismatch"):
         asyncio.run(st.search_async([0.0] * 3))
     st.close()
@@ -255,6 +259,8 @@ def test_list_query_conversion_matches_numpy():
         assert np.array_equal(st._query_array([1e39] * 8), np.array([1e39] * 8, dtype=np.float32))   # overflow -> inf via numpy
     assert st._query_array(np.arange(8)).dtype == np.float32                  # non-list input
     assert st._query_array([0.0] * 3).shape == (3,)                           # wrong length: numpy path, search() raises
+    assert st.search([0.0] * 3) == []
+    st.strict = True
     with pytest.raises(ValueError, match="dimension mismatch"):
         st.search([0.0] * 3)
     st.close()
@@ -524,3 +530,34 @@ def test_feeders_match_the_reference_on_the_loader_grid(tmp_path):
             assert outcome(du.load_vectors_from_jsonl, str(tmp_path / name), **kw) == want, (name, kw)
     finally:
         logging.disable(logging.NOTSET)
+
+
+def test_operator_boundary_never_raises_like_the_reference(tmp_path):
+    """Probed against the reference's unmodified VectorStore over the exact faiss stand-in (same call sequence, see
+    DESIGN.md section 1): a query / vector of the wrong dimension at the VectorStore or VectorIndex level is logged and
+    answered with [] / False (indexing.py:903-905, :1028-1030) -- only the WDBX facade raises (wdbx.py:323-326); limit <= 0
+    gives []; a filter whose comparison is a type error raises TypeError out of search (no try around it there either);
+    delete / update of unknown ids return False, get returns None.  Deliberate differences (DESIGN.md "decisions"): a
+    rejected vector is not counted, a deleted row is never returned, a duplicate id overwrites."""
+    st = wdbx_b200.VectorStore(4, tmp_path, num_shards=2, dist=wdbx_b200.DistContext(0, 1, 0), _engine_factory=FakeEngine)
+    assert st.search([1, 0, 0, 0], 5) == []
+    assert st.store("a", [1, 0, 0, 0], {"t": 1}) is True and st.store("b", [0, 1, 0, 0]) is True
+    assert st.store("w", [1, 2, 3]) is False and st.store("s", "abc") is False and st.store("e", []) is False
+    assert st.count() == 2 and "w" not in st.metadata
+    assert st.batch_store({"c": [1, 1, 0, 0], "d": [0, 0, 1, 0]}, {"c": {"t": 2}}) == 2
+    assert st.batch_store({"x": [1, 1], "y": [0, 0, 1, 0], "z": "oops"}, {}) == 1          # only y is a usable vector
+    assert st.count() == 5 and "x" not in st.metadata and st.get("x") is None
+    ix = st.indices[0]
+    assert ix.add("bad", np.zeros(3, np.float32)) is False
+    assert ix.batch_add({"r1": np.zeros(4, np.float32), "r2": np.zeros(2, np.float32)}) is False   # ragged: never raises
+    assert ix.search(np.zeros(3, np.float32), 3) == [] and ix.remove("nope") is False
+    assert st.search([1, 0.1, 0, 0], 0) == [] and st.search([1, 0.1, 0, 0], -1) == []
+    assert st.search([1, 0.1, 0], 3) == []
+    assert [r[0] for r in st.search([1, 0, 0, 0], 10, 0.7)] == ["a", "c"]
+    assert [r[0] for r in st.search([1, 0, 0, 0], 10, 0.0, {"t": {"$gte": 1}})] == ["a", "c"]
+    with pytest.raises(TypeError):
+        st.search([1, 0, 0, 0], 10, 0.0, {"t": {"$gt": "x"}})
+    assert st.get("zz") is None and st.update_metadata("zz", {}) is False and st.delete("zz") is False
+    assert st.delete("b") is True and st.delete("b") is False
+    assert "b" not in [r[0] for r in st.search([0, 1, 0, 0], 10)]
+    st.close()

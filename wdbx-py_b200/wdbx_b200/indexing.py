@@ -101,8 +101,9 @@ class B200FlatIndex(VectorIndex):
 
     # -- mutation ---------------------------------------------------------------------------
     def add(self, vector_id: str, vector: np.ndarray) -> bool:
-        return self._store._guard(False, self._store._add_rows, self.shard, [vector_id],
-                                  np.asarray(vector, dtype=np.float32)[None, :]) is not False
+        def run():
+            return self._store._add_rows(self.shard, [vector_id], np.asarray(vector, dtype=np.float32)[None, :])
+        return self._store._guard(False, run) is not False
 
     async def add_async(self, vector_id: str, vector: np.ndarray) -> bool:
         return await self._store._run(self.add, vector_id, vector)
@@ -110,9 +111,10 @@ class B200FlatIndex(VectorIndex):
     def batch_add(self, vectors: Dict[str, np.ndarray]) -> bool:
         if not vectors:
             return True
-        ids = list(vectors.keys())
-        mat = np.stack([np.asarray(v, dtype=np.float32) for v in vectors.values()])
-        return self._store._guard(False, self._store._add_rows, self.shard, ids, mat) is not False
+        def run():   # ragged input fails inside the guard: the operator boundary returns False, it never raises
+            mat = np.stack([np.asarray(v, dtype=np.float32) for v in vectors.values()])
+            return self._store._add_rows(self.shard, list(vectors.keys()), mat)
+        return self._store._guard(False, run) is not False
 
     async def batch_add_async(self, vectors: Dict[str, np.ndarray]) -> bool:
         return await self._store._run(self.batch_add, vectors)

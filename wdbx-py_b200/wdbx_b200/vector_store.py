@@ -384,12 +384,11 @@ class VectorStore:
 
     # ------------------------------------------------------------------ error convention
     def _guard(self, default, fn, *args):
-        """Reference convention: index errors are logged and swallowed (indexing.py:1028-1030);
-        GPU_STRICT re-raises."""
+        """Reference convention: index errors -- a query or vector of the wrong dimension included -- are logged and
+        swallowed (indexing.py:903-905, :1028-1030: the operator boundary never raises); GPU_STRICT re-raises.  The
+        facade validates dimensions itself and raises ValueError as the reference's does (wdbx.py:323-326)."""
         try:
             return fn(*args)
-        except ValueError:
-            raise
         except Exception as e:
             if self.strict:
                 raise
@@ -558,7 +557,15 @@ class VectorStore:
         shard_vectors: Dict[int, Dict[str, np.ndarray]] = {}
         with self._lock:
             for vector_id, vector in vectors.items():
-                vec = np.array(vector, dtype=np.float32)
+                try:
+                    vec = np.array(vector, dtype=np.float32)
+                    if vec.shape != (self.vector_dim,):
+                        raise ValueError(f"Vector dimension mismatch: expected {self.vector_dim}, got {vec.shape}")
+                except Exception as e:   # one bad vector does not take its shard's batch down; the count says so
+                    if self.strict:
+                        raise
+                    logger.error(f"Error storing vector {vector_id!r}: {e}")
+                    continue
                 loc = self._locate(vector_id)
                 shard = loc[0] if loc else self._get_shard_for_id(vector_id)
                 shard_vectors.setdefault(shard, {})[vector_id] = vec
@@ -880,8 +887,8 @@ class VectorStore:
         if self._batcher is not None and not filter_metadata:
             # micro-batching front-end: concurrent requests share one device pass (batcher.py)
             query_np = self._query_array(query_vector)
-            if query_np.shape != (self.vector_dim,):
-                raise ValueError(f"Vector dimension mismatch: expected {self.vector_dim}, got {query_np.shape[-1]}")
+            if query_np.shape != (self.vector_dim,):   # same outcome as the synchronous path: logged and [] (GPU_STRICT: raises)
+                return self.search(query_vector, limit, threshold, None)
             return await asyncio.wrap_future(self._batcher.submit(query_np, limit, threshold))
         return await self._run(self.search, query_vector, limit, threshold, filter_metadata)
 
