@@ -1,0 +1,73 @@
+"""Replay of tests/golden/api_probe_golden.json: the call sequences the generator ran against the reference's
+unmodified VectorStore / WDBX (tests/golden/make_api_golden.py) must give the same outcomes -- return values,
+exception types and messages -- through wdbx_b200, except at the steps the fixture lists as deliberate deviations.
+CPU: numpy engine double; `-m gpu`: the real engine on a B200."""
+import json
+import tempfile
+from pathlib import Path
+
+import pytest
+
+import wdbx_b200
+from tests.fake_engine import FakeEngine
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def _play():
+    # the generator's `play` / `norm` helpers only (nothing in them touches /root/reference)
+    src = (GOLDEN / "make_api_golden.py").read_text()
+    ns = {}
+    exec("import asyncio\n" + src[src.index("def norm(x):"):src.index("def main():")], ns)
+    return ns["play"]
+
+
+def _check(kind, script, want, got, deviations):
+    assert len(got) == len(want) == len(script)
+    for (name, method, args), w, g in zip(script, want, got):
+        if name in deviations.get(kind, {}):
+            ours, why = deviations[kind][name]
+            assert g == ours, (kind, name, "deviation expected", ours, "got", g, why)
+            assert g != w, (kind, name, "listed as a deviation but equals the reference")
+        else:
+            assert g == w, (kind, name, method, args, "reference", w, "ours", g)
+
+
+def _run(factory_kw):
+    g = json.loads((GOLDEN / "api_probe_golden.json").read_text())
+    play = _play()
+    with tempfile.TemporaryDirectory() as t1:
+        st = wdbx_b200.VectorStore(4, t1, num_shards=2, **factory_kw)
+        got = play(st, g["store_script"])
+        st.close()
+    _check("store", g["store_script"], g["store"], got, g["deviations"])
+    return g, play
+
+
+def test_vector_store_script_matches_the_reference():
+    _run({"dist": wdbx_b200.DistContext(0, 1, 0), "_engine_factory": FakeEngine})
+
+
+def test_facade_script_matches_the_reference(monkeypatch):
+    import wdbx_b200.vector_store as vsmod
+
+    g = json.loads((GOLDEN / "api_probe_golden.json").read_text())
+    orig = vsmod.VectorStore.__init__
+
+    def patched(self, *a, **kw):   # the facade builds its own store: give that one the numpy double too
+        kw.setdefault("_engine_factory", FakeEngine)
+        kw.setdefault("dist", wdbx_b200.DistContext(0, 1, 0))
+        orig(self, *a, **kw)
+
+    monkeypatch.setattr(vsmod.VectorStore, "__init__", patched)
+    with tempfile.TemporaryDirectory() as t2:
+        got = _play()(wdbx_b200.WDBX(vector_dimension=4, num_shards=2, data_dir=t2, log_level="ERROR"), g["facade_script"])
+    _check("facade", g["facade_script"], g["facade"], got, g["deviations"])
+
+
+@pytest.mark.gpu
+def test_scripts_match_the_reference_on_the_device(built_lib):
+    g, play = _run({})
+    with tempfile.TemporaryDirectory() as t2:
+        got = play(wdbx_b200.WDBX(vector_dimension=4, num_shards=2, data_dir=t2, log_level="ERROR"), g["facade_script"])
+    _check("facade", g["facade_script"], g["facade"], got, g["deviations"])
