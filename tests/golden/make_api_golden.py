@@ -87,26 +87,62 @@ FACADE_SCRIPT = [
     ["count after clear", "count_vectors", []],
     ["shutdown", "shutdown", []],
 ]
+# the operator boundary itself (VectorIndex, indexing.py:18-217): the reference's FaissIndex, ours = the shard facade
+# of a one-shard store.  {"__nd__": [...]} stands for a float32 ndarray (the ABC's argument type)
+def _v(*x):
+    return {"__nd__": list(x)}
+
+
+INDEX_SCRIPT = [
+    ["initialize", "initialize", []],
+    ["size empty", "size", []],
+    ["search empty", "search", [_v(1, 0, 0, 0), 3]],
+    ["add a", "add", ["a", _v(1, 0, 0, 0)]],
+    ["add b", "add", ["b", _v(0, 2, 0, 0)]],
+    ["add wrong dim", "add", ["w", _v(1, 0, 0)]],
+    ["batch_add", "batch_add", [{"c": _v(1, 1, 0, 0), "d": _v(0, 0, 0, 5)}]],
+    ["batch_add empty", "batch_add", [{}]],
+    ["batch_add ragged", "batch_add", [{"r1": _v(1, 1, 0, 0), "r2": _v(0, 0)}]],
+    ["size", "size", []],
+    ["search", "search", [_v(1, 0.5, 0, 0), 3]],
+    ["search limit > size", "search", [_v(1, 0.5, 0, 0), 50]],
+    ["search limit 0", "search", [_v(1, 0.5, 0, 0), 0]],
+    ["search wrong dim", "search", [_v(1, 0.5, 0), 2]],
+    ["search_async", "search_async", [_v(0, 1, 0, 0), 2]],
+    ["remove b", "remove", ["b"]],
+    ["remove b again", "remove", ["b"]],
+    ["remove_async missing", "remove_async", ["zz"]],
+    ["size after remove", "size", []],
+    ["optimize", "optimize", []],
+    ["stats required keys", "get_stats:required", []],
+    ["stats size", "get_stats:size", []],
+    ["clear", "clear", []],
+    ["size cleared", "size", []],
+    ["search cleared", "search", [_v(1, 0, 0, 0), 2]],
+    ["add_async after clear", "add_async", ["z", _v(0, 0, 0, 1)]],
+    ["search after clear", "search", [_v(0, 0, 0, 1), 2]],
+    ["shutdown", "shutdown", []],
+]
 # step -> [what ours returns instead, the decision behind it]
 DEVIATIONS = {
     "store": {
-        "search after delete": [["ok", [["a", 0.0, {"t": 9}], ["b", 0.0, {}], ["c", 0.0, {"t": 2}]]],
+        "search after delete": [["ok", [["a", 0.0, {"t": 9}], ["b", 0.0, {}], ["c", 0.0, {"t": 2}]], "list"],
                                 "decision 1 (deleted rows are never returned; the reference returns the row as str(row) "
                                 "with {} metadata) and decision 5 (ties: lower insertion id first)"],
-        "stats keys": [["ok", ["gpu", "index_type", "indices", "metadata_count", "num_shards", "use_gpu", "vector_count", "vector_dim"]],
+        "stats keys": [["ok", ["gpu", "index_type", "indices", "metadata_count", "num_shards", "use_gpu", "vector_count", "vector_dim"], "list"],
                        "additive: the engine's device counters under 'gpu'"],
     },
     "facade": {
         "stats keys": [["ok", ["distributed_enabled", "gpu", "gpu_enabled", "index_type", "indices", "metadata_count", "num_shards",
                                "plugins_enabled", "plugins_loaded", "total_vectors", "use_gpu", "vector_count", "vector_dim",
-                               "vector_dimension", "version"]], "additive: 'gpu'"],
+                               "vector_dimension", "version"], "list"], "additive: 'gpu'"],
     },
 }
 
 
 def norm(x):
-    if isinstance(x, float):
-        return round(x, 5)
+    if isinstance(x, float) or type(x).__name__ in ("float32", "float64"):
+        return round(float(x), 5)
     if isinstance(x, (list, tuple)):
         return [norm(v) for v in x]
     if isinstance(x, dict):
@@ -116,6 +152,15 @@ def norm(x):
 
 def play(obj, script):
     """shared with the tests: run a script against `obj`, normalised outcomes"""
+    import numpy as np
+
+    def dec(a):
+        if isinstance(a, dict) and "__nd__" in a:
+            return np.asarray(a["__nd__"], dtype=np.float32)
+        if isinstance(a, dict):
+            return {k: dec(v) for k, v in a.items()}
+        return a
+
     loop = asyncio.new_event_loop()
     out = []
     try:
@@ -125,11 +170,15 @@ def play(obj, script):
                     r = sorted(obj.get_stats().keys())
                 elif method == "get_stats:indices":
                     r = len(obj.get_stats()["indices"])
+                elif method == "get_stats:required":
+                    r = sorted(k for k in obj.get_stats() if k in ("type", "size", "dimension", "gpu_enabled"))
+                elif method == "get_stats:size":
+                    r = obj.get_stats()["size"]
                 else:
-                    r = getattr(obj, method)(*args)
+                    r = getattr(obj, method)(*[dec(a) for a in args])
                     if asyncio.iscoroutine(r):
                         r = loop.run_until_complete(r)
-                out.append(norm(["ok", r]))
+                out.append(norm(["ok", r]) + [type(r).__name__])
             except Exception as e:   # noqa: BLE001  (type + message are the recorded outcome)
                 out.append(["raises", type(e).__name__, str(e)[:60]])
     finally:
@@ -146,14 +195,20 @@ def main():
     from wdbx.core.vector_store import VectorStore   # the reference's classes, unmodified
     from wdbx.core.wdbx import WDBX
 
+    from wdbx.core.indexing import FaissIndex
+
+    with tempfile.TemporaryDirectory() as t0:
+        index = play(FaissIndex(4, Path(t0) / "ix", None), INDEX_SCRIPT)
     with tempfile.TemporaryDirectory() as t1, tempfile.TemporaryDirectory() as t2:
         store = play(VectorStore(vector_dim=4, data_dir=Path(t1), num_shards=2, index_type="faiss"), STORE_SCRIPT)
         facade = play(WDBX(vector_dimension=4, num_shards=2, data_dir=t2, enable_plugins=False,
                            config={"VECTOR_INDEX_TYPE": "faiss", "INDEX_TYPE": "faiss"}), FACADE_SCRIPT)
     OUT.write_text(json.dumps({"generator": "tests/golden/make_api_golden.py (reference VectorStore / WDBX over the exact faiss stand-in)",
-                               "store_script": STORE_SCRIPT, "store": store, "facade_script": FACADE_SCRIPT, "facade": facade,
+                               "index_script": INDEX_SCRIPT, "index": index, "store_script": STORE_SCRIPT, "store": store, "facade_script": FACADE_SCRIPT, "facade": facade,
                                "deviations": DEVIATIONS}, separators=(",", ":")))
-    print(f"wrote {OUT}: {len(store)} + {len(facade)} steps")
+    print(f"wrote {OUT}: {len(index)} + {len(store)} + {len(facade)} steps")
+    for (n, _, _), o in zip(INDEX_SCRIPT, index):
+        print("  index ", n, o)
     for (n, _, _), o in zip(STORE_SCRIPT, store):
         print("  store ", n, o)
     for (n, _, _), o in zip(FACADE_SCRIPT, facade):

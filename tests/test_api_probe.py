@@ -48,6 +48,20 @@ def test_vector_store_script_matches_the_reference():
     _run({"dist": wdbx_b200.DistContext(0, 1, 0), "_engine_factory": FakeEngine})
 
 
+def _index_script(factory_kw):
+    """the VectorIndex operator boundary: the reference's FaissIndex vs the shard facade of a one-shard store"""
+    g = json.loads((GOLDEN / "api_probe_golden.json").read_text())
+    with tempfile.TemporaryDirectory() as t0:
+        st = wdbx_b200.VectorStore(4, t0, num_shards=1, **factory_kw)
+        got = _play()(st.indices[0], g["index_script"])
+        st.close()
+    _check("index", g["index_script"], g["index"], got, g["deviations"])
+
+
+def test_vector_index_script_matches_the_reference():
+    _index_script({"dist": wdbx_b200.DistContext(0, 1, 0), "_engine_factory": FakeEngine})
+
+
 def test_facade_script_matches_the_reference(monkeypatch):
     import wdbx_b200.vector_store as vsmod
 
@@ -67,6 +81,7 @@ def test_facade_script_matches_the_reference(monkeypatch):
 
 @pytest.mark.gpu
 def test_scripts_match_the_reference_on_the_device(built_lib):
+    _index_script({})
     g, play = _run({})
     with tempfile.TemporaryDirectory() as t2:
         got = play(wdbx_b200.WDBX(vector_dimension=4, num_shards=2, data_dir=t2, log_level="ERROR"), g["facade_script"])
