@@ -1,0 +1,224 @@
+"""Model-based test of the host layer (hypothesis RuleBasedStateMachine; CPU, numpy engine double).
+
+Random sequences of the store's mutations -- store / overwrite, batch_store, bulk_load, delete, update_metadata, shard
+clear, clear, save + reload (also onto a different device count) -- run against ``wdbx_b200.VectorStore`` and against a
+plain-Python model of what the reference's semantics (plus DESIGN.md's documented decisions) say the store must hold.
+After every step: count, get, unfiltered search, post-filtered search (the reference's per-shard candidate set,
+vector_store.py:323-345) and the opt-in device pre-filter must agree with the model.  This is the class of bug ADVICE r1
+found by hand (bulk ids after a shard clear, non-canonical bulk ids, prefix collisions)."""
+import shutil
+import tempfile
+
+import numpy as np
+from hypothesis import HealthCheck, settings, strategies as st
+from hypothesis.stateful import RuleBasedStateMachine, initialize, invariant, rule
+
+import wdbx_b200
+from tests.fake_engine import FakeEngine
+from wdbx_b200.shard_map import shard_for_id
+
+DIM = 5
+S = 3
+EXPLICIT = [f"e{i}" for i in range(14)]
+
+
+def _vec(seed: int) -> np.ndarray:
+    return np.random.default_rng(seed).standard_normal(DIM).astype(np.float32)
+
+
+class StoreMachine(RuleBasedStateMachine):
+    devices = None          # subclass: GPU_DEVICES of the single-process multi-device layout
+
+    def _open(self):
+        cfg = {"GPU_STRICT": True}
+        if self.devices:
+            cfg["GPU_DEVICES"] = self.devices
+        return wdbx_b200.VectorStore(DIM, self.dir, num_shards=S, config=wdbx_b200.WDBXConfig(cfg),
+                                     dist=wdbx_b200.DistContext(0, 1, 0), _engine_factory=FakeEngine)
+
+    @initialize()
+    def start(self):
+        self.dir = tempfile.mkdtemp(prefix="wdbx_model_")
+        self.store = self._open()
+        self.model = {}        # id -> dict(vec, meta, shard, order)   live rows only
+        self.gone = set()      # ids that existed once and do not any more
+        self.order = 0         # insertion counter = the engine's gid order (tie rule)
+        self.prefixes = 0
+        self.seed = 1000
+
+    def teardown(self):
+        if getattr(self, "store", None) is not None:
+            self.store.close()
+        shutil.rmtree(getattr(self, "dir", ""), ignore_errors=True)
+
+    def _next_seed(self):
+        self.seed += 1
+        return self.seed
+
+    def _put(self, vid, vec, meta, shard_if_new):
+        if vid in self.model:
+            self.model[vid]["vec"] = vec          # overwrite in place: row (and tie order) kept
+            self.model[vid]["meta"] = meta
+        else:
+            self.model[vid] = {"vec": vec, "meta": meta, "shard": shard_if_new, "order": self.order}
+            self.gone.discard(vid)
+        self.order += 1
+
+    # ------------------------------------------------------------------ mutations
+    @rule(i=st.integers(0, len(EXPLICIT) - 1), g=st.integers(0, 2), with_meta=st.booleans())
+    def store_one(self, i, g, with_meta):
+        vid, vec = EXPLICIT[i], _vec(self._next_seed())
+        meta = {"g": g} if with_meta else None
+        assert self.store.store(vid, vec.tolist(), meta) is True
+        self._put(vid, vec, meta or {}, shard_for_id(vid, S))
+
+    @rule(target_bulk=st.booleans(), data=st.data())
+    def store_existing_bulk_id(self, target_bulk, data):
+        bulk_ids = [v for v in self.model if v.startswith("p")]
+        if not bulk_ids:
+            return
+        vid = data.draw(st.sampled_from(sorted(bulk_ids)))
+        vec = _vec(self._next_seed())
+        assert self.store.store(vid, vec.tolist(), {"g": 1}) is True
+        self._put(vid, vec, {"g": 1}, None)
+
+    @rule(data=st.data())
+    def store_a_gone_id_again(self, data):
+        """an id that was deleted / cleared (a former bulk id included) comes back as a fresh explicit row"""
+        if not self.gone:
+            return
+        vid = data.draw(st.sampled_from(sorted(self.gone)))
+        vec = _vec(self._next_seed())
+        assert self.store.store(vid, vec.tolist(), {"g": 2}) is True
+        self._put(vid, vec, {"g": 2}, shard_for_id(vid, S))
+
+    @rule(ids=st.lists(st.integers(0, len(EXPLICIT) - 1), min_size=1, max_size=5, unique=True), g=st.integers(0, 2))
+    def batch(self, ids, g):
+        vecs = {EXPLICIT[i]: _vec(self._next_seed()) for i in ids}
+        meta = {EXPLICIT[i]: {"g": g} for i in ids[::2]}
+        assert self.store.batch_store({k: v.tolist() for k, v in vecs.items()}, meta) == len(ids)
+        # rows are appended shard by shard, in dict order inside a shard: that is the insertion (tie) order
+        by_shard = {}
+        for vid in vecs:
+            shard = self.model[vid]["shard"] if vid in self.model else shard_for_id(vid, S)
+            by_shard.setdefault(shard, []).append(vid)
+        for shard, vids in by_shard.items():
+            for vid in vids:
+                self._put(vid, vecs[vid], meta.get(vid, {}), shard)
+
+    @rule(n=st.integers(1, 9))
+    def bulk(self, n):
+        prefix = f"p{self.prefixes}_"
+        self.prefixes += 1
+        X = np.stack([_vec(self._next_seed()) for _ in range(n)])
+        assert self.store.bulk_load(X, id_prefix=prefix) == n
+        base = self.order
+        for i in range(n):
+            self.model[f"{prefix}{i}"] = {"vec": X[i], "meta": {}, "shard": i % S, "order": base + i}
+        self.order += n
+
+    @rule(data=st.data())
+    def delete(self, data):
+        known = sorted(self.model) + ["e_unknown", "p0_999", "p0_01"]
+        vid = data.draw(st.sampled_from(known))
+        assert self.store.delete(vid) is (vid in self.model)
+        if self.model.pop(vid, None) is not None:
+            self.gone.add(vid)
+
+    @rule(data=st.data(), g=st.integers(0, 2))
+    def update_meta(self, data, g):
+        known = sorted(self.model) + ["e_unknown"]
+        vid = data.draw(st.sampled_from(known))
+        assert self.store.update_metadata(vid, {"g": g, "u": True}) is (vid in self.model)
+        if vid in self.model:
+            self.model[vid]["meta"] = {"g": g, "u": True}
+
+    @rule(shard=st.integers(0, S - 1))
+    def clear_shard(self, shard):
+        assert self.store.indices[shard].clear() is True
+        for vid in [v for v, m in self.model.items() if m["shard"] == shard]:
+            del self.model[vid]
+            self.gone.add(vid)
+
+    @rule()
+    def clear_all(self):
+        assert self.store.clear() == len(self.model)
+        self.gone.update(self.model)
+        self.model.clear()
+
+    @rule(other_devices=st.sampled_from([None, "0-1", "0-3"]))
+    def save_and_reload(self, other_devices):
+        assert self.store.save() is True
+        self.store.close()
+        keep, self.devices = self.devices, other_devices      # a store saved on G devices loads on G' (re-striped)
+        try:
+            self.store = self._open()
+        finally:
+            self.devices = keep
+        # (the reloaded store keeps running on `other_devices` until the next reload: layouts are interchangeable)
+
+    # ------------------------------------------------------------------ invariants
+    def _expected(self, q, limit, flt=None, prefilter=False):
+        """the reference's result list over the model's live rows"""
+        live = sorted(self.model.items(), key=lambda kv: kv[1]["order"])
+        if not live or limit <= 0:
+            return []
+        qn = q.astype(np.float64) / max(np.linalg.norm(q.astype(np.float64)), 1e-300)
+        scored = []
+        for vid, m in live:
+            x = m["vec"].astype(np.float64)
+            nx = np.linalg.norm(x)
+            scored.append((vid, float(x @ qn / nx) if nx > 0 else 0.0, m))
+        match = (lambda m: all(m["meta"].get(k) == v for k, v in flt.items())) if flt else (lambda m: True)
+        if flt and not prefilter:
+            # post-filter: one top-`limit` list per shard is the candidate set (vector_store.py:323-345)
+            cand = []
+            for s in range(S):
+                in_s = [t for t in scored if t[2]["shard"] == s]
+                k = min(limit, max(sum(1 for t in scored if t[2]["shard"] == ss) for ss in range(S)))
+                cand += sorted(in_s, key=lambda t: -t[1])[:k]
+            scored = cand
+        scored = [t for t in scored if match(t[2])]
+        return [(vid, m["meta"]) for vid, _, m in sorted(scored, key=lambda t: -t[1])[:min(limit, len(live))]]
+
+    @invariant()
+    def agrees_with_model(self):
+        if getattr(self, "store", None) is None:
+            return
+        st_ = self.store
+        assert st_.count() == len(self.model)
+        for vid in list(self.model)[:4] + sorted(self.gone)[:6] + sorted(self.gone)[-3:] + ["e_unknown", "p0_01"]:
+            got = st_.get(vid)
+            if vid in self.model:
+                assert got is not None and np.array_equal(np.asarray(got[0], np.float32), self.model[vid]["vec"]) \
+                    and got[1] == self.model[vid]["meta"], vid
+            else:
+                assert got is None, vid
+        q = _vec(self.seed * 7 + 3)
+        for limit in (1, 4, len(self.model) + 2):
+            got = st_.search(q.tolist(), limit=limit)
+            assert [(r[0], r[2]) for r in got] == self._expected(q, limit), ("search", limit)
+            assert all(a[1] >= b[1] for a, b in zip(got, got[1:]))
+        flt = {"g": 1}
+        got = st_.search(q.tolist(), limit=3, filter_metadata=flt)
+        assert [(r[0], r[2]) for r in got] == self._expected(q, 3, flt), "post-filter"
+        st_.prefilter = True
+        try:
+            got = st_.search(q.tolist(), limit=3, filter_metadata=flt)
+        finally:
+            st_.prefilter = False
+        assert [(r[0], r[2]) for r in got] == self._expected(q, 3, flt, prefilter=True), "pre-filter"
+
+
+class MultiDeviceStoreMachine(StoreMachine):
+    devices = "0-2"
+
+
+import os  # noqa: E402
+
+_settings = settings(max_examples=int(os.environ.get("WDBX_MODEL_EXAMPLES", "60")), stateful_step_count=int(os.environ.get("WDBX_MODEL_STEPS", "30")), deadline=None,
+                     suppress_health_check=[HealthCheck.too_slow, HealthCheck.filter_too_much, HealthCheck.data_too_large])
+TestStoreModel = StoreMachine.TestCase
+TestStoreModel.settings = _settings
+TestMultiDeviceStoreModel = MultiDeviceStoreMachine.TestCase
+TestMultiDeviceStoreModel.settings = _settings

@@ -510,7 +510,9 @@ class VectorStore:
                 self._bulk_cleared.setdefault(g0, set()).add(shard)
                 if self.metadata:
                     for i in range(shard, g1 - g0, self.num_shards):
-                        self.metadata.pop(f"{prefix}{i}", None)
+                        vid = f"{prefix}{i}"
+                        if vid not in self._loc:   # (re-stored since as an explicit row of another shard: keeps its metadata)
+                            self.metadata.pop(vid, None)
             self._row_gids[shard] = []
             self._version += 1
             self._shard_count[shard] = 0
