@@ -42,6 +42,8 @@ class StoreMachine(RuleBasedStateMachine):
         self.store = self._open()
         self.model = {}        # id -> dict(vec, meta, shard, order)   live rows only
         self.gone = set()      # ids that existed once and do not any more
+        self.used_prefixes = set()
+        self.explicit_live = set()   # live ids that are explicit rows (not rows of a bulk_load)
         self.order = 0         # insertion counter = the engine's gid order (tie rule)
         self.prefixes = 0
         self.seed = 1000
@@ -62,6 +64,7 @@ class StoreMachine(RuleBasedStateMachine):
         else:
             self.model[vid] = {"vec": vec, "meta": meta, "shard": shard_if_new, "order": self.order}
             self.gone.discard(vid)
+            self.explicit_live.add(vid)
         self.order += 1
 
     # ------------------------------------------------------------------ mutations
@@ -74,7 +77,7 @@ class StoreMachine(RuleBasedStateMachine):
 
     @rule(target_bulk=st.booleans(), data=st.data())
     def store_existing_bulk_id(self, target_bulk, data):
-        bulk_ids = [v for v in self.model if v.startswith("p")]
+        bulk_ids = [v for v in self.model if v not in self.explicit_live]
         if not bulk_ids:
             return
         vid = data.draw(st.sampled_from(sorted(bulk_ids)))
@@ -106,15 +109,35 @@ class StoreMachine(RuleBasedStateMachine):
             for vid in vids:
                 self._put(vid, vecs[vid], meta.get(vid, {}), shard)
 
-    @rule(n=st.integers(1, 9))
-    def bulk(self, n):
-        prefix = f"p{self.prefixes}_"
-        self.prefixes += 1
+    @rule(n=st.integers(1, 13), family=st.sampled_from([None, None, "q", "q1", "q12", "e"]))
+    def bulk(self, n, family):
+        """`family`: prefixes that can collide -- with each other ("q1" + "23" = "q12" + "3") or with explicit ids ("e")"""
+        import pytest
+
+        if family is None:
+            prefix = f"p{self.prefixes}_"
+            self.prefixes += 1
+        else:
+            prefix = family
         X = np.stack([_vec(self._next_seed()) for _ in range(n)])
+
+        def digits_only_extension(a, b):
+            longer, shorter = (a, b) if len(a) > len(b) else (b, a)
+            return longer.startswith(shorter) and longer[len(shorter):].isdigit()
+
+        clash = any(prefix == p or digits_only_extension(prefix, p) for p in self.used_prefixes)
+        clash = clash or any(v.startswith(prefix) and v[len(prefix):].isdigit() and str(int(v[len(prefix):])) == v[len(prefix):]
+                             and int(v[len(prefix):]) < n for v in self.model if v in self.explicit_live)
+        if clash:
+            with pytest.raises(ValueError):
+                self.store.bulk_load(X, id_prefix=prefix)
+            return
+        self.used_prefixes.add(prefix)
         assert self.store.bulk_load(X, id_prefix=prefix) == n
         base = self.order
         for i in range(n):
             self.model[f"{prefix}{i}"] = {"vec": X[i], "meta": {}, "shard": i % S, "order": base + i}
+            self.gone.discard(f"{prefix}{i}")
         self.order += n
 
     @rule(data=st.data())
@@ -124,6 +147,7 @@ class StoreMachine(RuleBasedStateMachine):
         assert self.store.delete(vid) is (vid in self.model)
         if self.model.pop(vid, None) is not None:
             self.gone.add(vid)
+            self.explicit_live.discard(vid)
 
     @rule(data=st.data(), g=st.integers(0, 2))
     def update_meta(self, data, g):
@@ -139,12 +163,15 @@ class StoreMachine(RuleBasedStateMachine):
         for vid in [v for v, m in self.model.items() if m["shard"] == shard]:
             del self.model[vid]
             self.gone.add(vid)
+            self.explicit_live.discard(vid)
 
     @rule()
     def clear_all(self):
         assert self.store.clear() == len(self.model)
         self.gone.update(self.model)
         self.model.clear()
+        self.explicit_live.clear()
+        self.used_prefixes.clear()
 
     @rule(other_devices=st.sampled_from([None, "0-1", "0-3"]))
     def save_and_reload(self, other_devices):

@@ -615,6 +615,12 @@ class VectorStore:
             for g0_, g1_, p_ in self._bulk:
                 if p_ == id_prefix:
                     raise ValueError(f"id_prefix {id_prefix!r} already used by a bulk_load")
+                # "q1" + "23" and "q12" + "3" would both be the id "q123": a prefix that extends (or is extended by)
+                # another bulk's prefix with digits only is ambiguous
+                longer, shorter = (id_prefix, p_) if len(id_prefix) > len(p_) else (p_, id_prefix)
+                rest = longer[len(shorter):]
+                if longer.startswith(shorter) and rest.isascii() and rest.isdigit():
+                    raise ValueError(f"id_prefix {id_prefix!r} is ambiguous next to the bulk prefix {p_!r}")
             for vid in self._loc:   # an explicit id "v5" would shadow bulk row 5 of prefix "v"
                 if vid.startswith(id_prefix):
                     tail = vid[len(id_prefix):]
