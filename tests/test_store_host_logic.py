@@ -561,3 +561,22 @@ def test_operator_boundary_never_raises_like_the_reference(tmp_path):
     assert st.delete("b") is True and st.delete("b") is False
     assert "b" not in [r[0] for r in st.search([0, 1, 0, 0], 10)]
     st.close()
+
+
+def test_index_level_mutations_invalidate_the_prefilter_bitmaps(tmp_path):
+    """Found by tests/test_store_model.py: a row added through the shard's index facade did not bump the store version,
+    so a cached allow bitmap (GPU_PREFILTER) stayed in use although it was SHORTER than the segment -- on the device
+    that is a read past the bitmap.  Every mutation path invalidates the cache now."""
+    st = wdbx_b200.VectorStore(4, tmp_path, num_shards=2, config=wdbx_b200.WDBXConfig({"GPU_STRICT": True, "GPU_PREFILTER": True}),
+                               dist=wdbx_b200.DistContext(0, 1, 0), _engine_factory=FakeEngine)
+    assert st.store("a", [1, 0, 0, 0], {"g": 1}) and st.store("b", [0.9, 0.1, 0, 0], {"g": 0})
+    flt = {"g": 1}
+    assert [r[0] for r in st.search([1, 0, 0, 0], limit=5, filter_metadata=flt)] == ["a"]      # bitmaps cached
+    v0 = st._version
+    assert st.indices[0].add("c", np.asarray([1, 0.01, 0, 0], np.float32)) and st._version > v0
+    assert [r[0] for r in st.search([1, 0, 0, 0], limit=5, filter_metadata=flt)] == ["a"]      # c has no metadata: not allowed
+    st.update_metadata("c", {"g": 1})
+    assert [r[0] for r in st.search([1, 0, 0, 0], limit=5, filter_metadata=flt)] == ["a", "c"]
+    assert st.indices[st._locate("c")[0]].remove("c") and "c" not in st.metadata               # no stale metadata either
+    assert [r[0] for r in st.search([1, 0, 0, 0], limit=5, filter_metadata=flt)] == ["a"]
+    st.close()

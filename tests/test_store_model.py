@@ -140,6 +140,40 @@ class StoreMachine(RuleBasedStateMachine):
             self.gone.discard(f"{prefix}{i}")
         self.order += n
 
+    @rule(i=st.integers(0, len(EXPLICIT) - 1), shard=st.integers(0, S - 1))
+    def index_add(self, i, shard):
+        """the operator boundary used directly: a new id lands in THAT shard (not its hash shard); an existing id is
+        overwritten where it lives (the reference's per-shard indices know nothing of each other, but an id maps to one
+        row in our store: DESIGN.md decision 2)"""
+        vid, vec = EXPLICIT[i], _vec(self._next_seed())
+        assert self.store.indices[shard].add(vid, vec) is True
+        meta = self.model[vid]["meta"] if vid in self.model else {}
+        self._put(vid, vec, meta, shard)
+
+    @rule(data=st.data(), shard=st.integers(0, S - 1))
+    def index_remove(self, data, shard):
+        vid = data.draw(st.sampled_from(sorted(self.model) + ["e_unknown"]))
+        here = vid in self.model and self.model[vid]["shard"] == shard
+        assert self.store.indices[shard].remove(vid) is here
+        if here:   # (the row's metadata goes with it: an id that is gone has none, whichever level removed it)
+            del self.model[vid]
+            self.gone.add(vid)
+            self.explicit_live.discard(vid)
+
+    @rule(kind=st.sampled_from(["short", "long", "text", "empty", "nested"]), i=st.integers(0, len(EXPLICIT) - 1))
+    def store_invalid(self, kind, i):
+        bad = {"short": [1.0] * (DIM - 1), "long": [1.0] * (DIM + 2), "text": "abc", "empty": [], "nested": [[1.0] * DIM]}[kind]
+        self.store.strict = False
+        try:
+            assert self.store.store(EXPLICIT[i], bad, {"g": 0}) is False
+            good = _vec(self._next_seed())
+            other = EXPLICIT[(i + 1) % len(EXPLICIT)]
+            assert self.store.batch_store({EXPLICIT[i]: bad, other: good.tolist()}, {other: {"g": 0}}) == 1
+        finally:
+            self.store.strict = True
+        shard = self.model[other]["shard"] if other in self.model else shard_for_id(other, S)
+        self._put(other, good, {"g": 0}, shard)
+
     @rule(data=st.data())
     def delete(self, data):
         known = sorted(self.model) + ["e_unknown", "p0_999", "p0_01"]

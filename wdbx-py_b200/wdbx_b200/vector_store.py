@@ -438,6 +438,7 @@ class VectorStore:
             raise ValueError(f"Vector dimension mismatch: expected {self.vector_dim}, got {mat.shape[-1]}")
         rank, world = self.dist.rank, self.dist.world
         with self._lock:
+            self._version += 1       # every mutation path ends here or in _remove_row / _clear_shard: cached allow bitmaps die
             fresh: List[int] = []
             for i, vid in enumerate(ids):
                 loc = self._locate(vid)
@@ -494,6 +495,10 @@ class VectorStore:
                 self._gid_to_id[gid] = None
             else:
                 self._bulk_dead.add(gid)
+            # an id that is gone has no metadata -- also when the row was removed through the shard's index facade
+            # (FaissIndex.remove knows nothing of the store's metadata, indexing.py:1050-1074; a stale entry would
+            # resurface under a later row of the same id)
+            self.metadata.pop(vector_id, None)
             self._shard_live[s] -= 1
             self._version += 1
             return True
@@ -876,15 +881,17 @@ class VectorStore:
         k = min(int(limit), self.count(), _lib.MAX_K)
         if k <= 0:
             return [[]]
+        floor = float(threshold) if threshold > 0 else float("-inf")
+        # the bitmaps cover exactly the rows the segments hold NOW: keep writers out until the engine has consumed them
+        # (the engine takes bitmap pointers without lengths; the ctypes call releases the GIL, not this lock)
         with self._lock:
             maps = self._allow_bitmaps(filter_metadata)
-        floor = float(threshold) if threshold > 0 else float("-inf")
-        if self.dist.world == 1:
-            scores, gids, counts = self.engine.search_filtered_host(q[None, :], k, self.metric, floor, maps)
-        else:   # SPMD: every rank passes the bitmaps of ITS rows; the ranks merge on the device (NVLink exchange)
-            scores, gids, counts = self.engine.search_filtered_host(q[None, :], k, self.metric, floor, maps, exchange=True)
-            if (counts < 0).any():
-                raise RuntimeError("fused exchange timed out: a peer rank did not join the collective search")
+            if self.dist.world == 1:
+                scores, gids, counts = self.engine.search_filtered_host(q[None, :], k, self.metric, floor, maps)
+            else:   # SPMD: every rank passes the bitmaps of ITS rows; the ranks merge on the device (NVLink exchange)
+                scores, gids, counts = self.engine.search_filtered_host(q[None, :], k, self.metric, floor, maps, exchange=True)
+        if (counts < 0).any():
+            raise RuntimeError("fused exchange timed out: a peer rank did not join the collective search")
         c = int(counts[0])
         return [[(self._id_of(int(g)), float(s)) for g, s in zip(gids[0, :c], scores[0, :c])]]
 
