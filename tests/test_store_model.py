@@ -6,6 +6,7 @@ plain-Python model of what the reference's semantics (plus DESIGN.md's documente
 After every step: count, get, unfiltered search, post-filtered search (the reference's per-shard candidate set,
 vector_store.py:323-345) and the opt-in device pre-filter must agree with the model.  This is the class of bug ADVICE r1
 found by hand (bulk ids after a shard clear, non-canonical bulk ids, prefix collisions)."""
+import asyncio
 import shutil
 import tempfile
 
@@ -260,6 +261,15 @@ class StoreMachine(RuleBasedStateMachine):
             got = st_.search(q.tolist(), limit=limit)
             assert [(r[0], r[2]) for r in got] == self._expected(q, limit), ("search", limit)
             assert all(a[1] >= b[1] for a, b in zip(got, got[1:]))
+        # threshold: applied after the merge, only when > 0 (vector_store.py:333-334); async and batch entry points
+        full = st_.search(q.tolist(), limit=len(self.model) + 2)
+        if full:
+            t = sorted(r[1] for r in full)[len(full) // 2] - 1e-4
+            want = [r for r in full if r[1] >= t] if t > 0 else full
+            assert st_.search(q.tolist(), limit=len(self.model) + 2, threshold=t) == want, "threshold"
+            assert asyncio.run(st_.search_async(q.tolist(), limit=4)) == full[:4], "async"
+            br = st_.search_batch(np.stack([q, -q]), limit=3)
+            assert br.ids()[0] == [r[0] for r in full[:3]] and br.ids()[1] == [r[0] for r in full[::-1][:3]], "batch"
         flt = {"g": 1}
         got = st_.search(q.tolist(), limit=3, filter_metadata=flt)
         assert [(r[0], r[2]) for r in got] == self._expected(q, 3, flt), "post-filter"
