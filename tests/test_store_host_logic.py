@@ -580,3 +580,26 @@ def test_index_level_mutations_invalidate_the_prefilter_bitmaps(tmp_path):
     assert st.indices[st._locate("c")[0]].remove("c") and "c" not in st.metadata               # no stale metadata either
     assert [r[0] for r in st.search([1, 0, 0, 0], limit=5, filter_metadata=flt)] == ["a"]
     st.close()
+
+
+def test_batcher_mixed_limits_and_cancelled_requests(tmp_path):
+    """One pass serves requests with different limits (a limit <= 0 gives [] as on the synchronous path -- it used to
+    become a negative slice) and a request whose caller went away (cancelled future) does not disturb the others."""
+    st = wdbx_b200.VectorStore(4, tmp_path, num_shards=2, config=wdbx_b200.WDBXConfig({"GPU_STRICT": True, "GPU_BATCH_WINDOW_US": 50000}),
+                               dist=wdbx_b200.DistContext(0, 1, 0), _engine_factory=FakeEngine)
+    rng = np.random.default_rng(8)
+    X = rng.standard_normal((40, 4), dtype=np.float32)
+    st.bulk_load(X, id_prefix="v")
+    q = rng.standard_normal(4).astype(np.float32)
+    want = st.search(q.tolist(), limit=7)
+    b = st._batcher
+    n0 = b.batches
+    futs = [b.submit(q, 7, 0.0), b.submit(q, -1, 0.0), b.submit(q, 0, 0.0), b.submit(q, 3, 0.0), b.submit(q, 100, want[2][1])]
+    gone = b.submit(q, 5, 0.0)
+    assert gone.cancel()
+    tail = b.submit(-q, 2, 0.0)
+    got = [f.result(timeout=10) for f in futs]
+    assert got[0] == want and got[1] == [] and got[2] == [] and got[3] == want[:3] and got[4] == want[:3]
+    assert [r[0] for r in tail.result(timeout=10)] == [r[0] for r in st.search((-q).tolist(), limit=2)]
+    assert b.batches - n0 == 1                     # all of it was one pass
+    st.close()

@@ -60,31 +60,42 @@ class MicroBatcher:
                 batch.append(nxt)
             self._serve(batch)
 
+    @staticmethod
+    def _deliver(fut: Future, result=None, error=None):
+        """a request whose caller has gone away (cancelled future: client timeout) must not take the rest of its batch down"""
+        try:
+            if error is not None:
+                fut.set_exception(error)
+            else:
+                fut.set_result(result)
+        except Exception:   # InvalidStateError: cancelled / already answered
+            pass
+
     def _serve(self, batch: List[Tuple[np.ndarray, int, float, Future]]):
         store = self._store
+        batch = [b for b in batch if not b[3].cancelled()]
+        if not batch:
+            return
         try:
             Q = np.stack([b[0] for b in batch])
             live = store.count()
             k = min(max(b[1] for b in batch), live, store.max_k)
             if k <= 0:
                 for _, _, _, fut in batch:
-                    fut.set_result([])
+                    self._deliver(fut, [])
                 return
             scores, gids, counts = store._search_arrays(Q, k, store.ALL)
             self.batches += 1
             self.requests += len(batch)
             for i, (_, limit, threshold, fut) in enumerate(batch):
-                c = min(int(counts[i]), limit)
+                c = max(0, min(int(counts[i]), limit))     # limit <= 0 -> [] like the synchronous path (never a negative slice)
                 res = [(store._id_of(int(g)), float(s)) for g, s in zip(gids[i, :c], scores[i, :c])]
                 if threshold > 0:
                     res = [r for r in res if r[1] >= threshold]
-                fut.set_result([(vid, sc, store.metadata.get(vid, {})) for vid, sc in res])
+                self._deliver(fut, [(vid, sc, store.metadata.get(vid, {})) for vid, sc in res])
         except Exception as e:  # reference convention: log + [] unless strict (indexing.py:1028-1030)
+            if not store.strict:
+                store._log_error(e)
             for _, _, _, fut in batch:
-                if fut.done():
-                    continue
-                if store.strict:
-                    fut.set_exception(e)
-                else:
-                    store._log_error(e)
-                    fut.set_result([])
+                if not fut.done():
+                    self._deliver(fut, [], e if store.strict else None)
