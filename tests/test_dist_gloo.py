@@ -144,3 +144,118 @@ def test_saved_store_is_restriped_across_world_sizes():
         # "late" = 2 * id3: same cosine, so the tie rule (lower insertion id first) orders them
         assert [r[0] for r in back.search(_dataset()[0][3].tolist(), limit=2)] == ["id3", "late"]
         back.close()
+
+
+# ---------------------------------------------------------------------------------------------- random op sequences
+def _random_ops(make_store, seed, steps=70):
+    """A seeded random walk over the store's mutations (the rules of tests/test_store_model.py, without hypothesis so
+    that every rank replays exactly the same sequence); after every step a probe of what the store answers."""
+    rng = np.random.default_rng(seed)
+    dim, S = 6, 3
+    store = make_store()
+    explicit = [f"e{i}" for i in range(12)]
+    live, prefixes, transcript = set(), 0, []
+    Q = rng.standard_normal((2, dim)).astype(np.float32)
+
+    def vec():
+        return rng.standard_normal(dim).astype(np.float32)
+
+    for step in range(steps):
+        op = int(rng.integers(0, 10))
+        if op == 0:
+            vid = explicit[int(rng.integers(0, len(explicit)))]
+            store.store(vid, vec().tolist(), {"g": int(rng.integers(0, 3))})
+            live.add(vid)
+        elif op == 1:
+            ids = [explicit[i] for i in rng.choice(len(explicit), size=int(rng.integers(1, 5)), replace=False)]
+            store.batch_store({v: vec().tolist() for v in ids}, {v: {"g": 1} for v in ids[::2]})
+            live.update(ids)
+        elif op == 2:
+            n = int(rng.integers(1, 12))
+            store.bulk_load(np.stack([vec() for _ in range(n)]), id_prefix=f"p{prefixes}_")
+            live.update(f"p{prefixes}_{i}" for i in range(n))
+            prefixes += 1
+        elif op == 3 and live:
+            vid = sorted(live)[int(rng.integers(0, len(live)))]
+            transcript.append(("delete", store.delete(vid)))
+            live.discard(vid)
+        elif op == 4 and live:
+            vid = sorted(live)[int(rng.integers(0, len(live)))]
+            store.update_metadata(vid, {"g": 2, "u": step})
+        elif op == 5:
+            s = int(rng.integers(0, S))
+            store.indices[s].clear()
+            live = {v for v in live if store._locate(v) is not None}
+        elif op == 6:
+            vid = explicit[int(rng.integers(0, len(explicit)))]
+            store.indices[int(rng.integers(0, S))].add(vid, vec())
+            live.add(vid)
+        elif op == 7 and live:
+            vid = sorted(live)[int(rng.integers(0, len(live)))]
+            removed = store.indices[int(rng.integers(0, S))].remove(vid)
+            transcript.append(("index_remove", removed))
+            if removed:
+                live.discard(vid)
+        elif op == 8 and step % 3 == 0:
+            assert store.save()
+            store.close()
+            store = make_store()
+        elif op == 9 and step % 7 == 0:
+            store.clear()
+            live, prefixes = set(), prefixes   # (prefix numbers keep growing: never reused here)
+        # (scores to 4 decimals: the numpy double sums a stripe and the whole matrix in different orders; the device
+        # engine's scores are bit-identical for every rank count, tests/test_gpu_multi.py)
+        probe = {"count": store.count(), "live": len(live)}
+        for b in range(2):
+            probe[f"q{b}"] = [(i, round(s, 4), m) for i, s, m in store.search(Q[b].tolist(), limit=5)]
+            probe[f"f{b}"] = [(i, round(s, 4)) for i, s, _ in store.search(Q[b].tolist(), limit=4, filter_metadata={"g": 1})]
+        if live:
+            vid = sorted(live)[0]
+            got = store.get(vid)
+            probe["get"] = [vid, None if got is None else [round(x, 6) for x in got[0]], None if got is None else got[1]]
+        transcript.append((step, op, probe))
+    assert store.count() == len(live)
+    store.close()
+    return transcript
+
+
+def _ops_worker(rank, world, port, data_dir, outdir, seed):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "wdbx-py_b200"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    import wdbx_b200
+    from tests.fake_engine import FakeEngine
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = wdbx_b200.WDBXConfig({"GPU_STRICT": True})
+    make = lambda: wdbx_b200.VectorStore(6, data_dir, num_shards=3, dist=wdbx_b200.DistContext(rank, world, rank), config=cfg,
+                                         _engine_factory=FakeEngine)
+    out = _random_ops(make, seed)
+    Path(outdir, f"rank{rank}.json").write_text(json.dumps(out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world,seed", [(2, 11), (3, 12)])
+def test_random_op_sequences_match_a_single_rank(world, seed):
+    """The same seeded walk of mutations (explicit / batch / bulk rows, deletes, shard clears, index-level add / remove,
+    save + reload, clear) on W gloo ranks and on one rank: every probe after every step is identical -- the striping of
+    rows, overwrites on the owning rank, tombstones and the persisted partitions never leak into an answer."""
+    import wdbx_b200
+    from tests.fake_engine import FakeEngine
+
+    cfg = wdbx_b200.WDBXConfig({"GPU_STRICT": True})
+    with tempfile.TemporaryDirectory() as d1:
+        want = json.loads(json.dumps(_random_ops(
+            lambda: wdbx_b200.VectorStore(6, d1, num_shards=3, dist=wdbx_b200.DistContext(0, 1, 0), config=cfg,
+                                          _engine_factory=FakeEngine), seed)))
+    with tempfile.TemporaryDirectory() as data_dir, tempfile.TemporaryDirectory() as outdir:
+        mp.spawn(_ops_worker, args=(world, _free_port(), data_dir, outdir, seed), nprocs=world, join=True)
+        got = [json.loads(Path(outdir, f"rank{r}.json").read_text()) for r in range(world)]
+    for r in range(world):
+        assert len(got[r]) == len(want)
+        for a, b in zip(got[r], want):
+            assert a == b, (r, a, b)
