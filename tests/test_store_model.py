@@ -27,6 +27,32 @@ def _vec(seed: int) -> np.ndarray:
     return np.random.default_rng(seed).standard_normal(DIM).astype(np.float32)
 
 
+class Flaky(FakeEngine):
+    """numpy engine double whose next append / overwrite / tombstone / clear can be made to fail (fault injection)"""
+    fail = set()
+
+    def _maybe_fail(self, op):
+        if op in Flaky.fail:
+            Flaky.fail.discard(op)
+            raise RuntimeError(f"injected device failure in {op}")
+
+    def append(self, segment, rows, gids=None):
+        self._maybe_fail("append")
+        return super().append(segment, rows, gids=gids)
+
+    def overwrite(self, segment, row, vector):
+        self._maybe_fail("overwrite")
+        return super().overwrite(segment, row, vector)
+
+    def tombstone(self, segment, row, dead=True):
+        self._maybe_fail("tombstone")
+        return super().tombstone(segment, row, dead)
+
+    def clear(self, segment=-1):
+        self._maybe_fail("clear")
+        return super().clear(segment)
+
+
 class StoreMachine(RuleBasedStateMachine):
     devices = None          # subclass: GPU_DEVICES of the single-process multi-device layout
 
@@ -34,8 +60,9 @@ class StoreMachine(RuleBasedStateMachine):
         cfg = {"GPU_STRICT": True}
         if self.devices:
             cfg["GPU_DEVICES"] = self.devices
+        Flaky.fail = set()
         return wdbx_b200.VectorStore(DIM, self.dir, num_shards=S, config=wdbx_b200.WDBXConfig(cfg),
-                                     dist=wdbx_b200.DistContext(0, 1, 0), _engine_factory=FakeEngine)
+                                     dist=wdbx_b200.DistContext(0, 1, 0), _engine_factory=Flaky)
 
     @initialize()
     def start(self):
@@ -174,6 +201,44 @@ class StoreMachine(RuleBasedStateMachine):
             self.store.strict = True
         shard = self.model[other]["shard"] if other in self.model else shard_for_id(other, S)
         self._put(other, good, {"g": 0}, shard)
+
+    @rule(what=st.sampled_from(["store_new", "store_existing", "delete", "clear_shard", "batch"]), data=st.data())
+    def device_failure(self, what, data):
+        """the engine call inside a mutation fails once (reference convention: logged, False returned): nothing of the
+        half-done mutation may remain -- no id, no metadata change, no count change -- and the store keeps working"""
+        if self.devices or len(getattr(self.store, "devices", [0])) > 1:
+            return      # (a device group reserves room first and cannot roll back a stripe: multi_engine.py)
+        self.store.strict = False
+        try:
+            if what == "store_new":
+                fresh = [v for v in EXPLICIT if v not in self.model]
+                if fresh:
+                    Flaky.fail = {"append"}
+                    assert self.store.store(fresh[0], _vec(self._next_seed()).tolist(), {"g": 1}) is False
+            elif what == "store_existing" and self.model:
+                vid = data.draw(st.sampled_from(sorted(self.model)))
+                Flaky.fail = {"overwrite"}
+                assert self.store.store(vid, _vec(self._next_seed()).tolist(), {"g": 1, "x": 1}) is False
+            elif what == "delete" and self.model:
+                vid = data.draw(st.sampled_from(sorted(self.model)))
+                Flaky.fail = {"tombstone"}
+                assert self.store.delete(vid) is False
+            elif what == "clear_shard":
+                Flaky.fail = {"clear"}
+                assert self.store.indices[data.draw(st.integers(0, S - 1))].clear() is False
+            elif what == "batch":
+                fresh = [v for v in EXPLICIT if v not in self.model][:3]
+                if fresh:
+                    Flaky.fail = {"append"}
+                    n = self.store.batch_store({v: _vec(self._next_seed()).tolist() for v in fresh}, {v: {"g": 1} for v in fresh})
+                    # the first shard's append failed; the other shards' vectors went in
+                    stored = [v for v in fresh if self.store._locate(v) is not None]
+                    assert n == len(stored) < len(fresh)
+                    for v in stored:
+                        self._put(v, np.asarray(self.store.get(v)[0], np.float32), {"g": 1}, shard_for_id(v, S))
+        finally:
+            Flaky.fail = set()
+            self.store.strict = True
 
     @rule(data=st.data())
     def delete(self, data):

@@ -673,8 +673,7 @@ class VectorStore:
         with self._lock:
             if self._locate(vector_id) is None:
                 return False
-            ok = self._guard(False, self._remove_row, vector_id)
-            self.metadata.pop(vector_id, None)
+            ok = self._guard(False, self._remove_row, vector_id)   # (drops the metadata with the row; a failed removal keeps both)
         if self.config.get("VECTOR_STORE_SAVE_IMMEDIATELY", False):
             self._save_metadata()
         return bool(ok)
