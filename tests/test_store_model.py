@@ -29,12 +29,14 @@ def _vec(seed: int) -> np.ndarray:
 
 class Flaky(FakeEngine):
     """numpy engine double whose next append / overwrite / tombstone / clear can be made to fail (fault injection)"""
-    fail = set()
+    fail = {}      # op -> fail on the n-th call from now (1 = the next one)
 
     def _maybe_fail(self, op):
         if op in Flaky.fail:
-            Flaky.fail.discard(op)
-            raise RuntimeError(f"injected device failure in {op}")
+            Flaky.fail[op] -= 1
+            if Flaky.fail[op] <= 0:
+                del Flaky.fail[op]
+                raise RuntimeError(f"injected device failure in {op}")
 
     def append(self, segment, rows, gids=None):
         self._maybe_fail("append")
@@ -60,7 +62,7 @@ class StoreMachine(RuleBasedStateMachine):
         cfg = {"GPU_STRICT": True}
         if self.devices:
             cfg["GPU_DEVICES"] = self.devices
-        Flaky.fail = set()
+        Flaky.fail = {}
         return wdbx_b200.VectorStore(DIM, self.dir, num_shards=S, config=wdbx_b200.WDBXConfig(cfg),
                                      dist=wdbx_b200.DistContext(0, 1, 0), _engine_factory=Flaky)
 
@@ -213,23 +215,23 @@ class StoreMachine(RuleBasedStateMachine):
             if what == "store_new":
                 fresh = [v for v in EXPLICIT if v not in self.model]
                 if fresh:
-                    Flaky.fail = {"append"}
+                    Flaky.fail = {"append": 1}
                     assert self.store.store(fresh[0], _vec(self._next_seed()).tolist(), {"g": 1}) is False
             elif what == "store_existing" and self.model:
                 vid = data.draw(st.sampled_from(sorted(self.model)))
-                Flaky.fail = {"overwrite"}
+                Flaky.fail = {"overwrite": 1}
                 assert self.store.store(vid, _vec(self._next_seed()).tolist(), {"g": 1, "x": 1}) is False
             elif what == "delete" and self.model:
                 vid = data.draw(st.sampled_from(sorted(self.model)))
-                Flaky.fail = {"tombstone"}
+                Flaky.fail = {"tombstone": 1}
                 assert self.store.delete(vid) is False
             elif what == "clear_shard":
-                Flaky.fail = {"clear"}
+                Flaky.fail = {"clear": 1}
                 assert self.store.indices[data.draw(st.integers(0, S - 1))].clear() is False
             elif what == "batch":
                 fresh = [v for v in EXPLICIT if v not in self.model][:3]
                 if fresh:
-                    Flaky.fail = {"append"}
+                    Flaky.fail = {"append": 1}
                     n = self.store.batch_store({v: _vec(self._next_seed()).tolist() for v in fresh}, {v: {"g": 1} for v in fresh})
                     # the first shard's append failed; the other shards' vectors went in
                     stored = [v for v in fresh if self.store._locate(v) is not None]
@@ -237,8 +239,34 @@ class StoreMachine(RuleBasedStateMachine):
                     for v in stored:
                         self._put(v, np.asarray(self.store.get(v)[0], np.float32), {"g": 1}, shard_for_id(v, S))
         finally:
-            Flaky.fail = set()
+            Flaky.fail = {}
             self.store.strict = True
+
+    @rule(n=st.integers(S, 9), fail_at=st.integers(1, S))
+    def bulk_load_fails_midway(self, n, fail_at):
+        """the device append of shard `fail_at - 1` fails: the shards before it hold their rows, the ids of the others do
+        not resolve, the prefix stays taken, and the error reaches the caller (bulk_load is the additive API: it raises)"""
+        import pytest
+
+        if len(getattr(self.store, "devices", [0])) > 1:
+            return
+        prefix = f"p{self.prefixes}_"
+        self.prefixes += 1
+        X = np.stack([_vec(self._next_seed()) for _ in range(n)])
+        Flaky.fail = {"append": fail_at}
+        try:
+            with pytest.raises(RuntimeError, match="injected"):
+                self.store.bulk_load(X, id_prefix=prefix)
+        finally:
+            Flaky.fail = {}
+        self.used_prefixes.add(prefix)
+        base = self.order
+        for i in range(n):
+            if i % S < fail_at - 1:
+                self.model[f"{prefix}{i}"] = {"vec": X[i], "meta": {}, "shard": i % S, "order": base + i}
+            else:
+                self.gone.add(f"{prefix}{i}")
+        self.order += n
 
     @rule(data=st.data())
     def delete(self, data):
