@@ -203,7 +203,24 @@ def main():
         store = play(VectorStore(vector_dim=4, data_dir=Path(t1), num_shards=2, index_type="faiss"), STORE_SCRIPT)
         facade = play(WDBX(vector_dimension=4, num_shards=2, data_dir=t2, enable_plugins=False,
                            config={"VECTOR_INDEX_TYPE": "faiss", "INDEX_TYPE": "faiss"}), FACADE_SCRIPT)
-    OUT.write_text(json.dumps({"generator": "tests/golden/make_api_golden.py (reference VectorStore / WDBX over the exact faiss stand-in)",
+    import inspect
+    from wdbx.core.indexing import VectorIndex
+
+    def surface(cls):
+        out = {}
+        for n in dir(cls):
+            f = getattr(cls, n)
+            if n.startswith("_") or not callable(f):
+                continue
+            out[n] = {"params": [p for p in inspect.signature(f).parameters if p != "self"],
+                      "defaults": {k: v.default for k, v in inspect.signature(f).parameters.items()
+                                   if v.default is not inspect.Parameter.empty and isinstance(v.default, (int, float, str, bool, type(None)))},
+                      "async": inspect.iscoroutinefunction(f)}
+        return out
+
+    surf = {"VectorIndex": surface(VectorIndex), "FaissIndex": surface(FaissIndex), "VectorStore": surface(VectorStore),
+            "WDBX": surface(WDBX), "VectorIndex.abstract": sorted(VectorIndex.__abstractmethods__)}
+    OUT.write_text(json.dumps({"surface": surf, "generator": "tests/golden/make_api_golden.py (reference VectorStore / WDBX over the exact faiss stand-in)",
                                "index_script": INDEX_SCRIPT, "index": index, "store_script": STORE_SCRIPT, "store": store, "facade_script": FACADE_SCRIPT, "facade": facade,
                                "deviations": DEVIATIONS}, separators=(",", ":")))
     print(f"wrote {OUT}: {len(index)} + {len(store)} + {len(facade)} steps")

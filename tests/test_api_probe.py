@@ -86,3 +86,37 @@ def test_scripts_match_the_reference_on_the_device(built_lib):
     with tempfile.TemporaryDirectory() as t2:
         got = play(wdbx_b200.WDBX(vector_dimension=4, num_shards=2, data_dir=t2, log_level="ERROR"), g["facade_script"])
     _check("facade", g["facade_script"], g["facade"], got, g["deviations"])
+
+
+def test_public_surface_matches_the_reference():
+    """Every public method of the reference's VectorIndex ABC / FaissIndex / VectorStore / WDBX facade exists here with
+    the same parameter names, the same simple defaults and the same sync / async nature (the fixture lists them as
+    inspected on the reference's classes).  Not carried over, by scope: the plugin registry of the
+    facade; `WDBX.vector_store` is the store attribute, which shadows the method of that name in the reference too."""
+    import inspect
+
+    from wdbx_b200.indexing import B200FlatIndex, VectorIndex
+
+    g = json.loads((GOLDEN / "api_probe_golden.json").read_text())["surface"]
+    ours = {"VectorIndex": VectorIndex, "FaissIndex": B200FlatIndex, "VectorStore": wdbx_b200.VectorStore, "WDBX": wdbx_b200.WDBX}
+    out_of_scope = {"WDBX": {"get_plugin", "register_plugin", "vector_store"}}
+    assert sorted(VectorIndex.__abstractmethods__) == g["VectorIndex.abstract"]
+    checked = 0
+    for cls_name, methods in g.items():
+        if cls_name not in ours:
+            continue
+        for name, want in methods.items():
+            if name in out_of_scope.get(cls_name, ()):
+                continue
+            f = getattr(ours[cls_name], name, None)
+            assert callable(f), f"{cls_name}.{name} is missing"
+            sig = inspect.signature(f)
+            params = [p for p in sig.parameters if p != "self"]
+            if want["params"]:                   # (the reference's VectorStore.optimize_async inspects as "()": nothing to compare)
+                assert params == want["params"], (cls_name, name, params, want["params"])
+            for k, v in want["defaults"].items():
+                if not (cls_name == "WDBX" and name == "__init__"):
+                    assert sig.parameters[k].default == v, (cls_name, name, k)
+            assert inspect.iscoroutinefunction(f) == want["async"], (cls_name, name)
+            checked += 1
+    assert checked >= 60
