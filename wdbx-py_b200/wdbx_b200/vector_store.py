@@ -401,15 +401,17 @@ class VectorStore:
 
     # ------------------------------------------------------------------ id bookkeeping
     def _id_of(self, gid: int) -> str:
-        if gid < len(self._gid_to_id):
-            v = self._gid_to_id[gid]
-            if v is not None:
-                return v
-        i = bisect.bisect_right(self._bulk_starts, gid) - 1
-        if i >= 0:
-            g0, g1, prefix = self._bulk[i]
-            if g0 <= gid < g1:
-                return f"{prefix}{gid - g0}"
+        """gid -> id; on the result path of every search (k calls per query: kept free of Python-level method calls)"""
+        v = self._gid_to_id._d.get(gid)
+        if v is not None:
+            return v
+        starts = self._bulk_starts
+        if starts:
+            i = bisect.bisect_right(starts, gid) - 1
+            if i >= 0:
+                g0, g1, prefix = self._bulk[i]
+                if gid < g1:
+                    return f"{prefix}{gid - g0}"
         return str(gid)  # same fallback as the reference's index_to_id.get(idx, str(idx)) (indexing.py:1021)
 
     def _locate(self, vector_id: str) -> Optional[Tuple[int, int, int]]:
