@@ -603,3 +603,40 @@ def test_batcher_mixed_limits_and_cancelled_requests(tmp_path):
     assert [r[0] for r in tail.result(timeout=10)] == [r[0] for r in st.search((-q).tolist(), limit=2)]
     assert b.batches - n0 == 1                     # all of it was one pass
     st.close()
+
+
+def test_async_front_end_completes_a_pass_with_one_loop_wakeup(tmp_path):
+    """search_async hands the batcher an asyncio future; the futures of one pass are completed by ONE thread-safe
+    call into their loop.  Cancelled waiters are skipped, engine errors follow the convention (strict: the awaiting
+    coroutine sees the exception; otherwise logged and [])."""
+    st = wdbx_b200.VectorStore(4, tmp_path, num_shards=1, config=wdbx_b200.WDBXConfig({"GPU_BATCH_WINDOW_US": 20000}),
+                               dist=wdbx_b200.DistContext(0, 1, 0), _engine_factory=FakeEngine)
+    rng = np.random.default_rng(5)
+    st.bulk_load(rng.standard_normal((30, 4), dtype=np.float32), id_prefix="v")
+    qs = [rng.standard_normal(4).astype(np.float32).tolist() for _ in range(12)]
+    want = [st.search(q, limit=4) for q in qs]
+
+    async def burst():
+        loop = asyncio.get_running_loop()
+        calls = []
+        orig = loop.call_soon_threadsafe
+        loop.call_soon_threadsafe = lambda *a, **kw: (calls.append(a[0].__name__), orig(*a, **kw))[1]
+        tasks = [asyncio.ensure_future(st.search_async(q, limit=4)) for q in qs]
+        await asyncio.sleep(0)                 # everybody has submitted; the window (20 ms) is still open
+        tasks[3].cancel()
+        res = await asyncio.gather(*tasks, return_exceptions=True)
+        loop.call_soon_threadsafe = orig
+        return res, calls
+
+    n0 = st._batcher.batches
+    res, calls = asyncio.run(burst())
+    assert isinstance(res[3], asyncio.CancelledError)
+    assert [r for i, r in enumerate(res) if i != 3] == [w for i, w in enumerate(want) if i != 3]
+    assert st._batcher.batches - n0 == 1 and calls.count("_complete_many") == 1
+    # engine failure inside the pass
+    st.engine.search_host = lambda *a, **kw: (_ for _ in ()).throw(RuntimeError("device lost"))
+    assert asyncio.run(st.search_async(qs[0], limit=4)) == []
+    st.strict = True
+    with pytest.raises(RuntimeError, match="device lost"):
+        asyncio.run(st.search_async(qs[0], limit=4))
+    st.close()

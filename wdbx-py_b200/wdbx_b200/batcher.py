@@ -20,6 +20,35 @@ from typing import List, Tuple
 import numpy as np
 
 
+class _LoopFuture:
+    """An asyncio future seen from the batcher thread: results are collected per event loop and handed over in one call."""
+    __slots__ = ("loop", "fut", "outcome")
+
+    def __init__(self, loop, fut):
+        self.loop, self.fut, self.outcome = loop, fut, None
+
+    def cancelled(self):
+        return self.fut.cancelled()
+
+    def done(self):
+        return self.outcome is not None or self.fut.done()
+
+    def set_result(self, result):
+        self.outcome = (result, None)
+
+    def set_exception(self, error):
+        self.outcome = (None, error)
+
+
+def _complete_many(items):
+    for fut, (result, error) in items:
+        if not fut.done():               # cancelled meanwhile (client gone)
+            if error is not None:
+                fut.set_exception(error)
+            else:
+                fut.set_result(result)
+
+
 class MicroBatcher:
     def __init__(self, store, max_batch: int = 8, window_us: float = 200.0):
         self._store = store
@@ -34,6 +63,13 @@ class MicroBatcher:
     def submit(self, query: np.ndarray, limit: int, threshold: float) -> Future:
         fut: Future = Future()
         self._q.put((query, int(limit), float(threshold), fut))
+        return fut
+
+    def submit_async(self, loop, query: np.ndarray, limit: int, threshold: float):
+        """The same for a coroutine: an asyncio future of `loop`.  All futures of one pass that belong to one loop are
+        completed by ONE ``call_soon_threadsafe`` (one wake-up of the loop per pass instead of one per request)."""
+        fut = loop.create_future()
+        self._q.put((query, int(limit), float(threshold), _LoopFuture(loop, fut)))
         return fut
 
     def close(self):
@@ -72,10 +108,25 @@ class MicroBatcher:
             pass
 
     def _serve(self, batch: List[Tuple[np.ndarray, int, float, Future]]):
-        store = self._store
         batch = [b for b in batch if not b[3].cancelled()]
         if not batch:
             return
+        try:
+            self._answer(batch)
+        finally:
+            # hand the asyncio futures of this pass to their loops: one thread-safe call per loop
+            per_loop = {}
+            for _, _, _, fut in batch:
+                if isinstance(fut, _LoopFuture) and fut.outcome is not None:
+                    per_loop.setdefault(fut.loop, []).append((fut.fut, fut.outcome))
+            for loop, items in per_loop.items():
+                try:
+                    loop.call_soon_threadsafe(_complete_many, items)
+                except RuntimeError:     # the loop is closed: nobody is waiting any more
+                    pass
+
+    def _answer(self, batch):
+        store = self._store
         try:
             Q = np.stack([b[0] for b in batch])
             live = store.count()
@@ -87,12 +138,15 @@ class MicroBatcher:
             scores, gids, counts = store._search_arrays(Q, k, store.ALL)
             self.batches += 1
             self.requests += len(batch)
+            # one conversion per array instead of one numpy scalar per element (this loop is the per-request cost)
+            gl, sl, cl = gids.tolist(), scores.tolist(), counts.tolist()
+            id_of, meta = store._id_of, store.metadata
             for i, (_, limit, threshold, fut) in enumerate(batch):
-                c = max(0, min(int(counts[i]), limit))     # limit <= 0 -> [] like the synchronous path (never a negative slice)
-                res = [(store._id_of(int(g)), float(s)) for g, s in zip(gids[i, :c], scores[i, :c])]
+                c = max(0, min(cl[i], limit))     # limit <= 0 -> [] like the synchronous path (never a negative slice)
+                res = [(id_of(g), s) for g, s in zip(gl[i][:c], sl[i][:c])]
                 if threshold > 0:
                     res = [r for r in res if r[1] >= threshold]
-                self._deliver(fut, [(vid, sc, store.metadata.get(vid, {})) for vid, sc in res])
+                self._deliver(fut, [(vid, sc, meta.get(vid, {})) for vid, sc in res])
         except Exception as e:  # reference convention: log + [] unless strict (indexing.py:1028-1030)
             if not store.strict:
                 store._log_error(e)

@@ -905,7 +905,7 @@ class VectorStore:
             query_np = self._query_array(query_vector)
             if query_np.shape != (self.vector_dim,):   # same outcome as the synchronous path: logged and [] (GPU_STRICT: raises)
                 return self.search(query_vector, limit, threshold, None)
-            return await asyncio.wrap_future(self._batcher.submit(query_np, limit, threshold))
+            return await self._batcher.submit_async(asyncio.get_running_loop(), query_np, limit, threshold)
         return await self._run(self.search, query_vector, limit, threshold, filter_metadata)
 
     ALL = ALL
