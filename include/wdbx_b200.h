@@ -9,8 +9,10 @@
  *   - every call returns WDBX_B200_OK (0) or a negative error code, never throws, never exits;
  *     wdbx_b200_last_error() returns a thread-local message for the last failure;
  *   - one engine owns the row partitions ("segments", one per logical WDBX shard) that live in
- *     the HBM of ONE device; one process drives one GPU, multi-GPU runs are one engine per rank
- *     and exchange packed keys (NCCL all-gather in the host layer) that wdbx_b200_merge() reduces;
+ *     the HBM of ONE device.  Several GPUs: either one engine per rank (one process per GPU), which exchange
+ *     packed keys on the device over NVLink peer memory (wdbx_b200_search_exchange*) or through an NCCL
+ *     all-gather in the host layer that wdbx_b200_merge() reduces -- or ONE process driving 2-8 engines as a
+ *     group (wdbx_b200_group_*);
  *   - there is NO CPU fallback: without a usable CUDA device every compute call fails with
  *     WDBX_B200_ERR_CUDA.
  *
@@ -253,6 +255,7 @@ int wdbx_b200_set_tuning(wdbx_b200_engine* e, int warps, int stages, int rows_un
 /* Change a routing knob of a live engine (the WDBX_B200_* environment variables read at creation):
  * "shadow_min_mb" (-1 = never use the bf16-shadow filter for small batches, else the store size in MiB from which
  * it is used), "gemm_min_batch" (0 = never use the tensor-core path), "gemm_mode", "pdl", "queries_per_pass",
+ * "filter_i8" (0 = small batches stream the bf16 shadow instead of the 1-byte one),
  * "overlap" (1 = consecutive device-resident small-batch searches on one stream overlap on the device: the next
  * search streams its first tiles while the previous one finishes its tail; results stay in launch order.  Contract:
  * the query buffer of such a search must not be produced by work enqueued on that stream after the previous search).
