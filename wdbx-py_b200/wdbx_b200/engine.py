@@ -2,7 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Optional, Tuple
+from typing import Dict, Optional
 
 import numpy as np
 

@@ -8,7 +8,6 @@ search is a single kernel launch instead of a Python loop over shards.
 """
 from __future__ import annotations
 
-import asyncio
 import logging
 from abc import ABC, abstractmethod
 from pathlib import Path
