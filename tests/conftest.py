@@ -16,6 +16,18 @@ for p in (ROOT, ROOT / "wdbx-py_b200"):
         sys.path.insert(0, str(p))
 
 
+try:   # the gates must not depend on a random seed: hypothesis tests replay a fixed set of examples
+    import os
+
+    from hypothesis import settings as _hyp_settings
+
+    _hyp_settings.register_profile("gate", derandomize=True)
+    _hyp_settings.register_profile("explore", derandomize=False)
+    _hyp_settings.load_profile("explore" if os.environ.get("WDBX_MODEL_RANDOM") else "gate")
+except ImportError:
+    pass
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
 

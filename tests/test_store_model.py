@@ -381,6 +381,7 @@ class MultiDeviceStoreMachine(StoreMachine):
 import os  # noqa: E402
 
 _settings = settings(max_examples=int(os.environ.get("WDBX_MODEL_EXAMPLES", "60")), stateful_step_count=int(os.environ.get("WDBX_MODEL_STEPS", "30")), deadline=None,
+                     derandomize=os.environ.get("WDBX_MODEL_RANDOM", "") == "",   # the gate runs a fixed walk; explore with WDBX_MODEL_RANDOM=1
                      suppress_health_check=[HealthCheck.too_slow, HealthCheck.filter_too_much, HealthCheck.data_too_large])
 TestStoreModel = StoreMachine.TestCase
 TestStoreModel.settings = _settings
