@@ -313,7 +313,7 @@ class StoreMachine(RuleBasedStateMachine):
         # (the reloaded store keeps running on `other_devices` until the next reload: layouts are interchangeable)
 
     # ------------------------------------------------------------------ invariants
-    def _expected(self, q, limit, flt=None, prefilter=False):
+    def _expected(self, q, limit, flt=None, prefilter=False, threshold=0.0):
         """the reference's result list over the model's live rows"""
         live = sorted(self.model.items(), key=lambda kv: kv[1]["order"])
         if not live or limit <= 0:
@@ -333,6 +333,8 @@ class StoreMachine(RuleBasedStateMachine):
                 k = min(limit, max(sum(1 for t in scored if t[2]["shard"] == ss) for ss in range(S)))
                 cand += sorted(in_s, key=lambda t: -t[1])[:k]
             scored = cand
+        if threshold > 0:     # after the merge, before the filter (vector_store.py:333-342); the pre-filter uses it as a floor
+            scored = [t for t in scored if t[1] >= threshold]
         scored = [t for t in scored if match(t[2])]
         return [(vid, m["meta"]) for vid, _, m in sorted(scored, key=lambda t: -t[1])[:min(limit, len(live))]]
 
@@ -372,6 +374,18 @@ class StoreMachine(RuleBasedStateMachine):
         finally:
             st_.prefilter = False
         assert [(r[0], r[2]) for r in got] == self._expected(q, 3, flt, prefilter=True), "pre-filter"
+        if full:   # threshold together with a filter, both semantics (t sits between two scores: no boundary ties)
+            ss = sorted((r[1] for r in full), reverse=True)
+            hi, lo = ss[len(ss) // 3], ss[min(len(ss) // 3 + 1, len(ss) - 1)]
+            t = (hi + lo) / 2 if hi - lo > 1e-4 else lo - 1e-3
+            got = st_.search(q.tolist(), limit=3, threshold=t, filter_metadata=flt)
+            assert [(r[0], r[2]) for r in got] == self._expected(q, 3, flt, threshold=t), "post-filter + threshold"
+            st_.prefilter = True
+            try:
+                got = st_.search(q.tolist(), limit=3, threshold=t, filter_metadata=flt)
+            finally:
+                st_.prefilter = False
+            assert [(r[0], r[2]) for r in got] == self._expected(q, 3, flt, prefilter=True, threshold=t), "pre-filter + threshold"
 
 
 class MultiDeviceStoreMachine(StoreMachine):
