@@ -640,3 +640,46 @@ def test_async_front_end_completes_a_pass_with_one_loop_wakeup(tmp_path):
     with pytest.raises(RuntimeError, match="device lost"):
         asyncio.run(st.search_async(qs[0], limit=4))
     st.close()
+
+
+@pytest.mark.parametrize("devices", [None, "0-2"])
+def test_limits_above_the_engine_maximum_are_served_by_paging(tmp_path, devices, monkeypatch):
+    """The reference returns up to `limit` rows (indexing.py:1005); the engine's widest list is MAX_K.  Larger limits
+    are answered by successive exact passes over the rows not returned yet (masked with the pre-filter's allow bitmaps):
+    the concatenation must be the exact ranking, duplicates (ties) and deleted rows included."""
+    import wdbx_b200._lib as lib
+
+    monkeypatch.setattr(lib, "MAX_K", 16)            # small pages: the walk below needs 1 + 87 // 16 of them
+    cfg = {"GPU_STRICT": True}
+    if devices:
+        cfg["GPU_DEVICES"] = devices
+    st = wdbx_b200.VectorStore(6, tmp_path, num_shards=3, config=wdbx_b200.WDBXConfig(cfg),
+                               dist=wdbx_b200.DistContext(0, 1, 0), _engine_factory=FakeEngine)
+    rng = np.random.default_rng(17)
+    X = rng.standard_normal((90, 6), dtype=np.float32)
+    if not devices:      # (the numpy double sums the stripes of a device group in different orders: its "ties" are not
+        X[40] = X[7]     #  bit-exact across devices as the real engine's are, tests/test_gpu_multi.py)
+        X[41] = X[7]     # a three-way tie somewhere in the ranking
+    st.bulk_load(X[:60], id_prefix="v")
+    st.batch_store({f"w{i}": X[60 + i] for i in range(30)}, {f"w{i}": {"i": i} for i in range(30)})
+    for vid in ("v3", "w4", "v59"):
+        st.delete(vid)
+    q = rng.standard_normal(6).astype(np.float32)
+    names = [f"v{i}" for i in range(60)] + [f"w{i}" for i in range(30)]
+    dead = np.zeros(90, bool)
+    dead[[3, 64, 59]] = True
+    from oracle import exact_search as oracle
+    rows, _ = oracle.topk_desc(oracle.scores_fp32(X, q, "cosine"), 90, dead=dead)
+    want = [names[r] for r in rows]
+    for limit in (17, 40, 87, 500):
+        got = st.search(q.tolist(), limit=limit)
+        assert [g[0] for g in got] == want[:limit], limit
+        assert all(a[1] >= b[1] for a, b in zip(got, got[1:]))
+        assert got[-1][2] == st.metadata.get(got[-1][0], {})
+    assert [g[0] for g in st.search(q.tolist(), limit=16)] == want[:16]          # at the maximum: the ordinary path
+    if not devices:
+        assert [g[0] for g in st.search(X[7].tolist(), limit=30)][:3] == ["v7", "v40", "v41"]
+    # threshold and filters keep their semantics (a filtered search stays one list of <= MAX_K per shard)
+    thr = st.search(q.tolist(), limit=80, threshold=0.2)
+    assert [g[0] for g in thr] == [g[0] for g in st.search(q.tolist(), limit=87) if g[1] >= 0.2]
+    st.close()

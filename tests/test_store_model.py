@@ -68,6 +68,11 @@ class StoreMachine(RuleBasedStateMachine):
 
     @initialize()
     def start(self):
+        # a small engine maximum: searches that ask for more than 8 neighbours are served by PAGING (allow bitmaps over the
+        # rows not returned yet, vector_store._search_paged) -- the full-ranking probes below walk several pages
+        import wdbx_b200._lib as lib
+
+        self._max_k, lib.MAX_K = lib.MAX_K, 8
         self.dir = tempfile.mkdtemp(prefix="wdbx_model_")
         self.store = self._open()
         self.model = {}        # id -> dict(vec, meta, shard, order)   live rows only
@@ -79,6 +84,9 @@ class StoreMachine(RuleBasedStateMachine):
         self.seed = 1000
 
     def teardown(self):
+        import wdbx_b200._lib as lib
+
+        lib.MAX_K = getattr(self, "_max_k", lib.MAX_K)
         if getattr(self, "store", None) is not None:
             self.store.close()
         shutil.rmtree(getattr(self, "dir", ""), ignore_errors=True)

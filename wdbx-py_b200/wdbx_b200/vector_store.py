@@ -809,6 +809,8 @@ class VectorStore:
         if k <= 0:
             return [[] for _ in range(nlists)]
         if limit > _lib.MAX_K and scope > _lib.MAX_K:
+            if sel == ALL and self.dist.world == 1 and hasattr(self.engine, "search_filtered_host"):
+                return [self._search_paged(q, min(int(limit), scope))]
             logger.warning("limit=%d clipped to the engine maximum of %d", limit, _lib.MAX_K)
         scores, gids, counts = self._search_arrays(q[None, :], k, sel)
         id_of = self._id_of
@@ -817,6 +819,41 @@ class VectorStore:
                     for i in range(nlists)]
         c = int(counts[0])
         return [[(id_of(g), s) for g, s in zip(gids[0, :c].tolist(), scores[0, :c].tolist())]]
+
+    def _search_paged(self, q: np.ndarray, want: int) -> List[Tuple[str, float]]:
+        """More than MAX_K neighbours (the reference returns up to `limit` rows, indexing.py:1005): successive exact passes
+        of MAX_K, each over the rows NOT returned so far -- they are masked out with the per-row allow bitmaps of the
+        pre-filter path (the select kernel consults them), so page n+1 continues exactly where page n stopped: the
+        concatenation is the exact top-`want`, ties included (the key order is total).  One full scan per page;
+        single process (one engine or a device group), unfiltered searches."""
+        out: List[Tuple[str, float]] = []
+        id_of = self._id_of
+        with self._lock:     # the bitmaps cover exactly the rows present now (see _search_prefiltered)
+            orders = [np.concatenate(r) if r else np.empty(0, np.uint32) for r in self._row_gids]   # ascending gids per shard
+            maps = []
+            for o in orders:
+                bits = np.ones(o.shape[0], dtype=np.uint8)
+                pad = (-bits.shape[0]) % 32
+                maps.append(np.packbits(np.concatenate([bits, np.zeros(pad, np.uint8)]), bitorder="little").view(np.uint32)
+                            if bits.size else np.zeros(0, np.uint32))
+            while len(out) < want:
+                k = min(_lib.MAX_K, want - len(out))
+                scores, gids, counts = self.engine.search_filtered_host(q[None, :], k, self.metric, float("-inf"), maps)
+                c = int(counts[0])
+                if c <= 0:
+                    break
+                page = gids[0, :c]
+                for s_, o in enumerate(orders):          # clear the bits of this page's rows in their shard
+                    if o.shape[0] == 0:
+                        continue
+                    pos = np.searchsorted(o, page)
+                    hit = (pos < o.shape[0]) & (o[np.minimum(pos, o.shape[0] - 1)] == page)
+                    p = pos[hit]
+                    np.bitwise_and.at(maps[s_], p >> 5, ~(np.uint32(1) << (p & 31).astype(np.uint32)))
+                out.extend((id_of(g), sc) for g, sc in zip(page.tolist(), scores[0, :c].tolist()))
+                if c < k:
+                    break
+        return out
 
     def _query_array(self, query_vector) -> np.ndarray:
         """fp32 array of a query given as a list of Python floats (the reference API's form).  struct.pack does
