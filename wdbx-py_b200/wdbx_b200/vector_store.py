@@ -835,7 +835,7 @@ class VectorStore:
                 bits = np.ones(o.shape[0], dtype=np.uint8)
                 pad = (-bits.shape[0]) % 32
                 maps.append(np.packbits(np.concatenate([bits, np.zeros(pad, np.uint8)]), bitorder="little").view(np.uint32)
-                            if bits.size else np.zeros(0, np.uint32))
+                            if bits.size else None)      # (None = "all rows" of an empty shard: nothing to copy)
             while len(out) < want:
                 k = min(_lib.MAX_K, want - len(out))
                 scores, gids, counts = self.engine.search_filtered_host(q[None, :], k, self.metric, float("-inf"), maps)
