@@ -97,13 +97,13 @@ class BatchResult:
         self.gids, self.scores, self.counts, self._store = gids, scores, counts, store
 
     def ids(self) -> List[List[str]]:
-        s = self._store
-        return [[s._id_of(int(g)) for g in self.gids[b, : self.counts[b]]] for b in range(self.gids.shape[0])]
+        id_of = self._store._id_of       # one tolist() per array: numpy scalars cost more than the mapping itself
+        return [[id_of(g) for g in row[:c]] for row, c in zip(self.gids.tolist(), self.counts.tolist())]
 
     def as_lists(self) -> List[List[Tuple[str, float]]]:
-        s = self._store
-        return [[(s._id_of(int(g)), float(v)) for g, v in zip(self.gids[b, :c], self.scores[b, :c])]
-                for b, c in enumerate(self.counts)]
+        id_of = self._store._id_of
+        return [[(id_of(g), v) for g, v in zip(grow[:c], srow[:c])]
+                for grow, srow, c in zip(self.gids.tolist(), self.scores.tolist(), self.counts.tolist())]
 
 
 class VectorStore:
